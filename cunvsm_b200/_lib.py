@@ -1,0 +1,103 @@
+"""ctypes binding of libnvsm_b200.so (C ABI: include/nvsm_b200.h).
+
+There is no fallback: if the shared library is missing or cannot be loaded this module
+raises at first use, and every compute entry point fails without a CUDA device.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnvsm_b200.so")
+
+# every symbol include/nvsm_b200.h declares
+SYMBOLS = [
+    "nvsm_last_error", "nvsm_version", "nvsm_create", "nvsm_destroy", "nvsm_set_stream", "nvsm_synchronize",
+    "nvsm_initialize", "nvsm_tensor_size", "nvsm_get_tensor", "nvsm_set_tensor", "nvsm_generate_labels",
+    "nvsm_compute_cost", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost",
+    "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
+    "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
+    "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
+    "nvsm_comm_init",
+]
+
+
+class NvsmConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_words", ctypes.c_long), ("num_entities", ctypes.c_long),
+        ("word_repr_size", ctypes.c_int), ("entity_repr_size", ctypes.c_int),
+        ("nonlinearity", ctypes.c_int), ("batch_normalization", ctypes.c_int),
+        ("clip_sigmoid", ctypes.c_int), ("bias_negative_samples", ctypes.c_int),
+        ("l2_normalize_phrase_reprs", ctypes.c_int), ("l2_normalize_entity_reprs", ctypes.c_int),
+        ("update_method", ctypes.c_int), ("adam_mode", ctypes.c_int),
+        ("num_random_entities", ctypes.c_int), ("max_batch_size", ctypes.c_int),
+        ("window_size", ctypes.c_int), ("regularization_lambda", ctypes.c_float),
+        ("device", ctypes.c_int), ("gemm_mode", ctypes.c_int), ("num_batch_slots", ctypes.c_int),
+        ("reserved", ctypes.c_int * 7),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libnvsm_b200.so and declare the prototypes. Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libnvsm_b200.so is not built (%s). Run `python -m cunvsm_b200.build`; there is no CPU "
+            "or PyTorch fallback for the NVSM step." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, cl, ci, cf = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
+    pl, pf = ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_float)
+    pul = ctypes.POINTER(ctypes.c_ulong)
+    cs = ctypes.c_char_p
+
+    def f(name, argtypes, restype=ci):
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+    f("nvsm_last_error", [], cs)
+    f("nvsm_version", [])
+    f("nvsm_create", [ctypes.POINTER(NvsmConfig), ctypes.POINTER(vp)])
+    f("nvsm_destroy", [vp], None)
+    f("nvsm_set_stream", [vp, vp])
+    f("nvsm_synchronize", [vp])
+    f("nvsm_initialize", [vp, pul])
+    f("nvsm_tensor_size", [vp, cs], cl)
+    f("nvsm_get_tensor", [vp, cs, pf, cl])
+    f("nvsm_set_tensor", [vp, cs, pf, cl])
+    f("nvsm_generate_labels", [pl, cl, cl, cl, pul, pl])
+    f("nvsm_compute_cost", [vp, pl, pf, pl, pf, cl])
+    f("nvsm_compute_gradients", [vp])
+    f("nvsm_update", [vp, cf, cf])
+    f("nvsm_get_cost", [vp, pf])
+    f("nvsm_read_cost", [vp, ci, pf])
+    f("nvsm_scaled_regularization_lambda", [vp], cf)
+    f("nvsm_train_step", [vp, pl, pf, pl, pf, cl, cf])
+    f("nvsm_stage_batch", [vp, ci, pl, pf, pl, pf, cl])
+    f("nvsm_compute_cost_staged", [vp, ci])
+    f("nvsm_train_step_staged", [vp, ci, cf])
+    f("nvsm_infer", [vp, pl, cl, cl, pf])
+    f("nvsm_increment_parameter", [vp, cs, cl, cf])
+    f("nvsm_set_profiling", [vp, ci])
+    f("nvsm_num_phases", [])
+    f("nvsm_phase_name", [ci], cs)
+    f("nvsm_get_phase_ms", [vp, pf, ci])
+    f("nvsm_reset_phase_ms", [vp])
+    f("nvsm_kernel_launches", [vp], cl)
+    f("nvsm_comm_unique_id", [ctypes.c_char_p])
+    f("nvsm_comm_init", [vp, ctypes.c_char_p, ci, ci])
+    _lib = L
+    return L
+
+
+class NvsmError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise NvsmError(load().nvsm_last_error().decode("utf-8", "replace"))

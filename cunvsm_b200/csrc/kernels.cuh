@@ -1,0 +1,682 @@
+// Hand-written sm_100a kernels of the NVSM/LSE step: embedding gather-mean, batch-norm
+// statistics, the fused score / NCE-loss / backward-through-dot kernel, batch-norm
+// backward, and the sparse scatter-add + optimiser kernels. All are HBM/L2-bandwidth
+// bound integer-indexed row traffic: one warp per n-gram, 128-bit accesses, warp-shuffle
+// reductions, vector REDG for the scatter.
+//
+// Reference behaviour each kernel replaces is cited per kernel (paths relative to the
+// reference tree). Tables are row-major [objects, dim] fp32, i.e. the memory image of the
+// reference's column-major dim x objects matrices.
+#pragma once
+
+#include "common.cuh"
+
+namespace nvsm {
+
+// =====================================================================================
+// gather_mean: P[o, :] = (1/window) * sum_w wt[o, w] * table[idx[o, w], :]
+// Replaces average_repr_kernel (cpp/params.cu:75-95) for both get_average_representations
+// (:138-172) and the plain gather get_representations (:97-121; window 1, no weights).
+// The mean divides by the window even when weighted (quirk pinned by
+// cpp/model_tests.cu:115-122).
+// =====================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ table, int dim,
+                                                          const idx_t* __restrict__ ids,
+                                                          const float* __restrict__ wts,
+                                                          long num_out, int window,
+                                                          float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim / VEC;
+    const float fwin = (float)window;
+    for (long o = warp0; o < num_out; o += nwarps) {
+        const idx_t* oid = ids + o * window;
+        const float* ow = wts ? wts + o * window : nullptr;
+        for (int c = lane; c < nvec; c += kWarp) {
+            float acc[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll 5
+            for (int w = 0; w < window; ++w) {
+                const idx_t id = __ldg(oid + w);
+                const float wt = ow ? __ldg(ow + w) : 1.0f;
+                float x[VEC];
+                load_vec_ro<VEC>(table + id * dim + c * VEC, x);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] += wt * x[v];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = acc[v] / fwin;
+            store_vec<VEC>(out + o * dim + c * VEC, acc);
+        }
+    }
+}
+
+// =====================================================================================
+// col_stats: sums[c] += sum_i Z[i, c], sums[dd + c] += sum_i Z[i, c]^2 (double).
+// First half of cudnnBatchNormalizationForwardTraining, per-activation mode
+// (cpp/cudnn_utils.cu:107-124). fp32 partials per thread, one double atomic per column
+// per block.
+// =====================================================================================
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ Z, long rows, int dd,
+                                                        double* __restrict__ sums) {
+    // thread t owns column (t % cols_per_pass) of every (t / cols_per_pass)-th row of its slab.
+    const int tpr = min(dd, (int)blockDim.x);          // threads per row
+    const int rpp = blockDim.x / tpr;                   // rows per pass
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    if (tr >= rpp) return;
+    const long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = min(rows, r0 + rows_per_block);
+    for (int c = tc; c < dd; c += tpr) {
+        float s = 0.f, q = 0.f;
+        for (long r = r0 + tr; r < r1; r += rpp) {
+            const float x = __ldg(Z + r * dd + c);
+            s += x;
+            q += x * x;
+        }
+        if (r0 + tr < r1) {
+            atomicAdd(sums + c, (double)s);
+            atomicAdd(sums + dd + c, (double)q);
+        }
+    }
+}
+
+// mean / invstd from the (all-reduced) sums; biased variance, eps inside the sqrt.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int dd, double batch, double eps,
+                                   float* __restrict__ mean, float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dd) return;
+    const double mu = sums[c] / batch;
+    double var = sums[dd + c] / batch - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + eps));
+}
+
+// Numerically careful variant: second pass accumulating sum (x - mean)^2.
+__global__ void __launch_bounds__(256) col_var_kernel(const float* __restrict__ Z, long rows, int dd,
+                                                      const double* __restrict__ sums, double batch,
+                                                      double* __restrict__ var_sums) {
+    const int tpr = min(dd, (int)blockDim.x);
+    const int rpp = blockDim.x / tpr;
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    if (tr >= rpp) return;
+    const long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = min(rows, r0 + rows_per_block);
+    for (int c = tc; c < dd; c += tpr) {
+        const float mu = (float)(sums[c] / batch);
+        float q = 0.f;
+        for (long r = r0 + tr; r < r1; r += rpp) {
+            const float d = __ldg(Z + r * dd + c) - mu;
+            q += d * d;
+        }
+        if (r0 + tr < r1) atomicAdd(var_sums + c, (double)q);
+    }
+}
+
+__global__ void bn_finalize2_kernel(const double* __restrict__ sums, const double* __restrict__ var_sums,
+                                    int dd, double batch, double eps, float* __restrict__ mean,
+                                    float* __restrict__ invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dd) return;
+    mean[c] = (float)(sums[c] / batch);
+    invstd[c] = (float)(1.0 / sqrt(var_sums[c] / batch + eps));
+}
+
+// =====================================================================================
+// score: everything between the projection and the backward GEMMs, without ever
+// materialising a d_d x B*R matrix. Per n-gram i (one warp):
+//   y      = f(BN?(Z[i]))                                  cpp/params.cu:425-446
+//   s_r    = +-(y . E[id[i,r]])        negatives negated    cpp/objective.cu:159-239
+//   p_r    = clamp(sigmoid(s_r))                            :242-246
+//   loss  += wbc_r * log p_r                                :249-305, intermediate_results.cu:80-124
+//   mult_r = wbc_r * (p_r in (eps, 1-eps) ? 1 - p_r : 0) / B     :354-371
+//   Gp[i]  = (sum_r mult_r * (+-E[id])) .* f'(y)            :420-425, params.cu:474-491
+//   column sums of Gp (-> grad_bias, BN backward)           params.cu:510-520
+// =====================================================================================
+struct ScoreParams {
+    const float* Z;        // [B, dd] pre-activation
+    const float* E;        // [D, dd]
+    const idx_t* ids;      // [B*R], positive first
+    const float* inst_w;   // [B]
+    long B;
+    int R, dd;
+    float w_scale;         // (z+1)/(2z) when rebalancing, else 1   (objective.cu:268-274)
+    float pos_scale;       // z when rebalancing, else 1            (objective.cu:282-290)
+    double sig_lo, sig_hi;     // forward clamp  [eps, 1 - eps], eps = 1e-7 or 0
+    double der_lo, der_hi;     // zero-gradient band, eps = 1e-6 or 0
+    float bsn;             // exp(-log(B_global))
+    ActParams act;
+    float* probs;          // [B*R]
+    float* mult;           // [B*R]
+    float* Gp;             // [B, dd]
+    double* loss_acc;      // [1]  sum_c wbc_c log p_c
+    double* col_sums;      // [2*dd]: sum_i dy, sum_i dy * xhat
+};
+
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
+    constexpr int RB = 4;  // entity rows in flight per warp
+    extern __shared__ float smem[];  // [2*dd] column sums + [1] loss
+    const int lane = threadIdx.x & 31;
+    const int dd = p.dd;
+    const int nvec = dd / VEC;
+    for (int t = threadIdx.x; t < 2 * dd + 1; t += blockDim.x) smem[t] = 0.f;
+    __syncthreads();
+
+    float cs[NCH][VEC], cx[NCH][VEC];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { cs[j][v] = 0.f; cx[j][v] = 0.f; }
+    float loss = 0.f;
+
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long i = warp0; i < p.B; i += nwarps) {
+        float y[NCH][VEC], xh[NCH][VEC], gp[NCH][VEC];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            float z[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { z[v] = 0.f; gp[j][v] = 0.f; }
+            if (c < nvec) load_vec_ro<VEC>(p.Z + i * dd + c * VEC, z);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                y[j][v] = 0.f; xh[j][v] = 0.f;
+                if (c < nvec) y[j][v] = act_forward(p.act, z[v], c * VEC + v, xh[j][v]);
+            }
+        }
+        const float wneg = __ldg(p.inst_w + i) * p.w_scale;
+        const float wpos = wneg * p.pos_scale;
+        const idx_t* rid = p.ids + i * p.R;
+
+        for (int r0 = 0; r0 < p.R; r0 += RB) {
+            float e[RB][NCH][VEC];
+            float dot[RB];
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) {
+                const bool valid = r0 + rr < p.R;
+                const idx_t id = valid ? __ldg(rid + r0 + rr) : 0;
+                dot[rr] = 0.f;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) e[rr][j][v] = 0.f;
+                    if (valid && c < nvec) load_vec_ro<VEC>(p.E + id * dd + c * VEC, e[rr][j]);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) dot[rr] += y[j][v] * e[rr][j][v];
+                dot[rr] = warp_sum(dot[rr]);
+            }
+            float my_p = 0.f, my_m = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < RB; ++rr) {
+                const int r = r0 + rr;
+                if (r < p.R) {
+                    const float sign = r == 0 ? 1.0f : -1.0f;
+                    const float s = sign * dot[rr];
+                    // numerically stable sigmoid (include/cuNVSM/cuda_utils.h:192-214)
+                    float prob;
+                    if (s >= 0.f) {
+                        prob = 1.0f / (1.0f + expf(-s));
+                    } else {
+                        const float ex = expf(s);
+                        prob = ex / (1.0f + ex);
+                    }
+                    prob = (float)fmin(fmax((double)prob, p.sig_lo), p.sig_hi);
+                    const float w = r == 0 ? wpos : wneg;
+                    loss += w * logf(prob);
+                    const double pd = (double)prob;
+                    const float der = (pd >= p.der_hi || pd <= p.der_lo) ? 0.0f : (float)(1.0 - pd);
+                    const float m = w * (der * p.bsn);
+                    if (lane == rr) { my_p = prob; my_m = m; }
+                    const float coef = sign * m;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) gp[j][v] += coef * e[rr][j][v];
+                }
+            }
+            if (lane < RB && r0 + lane < p.R) {
+                p.probs[i * p.R + r0 + lane] = my_p;
+                p.mult[i * p.R + r0 + lane] = my_m;
+            }
+        }
+        // d cost / d (pre-activation); column sums for grad_bias and BN backward.
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            float dy[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                dy[v] = act_deriv(p.act, y[j][v]) * gp[j][v];
+                cs[j][v] += dy[v];
+                cx[j][v] += dy[v] * xh[j][v];
+            }
+            if (c < nvec) store_vec<VEC>(p.Gp + i * dd + c * VEC, dy);
+        }
+    }
+    // block reduction of the per-warp partials, then one double atomic per column per block
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = lane + j * kWarp;
+        if (c < nvec) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                atomicAdd(&smem[c * VEC + v], cs[j][v]);
+                atomicAdd(&smem[dd + c * VEC + v], cx[j][v]);
+            }
+        }
+    }
+    if (lane == 0) atomicAdd(&smem[2 * dd], loss);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)smem[t]);
+    if (threadIdx.x == 0) atomicAdd(p.loss_acc, (double)smem[2 * dd]);
+}
+
+// =====================================================================================
+// bn_backward: dx = invstd * (dy - sum(dy)/B - xhat * sum(dy*xhat)/B), in place over Gp.
+// cudnnBatchNormalizationBackward, per-activation, gamma == 1 (cpp/cudnn_utils.cu:158-177;
+// formula pinned by cpp/cudnn_utils_tests.cu:143-176).
+// =====================================================================================
+__global__ void __launch_bounds__(256) bn_backward_kernel(float* __restrict__ Gp, const float* __restrict__ Z,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd,
+                                                          const double* __restrict__ col_sums, double batch,
+                                                          long rows, int dd) {
+    const long total = rows * dd;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % dd);
+        const float is = __ldg(invstd + c);
+        const float xh = (Z[t] - __ldg(mean + c)) * is;
+        const float sb = (float)(col_sums[c] / batch);
+        const float sg = (float)(col_sums[dd + c] / batch);
+        Gp[t] = is * (Gp[t] - sb - xh * sg);
+    }
+}
+
+// grad_bias = column sums of dy (both with and without batch-norm; cpp/params.cu:510-520).
+__global__ void col_sums_to_float_kernel(const double* __restrict__ col_sums, int dd, float* __restrict__ gb) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < dd) gb[c] = (float)col_sums[c];
+}
+
+// =====================================================================================
+// Split-K partial reduction for grad_transform: out[i] = sum_z part[z][i].
+// =====================================================================================
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int splits, long n,
+                                       float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long)z * n + i];
+    out[i] = s;
+}
+
+// =====================================================================================
+// Sparse scatter-add (replaces update_repr_kernel, cpp/storage.cu:37-49). The gradient of
+// the entity table is never materialised: grad_entity[:, c] = +-mult[c] * y[i(c)]
+// (cpp/objective.cu:381-401) is recomputed from Z on the fly.
+//   target[id[i,r], :] += scale * factor(c) * (+-mult[c]) * y[i, :]
+// factor(c) = 1/sqrt(acc[id] + eps) for Adagrad (adagrad_update_kernel,
+// cpp/updates_adagrad.cu:83-97, window 1), else 1.
+// =====================================================================================
+struct EntityScatterParams {
+    const float* Z;
+    ActParams act;
+    const idx_t* ids;
+    const float* mult;
+    long B;
+    int R, dd;
+    float* target;
+    float scale;
+    const float* acc;  // nullable
+    float eps;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) entity_scatter_kernel(const EntityScatterParams p) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = p.dd / VEC;
+    for (long i = warp0; i < p.B; i += nwarps) {
+        for (int c = lane; c < nvec; c += kWarp) {
+            float z[VEC], y[VEC];
+            load_vec_ro<VEC>(p.Z + i * p.dd + c * VEC, z);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float xh;
+                y[v] = act_forward(p.act, z[v], c * VEC + v, xh);
+            }
+            for (int r = 0; r < p.R; ++r) {
+                const long col = i * p.R + r;
+                const idx_t id = __ldg(p.ids + col);
+                float coef = p.scale * __ldg(p.mult + col);
+                if (r != 0) coef = -coef;
+                if (p.acc) coef = coef / sqrtf(__ldg(p.acc + id) + p.eps);
+                float g[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) g[v] = coef * y[v];
+                red_add_vec<VEC>(p.target + id * p.dd + c * VEC, g);
+            }
+        }
+    }
+}
+
+//   target[id[i,w], :] += scale * factor(i) * fw[i,w] * G[i, :]
+// (update_repr_kernel with window n and per-word weights; factor(i) =
+// 1/sqrt(mean_w acc[id[i,w]] + eps) for Adagrad.)
+struct WordScatterParams {
+    const float* G;  // [B, dw]
+    const idx_t* ids;
+    const float* fw;
+    long B;
+    int n, dw;
+    float* target;
+    float scale;
+    const float* acc;  // nullable
+    float eps;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) word_scatter_kernel(const WordScatterParams p) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = p.dw / VEC;
+    for (long i = warp0; i < p.B; i += nwarps) {
+        const idx_t* wid = p.ids + i * p.n;
+        const float* ww = p.fw + i * p.n;
+        float factor = 1.0f;
+        if (p.acc) {
+            float a = 0.f;
+            for (int w = 0; w < p.n; ++w) a += __ldg(p.acc + __ldg(wid + w));
+            a /= (float)p.n;
+            factor = 1.0f / sqrtf(a + p.eps);
+        }
+        for (int c = lane; c < nvec; c += kWarp) {
+            float g[VEC];
+            load_vec_ro<VEC>(p.G + i * p.dw + c * VEC, g);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) g[v] *= factor;
+#pragma unroll 5
+            for (int w = 0; w < p.n; ++w) {
+                const idx_t id = __ldg(wid + w);
+                const float coef = p.scale * __ldg(ww + w);
+                float u[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) u[v] = coef * g[v];
+                red_add_vec<VEC>(p.target + id * p.dw + c * VEC, u);
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// Per-object scalar second moments (Adagrad, sparse / dense-update Adam):
+//   acc[id] += scale * wt * mean_k grad[k, col]^2
+// (reduce_axis<square> + scale by 1/rows, then update_repr_kernel with one-thread blocks:
+// cpp/updates_adagrad.cu:130-158, cpp/updates_adam.cu:215-250.)
+// =====================================================================================
+// ysq[i] = mean_k y[i,k]^2 (entity side: mean_k grad_entity[k,c]^2 = mult[c]^2 * ysq[i]).
+__global__ void __launch_bounds__(256) row_meansq_act_kernel(const float* __restrict__ Z, const ActParams act,
+                                                             long rows, int dd, float inv_dim,
+                                                             float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long i = warp0; i < rows; i += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < dd; c += kWarp) {
+            float xh;
+            const float y = act_forward(act, __ldg(Z + i * dd + c), c, xh);
+            s += y * y;
+        }
+        s = warp_sum(s);
+        if (lane == 0) out[i] = s * inv_dim;
+    }
+}
+
+__global__ void __launch_bounds__(256) row_meansq_kernel(const float* __restrict__ G, long rows, int dim,
+                                                         float inv_dim, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long i = warp0; i < rows; i += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < dim; c += kWarp) {
+            const float g = __ldg(G + i * dim + c);
+            s += g * g;
+        }
+        s = warp_sum(s);
+        if (lane == 0) out[i] = s * inv_dim;
+    }
+}
+
+__global__ void entity_scalar_scatter_kernel(const idx_t* __restrict__ ids, const float* __restrict__ mult,
+                                             const float* __restrict__ ysq, long total, int R, float scale,
+                                             float* __restrict__ acc) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const float m = mult[c];
+    atomicAdd(acc + ids[c], scale * (m * m * ysq[c / R]));
+}
+
+__global__ void word_scalar_scatter_kernel(const idx_t* __restrict__ ids, const float* __restrict__ fw,
+                                           const float* __restrict__ msq, long total, int n, float scale,
+                                           float* __restrict__ acc) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    atomicAdd(acc + ids[c], scale * fw[c] * msq[c / n]);
+}
+
+// =====================================================================================
+// Dense helpers.
+// =====================================================================================
+__global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, long n, float s) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n >> 2;
+    float4* x4 = reinterpret_cast<float4*>(x);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = x4[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        x4[i] = v;
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= s;
+}
+
+// Sparse Adam step for the entity table (window 1), cpp/updates_adam.cu:132-151,339-385:
+//   E[id_c, :] += lr * bc * m[id_c, :] / (sqrt(v[id_c]) + eps)      for every column c.
+template <int VEC>
+__global__ void __launch_bounds__(256) adam_sparse_entity_kernel(const idx_t* __restrict__ ids, long total, int dd,
+                                                                 const float* __restrict__ m,
+                                                                 const float* __restrict__ v, float bc,
+                                                                 float eps, float lr,
+                                                                 float* __restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dd / VEC;
+    for (long c = warp0; c < total; c += nwarps) {
+        const idx_t id = __ldg(ids + c);
+        const float den = sqrtf(__ldg(v + id)) + eps;
+        for (int k = lane; k < nvec; k += kWarp) {
+            float mm[VEC], u[VEC];
+            load_vec<VEC>(m + id * dd + k * VEC, mm);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) u[q] = lr * (bc * mm[q] / den);
+            red_add_vec<VEC>(E + id * dd + k * VEC, u);
+        }
+    }
+}
+
+// Sparse Adam "gradient" for the word table (window n): overwrites G[i, :] with
+//   bc * mean_w m[id_w, :] / (sqrt(mean_w v[id_w]) + eps)      (adam_sparse_update_kernel)
+template <int VEC>
+__global__ void __launch_bounds__(256) adam_sparse_word_grad_kernel(const idx_t* __restrict__ ids, long B, int n,
+                                                                    int dw, const float* __restrict__ m,
+                                                                    const float* __restrict__ v, float bc,
+                                                                    float eps, float* __restrict__ G) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dw / VEC;
+    const float fn = (float)n;
+    for (long i = warp0; i < B; i += nwarps) {
+        const idx_t* wid = ids + i * n;
+        float av = 0.f;
+        for (int w = 0; w < n; ++w) av += __ldg(v + __ldg(wid + w));
+        av /= fn;
+        const float den = sqrtf(av) + eps;
+        for (int k = lane; k < nvec; k += kWarp) {
+            float am[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) am[q] = 0.f;
+            for (int w = 0; w < n; ++w) {
+                float mm[VEC];
+                load_vec<VEC>(m + __ldg(wid + w) * dw + k * VEC, mm);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) am[q] += mm[q];
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) am[q] = bc * (am[q] / fn) / den;
+            store_vec<VEC>(G + i * dw + k * VEC, am);
+        }
+    }
+}
+
+// DENSE_UPDATE Adam (cpp/updates_adam.cu:286-309): per-object scalar v.
+//   theta = theta * (1 - lambda*lr) + lr * bc * m / (sqrt(v[obj]) + eps)
+__global__ void __launch_bounds__(256) adam_dense_update_kernel(float* __restrict__ theta, const float* __restrict__ m,
+                                                                const float* __restrict__ v, long num_objects,
+                                                                int dim, float decay, float lr, float bc,
+                                                                float eps) {
+    const long total = num_objects * dim;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const float den = sqrtf(__ldg(v + t / dim)) + eps;
+        theta[t] = theta[t] * decay + ((m[t] / den) * bc) * lr;
+    }
+}
+
+// DENSE_UPDATE_DENSE_VARIANCE ("full_adam", cpp/updates_adam.cu:199-213,251-283,310-328),
+// one fused pass over theta / m / v / agg (agg = scatter-added gradient of this step):
+//   g  = agg - lambda * theta
+//   m  = s1 * m + lr1 * agg - (lr1' * lambda) * theta      (== s1*m + (1-b1) * g)
+//   v  = s2 * v + lr2 * g^2
+//   theta += lr * bc * m / (sqrt(v) + eps);   agg = 0 (ready for the next step)
+__global__ void __launch_bounds__(256) adam_full_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                        float* __restrict__ v, float* __restrict__ agg, long n,
+                                                        float s1, float lr1, float reg1, float s2, float lr2,
+                                                        float lambda, float lr, float bc, float eps) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n4 = n >> 2;
+    float4* t4 = reinterpret_cast<float4*>(theta);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4* a4 = reinterpret_cast<float4*>(agg);
+    auto one = [&](float& th, float& mm, float& vv, float& ag) {
+        const float g = ag + (-lambda * th);
+        mm = (mm * s1 + lr1 * ag) + (-reg1 * th);
+        vv = vv * s2 + (g * g) * lr2;
+        th = th + ((mm / (sqrtf(vv) + eps)) * bc) * lr;
+        ag = 0.f;
+    };
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 th = t4[i], mm = m4[i], vv = v4[i], ag = a4[i];
+        one(th.x, mm.x, vv.x, ag.x);
+        one(th.y, mm.y, vv.y, ag.y);
+        one(th.z, mm.z, vv.z, ag.z);
+        one(th.w, mm.w, vv.w, ag.w);
+        t4[i] = th; m4[i] = mm; v4[i] = vv; a4[i] = ag;
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        one(theta[i], m[i], v[i], agg[i]);
+}
+
+// Dense optimiser for the projection: T [dw*dd] followed by b [dd] in one launch.
+// SGD: cpp/storage.cu:198-228; Adagrad: cpp/updates_adagrad.cu:33-70; Adam:
+// cpp/updates_adam.cu:46-105 — the bias is never regularised and its Adam moments never
+// decay (pinned by cpp/updates_tests.cu:352-366,409-423).
+struct TransformUpdateParams {
+    float* T; float* b;
+    const float* gT; const float* gb;
+    long nT; int nb;
+    int method;      // 0 sgd, 1 adagrad, 2 adam
+    float lr, lambda;
+    float* aT; float* ab;   // adagrad acc / adam m
+    float* vT; float* vb;   // adam v
+    float s1, lr1, s2, lr2, bc, eps;
+};
+
+__global__ void __launch_bounds__(256) transform_update_kernel(const TransformUpdateParams p) {
+    const long total = p.nT + p.nb;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const bool is_bias = t >= p.nT;
+        const long k = is_bias ? t - p.nT : t;
+        float* th = is_bias ? p.b + k : p.T + k;
+        float g = is_bias ? p.gb[k] : p.gT[k];
+        const float lam = is_bias ? 0.f : p.lambda;
+        if (p.method == 0) {
+            *th = *th * (1.0f - lam * p.lr) + g * p.lr;
+        } else if (p.method == 1) {
+            float* a = is_bias ? p.ab + k : p.aT + k;
+            const float acc = *a + g * g;
+            *a = acc;
+            g = g / sqrtf(acc + p.eps);
+            *th = *th * (1.0f - lam * p.lr) + g * p.lr;
+        } else {
+            float* mm = is_bias ? p.ab + k : p.aT + k;
+            float* vv = is_bias ? p.vb + k : p.vT + k;
+            g = g + (-lam * *th);
+            const float m = *mm * (is_bias ? 1.0f : p.s1) + g * p.lr1;
+            const float v = *vv * (is_bias ? 1.0f : p.s2) + (g * g) * p.lr2;
+            *mm = m;
+            *vv = v;
+            g = (m * p.bc) / (sqrtf(v) + p.eps);
+            *th = *th + g * p.lr;
+        }
+    }
+}
+
+// Dense-ify grad_entity for inspection: out[c, :] = +-mult[c] * y[i(c), :].
+__global__ void __launch_bounds__(256) materialize_grad_entity_kernel(const float* __restrict__ Z, const ActParams act,
+                                                                      const float* __restrict__ mult, long total_cols,
+                                                                      int R, int dd, float* __restrict__ out) {
+    const long total = total_cols * dd;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long c = t / dd;
+        const int k = (int)(t % dd);
+        const long i = c / R;
+        float xh;
+        const float y = act_forward(act, Z[i * dd + k], k, xh);
+        const float g = y * mult[c];
+        out[t] = (c % R) != 0 ? -g : g;
+    }
+}
+
+// Y = f(BN?(Z)) for inspection / inference.
+__global__ void __launch_bounds__(256) materialize_activation_kernel(const float* __restrict__ Z, const ActParams act,
+                                                                     long rows, int dd, float* __restrict__ out) {
+    const long total = rows * dd;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        float xh;
+        out[t] = act_forward(act, Z[t], (int)(t % dd), xh);
+    }
+}
+
+__global__ void increment_kernel(float* p, float eps) { *p += eps; }
+
+}  // namespace nvsm

@@ -1,0 +1,1056 @@
+// libnvsm_b200.so — host side of the B200-native NVSM/LSE training step and its C ABI
+// (include/nvsm_b200.h). One nvsm_model owns the parameter tables, the optimiser state and
+// a fixed per-step workspace in HBM; every step is a short, allocation-free sequence of
+// kernel launches on one stream.
+#include "../../include/nvsm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+using namespace nvsm;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+
+#define CU(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)                 \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+enum Phase {
+    PH_H2D = 0, PH_GATHER, PH_GEMM_FWD, PH_BN_STATS, PH_SCORE, PH_BN_BWD, PH_GEMM_GT, PH_GEMM_GP,
+    PH_UPD_ENTITIES, PH_UPD_WORDS, PH_UPD_TRANSFORM, PH_ALLREDUCE, PH_COUNT
+};
+const char* kPhaseNames[PH_COUNT] = {
+    "h2d", "gather_mean", "gemm_fwd", "bn_stats", "score_loss_bwd", "bn_backward", "gemm_grad_transform",
+    "gemm_grad_phrase", "update_entities", "update_words", "update_transform", "allreduce"};
+
+struct BatchSlot {
+    idx_t* features = nullptr;   // [maxB*n]
+    float* fweights = nullptr;   // [maxB*n]
+    idx_t* ids = nullptr;        // [maxB*R]
+    float* weights = nullptr;    // [maxB]
+    long B = 0;
+    cudaEvent_t ready = nullptr;     // H2D done
+    cudaEvent_t consumed = nullptr;  // last step reading it has been enqueued and finished
+    bool ever_consumed = false;
+    bool in_use = false;  // a forward result reads it and no `consumed` event covers that yet
+};
+
+struct TableOpt {  // optimiser state of one embedding table
+    float* m = nullptr;    // Adam first moment [N, dim]
+    float* v = nullptr;    // Adam second moment: [N] (sparse / dense-update) or [N, dim] (full)
+    float* acc = nullptr;  // Adagrad [N]
+    float* agg = nullptr;  // full Adam: scatter-added gradient of the running step [N, dim], kept zero between steps
+    unsigned long t = 1;
+};
+
+}  // namespace
+
+struct nvsm_model {
+    nvsm_config cfg;
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    bool own_stream = false;
+    long V, D;
+    int dw, dd, n, z, R;
+    long maxB;
+
+    // parameters
+    float *W = nullptr, *E = nullptr, *T = nullptr, *b = nullptr;
+    TableOpt optW, optE;
+    float *T_a = nullptr, *b_a = nullptr, *T_v = nullptr, *b_v = nullptr;  // transform acc/m, v
+    unsigned long t_transform = 1;
+
+    // batches
+    std::vector<BatchSlot> slots;  // cfg.num_batch_slots staged + 2 live (host-fed) slots
+    int next_live = 0;
+    BatchSlot* cur = nullptr;      // batch of the running forward result
+    long B = 0;                    // local instances of the running step
+    long Bglobal = 0;
+
+    // per-step workspace
+    float *P = nullptr, *Z = nullptr, *Gp = nullptr, *gP = nullptr;
+    float *probs = nullptr, *mult = nullptr, *rowtmp = nullptr;
+    float *mean = nullptr, *invstd = nullptr;
+    double* dsums = nullptr;   // [2*dd fwd sums][dd var sums][2*dd bwd col sums][1 loss]
+    float *gT = nullptr, *gb = nullptr, *gT_part = nullptr;
+    int gt_splits = 1;
+    float* scratch = nullptr;  // inspection buffer max(B*R*dd, ...) allocated on demand
+    size_t scratch_bytes = 0;
+    // loss read-back ring: every forward ends with an async D2H of its loss sum
+    static constexpr int kCostRing = 16;
+    double* loss_host = nullptr;  // pinned [kCostRing]
+    cudaEvent_t loss_ev[kCostRing] = {nullptr};
+    long loss_B[kCostRing] = {0};
+    long forward_count = 0;
+    bool have_forward = false, have_gradients = false;
+
+    // instrumentation
+    long launches = 0;
+    bool profiling = false;
+    struct Ev { int phase; cudaEvent_t a, b; };
+    std::vector<Ev> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double phase_ms[PH_COUNT] = {0};
+    int open_phase = -1;
+    cudaEvent_t open_ev = nullptr;
+
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int nranks = 1, rank = 0;
+
+    double* fwd_sums() { return dsums; }
+    double* var_sums() { return dsums + 2 * dd; }
+    double* bwd_sums() { return dsums + 3 * dd; }
+    double* loss_acc() { return dsums + 5 * dd; }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------
+template <typename T>
+int dev_alloc(T** p, size_t count, bool zero = true) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    return 0;
+}
+
+cudaEvent_t get_event(nvsm_model* m) {
+    if (!m->ev_pool.empty()) {
+        cudaEvent_t e = m->ev_pool.back();
+        m->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void phase_begin(nvsm_model* m, int phase) {
+    if (!m->profiling) return;
+    m->open_phase = phase;
+    m->open_ev = get_event(m);
+    cudaEventRecord(m->open_ev, m->stream);
+}
+
+void phase_end(nvsm_model* m) {
+    if (!m->profiling || m->open_phase < 0) return;
+    cudaEvent_t e = get_event(m);
+    cudaEventRecord(e, m->stream);
+    m->pending.push_back({m->open_phase, m->open_ev, e});
+    m->open_phase = -1;
+}
+
+int collect_phases(nvsm_model* m) {
+    if (m->pending.empty()) return 0;
+    CU(cudaStreamSynchronize(m->stream));
+    for (auto& ev : m->pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev.a, ev.b);
+        m->phase_ms[ev.phase] += ms;
+        m->ev_pool.push_back(ev.a);
+        m->ev_pool.push_back(ev.b);
+    }
+    m->pending.clear();
+    return 0;
+}
+
+int grid_for(const nvsm_model* m, long work_items, int items_per_block, int blocks_per_sm) {
+    long need = (work_items + items_per_block - 1) / items_per_block;
+    long cap = (long)m->num_sms * blocks_per_sm;
+    return (int)std::max<long>(1, std::min(need, cap));
+}
+
+#define LAUNCH(m, kernel, grid, block, smem, ...)                                   \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), (m)->stream>>>(__VA_ARGS__);              \
+        (m)->launches++;                                                            \
+        cudaError_t le_ = cudaPeekAtLastError();                                    \
+        if (le_ != cudaSuccess)                                                     \
+            return fail("launch %s: %s (%s:%d)", #kernel, cudaGetErrorString(le_),  \
+                        __FILE__, __LINE__);                                        \
+    } while (0)
+
+ActParams act_params(const nvsm_model* m, bool use_bn) {
+    ActParams a;
+    a.nonlinearity = m->cfg.nonlinearity;
+    a.use_bn = use_bn ? 1 : 0;
+    // func::clip(-1, 1): bounds one ulp outside (include/cuNVSM/cuda_utils.h:91-95)
+    a.clip_min = std::nextafter(-1.0f, -1.0f - 1e-5f);
+    a.clip_max = std::nextafter(1.0f, 1.0f + 1e-5f);
+    a.mean = m->mean;
+    a.invstd = m->invstd;
+    a.bias = m->b;
+    return a;
+}
+
+bool vec4_ok(int dim) { return dim % 4 == 0; }
+
+// ------------------------------------------------------------------------------------
+// GEMM dispatch (fp32 SIMT path)
+// ------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+int run_sgemm(nvsm_model* m, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, float* C,
+              int ldc, int splits, float alpha, const float* bias) {
+    int kps = (K + splits - 1) / splits;
+    kps = (kps + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+    dim3 grid((N + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, (K + kps - 1) / kps);
+    LAUNCH(m, (sgemm_kernel<TA, TB>), grid, 256, 0, M, N, K, A, lda, Bm, ldb, C, ldc, kps, alpha, bias);
+    return 0;
+}
+
+int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
+    if (m->nranks <= 1) return 0;
+    phase_end(m);
+    phase_begin(m, PH_ALLREDUCE);
+    int rc = nccl_api().AllReduce(buf, buf, count, is_double ? kNcclFloat64 : kNcclFloat32, kNcclSum, m->comm,
+                                  (void*)m->stream);
+    phase_end(m);
+    if (rc != 0) return fail("ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// forward: Model::compute_cost on a device-resident batch
+// ------------------------------------------------------------------------------------
+template <int VEC, int NCH>
+int launch_score(nvsm_model* m, const ScoreParams& sp) {
+    const int grid = grid_for(m, sp.B, 8, 3);
+    const size_t smem = (2 * (size_t)sp.dd + 1) * sizeof(float);
+    LAUNCH(m, (score_kernel<VEC, NCH>), grid, 256, smem, sp);
+    return 0;
+}
+
+int dispatch_score(nvsm_model* m, const ScoreParams& sp) {
+    const int dd = sp.dd;
+    if (vec4_ok(dd)) {
+        const int nch = (dd / 4 + 31) / 32;
+        if (nch <= 1) return launch_score<4, 1>(m, sp);
+        if (nch <= 2) return launch_score<4, 2>(m, sp);
+        if (nch <= 3) return launch_score<4, 3>(m, sp);
+        if (nch <= 4) return launch_score<4, 4>(m, sp);
+        if (nch <= 8) return launch_score<4, 8>(m, sp);
+    } else {
+        const int nch = (dd + 31) / 32;
+        if (nch <= 1) return launch_score<1, 1>(m, sp);
+        if (nch <= 4) return launch_score<1, 4>(m, sp);
+        if (nch <= 16) return launch_score<1, 16>(m, sp);
+    }
+    return fail("entity_repr_size %d is not supported (max 1024 when a multiple of 4, else 512)", dd);
+}
+
+int forward(nvsm_model* m, BatchSlot* s) {
+    const long B = s->B;
+    if (B <= 0) return fail("empty batch");
+    m->cur = s;
+    s->in_use = true;
+    m->B = B;
+    m->Bglobal = B * m->nranks;
+    m->have_forward = false;
+    m->have_gradients = false;
+    CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
+    const bool bn = m->cfg.batch_normalization != 0;
+    const int dw = m->dw, dd = m->dd;
+
+    CU(cudaMemsetAsync(m->dsums, 0, (5 * (size_t)dd + 1) * sizeof(double), m->stream));
+
+    // (1) phrase representations: weighted mean of the word rows.
+    phase_begin(m, PH_GATHER);
+    {
+        const int grid = grid_for(m, B, 8, 8);
+        if (vec4_ok(dw))
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P);
+        else
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P);
+    }
+    phase_end(m);
+
+    // (2) projection Z = P . T (+ b when batch-norm is off).
+    phase_begin(m, PH_GEMM_FWD);
+    TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, dw, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
+    phase_end(m);
+
+    // (3) batch statistics over the (global) batch.
+    if (bn) {
+        phase_begin(m, PH_BN_STATS);
+        const int grid = grid_for(m, B, 64, 4);
+        LAUNCH(m, col_stats_kernel, grid, 256, 0, m->Z, B, dd, m->fwd_sums());
+        phase_end(m);
+        TRY(allreduce(m, m->fwd_sums(), dd, true));
+        phase_begin(m, PH_BN_STATS);
+        LAUNCH(m, col_var_kernel, grid, 256, 0, m->Z, B, dd, m->fwd_sums(), (double)m->Bglobal, m->var_sums());
+        phase_end(m);
+        TRY(allreduce(m, m->var_sums(), dd, true));
+        phase_begin(m, PH_BN_STATS);
+        LAUNCH(m, bn_finalize2_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), m->var_sums(), dd,
+               (double)m->Bglobal, 1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd);
+        phase_end(m);
+    }
+
+    // (4) scores, loss, multipliers and d cost / d pre-activation in one pass.
+    phase_begin(m, PH_SCORE);
+    {
+        ScoreParams sp;
+        sp.Z = m->Z; sp.E = m->E; sp.ids = s->ids; sp.inst_w = s->weights;
+        sp.B = B; sp.R = m->R; sp.dd = dd;
+        const bool rebalance = !m->cfg.bias_negative_samples && m->z > 1;
+        sp.w_scale = rebalance ? (float)(((double)(float)m->z + 1.0) / (2.0 * (double)(float)m->z)) : 1.0f;
+        sp.pos_scale = rebalance ? (float)m->z : 1.0f;
+        const float ef = m->cfg.clip_sigmoid ? 1e-7f : 0.0f;
+        const float eb = m->cfg.clip_sigmoid ? 1e-6f : 0.0f;
+        sp.sig_lo = (double)ef; sp.sig_hi = 1.0 - (double)ef;
+        sp.der_lo = (double)eb; sp.der_hi = 1.0 - (double)eb;
+        sp.bsn = (float)std::exp(-std::log((double)m->Bglobal));
+        sp.act = act_params(m, bn);
+        sp.probs = m->probs; sp.mult = m->mult; sp.Gp = m->Gp;
+        sp.loss_acc = m->loss_acc(); sp.col_sums = m->bwd_sums();
+        TRY(dispatch_score(m, sp));
+    }
+    phase_end(m);
+    TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true));
+    {
+        const int slot = (int)(m->forward_count % nvsm_model::kCostRing);
+        CU(cudaMemcpyAsync(m->loss_host + slot, m->loss_acc(), sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaEventRecord(m->loss_ev[slot], m->stream));
+        m->loss_B[slot] = m->Bglobal;
+        m->forward_count++;
+    }
+    m->have_forward = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// backward: Model::compute_gradients
+// ------------------------------------------------------------------------------------
+int backward(nvsm_model* m) {
+    if (!m->have_forward) return fail("compute_gradients called without a forward result");
+    const long B = m->B;
+    const bool bn = m->cfg.batch_normalization != 0;
+    const int dw = m->dw, dd = m->dd;
+
+    phase_begin(m, PH_BN_BWD);
+    LAUNCH(m, col_sums_to_float_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, m->gb);
+    if (bn) {
+        const int grid = grid_for(m, B * dd, 256 * 8, 8);
+        LAUNCH(m, bn_backward_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->bwd_sums(),
+               (double)m->Bglobal, B, dd);
+    }
+    phase_end(m);
+
+    // grad_transform[dw, dd] = P^T . dX  (K = B: split-K partials + deterministic reduce)
+    phase_begin(m, PH_GEMM_GT);
+    {
+        const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
+        int splits = std::max(1, std::min(m->gt_splits, (2 * m->num_sms + tiles - 1) / tiles));
+        splits = (int)std::min<long>(splits, std::max<long>(1, B / 64));
+        int kps = (int)((B + splits - 1) / splits);
+        kps = (kps + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+        const int nz = (int)((B + kps - 1) / kps);
+        TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, dw, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
+        const long nT = (long)dw * dd;
+        LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, nz, nT, m->gT);
+    }
+    phase_end(m);
+    TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
+
+    // grad_phrase[B, dw] = dX . T^T, scaled by 1/n (cpp/objective.cu:453-476)
+    phase_begin(m, PH_GEMM_GP);
+    {
+        const float inv_n = (float)std::exp(-std::log((double)m->n));
+        TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
+    }
+    phase_end(m);
+    m->have_gradients = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// update: Model::update — entities, words, transform (cpp/model.cu:187-220)
+// ------------------------------------------------------------------------------------
+struct AdamConsts {
+    float b1, b2, lr1, lr2, s1, s2, eps;
+};
+
+AdamConsts adam_consts() {
+    AdamConsts c;
+    c.b1 = 0.9f; c.b2 = 0.999f;  // include/cuNVSM/updates.h:205-211
+    c.lr1 = (float)(1.0 - (double)c.b1);
+    c.lr2 = (float)(1.0 - (double)c.b2);
+    c.s1 = (float)(1.0 - (double)(1.0f * c.lr1));  // storage decay with lambda = 1, lr = 1 - beta
+    c.s2 = (float)(1.0 - (double)(1.0f * c.lr2));
+    c.eps = 1e-6f;  // DEFAULT_EPSILON, include/cuNVSM/updates.h:21
+    return c;
+}
+
+float adam_bias_correction(const AdamConsts& c, unsigned long t) {
+    return (float)(std::sqrt(1.0 - std::pow((double)c.b2, (double)t)) / (1.0 - std::pow((double)c.b1, (double)t)));
+}
+
+int scale_table(nvsm_model* m, float* x, long count, float s) {
+    const int grid = grid_for(m, count / 4 + 1, 256, 8);
+    LAUNCH(m, scale_kernel, grid, 256, 0, x, count, s);
+    return 0;
+}
+
+int scatter_entities(nvsm_model* m, float* target, float scale, const float* acc, float eps) {
+    EntityScatterParams p;
+    p.Z = m->Z; p.act = act_params(m, m->cfg.batch_normalization != 0);
+    p.ids = m->cur->ids; p.mult = m->mult; p.B = m->B; p.R = m->R; p.dd = m->dd;
+    p.target = target; p.scale = scale; p.acc = acc; p.eps = eps;
+    const int grid = grid_for(m, m->B, 8, 8);
+    if (vec4_ok(m->dd)) LAUNCH(m, entity_scatter_kernel<4>, grid, 256, 0, p);
+    else LAUNCH(m, entity_scatter_kernel<1>, grid, 256, 0, p);
+    return 0;
+}
+
+int scatter_words(nvsm_model* m, float* target, float scale, const float* acc, float eps) {
+    WordScatterParams p;
+    p.G = m->gP; p.ids = m->cur->features; p.fw = m->cur->fweights; p.B = m->B; p.n = m->n; p.dw = m->dw;
+    p.target = target; p.scale = scale; p.acc = acc; p.eps = eps;
+    const int grid = grid_for(m, m->B, 8, 8);
+    if (vec4_ok(m->dw)) LAUNCH(m, word_scatter_kernel<4>, grid, 256, 0, p);
+    else LAUNCH(m, word_scatter_kernel<1>, grid, 256, 0, p);
+    return 0;
+}
+
+// acc_E[id] += scale * mean_k grad_entity[k, c]^2
+int scatter_entity_meansq(nvsm_model* m, float* acc, float scale) {
+    const float inv_dim = (float)std::exp(-std::log((double)m->dd));
+    LAUNCH(m, row_meansq_act_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->Z,
+           act_params(m, m->cfg.batch_normalization != 0), m->B, m->dd, inv_dim, m->rowtmp);
+    const long total = m->B * m->R;
+    LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, m->mult, m->rowtmp,
+           total, m->R, scale, acc);
+    return 0;
+}
+
+int scatter_word_meansq(nvsm_model* m, float* acc, float scale) {
+    const float inv_dim = (float)std::exp(-std::log((double)m->dw));
+    LAUNCH(m, row_meansq_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->gP, m->B, m->dw, inv_dim, m->rowtmp);
+    const long total = m->B * m->n;
+    LAUNCH(m, word_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->features, m->cur->fweights,
+           m->rowtmp, total, m->n, scale, acc);
+    return 0;
+}
+
+int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
+    float* theta = entities ? m->E : m->W;
+    TableOpt& opt = entities ? m->optE : m->optW;
+    const long N = entities ? m->D : m->V;
+    const int dim = entities ? m->dd : m->dw;
+    const long count = N * dim;
+    auto scatter = [&](float* target, float scale, const float* acc, float eps) {
+        return entities ? scatter_entities(m, target, scale, acc, eps) : scatter_words(m, target, scale, acc, eps);
+    };
+    auto scatter_meansq = [&](float* acc, float scale) {
+        return entities ? scatter_entity_meansq(m, acc, scale) : scatter_word_meansq(m, acc, scale);
+    };
+    // RepresentationsStorage::update (cpp/storage.cu:51-102): dense decay, then scatter.
+    auto sgd = [&](const float* acc, float eps) -> int {
+        if (lambda > 0.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
+        return scatter(theta, lr, acc, eps);
+    };
+    const int method = m->cfg.update_method;
+    if (method == NVSM_SGD) return sgd(nullptr, 0.f);
+    if (method == NVSM_ADAGRAD) {  // cpp/updates_adagrad.cu:99-179
+        TRY(scatter_meansq(opt.acc, 1.0f));
+        return sgd(opt.acc, 1e-6f);
+    }
+    // Adam, cpp/updates_adam.cu:153-385
+    const AdamConsts c = adam_consts();
+    const float bc = adam_bias_correction(c, opt.t);
+    opt.t += 1;
+    const int mode = m->cfg.adam_mode;
+    if (mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE) {
+        TRY(scatter(opt.agg, 1.0f, nullptr, 0.f));
+        const float reg1 = (float)((1.0 - (double)c.b1) * (double)lambda);
+        const int grid = grid_for(m, count / 4 + 1, 256, 8);
+        LAUNCH(m, adam_full_kernel, grid, 256, 0, theta, opt.m, opt.v, opt.agg, count, c.s1, c.lr1, reg1, c.s2,
+               c.lr2, lambda, lr, bc, c.eps);
+        return 0;
+    }
+    // SPARSE and DENSE_UPDATE share the moment updates: m dense decay + scatter, scalar v.
+    TRY(scale_table(m, opt.m, count, c.s1));
+    TRY(scatter(opt.m, c.lr1, nullptr, 0.f));
+    TRY(scale_table(m, opt.v, N, c.s2));
+    TRY(scatter_meansq(opt.v, c.lr2));
+    if (mode == NVSM_ADAM_DENSE_UPDATE) {
+        const int grid = grid_for(m, count, 256 * 4, 8);
+        LAUNCH(m, adam_dense_update_kernel, grid, 256, 0, theta, opt.m, opt.v, N, dim,
+               (float)(1.0 - (double)(lambda * lr)), lr, bc, c.eps);
+        return 0;
+    }
+    // SPARSE: window-averaged step, applied through the SGD scatter with dense decay.
+    if (lambda > 0.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
+    if (entities) {
+        const long total = m->B * m->R;
+        const int grid = grid_for(m, total, 8, 8);
+        if (vec4_ok(dim))
+            LAUNCH(m, adam_sparse_entity_kernel<4>, grid, 256, 0, m->cur->ids, total, dim, opt.m, opt.v, bc, c.eps, lr, theta);
+        else
+            LAUNCH(m, adam_sparse_entity_kernel<1>, grid, 256, 0, m->cur->ids, total, dim, opt.m, opt.v, bc, c.eps, lr, theta);
+        return 0;
+    }
+    {
+        const int grid = grid_for(m, m->B, 8, 8);
+        if (vec4_ok(dim))
+            LAUNCH(m, adam_sparse_word_grad_kernel<4>, grid, 256, 0, m->cur->features, m->B, m->n, dim, opt.m, opt.v, bc, c.eps, m->gP);
+        else
+            LAUNCH(m, adam_sparse_word_grad_kernel<1>, grid, 256, 0, m->cur->features, m->B, m->n, dim, opt.m, opt.v, bc, c.eps, m->gP);
+    }
+    return scatter(theta, lr, nullptr, 0.f);
+}
+
+int update_transform(nvsm_model* m, float lr, float lambda) {
+    TransformUpdateParams p;
+    p.T = m->T; p.b = m->b; p.gT = m->gT; p.gb = m->gb;
+    p.nT = (long)m->dw * m->dd; p.nb = m->dd;
+    p.method = m->cfg.update_method;
+    p.lr = lr; p.lambda = lambda;
+    p.aT = m->T_a; p.ab = m->b_a; p.vT = m->T_v; p.vb = m->b_v;
+    const AdamConsts c = adam_consts();
+    p.s1 = c.s1; p.lr1 = c.lr1; p.s2 = c.s2; p.lr2 = c.lr2; p.eps = c.eps;
+    p.bc = 1.0f;
+    if (p.method == NVSM_ADAM) {
+        p.bc = adam_bias_correction(c, m->t_transform);
+        m->t_transform += 1;
+    }
+    LAUNCH(m, transform_update_kernel, (int)((p.nT + p.nb + 255) / 256), 256, 0, p);
+    return 0;
+}
+
+int update(nvsm_model* m, float lr, float lambda) {
+    if (!m->have_gradients) return fail("update called without gradients");
+    if (lr < 0.f || lambda < 0.f) return fail("learning rate and lambda must be >= 0");
+    phase_begin(m, PH_UPD_ENTITIES);
+    TRY(update_table(m, true, lr, lambda));
+    phase_end(m);
+    phase_begin(m, PH_UPD_WORDS);
+    TRY(update_table(m, false, lr, lambda));
+    phase_end(m);
+    phase_begin(m, PH_UPD_TRANSFORM);
+    TRY(update_transform(m, lr, lambda));
+    phase_end(m);
+    // The batch slot may be overwritten once everything enqueued so far has run.
+    CU(cudaEventRecord(m->cur->consumed, m->stream));
+    m->cur->ever_consumed = true;
+    m->cur->in_use = false;
+    m->have_gradients = false;  // grad_phrase may have been overwritten (sparse Adam)
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------
+int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float* fw, const long* ids,
+                 const float* w, long B, bool use_copy_stream) {
+    if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
+    if (!features || !fw || !ids || !w) return fail("null batch pointer");
+    cudaStream_t cs = use_copy_stream ? m->copy_stream : m->stream;
+    if (cs != m->stream) {
+        if (s->in_use) {  // forward without update: order after everything enqueued so far
+            CU(cudaEventRecord(s->consumed, m->stream));
+            s->ever_consumed = true;
+        }
+        if (s->ever_consumed) CU(cudaStreamWaitEvent(cs, s->consumed, 0));
+    }
+    s->in_use = false;
+    if (cs == m->stream) phase_begin(m, PH_H2D);
+    CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->ids, ids, sizeof(long) * B * m->R, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
+    if (cs == m->stream) phase_end(m);
+    CU(cudaEventRecord(s->ready, cs));
+    s->B = B;
+    return 0;
+}
+
+BatchSlot* next_live_slot(nvsm_model* m) {
+    BatchSlot* s = &m->slots[m->cfg.num_batch_slots + m->next_live];
+    m->next_live ^= 1;
+    return s;
+}
+
+int ensure_scratch(nvsm_model* m, size_t bytes) {
+    if (m->scratch_bytes >= bytes) return 0;
+    if (m->scratch) cudaFree(m->scratch);
+    m->scratch = nullptr;
+    m->scratch_bytes = 0;
+    CU(cudaMalloc((void**)&m->scratch, bytes));
+    m->scratch_bytes = bytes;
+    return 0;
+}
+
+struct TensorRef {
+    float* ptr = nullptr;
+    long count = -1;
+    int kind = 0;  // 0 plain, 1 word_projections (materialise), 2 grad_entity_repr (materialise)
+};
+
+TensorRef find_tensor(nvsm_model* m, const std::string& s) {
+    TensorRef r;
+    const long B = m->B;
+    const bool fullE = m->cfg.update_method == NVSM_ADAM && m->cfg.adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE;
+    auto set = [&](float* p, long c) { r.ptr = p; r.count = p ? c : -1; };
+    if (s == "word_representations-representations" || s == "W") set(m->W, m->V * m->dw);
+    else if (s == "entity_representations-representations" || s == "E") set(m->E, m->D * m->dd);
+    else if (s == "word_entity_mapping-transform" || s == "T") set(m->T, (long)m->dw * m->dd);
+    else if (s == "word_entity_mapping-bias" || s == "b") set(m->b, m->dd);
+    else if (s == "phrase_reprs") set(m->P, B * m->dw);
+    else if (s == "pre_activation") set(m->Z, B * m->dd);
+    else if (s == "word_projections") { set(m->Z, B * m->dd); r.kind = 1; }
+    else if (s == "similarity_probs") set(m->probs, B * m->R);
+    else if (s == "instance_multipliers") set(m->mult, B * m->R);
+    else if (s == "grad_transform") set(m->gT, (long)m->dw * m->dd);
+    else if (s == "grad_bias") set(m->gb, m->dd);
+    else if (s == "grad_phrase_reprs") set(m->gP, B * m->dw);
+    else if (s == "grad_projection") set(m->Gp, B * m->dd);
+    else if (s == "grad_entity_repr") { set(m->Z, B * m->R * m->dd); r.kind = 2; }
+    else if (s == "bn_mean") set(m->mean, m->dd);
+    else if (s == "bn_invstd") set(m->invstd, m->dd);
+    else if (s == "word_representations-m") set(m->optW.m, m->V * m->dw);
+    else if (s == "word_representations-v") set(m->optW.v, fullE ? m->V * m->dw : m->V);
+    else if (s == "word_representations-acc") set(m->optW.acc, m->V);
+    else if (s == "entity_representations-m") set(m->optE.m, m->D * m->dd);
+    else if (s == "entity_representations-v") set(m->optE.v, fullE ? m->D * m->dd : m->D);
+    else if (s == "entity_representations-acc") set(m->optE.acc, m->D);
+    else if (s == "word_entity_mapping-transform-m" || s == "word_entity_mapping-transform-acc") set(m->T_a, (long)m->dw * m->dd);
+    else if (s == "word_entity_mapping-bias-m" || s == "word_entity_mapping-bias-acc") set(m->b_a, m->dd);
+    else if (s == "word_entity_mapping-transform-v") set(m->T_v, (long)m->dw * m->dd);
+    else if (s == "word_entity_mapping-bias-v") set(m->b_v, m->dd);
+    return r;
+}
+
+unsigned long rng_state_of(const std::minstd_rand0& rng) {
+    std::ostringstream ss;
+    ss << rng;
+    return std::stoul(ss.str());
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char* nvsm_last_error(void) { return g_error.c_str(); }
+int nvsm_version(void) { return 100; }
+
+int nvsm_num_phases(void) { return PH_COUNT; }
+const char* nvsm_phase_name(int phase) { return (phase >= 0 && phase < PH_COUNT) ? kPhaseNames[phase] : ""; }
+
+void nvsm_destroy(nvsm_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->comm) nccl_api().CommDestroy(m->comm);
+    float* fl[] = {m->W, m->E, m->T, m->b, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
+                   m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
+                   m->mult, m->rowtmp, m->mean, m->invstd, m->gT, m->gb, m->gT_part, m->scratch};
+    for (float* p : fl)
+        if (p) cudaFree(p);
+    if (m->dsums) cudaFree(m->dsums);
+    for (auto& s : m->slots) {
+        if (s.features) cudaFree(s.features);
+        if (s.fweights) cudaFree(s.fweights);
+        if (s.ids) cudaFree(s.ids);
+        if (s.weights) cudaFree(s.weights);
+        if (s.ready) cudaEventDestroy(s.ready);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    for (auto& ev : m->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto e : m->ev_pool) cudaEventDestroy(e);
+    if (m->loss_host) cudaFreeHost(m->loss_host);
+    for (auto e : m->loss_ev)
+        if (e) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
+    if (!cfg || !out) return fail("null argument");
+    *out = nullptr;
+    if (cfg->num_words <= 0 || cfg->num_entities <= 0) return fail("num_words and num_entities must be > 0");
+    if (cfg->word_repr_size <= 0 || cfg->entity_repr_size <= 0) return fail("representation sizes must be > 0");
+    if (cfg->word_repr_size > 1024 || cfg->entity_repr_size > 1024) return fail("representation sizes above 1024 are not supported");
+    if (cfg->entity_repr_size % 4 != 0 && cfg->entity_repr_size > 512) return fail("entity_repr_size must be a multiple of 4 above 512");
+    if (cfg->nonlinearity != NVSM_TANH && cfg->nonlinearity != NVSM_HARD_TANH) return fail("nonlinearity %d not implemented.", cfg->nonlinearity);
+    if (cfg->l2_normalize_phrase_reprs || cfg->l2_normalize_entity_reprs) return fail("l2 normalisation of representations is not implemented in this build");
+    if (cfg->update_method < NVSM_SGD || cfg->update_method > NVSM_ADAM) return fail("invalid update_method %d", cfg->update_method);
+    if (cfg->update_method == NVSM_ADAM && (cfg->adam_mode < NVSM_ADAM_SPARSE || cfg->adam_mode > NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE)) return fail("Invalid mode configuration.");
+    if (cfg->num_random_entities < 0) return fail("num_random_entities must be >= 0");
+    if (cfg->max_batch_size <= 0 || cfg->window_size <= 0) return fail("max_batch_size and window_size must be > 0");
+    if (cfg->gemm_mode != NVSM_GEMM_FP32) return fail("gemm_mode %d is not available in this build", cfg->gemm_mode);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("no CUDA device: libnvsm_b200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    nvsm_model* m = new nvsm_model();
+    m->cfg = *cfg;
+    if (m->cfg.num_batch_slots < 1) m->cfg.num_batch_slots = 1;
+    m->device = cfg->device;
+    m->V = cfg->num_words; m->D = cfg->num_entities;
+    m->dw = cfg->word_repr_size; m->dd = cfg->entity_repr_size;
+    m->n = cfg->window_size; m->z = cfg->num_random_entities; m->R = m->z + 1;
+    m->maxB = cfg->max_batch_size;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, m->device);
+    m->num_sms = prop.multiProcessorCount;
+
+    auto build = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->own_stream = true;
+        CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        const long V = m->V, D = m->D, maxB = m->maxB;
+        const int dw = m->dw, dd = m->dd;
+        TRY(dev_alloc(&m->W, V * dw)); TRY(dev_alloc(&m->E, D * dd));
+        TRY(dev_alloc(&m->T, (size_t)dw * dd)); TRY(dev_alloc(&m->b, dd));
+        const int method = cfg->update_method;
+        if (method == NVSM_ADAGRAD) {
+            TRY(dev_alloc(&m->optW.acc, V)); TRY(dev_alloc(&m->optE.acc, D));
+            TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
+        } else if (method == NVSM_ADAM) {
+            const bool full = cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE;
+            TRY(dev_alloc(&m->optW.m, V * dw)); TRY(dev_alloc(&m->optE.m, D * dd));
+            TRY(dev_alloc(&m->optW.v, full ? V * dw : V)); TRY(dev_alloc(&m->optE.v, full ? D * dd : D));
+            if (full) { TRY(dev_alloc(&m->optW.agg, V * dw)); TRY(dev_alloc(&m->optE.agg, D * dd)); }
+            TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
+            TRY(dev_alloc(&m->T_v, (size_t)dw * dd)); TRY(dev_alloc(&m->b_v, dd));
+        }
+        TRY(dev_alloc(&m->P, maxB * dw)); TRY(dev_alloc(&m->Z, maxB * dd));
+        TRY(dev_alloc(&m->Gp, maxB * dd)); TRY(dev_alloc(&m->gP, maxB * dw));
+        TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
+        TRY(dev_alloc(&m->rowtmp, maxB));
+        TRY(dev_alloc(&m->mean, dd)); TRY(dev_alloc(&m->invstd, dd));
+        TRY(dev_alloc(&m->dsums, 5 * (size_t)dd + 1));
+        TRY(dev_alloc(&m->gT, (size_t)dw * dd)); TRY(dev_alloc(&m->gb, dd));
+        const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
+        m->gt_splits = std::max(1, (2 * m->num_sms + tiles - 1) / tiles);
+        TRY(dev_alloc(&m->gT_part, (size_t)m->gt_splits * dw * dd, false));
+        m->slots.resize(m->cfg.num_batch_slots + 2);
+        for (auto& s : m->slots) {
+            TRY(dev_alloc(&s.features, maxB * m->n)); TRY(dev_alloc(&s.fweights, maxB * m->n));
+            TRY(dev_alloc(&s.ids, maxB * m->R)); TRY(dev_alloc(&s.weights, maxB));
+            CU(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+        }
+        CU(cudaHostAlloc((void**)&m->loss_host, sizeof(double) * nvsm_model::kCostRing, cudaHostAllocDefault));
+        for (auto& e : m->loss_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // score kernel: column-sum staging in dynamic shared memory
+        CU(cudaDeviceSynchronize());
+        return 0;
+    };
+    if (build() != 0) {
+        std::string keep = g_error;
+        nvsm_destroy(m);
+        g_error = keep;
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+int nvsm_set_stream(nvsm_model* m, void* cuda_stream) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    if (m->own_stream) cudaStreamDestroy(m->stream);
+    m->stream = (cudaStream_t)cuda_stream;
+    m->own_stream = false;
+    return 0;
+}
+
+int nvsm_synchronize(nvsm_model* m) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->copy_stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int nvsm_initialize(nvsm_model* m, unsigned long* rng_state) {
+    if (!m || !rng_state) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    std::minstd_rand0 rng;
+    rng.seed(*rng_state);
+    // init_matrix_glorot: rows = feature dim, cols = #objects, linear memory order; W, E, T.
+    auto glorot = [&](float* dst, long rows, long cols) -> int {
+        const float mx = (float)std::sqrt(6.0 / (double)(rows + cols));
+        std::vector<float> h((size_t)rows * cols);
+        for (size_t i = 0; i < h.size(); ++i)
+            h[i] = 2 * mx * (std::generate_canonical<float, 1>(rng) - 0.5);
+        CU(cudaMemcpyAsync(dst, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        return 0;
+    };
+    TRY(glorot(m->W, m->dw, m->V));
+    TRY(glorot(m->E, m->dd, m->D));
+    TRY(glorot(m->T, m->dd, m->dw));
+    CU(cudaMemsetAsync(m->b, 0, sizeof(float) * m->dd, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    *rng_state = rng_state_of(rng);
+    return 0;
+}
+
+long nvsm_tensor_size(nvsm_model* m, const char* name) {
+    if (!m || !name) return -1;
+    return find_tensor(m, name).count;
+}
+
+int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
+    if (!m || !name || !host_out) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    TensorRef r = find_tensor(m, name);
+    if (r.count < 0) return fail("unknown tensor '%s'", name);
+    if (r.count != n) return fail("tensor '%s' has %ld elements, caller asked for %ld", name, r.count, n);
+    const float* src = r.ptr;
+    if (r.kind != 0) {
+        if (!m->have_forward) return fail("tensor '%s' needs a forward result", name);
+        TRY(ensure_scratch(m, sizeof(float) * (size_t)n));
+        const ActParams act = act_params(m, m->cfg.batch_normalization != 0);
+        const int grid = grid_for(m, n, 256 * 4, 8);
+        if (r.kind == 1)
+            LAUNCH(m, materialize_activation_kernel, grid, 256, 0, m->Z, act, m->B, m->dd, m->scratch);
+        else
+            LAUNCH(m, materialize_grad_entity_kernel, grid, 256, 0, m->Z, act, m->mult, m->B * m->R, m->R, m->dd, m->scratch);
+        src = m->scratch;
+    }
+    CU(cudaMemcpyAsync(host_out, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int nvsm_set_tensor(nvsm_model* m, const char* name, const float* host_in, long n) {
+    if (!m || !name || !host_in) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    TensorRef r = find_tensor(m, name);
+    if (r.count < 0 || r.kind != 0) return fail("unknown or read-only tensor '%s'", name);
+    if (r.count != n) return fail("tensor '%s' has %ld elements, caller passed %ld", name, r.count, n);
+    CU(cudaMemcpyAsync(r.ptr, host_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int nvsm_generate_labels(const long* labels, long num_labels, long z, long num_objects, unsigned long* rng_state,
+                         long* out) {
+    if (!labels || !rng_state || !out) return fail("null argument");
+    if (num_labels < 0 || z < 0 || num_objects <= 0) return fail("invalid sampler arguments");
+    std::minstd_rand0 rng;
+    rng.seed(*rng_state);
+    const long R = z + 1;
+    for (long i = 0; i < num_labels; ++i) {
+        out[i * R] = labels[i];
+        for (long k = 1; k <= z; ++k) out[i * R + k] = std::uniform_int_distribution<long>(0, num_objects - 1)(rng);
+    }
+    *rng_state = rng_state_of(rng);
+    return 0;
+}
+
+int nvsm_compute_cost(nvsm_model* m, const long* features, const float* fw, const long* ids, const float* w,
+                      long B) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    BatchSlot* s = next_live_slot(m);
+    TRY(upload_batch(m, s, features, fw, ids, w, B, false));
+    return forward(m, s);
+}
+
+int nvsm_compute_gradients(nvsm_model* m) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    return backward(m);
+}
+
+int nvsm_update(nvsm_model* m, float lr, float lambda) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    return update(m, lr, lambda);
+}
+
+int nvsm_read_cost(nvsm_model* m, int steps_back, float* cost) {
+    if (!m || !cost) return fail("null argument");
+    if (steps_back < 0 || steps_back >= nvsm_model::kCostRing - 1) return fail("steps_back %d out of range", steps_back);
+    if (m->forward_count - steps_back <= 0) return fail("get_cost called without a forward result");
+    CU(cudaSetDevice(m->device));
+    const int slot = (int)((m->forward_count - 1 - steps_back) % nvsm_model::kCostRing);
+    CU(cudaEventSynchronize(m->loss_ev[slot]));
+    // cost = -(sum_c mass_c) / B   (cpp/intermediate_results.cu:94-120)
+    float s = (float)m->loss_host[slot];
+    s /= (float)m->loss_B[slot];
+    *cost = -s;
+    return 0;
+}
+
+int nvsm_get_cost(nvsm_model* m, float* cost) { return nvsm_read_cost(m, 0, cost); }
+
+float nvsm_scaled_regularization_lambda(nvsm_model* m) {
+    if (!m || m->Bglobal <= 0) return 0.f;
+    return m->cfg.regularization_lambda / (float)m->Bglobal;
+}
+
+int nvsm_train_step(nvsm_model* m, const long* features, const float* fw, const long* ids, const float* w, long B,
+                    float lr) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    BatchSlot* s = next_live_slot(m);
+    TRY(upload_batch(m, s, features, fw, ids, w, B, true));
+    TRY(forward(m, s));
+    TRY(backward(m));
+    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+}
+
+int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float* fw, const long* ids,
+                     const float* w, long B) {
+    if (!m) return fail("null model");
+    if (slot < 0 || slot >= m->cfg.num_batch_slots) return fail("slot %d out of range [0, %d)", slot, m->cfg.num_batch_slots);
+    CU(cudaSetDevice(m->device));
+    TRY(upload_batch(m, &m->slots[slot], features, fw, ids, w, B, false));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int nvsm_compute_cost_staged(nvsm_model* m, int slot) {
+    if (!m) return fail("null model");
+    if (slot < 0 || slot >= m->cfg.num_batch_slots) return fail("slot %d out of range", slot);
+    CU(cudaSetDevice(m->device));
+    return forward(m, &m->slots[slot]);
+}
+
+int nvsm_train_step_staged(nvsm_model* m, int slot, float lr) {
+    TRY(nvsm_compute_cost_staged(m, slot));
+    TRY(backward(m));
+    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+}
+
+int nvsm_infer(nvsm_model* m, const long* words, long N, long window, float* out) {
+    if (!m || !words || !out) return fail("null argument");
+    if (N <= 0 || window <= 0) return fail("empty inference request");
+    CU(cudaSetDevice(m->device));
+    // Model::infer: gather-mean (no word weights), projection + bias, activation, no batch-norm.
+    idx_t* d_words = nullptr;
+    float *d_p = nullptr, *d_z = nullptr;
+    CU(cudaMalloc((void**)&d_words, sizeof(long) * N * window));
+    CU(cudaMalloc((void**)&d_p, sizeof(float) * N * m->dw));
+    CU(cudaMalloc((void**)&d_z, sizeof(float) * N * m->dd));
+    auto run = [&]() -> int {
+        CU(cudaMemcpyAsync(d_words, words, sizeof(long) * N * window, cudaMemcpyHostToDevice, m->stream));
+        const int grid = grid_for(m, N, 8, 8);
+        if (vec4_ok(m->dw))
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p);
+        else
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p);
+        TRY((run_sgemm<false, false>(m, (int)N, m->dd, m->dw, d_p, m->dw, m->T, m->dd, d_z, m->dd, 1, 1.0f, m->b)));
+        LAUNCH(m, materialize_activation_kernel, grid_for(m, N * m->dd, 1024, 8), 256, 0, d_z, act_params(m, false), N, m->dd, d_z);
+        CU(cudaMemcpyAsync(out, d_z, sizeof(float) * N * m->dd, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        return 0;
+    };
+    const int rc = run();
+    cudaFree(d_words); cudaFree(d_p); cudaFree(d_z);
+    return rc;
+}
+
+int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx, float epsilon) {
+    if (!m || !name) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    TensorRef r = find_tensor(m, name);
+    if (r.count < 0 || r.kind != 0) return fail("unknown tensor '%s'", name);
+    if (idx < 0 || idx >= r.count) return fail("index %ld out of range for '%s'", idx, name);
+    LAUNCH(m, increment_kernel, 1, 1, 0, r.ptr + idx, epsilon);
+    return 0;
+}
+
+int nvsm_set_profiling(nvsm_model* m, int enabled) {
+    if (!m) return fail("null model");
+    TRY(collect_phases(m));
+    m->profiling = enabled != 0;
+    return 0;
+}
+
+int nvsm_get_phase_ms(nvsm_model* m, float* ms_out, int capacity) {
+    if (!m || !ms_out) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    TRY(collect_phases(m));
+    for (int i = 0; i < capacity && i < PH_COUNT; ++i) ms_out[i] = (float)m->phase_ms[i];
+    return 0;
+}
+
+int nvsm_reset_phase_ms(nvsm_model* m) {
+    if (!m) return fail("null model");
+    TRY(collect_phases(m));
+    for (int i = 0; i < PH_COUNT; ++i) m->phase_ms[i] = 0.0;
+    return 0;
+}
+
+long nvsm_kernel_launches(nvsm_model* m) { return m ? m->launches : 0; }
+
+int nvsm_comm_unique_id(char* id_out_128) {
+    if (!id_out_128) return fail("null argument");
+    const char* why = "";
+    if (!nccl_api().load(&why)) return fail("NCCL unavailable: %s", why);
+    NcclUniqueId id;
+    const int rc = nccl_api().GetUniqueId(&id);
+    if (rc != 0) return fail("ncclGetUniqueId: %s", nccl_api().GetErrorString(rc));
+    memcpy(id_out_128, id.internal, 128);
+    return 0;
+}
+
+int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank) {
+    if (!m || !id_128) return fail("null argument");
+    if (num_ranks < 1 || rank < 0 || rank >= num_ranks) return fail("invalid rank %d of %d", rank, num_ranks);
+    if (num_ranks == 1) { m->nranks = 1; m->rank = 0; return 0; }
+    const char* why = "";
+    if (!nccl_api().load(&why)) return fail("NCCL unavailable: %s", why);
+    CU(cudaSetDevice(m->device));
+    NcclUniqueId id;
+    memcpy(id.internal, id_128, 128);
+    const int rc = nccl_api().CommInitRank(&m->comm, num_ranks, id, rank);
+    if (rc != 0) return fail("ncclCommInitRank: %s", nccl_api().GetErrorString(rc));
+    m->nranks = num_ranks;
+    m->rank = rank;
+    return 0;
+}
+
+}  // extern "C"

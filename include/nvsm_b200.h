@@ -1,0 +1,169 @@
+/*
+ * nvsm_b200.h — C ABI of the B200-native NVSM/LSE training step.
+ *
+ * Drop-in boundary for the per-batch hot path of cvangysel/cuNVSM. The reference
+ * has no FFI of its own: its boundary is the C++ class surface of
+ * include/cuNVSM/{model,objective,params,storage,updates}.h. Every entry point
+ * below names the reference interface it replaces (file:line in the reference
+ * tree); the C++ façade in include/cuNVSM/ (this repo) and the Python mirror in
+ * cunvsm_b200/ are thin layers over exactly these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - index type is `long` (the reference's `int32` typedef is `long`,
+ *     include/cuNVSM/base.h:28), floats are float32 (release build,
+ *     cpp/CMakeLists.txt:17).
+ *   - tensors cross the boundary row-major [objects, dim] — the memory image of the
+ *     reference's column-major dim x objects device_matrix (cpp/storage.cu:6-10).
+ *   - every function returns 0 on success, non-zero on error; nvsm_last_error()
+ *     holds the message. (The reference aborts via glog CHECK / LOG(FATAL); the C++
+ *     façade restores that behaviour on a non-zero return.)
+ *   - there is no CPU fallback: every compute entry point requires a CUDA device.
+ */
+#ifndef NVSM_B200_H
+#define NVSM_B200_H
+
+#if defined(__GNUC__)
+#define NVSM_API __attribute__((visibility("default")))
+#else
+#define NVSM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nvsm_model nvsm_model;
+
+/* proto/nvsm.proto:11-14 */
+enum { NVSM_TANH = 0, NVSM_HARD_TANH = 1 };
+/* proto/nvsm.proto:41-45 */
+enum { NVSM_SGD = 0, NVSM_ADAGRAD = 1, NVSM_ADAM = 2 };
+/* proto/nvsm.proto:51-56; CLI names sparse_adam / dense_adam / full_adam (cpp/main.cu:479-485) */
+enum { NVSM_ADAM_SPARSE = 1, NVSM_ADAM_DENSE_UPDATE = 2, NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE = 3 };
+/* projection GEMM arithmetic */
+enum { NVSM_GEMM_FP32 = 0, NVSM_GEMM_TF32 = 1, NVSM_GEMM_3XTF32 = 2 };
+
+/* lse::ModelDesc + lse::TrainConfig (proto/nvsm.proto:7-71) flattened; replaces the
+ * arguments of Model::Model (include/cuNVSM/model.h:82-85). */
+typedef struct nvsm_config {
+    long num_words;               /* |V| */
+    long num_entities;            /* |D| */
+    int word_repr_size;           /* d_w */
+    int entity_repr_size;         /* d_d */
+    int nonlinearity;             /* NVSM_TANH | NVSM_HARD_TANH */
+    int batch_normalization;      /* ModelDesc.TransformDesc.batch_normalization */
+    int clip_sigmoid;             /* forced on by the CLI, cpp/main.cu:645 */
+    int bias_negative_samples;
+    int l2_normalize_phrase_reprs; /* not implemented: must be 0 */
+    int l2_normalize_entity_reprs; /* not implemented: must be 0 */
+    int update_method;            /* NVSM_SGD | NVSM_ADAGRAD | NVSM_ADAM */
+    int adam_mode;                /* NVSM_ADAM_* when update_method == NVSM_ADAM */
+    int num_random_entities;      /* z */
+    int max_batch_size;           /* largest num_instances a step will see */
+    int window_size;              /* n */
+    float regularization_lambda;
+    int device;                   /* CUDA device ordinal */
+    int gemm_mode;                /* NVSM_GEMM_* */
+    int num_batch_slots;          /* device-resident batch slots for nvsm_stage_batch (>= 1) */
+    int reserved[7];
+} nvsm_config;
+
+NVSM_API const char* nvsm_last_error(void);
+NVSM_API int nvsm_version(void);
+
+/* Model::Model / ~Model — include/cuNVSM/model.h:82-85, cpp/model.cu:6-35,95-103. */
+NVSM_API int nvsm_create(const nvsm_config* config, nvsm_model** out);
+NVSM_API void nvsm_destroy(nvsm_model* m);
+
+/* Run all work of this model on an existing CUDA stream (a cudaStream_t). The
+ * reference issues everything on the per-thread default stream (cpp/model.cu:13-14). */
+NVSM_API int nvsm_set_stream(nvsm_model* m, void* cuda_stream);
+NVSM_API int nvsm_synchronize(nvsm_model* m);
+
+/* ModelBase::initialize — cpp/model.cu:37-43 + init_matrix_glorot,
+ * include/cuNVSM/cuda_utils.h:35-56. *rng_state is the std::minstd_rand0 state
+ * (the reference's RNG*, include/cuNVSM/base.h:36), advanced in place. */
+NVSM_API int nvsm_initialize(nvsm_model* m, unsigned long* rng_state);
+
+/* ModelBase::get_data — cpp/model.cu:64-93 (names from cpp/params.cu:29-33 +
+ * cpp/storage.cu:115-121,242-250): "word_representations-representations" [V,d_w],
+ * "entity_representations-representations" [D,d_d], "word_entity_mapping-transform"
+ * [d_w,d_d], "word_entity_mapping-bias" [d_d]. Also readable (tests / gradient
+ * checks): per-step tensors "phrase_reprs" [B,d_w], "word_projections" [B,d_d],
+ * "similarity_probs" [B*R], "instance_multipliers" [B*R], "grad_transform" [d_w,d_d],
+ * "grad_bias" [d_d], "grad_phrase_reprs" [B,d_w], "grad_entity_repr" [B*R,d_d]
+ * and optimiser state "<param>-{m,v,acc}". */
+NVSM_API long nvsm_tensor_size(nvsm_model* m, const char* name);
+NVSM_API int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n);
+NVSM_API int nvsm_set_tensor(nvsm_model* m, const char* name, const float* host_in, long n);
+
+/* Objective::generate_labels / UniformLabelGenerator::generate — cpp/objective.cu:5-28,
+ * cpp/labels.cu:3-22: out[i*(z+1)] = labels[i]; out[i*(z+1)+1..z] ~ U{0..num_objects-1}
+ * drawn serially from minstd_rand0 exactly like the reference (bit-exact ids). Host only. */
+NVSM_API int nvsm_generate_labels(const long* labels, long num_labels, long num_negative_labels,
+                         long num_objects, unsigned long* rng_state, long* out);
+
+/* Model::compute_cost — include/cuNVSM/model.h:99-100, cpp/objective.cu:30-313, with the
+ * sampled entity ids passed in (so the sampler stays swappable). All four arrays are HOST
+ * buffers laid out as TextEntity::Batch (include/cuNVSM/data.h:114-177): features
+ * [B*n], feature_weights [B*n], entity_ids [B*(z+1)] positive first, weights [B]. Copies
+ * them to the device and enqueues the forward pass; does not synchronise. */
+NVSM_API int nvsm_compute_cost(nvsm_model* m, const long* features, const float* feature_weights,
+                      const long* entity_ids, const float* weights, long num_instances);
+
+/* Model::compute_gradients — include/cuNVSM/model.h:109, cpp/objective.cu:315-481. */
+NVSM_API int nvsm_compute_gradients(nvsm_model* m);
+
+/* Model::update — include/cuNVSM/model.h:111-113, cpp/model.cu:187-220. */
+NVSM_API int nvsm_update(nvsm_model* m, float learning_rate, float scaled_regularization_lambda);
+
+/* ForwardResult::get_cost / scaled_regularization_lambda —
+ * cpp/intermediate_results.cu:80-129. get_cost synchronises (device->host read). */
+NVSM_API int nvsm_get_cost(nvsm_model* m, float* cost);
+/* Same, for the forward pass `steps_back` calls ago (0 = latest, < 15): waits only for that
+ * step's loss read-back, so a training loop can read step k-1 while step k runs. */
+NVSM_API int nvsm_read_cost(nvsm_model* m, int steps_back, float* cost);
+NVSM_API float nvsm_scaled_regularization_lambda(nvsm_model* m);
+
+/* One whole training step on host buffers = compute_cost + compute_gradients + update
+ * (the body of iterate_data, cpp/main.cu:405-431), scaled lambda = lambda / B. Does not
+ * synchronise; call nvsm_get_cost to read the loss of the step. */
+NVSM_API int nvsm_train_step(nvsm_model* m, const long* features, const float* feature_weights,
+                    const long* entity_ids, const float* weights, long num_instances,
+                    float learning_rate);
+
+/* Device-resident batches: copy a host batch into slot `slot` once, then run steps on it
+ * without host traffic. */
+NVSM_API int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float* feature_weights,
+                     const long* entity_ids, const float* weights, long num_instances);
+NVSM_API int nvsm_compute_cost_staged(nvsm_model* m, int slot);
+NVSM_API int nvsm_train_step_staged(nvsm_model* m, int slot, float learning_rate);
+
+/* Model::infer — include/cuNVSM/model.h:95-97, cpp/model.cu:105-133 (no batch-norm at
+ * inference). words: host [num_phrases*window]; out: host [num_phrases, d_d]. */
+NVSM_API int nvsm_infer(nvsm_model* m, const long* words, long num_phrases, long window, float* out);
+
+/* Storage::increment_parameter — cpp/storage.cu:123-131,259-272 (gradient checking). */
+NVSM_API int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx, float epsilon);
+
+/* Instrumentation. Phase timing uses CUDA events on the model's stream. */
+NVSM_API int nvsm_set_profiling(nvsm_model* m, int enabled);
+NVSM_API int nvsm_num_phases(void);
+NVSM_API const char* nvsm_phase_name(int phase);
+NVSM_API int nvsm_get_phase_ms(nvsm_model* m, float* ms_out, int capacity); /* sums since last reset */
+NVSM_API int nvsm_reset_phase_ms(nvsm_model* m);
+NVSM_API long nvsm_kernel_launches(nvsm_model* m); /* kernels launched by this model so far */
+
+/* Multi-GPU (one process per GPU). The batch is sharded by n-gram row; the library
+ * all-reduces batch-norm statistics and the dense gradients with NCCL (new: the reference
+ * is single-GPU). id: 128 bytes from nvsm_comm_unique_id on rank 0, broadcast by the
+ * caller (torch.distributed). After init, the batch size used for 1/B and lambda/B is the
+ * sum over ranks. */
+NVSM_API int nvsm_comm_unique_id(char* id_out_128);
+NVSM_API int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVSM_B200_H */

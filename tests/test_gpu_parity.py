@@ -1,0 +1,289 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, plus the reference's golden vectors and size-independent properties at the
+BASELINE.json sizes.
+
+Tolerances (fp32 arithmetic, NVSM_GEMM_FP32):
+  * sampled / passed indices: bit-exact.
+  * forward tensors, loss, gradients vs the float32 oracle: rtol 2e-4 with an absolute floor
+    of 1e-6 x max|expected| (summation order differs: warp-shuffle trees, split-K, atomics).
+  * parameters after optimiser steps: rtol 5e-4, same floor.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cunvsm_b200 as nv
+from oracle import binding as O
+from tests.util import assert_close, make_batch, twin_models
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_goldens.json")))
+RTOL = 2e-4
+
+
+def run_forward_backward(gm, om, rng, B, n, V, D, z, weighted=True, seed=3):
+    nrng = np.random.default_rng(seed)
+    f, fw, labels, w = make_batch(nrng, B, n, V, D, z, weighted)
+    batch = nv.Batch(B, n).fill(f, labels, fw, w)
+    state0 = rng.state
+    ids_ref, _ = O.generate_labels(labels, z, D, state0)
+    res = gm.compute_cost(batch, rng)
+    ids = gm._keepalive[1]
+    assert (ids == ids_ref).all(), "sampled entity ids must be bit-exact"
+    cost = res.get_cost()
+    ocost = om.compute_cost(f, fw, ids_ref, w, n)
+    gm.compute_gradients(res)
+    om.compute_gradients()
+    return batch, ids_ref, cost, ocost
+
+
+def compare_step_tensors(gm, om, cost, ocost, rtol=RTOL):
+    assert abs(cost - ocost) <= rtol * abs(ocost) + 1e-7
+    assert_close(gm.get_tensor("phrase_reprs"), om.get("P"), rtol, what="P")
+    assert_close(gm.get_tensor("word_projections"), om.get("Y"), rtol, 2e-6, what="Y")
+    assert_close(gm.get_tensor("similarity_probs"), om.get("probs"), rtol, what="probs")
+    assert_close(gm.get_tensor("instance_multipliers"), om.get("mult"), rtol, 1e-5, what="mult")
+    assert_close(gm.get_tensor("grad_transform"), om.get("gT"), rtol, 1e-5, what="gT")
+    assert_close(gm.get_tensor("grad_bias"), om.get("gb"), rtol, 1e-5, what="gb")
+    assert_close(gm.get_tensor("grad_phrase_reprs"), om.get("gP"), rtol, 1e-5, what="gP")
+    assert_close(gm.get_tensor("grad_entity_repr"), om.get("gE"), rtol, 1e-5, what="gE")
+
+
+def test_reference_golden_transform_backward():
+    """cpp/model_tests.cu:341-466 through the CUDA path (fp32 => 1e-5 relative)."""
+    g = GOLD["transform_backward"]; c = g["config"]
+    desc = nv.ModelDesc(word_repr_size=c["word_repr_size"], entity_repr_size=c["entity_repr_size"],
+                        bias_negative_samples=True)
+    tc = nv.TrainConfig(batch_size=c["batch_size"], window_size=c["window_size"],
+                        num_random_entities=c["num_random_entities"], regularization_lambda=0.01)
+    m = nv.Model(c["num_words"], c["num_entities"], desc, tc)
+    rng = nv.RNG(c["seed"])
+    m.initialize(rng)
+    B, n = c["batch_size"], c["window_size"]
+    batch = nv.Batch(B, n).fill(np.full((B, n), c["feature_value"]), np.full(B, c["label"]))
+    res = m.compute_cost(batch, rng)
+    assert abs(res.get_cost() - 6.17158013374) < 2e-5
+    m.compute_gradients(res)
+    assert_close(m.get_tensor("grad_transform"), g["grad_transform"], 2e-5, 1e-5)
+    assert_close(m.get_tensor("grad_bias"), g["grad_bias"], 2e-5, 1e-5)
+    assert_close(m.get_tensor("grad_phrase_reprs"), g["grad_phrase"], 5e-5, 1e-4)
+
+
+def test_reference_golden_bn_forward():
+    """cpp/model_tests.cu:468-521 (batch-norm + tanh forward). The library fixes eps at the
+    value the objective uses (1e-4, cpp/objective.cu:114) while that test uses 1e-5, so compare
+    with the float64 oracle at 1e-4 instead of the literal vector."""
+    desc = nv.ModelDesc(word_repr_size=3, entity_repr_size=5, batch_normalization=True)
+    tc = nv.TrainConfig(batch_size=2, window_size=1, num_random_entities=1)
+    m = nv.Model(2, 1, desc, tc)
+    m.set_tensor(nv.TRANSFORM, np.arange(15)); m.set_tensor(nv.BIAS, np.arange(5) * 1e-3)
+    m.set_tensor(nv.WORD_REPRS, [0.01, 0.02, 0.03, 0.001, 0.002, 0.003]); m.set_tensor(nv.ENTITY_REPRS, np.zeros(5))
+    om = O.Model(2, 1, 3, 5, batch_normalization=True, bn_epsilon=1e-4)
+    om.set("T", np.arange(15.0)); om.set("b", np.arange(5) * 1e-3)
+    om.set("W", [0.01, 0.02, 0.03, 0.001, 0.002, 0.003]); om.set("E", np.zeros(5))
+    batch = nv.Batch(2, 1).fill([[0], [1]], [0, 0])
+    m.compute_cost(batch, entity_ids=[0, 0, 0, 0])
+    om.compute_cost([0, 1], [1.0, 1.0], [0, 0, 0, 0], [1.0, 1.0], 1)
+    assert_close(m.get_tensor("word_projections"), om.get("Y"), 1e-4)
+
+
+CASES = {
+    # BASELINE.json configs[0]: LSE tanh, batch 4096, |V|=2k |D|=200 d_w=64 d_d=64 z=4
+    "C1_lse": dict(V=2000, D=200, dw=64, dd=64, n=10, z=4, B=4096, nonlinearity=nv.TANH, bn=False),
+    "lse_bias_neg": dict(V=300, D=1000, dw=128, dd=128, n=10, z=32, B=512, nonlinearity=nv.TANH, bn=False, bias_neg=True),
+    # NVSM shape (d_w=300, d_d=256, n=10, z=10, hard_tanh + BN) at a batch the oracle finishes in seconds
+    "nvsm_small": dict(V=5000, D=4000, dw=300, dd=256, n=10, z=10, B=2048, nonlinearity=nv.HARD_TANH, bn=True),
+    "nvsm_tanh_bn": dict(V=500, D=400, dw=300, dd=256, n=10, z=10, B=1024, nonlinearity=nv.TANH, bn=True),
+    # dims that are not multiples of 4 exercise the scalar kernels; ragged batch (not a multiple of anything)
+    "odd_dims": dict(V=20, D=15, dw=3, dd=5, n=3, z=1, B=1000, nonlinearity=nv.TANH, bn=True),
+    "odd_dims_hard": dict(V=50, D=40, dw=10, dd=6, n=4, z=3, B=777, nonlinearity=nv.HARD_TANH, bn=False),
+    "wide": dict(V=100, D=100, dw=512, dd=384, n=2, z=2, B=256, nonlinearity=nv.TANH, bn=False),
+    "single_instance": dict(V=10, D=10, dw=8, dd=8, n=1, z=1, B=1, nonlinearity=nv.TANH, bn=False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_forward_backward_matches_oracle(name):
+    c = dict(CASES[name])
+    V, D, n, z, B = c["V"], c["D"], c["n"], c["z"], c["B"]
+    gm, om, rng = twin_models(**c)
+    _, _, cost, ocost = run_forward_backward(gm, om, rng, B, n, V, D, z)
+    compare_step_tensors(gm, om, cost, ocost)
+
+
+OPTIMISERS = [("sgd", nv.SGD, 0), ("adagrad", nv.ADAGRAD, 0), ("sparse_adam", nv.ADAM, nv.SPARSE),
+              ("dense_adam", nv.ADAM, nv.DENSE_UPDATE), ("full_adam", nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)]
+STATE_NAMES = {
+    "word_representations-m": "word_m", "word_representations-v": "word_v", "word_representations-acc": "word_acc",
+    "entity_representations-m": "entity_m", "entity_representations-v": "entity_v",
+    "entity_representations-acc": "entity_acc", "word_entity_mapping-transform-m": "T_m",
+    "word_entity_mapping-transform-v": "T_v", "word_entity_mapping-bias-m": "b_m", "word_entity_mapping-bias-v": "b_v",
+}
+
+
+@pytest.mark.parametrize("opt", OPTIMISERS, ids=[o[0] for o in OPTIMISERS])
+@pytest.mark.parametrize("bn", [False, True], ids=["nobn", "bn"])
+def test_three_training_steps_match_oracle(opt, bn):
+    """compute_cost -> compute_gradients -> update, three times, every optimiser of
+    cpp/updates*.cu; parameters and optimiser state compared after each step."""
+    _, method, mode = opt
+    V, D, dw, dd, n, z, B = 300, 200, 32, 24, 5, 3, 512
+    lr = 0.01 if method != nv.ADAM else 0.001
+    gm, om, rng = twin_models(V, D, dw, dd, n=n, z=z, B=B, nonlinearity=nv.HARD_TANH if bn else nv.TANH, bn=bn,
+                              method=method, adam_mode=mode, lam=0.01)
+    for step in range(3):
+        batch, ids, cost, ocost = run_forward_backward(gm, om, rng, B, n, V, D, z, seed=100 + step)
+        assert abs(cost - ocost) <= 5e-4 * abs(ocost)
+        lam = gm.L.nvsm_scaled_regularization_lambda(gm.h)
+        assert abs(lam - om.scaled_lambda()) <= 1e-7 * abs(lam)
+        gm.update(None, lr, lam)
+        om.update(lr, om.scaled_lambda())
+        for gname, oname in ((nv.WORD_REPRS, "W"), (nv.ENTITY_REPRS, "E"), (nv.TRANSFORM, "T"), (nv.BIAS, "b")):
+            assert_close(gm.get_tensor(gname), om.get(oname), 5e-4, 1e-5, what="%s step %d" % (oname, step))
+        for gname, oname in STATE_NAMES.items():
+            if gm.tensor_size(gname) > 0 and len(om.get(oname)) == gm.tensor_size(gname):
+                assert_close(gm.get_tensor(gname), om.get(oname), 1e-3, 1e-5, what="%s step %d" % (oname, step))
+
+
+def test_unweighted_rebalanced_lse_and_duplicates():
+    """z > 1 without bias_negative_samples re-weights positives/negatives
+    (cpp/objective.cu:268-290); tiny D forces id collisions (negatives == positive, duplicate rows
+    inside one n-gram) so the scatter must accumulate."""
+    c = dict(V=7, D=3, dw=16, dd=16, n=6, z=5, B=2048, nonlinearity=nv.TANH, bn=False, bias_neg=False, method=nv.SGD)
+    gm, om, rng = twin_models(**c)
+    batch, ids, cost, ocost = run_forward_backward(gm, om, rng, c["B"], c["n"], c["V"], c["D"], c["z"], weighted=False)
+    compare_step_tensors(gm, om, cost, ocost)
+    lam = gm.L.nvsm_scaled_regularization_lambda(gm.h)
+    gm.update(None, 0.05, lam); om.update(0.05, om.scaled_lambda())
+    assert_close(gm.get_tensor(nv.ENTITY_REPRS), om.get("E"), 5e-4, 1e-5)
+    assert_close(gm.get_tensor(nv.WORD_REPRS), om.get("W"), 5e-4, 1e-5)
+
+
+def test_clip_sigmoid_saturation_band():
+    """Large scores saturate the sigmoid: the forward clamp (1e-7) and the backward zero band
+    (1e-6) must agree with the oracle (cpp/objective.cu:242-246,354-371)."""
+    c = dict(V=10, D=10, dw=8, dd=8, n=2, z=2, B=64, nonlinearity=nv.HARD_TANH, bn=False)
+    gm, om, rng = twin_models(**c)
+    big = np.random.default_rng(0).uniform(-30, 30, size=10 * 8).astype(np.float32)
+    gm.set_tensor(nv.ENTITY_REPRS, big); om.set("E", big)
+    T = np.random.default_rng(1).uniform(-5, 5, size=64).astype(np.float32)
+    gm.set_tensor(nv.TRANSFORM, T); om.set("T", T)
+    _, _, cost, ocost = run_forward_backward(gm, om, rng, 64, 2, 10, 10, 2)
+    probs = gm.get_tensor("similarity_probs")
+    assert probs.min() >= np.float32(1e-7) and probs.max() <= 1.0
+    assert (gm.get_tensor("instance_multipliers") == 0).sum() > 0
+    compare_step_tensors(gm, om, cost, ocost)
+
+
+def test_infer_matches_oracle():
+    gm, om, rng = twin_models(200, 50, 64, 32, n=4, z=1, B=16, nonlinearity=nv.HARD_TANH, bn=True)
+    words = np.random.default_rng(5).integers(0, 200, size=(33, 4))
+    assert_close(gm.infer(words, 4), om.infer(words, 4), RTOL)
+
+
+def test_staged_batch_equals_host_batch():
+    c = dict(V=500, D=300, dw=64, dd=64, n=5, z=4, B=1024, nonlinearity=nv.TANH, bn=True)
+    gm, om, rng = twin_models(**c, num_batch_slots=2)
+    f, fw, labels, w = make_batch(np.random.default_rng(9), 1024, 5, 500, 300, 4)
+    batch = nv.Batch(1024, 5).fill(f, labels, fw, w)
+    ids = gm.generate_labels(labels, rng)
+    a = gm.compute_cost(batch, entity_ids=ids).get_cost()
+    gm.stage_batch(1, batch, ids)
+    b = gm.compute_cost_staged(1).get_cost()
+    assert abs(a - b) <= 1e-6 * abs(a)
+
+
+def test_errors_are_reported_not_swallowed():
+    with pytest.raises(nv.NvsmError):
+        nv.Model(10, 10, nv.ModelDesc(l2_normalize_phrase_reprs=True), nv.TrainConfig())
+    m = nv.Model(10, 10, nv.ModelDesc(), nv.TrainConfig(batch_size=8, window_size=2))
+    with pytest.raises(nv.NvsmError):
+        m.compute_gradients()          # no forward result
+    with pytest.raises(nv.NvsmError):
+        m.get_tensor("word_representations-representations"[:-1] + "x") if m.tensor_size("nope") >= 0 else m.update(None, 0.1, 0.0)
+    batch = nv.Batch(16, 2).fill(np.zeros((16, 2)), np.zeros(16))
+    with pytest.raises(nv.NvsmError):
+        m.compute_cost(batch, nv.RNG(1))  # larger than max_batch_size
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at full size: size-independent properties.
+# ---------------------------------------------------------------------------------------------
+def _c2_model(method=nv.SGD, mode=0, lam=0.0):
+    desc = nv.ModelDesc(word_repr_size=300, entity_repr_size=256, batch_normalization=True,
+                        nonlinearity=nv.HARD_TANH, clip_sigmoid=True)
+    tc = nv.TrainConfig(batch_size=51200, window_size=10, num_random_entities=10, regularization_lambda=lam,
+                        update_method=method, adam_mode=mode)
+    m = nv.Model(50000, 50000, desc, tc)
+    m.initialize(nv.RNG(1))
+    return m
+
+
+def test_full_size_c2_properties():
+    B, n, z, V, D = 51200, 10, 10, 50000, 50000
+    m = _c2_model()
+    nrng = np.random.default_rng(11)
+    f, fw, labels, w = make_batch(nrng, B, n, V, D, z, weighted=False)
+    rng = nv.RNG(12345)
+    ids = m.generate_labels(labels, rng)
+    batch = nv.Batch(B, n).fill(f, labels, fw, w)
+    res = m.compute_cost(batch, entity_ids=ids)
+    cost = res.get_cost()
+    assert np.isfinite(cost) and 0.0 < cost < 50.0
+    m.compute_gradients(res)
+    gT, gb, gP = m.get_tensor("grad_transform"), m.get_tensor("grad_bias"), m.get_tensor("grad_phrase_reprs")
+    mult = m.get_tensor("instance_multipliers")
+    # (1) batch-norm backward: the batch sum of d cost / d pre-activation vanishes per feature, so
+    #     grad_phrase summed over the batch is ~0 (sum_i dX_i = 0 => sum_i T^T dX_i = 0).
+    gp_sum = gP.reshape(B, 300).sum(0)
+    assert np.abs(gp_sum).max() <= 1e-3 * np.abs(gP).sum() / 300 + 1e-7
+    # (2) permutation invariance: shuffling the n-grams changes only summation order.
+    perm = nrng.permutation(B)
+    b2 = nv.Batch(B, n).fill(f[perm], labels[perm], fw[perm], w[perm])
+    ids2 = ids.reshape(B, z + 1)[perm].ravel()
+    res2 = m.compute_cost(b2, entity_ids=ids2)
+    assert abs(res2.get_cost() - cost) <= 1e-5 * abs(cost)
+    m.compute_gradients(res2)
+    assert_close(m.get_tensor("grad_transform"), gT, 1e-3, 1e-4)
+    assert_close(m.get_tensor("grad_bias"), gb, 1e-3, 1e-3)
+    assert_close(m.get_tensor("instance_multipliers").reshape(B, z + 1)[np.argsort(perm)], mult.reshape(B, z + 1), 1e-3, 1e-5)
+    # (3) checksum of the sparse SGD update (lambda = 0): the column sums of the table delta equal
+    #     the column sums of lr * sum_c grad_entity[c] / lr * sum_{i,w} fw * grad_phrase[i].
+    E0 = m.get_tensor(nv.ENTITY_REPRS).astype(np.float64).reshape(D, 256)
+    W0 = m.get_tensor(nv.WORD_REPRS).astype(np.float64).reshape(V, 300)
+    Y = m.get_tensor("word_projections").astype(np.float64).reshape(B, 256)
+    mult2 = m.get_tensor("instance_multipliers").astype(np.float64).reshape(B, z + 1)
+    gP2 = m.get_tensor("grad_phrase_reprs").astype(np.float64).reshape(B, 300)
+    sign = np.where(np.arange(z + 1) == 0, 1.0, -1.0)
+    lr = 0.5
+    m.update(None, lr, 0.0)
+    dE = m.get_tensor(nv.ENTITY_REPRS).astype(np.float64).reshape(D, 256) - E0
+    dW = m.get_tensor(nv.WORD_REPRS).astype(np.float64).reshape(V, 300) - W0
+    expect_E = lr * ((mult2 * sign).sum(1)[:, None] * Y).sum(0)
+    expect_W = lr * n * gP2.sum(0)
+    assert_close(dE.sum(0), expect_E, 2e-2, 2e-2)
+    assert_close(dW.sum(0), expect_W, 2e-2, 5e-2)
+    # rows never referenced stay bit-identical
+    untouched = np.setdiff1d(np.arange(D), np.unique(ids2))
+    assert (dE[untouched] == 0).all()
+
+
+def test_full_size_c2_full_adam_runs_and_learns():
+    """A few full_adam steps at the headline configuration: finite, and the loss goes down."""
+    B, n, z, V, D = 51200, 10, 10, 50000, 50000
+    m = _c2_model(nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE, lam=0.01)
+    nrng = np.random.default_rng(2)
+    f, fw, labels, w = make_batch(nrng, B, n, V, D, z, weighted=False)
+    labels = f[:, 0] % D  # learnable signal: the document is a function of the first word
+    batch = nv.Batch(B, n).fill(f, labels, fw, w)
+    rng = nv.RNG(99)
+    costs = []
+    for step in range(8):
+        ids = m.generate_labels(labels, rng)
+        m.train_step(batch, ids, 0.001)
+        costs.append(m.last_cost())
+    assert np.isfinite(costs).all()
+    assert costs[-1] < costs[0]
