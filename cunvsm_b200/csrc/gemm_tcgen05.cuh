@@ -1,0 +1,290 @@
+// Projection GEMMs on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32,
+// operands staged in shared memory by TMA (128-byte swizzle), fp32 accumulators in TMEM,
+// read back with tcgen05.ld for the epilogue. One warp-specialised CTA per output tile:
+//   warp 0     TMA producer (one elected lane)
+//   warp 1     MMA issuer   (one elected lane)
+//   warps 2-5  epilogue     (each owns the 32 TMEM lanes of its warp_id % 4 quarter)
+// connected by a ring of `stages` full/empty mbarriers and one accumulator-ready mbarrier.
+//
+// The three contractions of the step (replacing cuBLAS SGEMM behind device_matrix's
+// matrix_mult; cpp/params.cu:417-421,528-531, cpp/objective.cu:453-456):
+//   forward         Z [B, dd]  = P [B, dw] . Tt[dd, dw]^T          A K-major, B K-major
+//   grad_phrase     gP[B, dw]  = dX[B, dd] . T [dw, dd]^T / n      A K-major, B K-major
+//   grad_transform  gT[dw, dd] = P [B, dw]^T . dX[B, dd]           A MN-major, B MN-major,
+//                                                                  split-K over the batch
+// "K-major" = reduction index contiguous in memory; "MN-major" = output index contiguous.
+//
+// Shared-memory tile formats (all 128B-swizzled, 8-row atoms of 1024 bytes):
+//   K-major  : rows of 32 fp32 (128 B) along k; 8-row atoms stacked along M/N (SBO = 1024).
+//   MN-major : rows of 32 fp32 (128 B) along M/N; for 32-bit operands the hardware only takes
+//              the SWIZZLE_128B_BASE32B format (TMA: SWIZZLE_128B_ATOM_32B): 32-byte chunks
+//              XOR-ed with k-row % 4, 4 k-rows per 512-byte atom, atoms stacked along k
+//              (SBO = 512); 32-wide M/N groups are separate TMA boxes, LBO bytes apart.
+// One tcgen05.mma consumes K = 8 tf32: 32 bytes further along a K-major row, or one whole
+// atom (1024 B) further in an MN-major tile.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nvsm {
+namespace tc {
+
+constexpr int kBlockM = 128;        // UMMA M (cta_group::1)
+constexpr int kBlockK = 32;         // fp32 elements per 128-byte swizzled row
+constexpr int kUmmaK = 8;           // tf32 K per instruction
+constexpr int kThreads = 192;
+constexpr uint32_t kATileBytes = kBlockM * kBlockK * 4;  // 16 KB
+constexpr uint32_t kGroupBytes = kBlockK * 32 * 4;       // one 32(MN) x 32(k) box: 4 KB
+
+struct Params {
+    int M, N, K;           // problem: C[M, N] = A . B over K
+    int n_pad;             // N rounded up to a multiple of 16 (<= 512)
+    int n_half0, n_half1;  // the one or two UMMA N extents (multiples of 16, <= 256)
+    int b_boxes, b_box_rows;  // K-major B: TMA boxes per stage and rows per box
+    int kb_per_split;      // k-blocks (of 32) handled by one CTA along grid.y
+    int stages;
+    uint32_t stage_bytes;
+    uint32_t tmem_cols;    // power of two >= n_pad
+    float* C;
+    int ldc;
+    long split_stride;     // elements between split-K partial outputs
+    float alpha;
+    const float* bias;     // nullable, per output column
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t it = 0; it < (1u << 27); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (sm_100 "version 1").
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks, 8-row atoms; K-major operands),
+//              1 = SWIZZLE_128B_BASE32B (32-byte chunks, 4-row atoms) — the only layout the
+//                  hardware accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+// 32-bit instruction descriptor: tf32 x tf32 -> f32, M = 128.
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format: F32
+    d |= 2u << 7;                    // A format: TF32
+    d |= 2u << 10;                   // B format: TF32
+    d |= (a_mn ? 1u : 0u) << 15;     // A major: 0 = K, 1 = MN
+    d |= (b_mn ? 1u : 0u) << 16;     // B major
+    d |= (uint32_t)(n >> 3) << 17;   // N / 8
+    d |= (uint32_t)(kBlockM >> 4) << 24;  // M / 16
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8];
+    __shared__ __align__(8) uint64_t empty_bar[8];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBlockM;
+    const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
+    const int kb0 = blockIdx.y * p.kb_per_split;
+    const int num_kb = max(0, min(p.kb_per_split, num_kb_total - kb0));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&accum_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t bar = smem_u32(&full_bar[s]);
+                const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
+                const uint32_t b_dst = a_dst + kATileBytes;
+                const int k0 = (kb0 + kb) * kBlockK;
+                mbar_expect_tx(bar, p.stage_bytes);
+                if constexpr (!A_MN) {
+                    tma_load_2d(a_dst, &tmA, bar, k0, m0);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < kBlockM / 32; ++g) tma_load_2d(a_dst + g * kGroupBytes, &tmA, bar, m0 + 32 * g, k0);
+                }
+                if constexpr (!B_MN) {
+                    for (int bx = 0; bx < p.b_boxes; ++bx)
+                        tma_load_2d(b_dst + (uint32_t)bx * p.b_box_rows * 128u, &tmB, bar, k0, bx * p.b_box_rows);
+                } else {
+                    for (int g = 0; g < p.n_pad / 32; ++g) tma_load_2d(b_dst + g * kGroupBytes, &tmB, bar, 32 * g, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc0 = make_idesc(p.n_half0, A_MN, B_MN);
+            const uint32_t idesc1 = make_idesc(p.n_half1 > 0 ? p.n_half1 : 16, A_MN, B_MN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_base + (uint32_t)s * p.stage_bytes;
+                const uint32_t b_base = a_base + kATileBytes;
+#pragma unroll
+                for (int j = 0; j < kBlockK / kUmmaK; ++j) {
+                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+                    // K-major: 32 B further along the swizzled 128-byte row per K = 8.
+                    // MN-major: 8 k-rows = two 4-row atoms (SBO = 512 B apart) per K = 8.
+                    const uint64_t a_desc = A_MN ? make_desc(a_base + j * 1024u, kGroupBytes, 512u, 1u)
+                                                 : make_desc(a_base + j * 32u, 16u, 1024u, 2u);
+                    const uint64_t b_desc0 = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
+                                                  : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
+                    umma_tf32(tmem_base, a_desc, b_desc0, idesc0, acc);
+                    if (p.n_half1 > 0) {
+                        const uint32_t off = B_MN ? (uint32_t)(p.n_half0 / 32) * kGroupBytes : (uint32_t)p.n_half0 * 128u;
+                        const uint64_t b_desc1 = B_MN ? make_desc(b_base + off + j * 1024u, kGroupBytes, 512u, 1u)
+                                                      : make_desc(b_base + off + j * 32u, 16u, 1024u, 2u);
+                        umma_tf32(tmem_base + (uint32_t)p.n_half0, a_desc, b_desc1, idesc1, acc);
+                    }
+                }
+                umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+            }
+            umma_commit(smem_u32(&accum_bar));          // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        float* crow = p.C + (long)blockIdx.y * p.split_stride + (long)m * p.ldc;
+        if (num_kb > 0) {
+            mbar_wait(smem_u32(&accum_bar), 0);
+            tc_fence_after();
+        }
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+            float v[16];
+            if (num_kb > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            if (m < p.M) {
+                if (c0 + 16 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 o;
+                        o.x = p.alpha * v[i + 0]; o.y = p.alpha * v[i + 1];
+                        o.z = p.alpha * v[i + 2]; o.w = p.alpha * v[i + 3];
+                        if (p.bias) {
+                            o.x += __ldg(p.bias + c0 + i + 0); o.y += __ldg(p.bias + c0 + i + 1);
+                            o.z += __ldg(p.bias + c0 + i + 2); o.w += __ldg(p.bias + c0 + i + 3);
+                        }
+                        *reinterpret_cast<float4*>(crow + c0 + i) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = c0 + i;
+                        if (n < p.N) crow[n] = p.alpha * v[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace nvsm

@@ -291,26 +291,39 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
 // cudnnBatchNormalizationBackward, per-activation, gamma == 1 (cpp/cudnn_utils.cu:158-177;
 // formula pinned by cpp/cudnn_utils_tests.cu:143-176).
 // =====================================================================================
+// Per-column constants of the backward pass, once per step: grad_bias = sum(dy) (with and
+// without batch-norm, cpp/params.cu:510-520) and the two batch means BN backward needs.
+__global__ void bn_backward_prep_kernel(const double* __restrict__ col_sums, int dd, double batch,
+                                        float* __restrict__ gb, float* __restrict__ mean_dy,
+                                        float* __restrict__ mean_dyx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dd) return;
+    gb[c] = (float)col_sums[c];
+    mean_dy[c] = (float)(col_sums[c] / batch);
+    mean_dyx[c] = (float)(col_sums[dd + c] / batch);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) bn_backward_kernel(float* __restrict__ Gp, const float* __restrict__ Z,
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ invstd,
-                                                          const double* __restrict__ col_sums, double batch,
-                                                          long rows, int dd) {
-    const long total = rows * dd;
+                                                          const float* __restrict__ mean_dy,
+                                                          const float* __restrict__ mean_dyx, long rows, int dd) {
+    const int nvec = dd / VEC;
+    const long total = rows * nvec;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(t % dd);
-        const float is = __ldg(invstd + c);
-        const float xh = (Z[t] - __ldg(mean + c)) * is;
-        const float sb = (float)(col_sums[c] / batch);
-        const float sg = (float)(col_sums[dd + c] / batch);
-        Gp[t] = is * (Gp[t] - sb - xh * sg);
+        const int c = (int)(t % nvec) * VEC;
+        float g[VEC], z[VEC];
+        load_vec<VEC>(Gp + t * VEC, g);
+        load_vec_ro<VEC>(Z + t * VEC, z);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float is = __ldg(invstd + c + v);
+            const float xh = (z[v] - __ldg(mean + c + v)) * is;
+            g[v] = is * (g[v] - __ldg(mean_dy + c + v) - xh * __ldg(mean_dyx + c + v));
+        }
+        store_vec<VEC>(Gp + t * VEC, g);
     }
-}
-
-// grad_bias = column sums of dy (both with and without batch-norm; cpp/params.cu:510-520).
-__global__ void col_sums_to_float_kernel(const double* __restrict__ col_sums, int dd, float* __restrict__ gb) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < dd) gb[c] = (float)col_sums[c];
 }
 
 // =====================================================================================

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 
@@ -92,6 +93,7 @@ struct nvsm_model {
 
     // parameters
     float *W = nullptr, *E = nullptr, *T = nullptr, *b = nullptr;
+    float* Tt = nullptr;  // T transposed [dd, dw]: K-major B operand of the forward tensor-core GEMM
     TableOpt optW, optE;
     float *T_a = nullptr, *b_a = nullptr, *T_v = nullptr, *b_v = nullptr;  // transform acc/m, v
     unsigned long t_transform = 1;
@@ -106,10 +108,11 @@ struct nvsm_model {
     // per-step workspace
     float *P = nullptr, *Z = nullptr, *Gp = nullptr, *gP = nullptr;
     float *probs = nullptr, *mult = nullptr, *rowtmp = nullptr;
-    float *mean = nullptr, *invstd = nullptr;
+    float *mean = nullptr, *invstd = nullptr, *mean_dy = nullptr, *mean_dyx = nullptr;
     double* dsums = nullptr;   // [2*dd fwd sums][dd var sums][2*dd bwd col sums][1 loss]
     float *gT = nullptr, *gb = nullptr, *gT_part = nullptr;
     int gt_splits = 1;
+    bool use_tc = false;  // projection GEMMs on tcgen05 (gemm_mode != FP32 and shapes allow)
     float* scratch = nullptr;  // inspection buffer max(B*R*dd, ...) allocated on demand
     size_t scratch_bytes = 0;
     // loss read-back ring: every forward ends with an async D2H of its loss sum
@@ -236,6 +239,114 @@ int run_sgemm(nvsm_model* m, int M, int N, int K, const float* A, int lda, const
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// GEMM dispatch (tcgen05 / TMA path)
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [outer, inner] with a {box_inner, box_outer} box, 128B swizzle, zero OOB fill.
+int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer, long row_stride_elems,
+                    int box_inner, int box_outer, bool atom32 = false) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled is unavailable in this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_elems * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) inner=%ld outer=%ld box=%dx%d", (int)r, inner, outer, box_inner, box_outer);
+    return 0;
+}
+
+// 227 KB opt-in limit minus the kernel's static shared memory (barriers), with headroom.
+constexpr uint32_t kTcMaxDynSmem = 232448u - 1024u;
+
+bool tc_shapes_ok(int dw, int dd) {
+    // TMA needs 16-byte row strides; grad_transform's MN-major B tile needs dd % 32 == 0.
+    return dw % 4 == 0 && dd % 32 == 0 && dd <= 512 && dw <= 512;
+}
+
+// C[M, N] = alpha * A . B (+ bias), reduction length K.
+//   mn_major == false: A is [M, K] row-major, Bm is [N, K] row-major      (both K-major)
+//   mn_major == true : A is [K, M] row-major, Bm is [K, N] row-major      (both MN-major)
+// splits > 1 writes `splits` partial products to C + z * split_stride.
+int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, const float* Bm, float* C,
+                int ldc, int splits, long split_stride, float alpha, const float* bias, int* splits_out = nullptr) {
+    tc::Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.n_pad = mn_major ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
+    if (p.n_pad > 512) return fail("tensor-core GEMM: N=%d too wide", N);
+    if (p.n_pad <= 256) { p.n_half0 = p.n_pad; p.n_half1 = 0; }
+    else {
+        const int unit = mn_major ? 32 : 16;
+        p.n_half0 = ((p.n_pad / 2) + unit - 1) / unit * unit;
+        p.n_half1 = p.n_pad - p.n_half0;
+    }
+    p.b_boxes = p.n_pad > 256 ? 2 : 1;
+    p.b_box_rows = p.n_pad / p.b_boxes;
+    if (!mn_major && (p.b_box_rows % 8 != 0)) return fail("tensor-core GEMM: unsupported N=%d", N);
+    const int num_kb = (K + tc::kBlockK - 1) / tc::kBlockK;
+    splits = std::max(1, std::min(splits, num_kb));
+    p.kb_per_split = (num_kb + splits - 1) / splits;
+    const int grid_y = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.stage_bytes = tc::kATileBytes + (uint32_t)p.n_pad * 128u;
+    p.stages = (int)std::min<uint32_t>(6u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
+    if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
+    p.tmem_cols = 32;
+    while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
+    p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
+    CUtensorMap tmA, tmB;
+    if (!mn_major) {
+        TRY(make_tensor_map(&tmA, A, K, M, K, tc::kBlockK, tc::kBlockM));
+        TRY(make_tensor_map(&tmB, Bm, K, N, K, tc::kBlockK, std::min(p.b_box_rows, 256)));
+    } else {
+        TRY(make_tensor_map(&tmA, A, M, K, M, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmB, Bm, N, K, N, 32, tc::kBlockK, true));
+    }
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+    dim3 grid((M + tc::kBlockM - 1) / tc::kBlockM, grid_y);
+    if (!mn_major) {
+        static bool attr = false;
+        if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
+        LAUNCH(m, (tc::gemm_tc_kernel<false, false>), grid, tc::kThreads, smem, tmA, tmB, p);
+    } else {
+        static bool attr = false;
+        if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
+        LAUNCH(m, (tc::gemm_tc_kernel<true, true>), grid, tc::kThreads, smem, tmA, tmB, p);
+    }
+    if (splits_out) *splits_out = grid_y;
+    return 0;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    for (int r = blockIdx.y * 32 + threadIdx.y; r < min(rows, (int)(blockIdx.y + 1) * 32); r += blockDim.y)
+        if (c < cols) tile[r - blockIdx.y * 32][threadIdx.x] = in[(long)r * cols + c];
+    __syncthreads();
+    const int r2 = blockIdx.y * 32 + threadIdx.x;
+    for (int c2 = blockIdx.x * 32 + threadIdx.y; c2 < min(cols, (int)(blockIdx.x + 1) * 32); c2 += blockDim.y)
+        if (r2 < rows) out[(long)c2 * rows + r2] = tile[threadIdx.x][c2 - blockIdx.x * 32];
+}
+
 int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
     if (m->nranks <= 1) return 0;
     phase_end(m);
@@ -304,7 +415,12 @@ int forward(nvsm_model* m, BatchSlot* s) {
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
     phase_begin(m, PH_GEMM_FWD);
-    TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, dw, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
+    if (m->use_tc) {
+        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt);
+        TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->Tt, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b));
+    } else {
+        TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, dw, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
+    }
     phase_end(m);
 
     // (3) batch statistics over the (global) batch.
@@ -366,11 +482,16 @@ int backward(nvsm_model* m) {
     const int dw = m->dw, dd = m->dd;
 
     phase_begin(m, PH_BN_BWD);
-    LAUNCH(m, col_sums_to_float_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, m->gb);
+    LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal, m->gb,
+           m->mean_dy, m->mean_dyx);
     if (bn) {
-        const int grid = grid_for(m, B * dd, 256 * 8, 8);
-        LAUNCH(m, bn_backward_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->bwd_sums(),
-               (double)m->Bglobal, B, dd);
+        if (vec4_ok(dd)) {
+            const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
+            LAUNCH(m, bn_backward_kernel<4>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd);
+        } else {
+            const int grid = grid_for(m, B * dd, 256 * 4, 8);
+            LAUNCH(m, bn_backward_kernel<1>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd);
+        }
     }
     phase_end(m);
 
@@ -383,9 +504,16 @@ int backward(nvsm_model* m) {
         int kps = (int)((B + splits - 1) / splits);
         kps = (kps + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
         const int nz = (int)((B + kps - 1) / kps);
-        TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, dw, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
         const long nT = (long)dw * dd;
-        LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, nz, nT, m->gT);
+        int nparts = nz;
+        if (m->use_tc) {
+            const int mtiles = (dw + tc::kBlockM - 1) / tc::kBlockM;
+            const int want = std::max(1, std::min(m->gt_splits, m->num_sms / mtiles));
+            TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->Gp, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts));
+        } else {
+            TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, dw, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
+        }
+        LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, nparts, nT, m->gT);
     }
     phase_end(m);
     TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
@@ -394,7 +522,10 @@ int backward(nvsm_model* m) {
     phase_begin(m, PH_GEMM_GP);
     {
         const float inv_n = (float)std::exp(-std::log((double)m->n));
-        TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
+        if (m->use_tc)
+            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, m->T, m->gP, dw, 1, 0, inv_n, nullptr));
+        else
+            TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
     }
     phase_end(m);
     m->have_gradients = true;
@@ -683,9 +814,9 @@ void nvsm_destroy(nvsm_model* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->comm) nccl_api().CommDestroy(m->comm);
-    float* fl[] = {m->W, m->E, m->T, m->b, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
+    float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
                    m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
-                   m->mult, m->rowtmp, m->mean, m->invstd, m->gT, m->gb, m->gT_part, m->scratch};
+                   m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->gT, m->gb, m->gT_part, m->scratch};
     for (float* p : fl)
         if (p) cudaFree(p);
     if (m->dsums) cudaFree(m->dsums);
@@ -720,7 +851,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     if (cfg->update_method == NVSM_ADAM && (cfg->adam_mode < NVSM_ADAM_SPARSE || cfg->adam_mode > NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE)) return fail("Invalid mode configuration.");
     if (cfg->num_random_entities < 0) return fail("num_random_entities must be >= 0");
     if (cfg->max_batch_size <= 0 || cfg->window_size <= 0) return fail("max_batch_size and window_size must be > 0");
-    if (cfg->gemm_mode != NVSM_GEMM_FP32) return fail("gemm_mode %d is not available in this build", cfg->gemm_mode);
+    if (cfg->gemm_mode != NVSM_GEMM_FP32 && cfg->gemm_mode != NVSM_GEMM_TF32) return fail("gemm_mode %d is not available in this build", cfg->gemm_mode);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("no CUDA device: libnvsm_b200 has no CPU fallback");
@@ -735,6 +866,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     m->dw = cfg->word_repr_size; m->dd = cfg->entity_repr_size;
     m->n = cfg->window_size; m->z = cfg->num_random_entities; m->R = m->z + 1;
     m->maxB = cfg->max_batch_size;
+    m->use_tc = cfg->gemm_mode != NVSM_GEMM_FP32 && tc_shapes_ok(m->dw, m->dd);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, m->device);
     m->num_sms = prop.multiProcessorCount;
@@ -747,6 +879,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const int dw = m->dw, dd = m->dd;
         TRY(dev_alloc(&m->W, V * dw)); TRY(dev_alloc(&m->E, D * dd));
         TRY(dev_alloc(&m->T, (size_t)dw * dd)); TRY(dev_alloc(&m->b, dd));
+        TRY(dev_alloc(&m->Tt, (size_t)dw * dd));
         const int method = cfg->update_method;
         if (method == NVSM_ADAGRAD) {
             TRY(dev_alloc(&m->optW.acc, V)); TRY(dev_alloc(&m->optE.acc, D));
@@ -764,10 +897,11 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
         TRY(dev_alloc(&m->rowtmp, maxB));
         TRY(dev_alloc(&m->mean, dd)); TRY(dev_alloc(&m->invstd, dd));
+        TRY(dev_alloc(&m->mean_dy, dd)); TRY(dev_alloc(&m->mean_dyx, dd));
         TRY(dev_alloc(&m->dsums, 5 * (size_t)dd + 1));
         TRY(dev_alloc(&m->gT, (size_t)dw * dd)); TRY(dev_alloc(&m->gb, dd));
         const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
-        m->gt_splits = std::max(1, (2 * m->num_sms + tiles - 1) / tiles);
+        m->gt_splits = std::max(m->num_sms, (2 * m->num_sms + tiles - 1) / tiles);
         TRY(dev_alloc(&m->gT_part, (size_t)m->gt_splits * dw * dd, false));
         m->slots.resize(m->cfg.num_batch_slots + 2);
         for (auto& s : m->slots) {
@@ -1025,6 +1159,36 @@ int nvsm_reset_phase_ms(nvsm_model* m) {
 }
 
 long nvsm_kernel_launches(nvsm_model* m) { return m ? m->launches : 0; }
+
+// Test hook for the tensor-core GEMM in isolation (tests/test_gpu_gemm.py): host in / host out.
+// variant 0: A[M,K], B[N,K] (K-major); variant 1: A[K,M], B[K,N] (MN-major, split-K + reduce).
+int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const float* A, const float* Bh,
+                      float* C, float alpha, const float* bias, int splits) {
+    if (!m || !A || !Bh || !C) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dP = nullptr, *dbias = nullptr;
+    const size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
+    auto run = [&]() -> int {
+        CU(cudaMalloc((void**)&dA, na * 4)); CU(cudaMalloc((void**)&dB, nb * 4)); CU(cudaMalloc((void**)&dC, nc * 4));
+        CU(cudaMemcpy(dA, A, na * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dB, Bh, nb * 4, cudaMemcpyHostToDevice));
+        if (bias) { CU(cudaMalloc((void**)&dbias, (size_t)N * 4)); CU(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+        if (variant == 0) {
+            TRY(run_gemm_tc(m, false, M, N, K, dA, dB, dC, N, 1, 0, alpha, dbias));
+        } else {
+            splits = std::max(1, splits);
+            CU(cudaMalloc((void**)&dP, nc * 4 * splits));
+            int nparts = 1;
+            TRY(run_gemm_tc(m, true, M, N, K, dA, dB, dP, N, splits, (long)nc, alpha, nullptr, &nparts));
+            LAUNCH(m, reduce_partials_kernel, (int)((nc + 255) / 256), 256, 0, dP, nparts, (long)nc, dC);
+        }
+        CU(cudaStreamSynchronize(m->stream));
+        CU(cudaMemcpy(C, dC, nc * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    const int rc = run();
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dP); cudaFree(dbias);
+    return rc;
+}
 
 int nvsm_comm_unique_id(char* id_out_128) {
     if (!id_out_128) return fail("null argument");

@@ -155,6 +155,12 @@ NVSM_API int nvsm_get_phase_ms(nvsm_model* m, float* ms_out, int capacity); /* s
 NVSM_API int nvsm_reset_phase_ms(nvsm_model* m);
 NVSM_API long nvsm_kernel_launches(nvsm_model* m); /* kernels launched by this model so far */
 
+/* Test hook: the tcgen05/TMA GEMM in isolation on host matrices. variant 0: A[M,K], B[N,K]
+ * (both K-major) -> C[M,N] = alpha A.B^T + bias; variant 1: A[K,M], B[K,N] (both MN-major,
+ * split-K) -> C[M,N] = alpha A^T.B. */
+NVSM_API int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const float* A, const float* B,
+                               float* C, float alpha, const float* bias, int splits);
+
 /* Multi-GPU (one process per GPU). The batch is sharded by n-gram row; the library
  * all-reduces batch-norm statistics and the dense gradients with NCCL (new: the reference
  * is single-GPU). id: 128 bytes from nvsm_comm_unique_id on rank 0, broadcast by the

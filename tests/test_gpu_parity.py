@@ -114,6 +114,25 @@ def test_forward_backward_matches_oracle(name):
     compare_step_tensors(gm, om, cost, ocost)
 
 
+TF32_CASES = ["C1_lse", "lse_bias_neg", "nvsm_small", "nvsm_tanh_bn", "wide"]
+
+
+@pytest.mark.parametrize("name", TF32_CASES)
+def test_forward_backward_tf32_tensor_core_gemms(name):
+    """NVSM_GEMM_TF32: the three projection GEMMs run on tcgen05 with kind::tf32 (10-bit operand
+    mantissas, fp32 accumulation). Everything downstream of a GEMM inherits ~1e-3 relative error,
+    so the tolerance is 5e-3 relative with a 2e-3 x max|expected| floor; indices stay bit-exact."""
+    c = dict(CASES[name])
+    V, D, n, z, B = c["V"], c["D"], c["n"], c["z"], c["B"]
+    gm, om, rng = twin_models(**c, gemm_mode=nv.GEMM_TF32)
+    _, _, cost, ocost = run_forward_backward(gm, om, rng, B, n, V, D, z)
+    assert abs(cost - ocost) <= 2e-3 * abs(ocost)
+    assert_close(gm.get_tensor("phrase_reprs"), om.get("P"), RTOL, what="P")
+    for g, o in (("word_projections", "Y"), ("similarity_probs", "probs"), ("instance_multipliers", "mult"),
+                 ("grad_transform", "gT"), ("grad_bias", "gb"), ("grad_phrase_reprs", "gP"), ("grad_entity_repr", "gE")):
+        assert_close(gm.get_tensor(g), om.get(o), 5e-3, 2e-3, what=o)
+
+
 OPTIMISERS = [("sgd", nv.SGD, 0), ("adagrad", nv.ADAGRAD, 0), ("sparse_adam", nv.ADAM, nv.SPARSE),
               ("dense_adam", nv.ADAM, nv.DENSE_UPDATE), ("full_adam", nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)]
 STATE_NAMES = {
@@ -264,8 +283,12 @@ def test_full_size_c2_properties():
     dW = m.get_tensor(nv.WORD_REPRS).astype(np.float64).reshape(V, 300) - W0
     expect_E = lr * ((mult2 * sign).sum(1)[:, None] * Y).sum(0)
     expect_W = lr * n * gP2.sum(0)
-    assert_close(dE.sum(0), expect_E, 2e-2, 2e-2)
-    assert_close(dW.sum(0), expect_W, 2e-2, 5e-2)
+    # tolerance relative to the total mass that was scattered into each column (the signed column
+    # sums themselves nearly cancel under batch-norm)
+    mass_E = lr * (np.abs(mult2).sum(1)[:, None] * np.abs(Y)).sum(0)
+    mass_W = lr * n * np.abs(gP2).sum(0)
+    assert (np.abs(dE.sum(0) - expect_E) <= 1e-4 * mass_E + 1e-9).all()
+    assert (np.abs(dW.sum(0) - expect_W) <= 1e-4 * mass_W + 1e-9).all()
     # rows never referenced stay bit-identical
     untouched = np.setdiff1d(np.arange(D), np.unique(ids2))
     assert (dE[untouched] == 0).all()
