@@ -52,7 +52,18 @@ struct Params {
     long split_stride;     // elements between split-K partial outputs
     float alpha;
     const float* bias;     // nullable, per output column
+    int debug;             // bit0: skip global stores, bit1: skip MMAs, bit2: skip TMEM loads (timing experiments)
+    unsigned long long* trace;  // nullable: per-CTA globaltimer stamps (timing experiments)
+    double* col_stats;     // nullable: [2*N] += column sums and sums of squares of the stored C
+                           // (batch-norm statistics fused into the forward projection)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
+    return t;
+}
+#define NVSM_STAMP(slot) do { if (p.trace) p.trace[(long)(blockIdx.x + gridDim.x * blockIdx.y) * 8 + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -141,6 +152,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Column totals of a 32-row x 16-column register tile (one row per lane): recursive halving,
+// 16 shuffles. Afterwards v[0] of lane L is the total of column (L >> 1) & 15.
+__device__ __forceinline__ float column_totals16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool hi = lane & bit;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = hi ? v[half + i] : v[i];
+            const float send = hi ? v[i] : v[half + i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -149,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t empty_bar[8];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_stats[2 * 512];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +185,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kb0 = blockIdx.y * p.kb_per_split;
     const int num_kb = max(0, min(p.kb_per_split, num_kb_total - kb0));
 
+    if (threadIdx.x == 0) NVSM_STAMP(0);
+    if (p.debug & 8) return;      // experiment: CTA launch throughput only
+    if (p.col_stats)
+        for (int t = threadIdx.x; t < 2 * p.n_pad; t += kThreads) s_stats[t] = 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
@@ -176,8 +208,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) NVSM_STAMP(1);
+    const bool skip_main = p.debug & 16;   // experiment: setup + teardown only
 
-    if (warp == 0) {
+    if (skip_main) {
+    } else if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -215,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(smem_u32(&full_bar[s]), ph);
                 tc_fence_after();
+
                 const uint32_t a_base = smem_base + (uint32_t)s * p.stage_bytes;
                 const uint32_t b_base = a_base + kATileBytes;
 #pragma unroll
@@ -226,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                  : make_desc(a_base + j * 32u, 16u, 1024u, 2u);
                     const uint64_t b_desc0 = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
                                                   : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
-                    umma_tf32(tmem_base, a_desc, b_desc0, idesc0, acc);
+                    if (!(p.debug & 2)) umma_tf32(tmem_base, a_desc, b_desc0, idesc0, acc);
                     if (p.n_half1 > 0) {
                         const uint32_t off = B_MN ? (uint32_t)(p.n_half0 / 32) * kGroupBytes : (uint32_t)p.n_half0 * 128u;
                         const uint64_t b_desc1 = B_MN ? make_desc(b_base + off + j * 1024u, kGroupBytes, 512u, 1u)
@@ -245,44 +281,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* crow = p.C + (long)blockIdx.y * p.split_stride + (long)m * p.ldc;
         if (num_kb > 0) {
             mbar_wait(smem_u32(&accum_bar), 0);
+            if (warp == 2 && lane == 0) NVSM_STAMP(2);
             tc_fence_after();
         }
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        if (warp == 2 && lane == 0) NVSM_STAMP(3);
+        // hoist everything the loop needs out of constant memory once
+        const float alpha = p.alpha;
+        const float* __restrict__ bias = p.bias;
+        const int Nv = p.N, n_pad = p.n_pad;
+        const bool row_ok = m < p.M;
+        const bool do_store = row_ok && !(p.debug & 1);
+        const bool do_ld = num_kb > 0 && !(p.debug & 4);
+        const bool vec_ok = (p.ldc & 3) == 0;
+        const bool stats = p.col_stats != nullptr;
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
             float v[16];
-            if (num_kb > 0) {
+            if (do_ld) {
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
-            if (m < p.M) {
-                if (c0 + 16 <= p.N && (p.ldc & 3) == 0) {
+            const bool full = c0 + 16 <= Nv;
+            float bv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bv[i] = 0.f;
+            if (bias) {
+                if (full) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        float4 o;
-                        o.x = p.alpha * v[i + 0]; o.y = p.alpha * v[i + 1];
-                        o.z = p.alpha * v[i + 2]; o.w = p.alpha * v[i + 3];
-                        if (p.bias) {
-                            o.x += __ldg(p.bias + c0 + i + 0); o.y += __ldg(p.bias + c0 + i + 1);
-                            o.z += __ldg(p.bias + c0 + i + 2); o.w += __ldg(p.bias + c0 + i + 3);
-                        }
-                        *reinterpret_cast<float4*>(crow + c0 + i) = o;
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                        bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = c0 + i;
-                        if (n < p.N) crow[n] = p.alpha * v[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
-                    }
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < Nv) bv[i] = __ldg(bias + c0 + i);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, v[i], bv[i]);
+            if (do_store) {
+                if (full && vec_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(crow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < Nv) crow[c0 + i] = v[i];
+                }
+            }
+            if (stats) {
+                // rows / columns outside the problem must contribute zeros
+                float sq[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = (row_ok && (full || c0 + i < Nv)) ? v[i] : 0.f;
+                    sq[i] = v[i] * v[i];
+                }
+                const float tot = column_totals16(v, lane);
+                const float tot2 = column_totals16(sq, lane);
+                if ((lane & 1) == 0) {
+                    const int col = c0 + ((lane >> 1) & 15);
+                    atomicAdd(&s_stats[col], tot);
+                    atomicAdd(&s_stats[n_pad + col], tot2);
+                }
+            }
+            if (warp == 2 && lane == 0 && c0 == 0) NVSM_STAMP(4);
+            if (warp == 2 && lane == 0 && c0 == 128) NVSM_STAMP(5);
         }
     }
+    if (warp == 2 && lane == 0) NVSM_STAMP(6);
     tc_fence_before();
     __syncthreads();
+    if (p.col_stats) {
+        for (int t = threadIdx.x; t < 2 * p.n_pad; t += kThreads) {
+            const int which = t / p.n_pad, col = t % p.n_pad;
+            if (col < p.N) atomicAdd(p.col_stats + (long)which * p.N + col, (double)s_stats[t]);
+        }
+    }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+        if (lane == 0) NVSM_STAMP(7);
     }
 }
 

@@ -84,6 +84,63 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
     }
 }
 
+// Same statistics for dd % 4 == 0, without atomics: every thread owns one float4 column group
+// and streams its slab of rows with four independent 128-bit loads in flight (Z is L2-resident:
+// it was just written by the projection GEMM); the row groups of a block are combined in
+// shared memory and each block writes one fp32 partial row [2*dd]. col_stats_reduce_kernel
+// then sums the partials in double (deterministic).
+__global__ void __launch_bounds__(256) col_stats4_kernel(const float* __restrict__ Z, long rows, int dd,
+                                                         float* __restrict__ partials) {
+    extern __shared__ float sm[];  // [rpp][2*dd]
+    const int nvec = dd >> 2;
+    const int tpr = min(nvec, (int)blockDim.x);
+    const int rpp = blockDim.x / tpr;
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    const long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = min(rows, r0 + rows_per_block);
+    if (tr < rpp) {
+        for (int c = tc; c < nvec; c += tpr) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+            const float4* base = reinterpret_cast<const float4*>(Z) + c;
+            long r = r0 + tr;
+            for (; r + 3 * rpp < r1; r += 4 * rpp) {
+                const float4 x0 = __ldg(base + (r) * nvec), x1 = __ldg(base + (r + rpp) * nvec);
+                const float4 x2 = __ldg(base + (r + 2 * rpp) * nvec), x3 = __ldg(base + (r + 3 * rpp) * nvec);
+                s.x += (x0.x + x1.x) + (x2.x + x3.x); s.y += (x0.y + x1.y) + (x2.y + x3.y);
+                s.z += (x0.z + x1.z) + (x2.z + x3.z); s.w += (x0.w + x1.w) + (x2.w + x3.w);
+                q.x += (x0.x * x0.x + x1.x * x1.x) + (x2.x * x2.x + x3.x * x3.x);
+                q.y += (x0.y * x0.y + x1.y * x1.y) + (x2.y * x2.y + x3.y * x3.y);
+                q.z += (x0.z * x0.z + x1.z * x1.z) + (x2.z * x2.z + x3.z * x3.z);
+                q.w += (x0.w * x0.w + x1.w * x1.w) + (x2.w * x2.w + x3.w * x3.w);
+            }
+            for (; r < r1; r += rpp) {
+                const float4 x = __ldg(base + r * nvec);
+                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+                q.x += x.x * x.x; q.y += x.y * x.y; q.z += x.z * x.z; q.w += x.w * x.w;
+            }
+            float* o = sm + (long)tr * 2 * dd;
+            *reinterpret_cast<float4*>(o + 4 * c) = s;
+            *reinterpret_cast<float4*>(o + dd + 4 * c) = q;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) {
+        float a = 0.f;
+        for (int g = 0; g < rpp; ++g) a += sm[(long)g * 2 * dd + t];
+        partials[(long)blockIdx.x * 2 * dd + t] = a;
+    }
+}
+
+__global__ void col_stats_reduce_kernel(const float* __restrict__ partials, int nblocks, int n,
+                                        double* __restrict__ sums) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += (double)partials[(long)b * n + t];
+    sums[t] = a;
+}
+
 // mean / invstd from the (all-reduced) sums; biased variance, eps inside the sqrt.
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int dd, double batch, double eps,
                                    float* __restrict__ mean, float* __restrict__ invstd) {
@@ -147,16 +204,38 @@ struct ScoreParams {
     int R, dd;
     float w_scale;         // (z+1)/(2z) when rebalancing, else 1   (objective.cu:268-274)
     float pos_scale;       // z when rebalancing, else 1            (objective.cu:282-290)
-    double sig_lo, sig_hi;     // forward clamp  [eps, 1 - eps], eps = 1e-7 or 0
-    double der_lo, der_hi;     // zero-gradient band, eps = 1e-6 or 0
+    // The reference clamps / tests the float probability against double constants
+    // (`1.0 - epsilon_`). For a float p those comparisons are equivalent to comparisons with
+    // the float thresholds below (host: smallest float >= / largest float <= the double).
+    float sig_lo_cmp, sig_lo_val;   // p <  sig_lo_cmp -> sig_lo_val     forward clamp, eps 1e-7 | 0
+    float sig_hi_cmp, sig_hi_val;   // p >  sig_hi_cmp -> sig_hi_val
+    float der_lo_cmp, der_hi_cmp;   // p <= der_lo_cmp || p >= der_hi_cmp -> zero gradient (eps 1e-6 | 0)
     float bsn;             // exp(-log(B_global))
     ActParams act;
     float* probs;          // [B*R]
     float* mult;           // [B*R]
     float* Gp;             // [B, dd]
+    float* Y;              // [B, dd] post-activation (nullable; kept for the pull-style update)
     double* loss_acc;      // [1]  sum_c wbc_c log p_c
     double* col_sums;      // [2*dd]: sum_i dy, sum_i dy * xhat
 };
+
+// Reduce four per-lane partial sums across the warp with 6 shuffles (instead of 20): after the
+// call, `d0` of lane L holds the warp total of partial ((L >> 3) & 3).
+__device__ __forceinline__ float warp_sum4_transposed(float d0, float d1, float d2, float d3, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    float a0 = b4 ? d2 : d0, a1 = b4 ? d3 : d1;
+    const float s0 = b4 ? d0 : d2, s1 = b4 ? d1 : d3;
+    a0 += __shfl_xor_sync(kFull, s0, 16);
+    a1 += __shfl_xor_sync(kFull, s1, 16);
+    float b = b3 ? a1 : a0;
+    const float s = b3 ? a0 : a1;
+    b += __shfl_xor_sync(kFull, s, 8);
+    b += __shfl_xor_sync(kFull, b, 4);
+    b += __shfl_xor_sync(kFull, b, 2);
+    b += __shfl_xor_sync(kFull, b, 1);
+    return b;
+}
 
 template <int VEC, int NCH>
 __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
@@ -174,6 +253,8 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { cs[j][v] = 0.f; cx[j][v] = 0.f; }
     float loss = 0.f;
+    const int my_slot = (lane >> 3) & 3;      // which of the RB rows this lane finishes
+    const bool slot_leader = (lane & 7) == 0;
 
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -191,6 +272,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
                 y[j][v] = 0.f; xh[j][v] = 0.f;
                 if (c < nvec) y[j][v] = act_forward(p.act, z[v], c * VEC + v, xh[j][v]);
             }
+            if (p.Y && c < nvec) store_vec<VEC>(p.Y + i * dd + c * VEC, y[j]);
         }
         const float wneg = __ldg(p.inst_w + i) * p.w_scale;
         const float wpos = wneg * p.pos_scale;
@@ -213,45 +295,44 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
                 }
             }
 #pragma unroll
-            for (int rr = 0; rr < RB; ++rr) {
+            for (int rr = 0; rr < RB; ++rr)
 #pragma unroll
                 for (int j = 0; j < NCH; ++j)
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) dot[rr] += y[j][v] * e[rr][j][v];
-                dot[rr] = warp_sum(dot[rr]);
+            // every lane finishes the scalar chain of ONE row (slot (lane >> 3) & 3)
+            const float d = warp_sum4_transposed(dot[0], dot[1], dot[2], dot[3], lane);
+            const int r = r0 + my_slot;
+            float coef = 0.f;
+            if (r < p.R) {
+                const float sign = r == 0 ? 1.0f : -1.0f;
+                const float s = sign * d;
+                // numerically stable sigmoid (include/cuNVSM/cuda_utils.h:192-214)
+                float prob;
+                if (s >= 0.f) {
+                    prob = 1.0f / (1.0f + expf(-s));
+                } else {
+                    const float ex = expf(s);
+                    prob = ex / (1.0f + ex);
+                }
+                prob = prob < p.sig_lo_cmp ? p.sig_lo_val : (prob > p.sig_hi_cmp ? p.sig_hi_val : prob);
+                const float w = r == 0 ? wpos : wneg;
+                const float der = (prob >= p.der_hi_cmp || prob <= p.der_lo_cmp) ? 0.0f : 1.0f - prob;
+                const float m = w * (der * p.bsn);
+                if (slot_leader) {
+                    loss += w * logf(prob);
+                    p.probs[i * p.R + r] = prob;
+                    p.mult[i * p.R + r] = m;
+                }
+                coef = sign * m;
             }
-            float my_p = 0.f, my_m = 0.f;
 #pragma unroll
             for (int rr = 0; rr < RB; ++rr) {
-                const int r = r0 + rr;
-                if (r < p.R) {
-                    const float sign = r == 0 ? 1.0f : -1.0f;
-                    const float s = sign * dot[rr];
-                    // numerically stable sigmoid (include/cuNVSM/cuda_utils.h:192-214)
-                    float prob;
-                    if (s >= 0.f) {
-                        prob = 1.0f / (1.0f + expf(-s));
-                    } else {
-                        const float ex = expf(s);
-                        prob = ex / (1.0f + ex);
-                    }
-                    prob = (float)fmin(fmax((double)prob, p.sig_lo), p.sig_hi);
-                    const float w = r == 0 ? wpos : wneg;
-                    loss += w * logf(prob);
-                    const double pd = (double)prob;
-                    const float der = (pd >= p.der_hi || pd <= p.der_lo) ? 0.0f : (float)(1.0 - pd);
-                    const float m = w * (der * p.bsn);
-                    if (lane == rr) { my_p = prob; my_m = m; }
-                    const float coef = sign * m;
+                const float cf = __shfl_sync(kFull, coef, rr * 8);
 #pragma unroll
-                    for (int j = 0; j < NCH; ++j)
+                for (int j = 0; j < NCH; ++j)
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) gp[j][v] += coef * e[rr][j][v];
-                }
-            }
-            if (lane < RB && r0 + lane < p.R) {
-                p.probs[i * p.R + r0 + lane] = my_p;
-                p.mult[i * p.R + r0 + lane] = my_m;
+                    for (int v = 0; v < VEC; ++v) gp[j][v] += cf * e[rr][j][v];
             }
         }
         // d cost / d (pre-activation); column sums for grad_bias and BN backward.
@@ -280,6 +361,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
             }
         }
     }
+    loss = warp_sum(loss);
     if (lane == 0) atomicAdd(&smem[2 * dd], loss);
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)smem[t]);

@@ -21,6 +21,7 @@
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include "pull_update.cuh"
 
 using namespace nvsm;
 
@@ -107,11 +108,18 @@ struct nvsm_model {
 
     // per-step workspace
     float *P = nullptr, *Z = nullptr, *Gp = nullptr, *gP = nullptr;
+    float* Y = nullptr;  // post-activation projections, kept only for the pull-style (full Adam) update
     float *probs = nullptr, *mult = nullptr, *rowtmp = nullptr;
     float *mean = nullptr, *invstd = nullptr, *mean_dy = nullptr, *mean_dyx = nullptr;
+    float* stat_part = nullptr;  // [2 * num_sms][2*dd] per-block partial column statistics
     double* dsums = nullptr;   // [2*dd fwd sums][dd var sums][2*dd bwd col sums][1 loss]
     float *gT = nullptr, *gb = nullptr, *gT_part = nullptr;
     int gt_splits = 1;
+    // pull-style full Adam: per-step reference buckets (counting sort by row)
+    bool pull = false;
+    int *e_counts = nullptr, *e_offsets = nullptr, *e_refs = nullptr;
+    int *w_counts = nullptr, *w_offsets = nullptr, *w_refs = nullptr;
+    int* scan_tmp = nullptr;  // block totals of the two-level scan
     bool use_tc = false;  // projection GEMMs on tcgen05 (gemm_mode != FP32 and shapes allow)
     float* scratch = nullptr;  // inspection buffer max(B*R*dd, ...) allocated on demand
     size_t scratch_bytes = 0;
@@ -277,7 +285,9 @@ int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer,
 }
 
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), with headroom.
-constexpr uint32_t kTcMaxDynSmem = 232448u - 1024u;
+constexpr uint32_t kTcMaxDynSmem = 232448u - 6144u;
+
+unsigned long long* g_tc_trace = nullptr;  // set by nvsm_bench_gemm_tc for timing experiments
 
 bool tc_shapes_ok(int dw, int dd) {
     // TMA needs 16-byte row strides; grad_transform's MN-major B tile needs dd % 32 == 0.
@@ -289,7 +299,8 @@ bool tc_shapes_ok(int dw, int dd) {
 //   mn_major == true : A is [K, M] row-major, Bm is [K, N] row-major      (both MN-major)
 // splits > 1 writes `splits` partial products to C + z * split_stride.
 int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, const float* Bm, float* C,
-                int ldc, int splits, long split_stride, float alpha, const float* bias, int* splits_out = nullptr) {
+                int ldc, int splits, long split_stride, float alpha, const float* bias, int* splits_out = nullptr,
+                double* col_stats = nullptr) {
     tc::Params p;
     p.M = M; p.N = N; p.K = K;
     p.n_pad = mn_major ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
@@ -313,6 +324,10 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
     p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
+    p.col_stats = col_stats;
+    p.trace = g_tc_trace;
+    { const char* dbg = getenv("NVSM_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
     CUtensorMap tmA, tmB;
     if (!mn_major) {
         TRY(make_tensor_map(&tmA, A, K, M, K, tc::kBlockK, tc::kBlockM));
@@ -424,7 +439,23 @@ int forward(nvsm_model* m, BatchSlot* s) {
     phase_end(m);
 
     // (3) batch statistics over the (global) batch.
-    if (bn) {
+    if (bn && m->use_tc) {
+        // One pass over the L2-resident Z for sums and sums of squares (fp32 over ~100-row
+        // slabs, double across slabs); one all-reduce, then mean / invstd.
+        phase_begin(m, PH_BN_STATS);
+        {
+            const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
+            const int nblk = grid_for(m, B, 32, 2);   // <= 2 blocks per SM
+            LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
+            LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 127) / 128, 128, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
+        }
+        phase_end(m);
+        TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true));
+        phase_begin(m, PH_BN_STATS);
+        LAUNCH(m, bn_finalize_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), dd, (double)m->Bglobal,
+               1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd);
+        phase_end(m);
+    } else if (bn) {
         phase_begin(m, PH_BN_STATS);
         const int grid = grid_for(m, B, 64, 4);
         LAUNCH(m, col_stats_kernel, grid, 256, 0, m->Z, B, dd, m->fwd_sums());
@@ -451,11 +482,16 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.pos_scale = rebalance ? (float)m->z : 1.0f;
         const float ef = m->cfg.clip_sigmoid ? 1e-7f : 0.0f;
         const float eb = m->cfg.clip_sigmoid ? 1e-6f : 0.0f;
-        sp.sig_lo = (double)ef; sp.sig_hi = 1.0 - (double)ef;
-        sp.der_lo = (double)eb; sp.der_hi = 1.0 - (double)eb;
+        // float thresholds equivalent to the reference's float-vs-double comparisons
+        auto fceil = [](double d) { float f = (float)d; if ((double)f < d) f = std::nextafter(f, INFINITY); return f; };
+        auto ffloor = [](double d) { float f = (float)d; if ((double)f > d) f = std::nextafter(f, -INFINITY); return f; };
+        const double slo = (double)ef, shi = 1.0 - (double)ef, dlo = (double)eb, dhi = 1.0 - (double)eb;
+        sp.sig_lo_cmp = fceil(slo); sp.sig_lo_val = (float)slo;
+        sp.sig_hi_cmp = ffloor(shi); sp.sig_hi_val = (float)shi;
+        sp.der_lo_cmp = ffloor(dlo); sp.der_hi_cmp = fceil(dhi);
         sp.bsn = (float)std::exp(-std::log((double)m->Bglobal));
         sp.act = act_params(m, bn);
-        sp.probs = m->probs; sp.mult = m->mult; sp.Gp = m->Gp;
+        sp.probs = m->probs; sp.mult = m->mult; sp.Gp = m->Gp; sp.Y = m->Y;
         sp.loss_acc = m->loss_acc(); sp.col_sums = m->bwd_sums();
         TRY(dispatch_score(m, sp));
     }
@@ -601,6 +637,53 @@ int scatter_word_meansq(nvsm_model* m, float* acc, float scale) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// pull-style full Adam (pull_update.cuh)
+// ------------------------------------------------------------------------------------
+int build_buckets(nvsm_model* m, const idx_t* ids, long total, long num_rows, int* counts, int* offsets, int* refs) {
+    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (num_rows + 1), m->stream));
+    const int g = (int)((total + 255) / 256);
+    LAUNCH(m, ref_count_kernel, g, 256, 0, ids, total, counts);
+    const int nb = (int)((num_rows + 1023) / 1024);
+    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, counts, num_rows, offsets, m->scan_tmp);
+    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->scan_tmp, (long)nb, m->scan_tmp + 1024, (int*)nullptr);
+    LAUNCH(m, scan_add_kernel, nb, 1024, 0, offsets, num_rows, m->scan_tmp + 1024, total);
+    LAUNCH(m, ref_fill_kernel, g, 256, 0, ids, total, offsets, counts, refs);
+    return 0;
+}
+
+template <int VEC, int NCH>
+int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
+    const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
+    if (entities)
+        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
+               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k);
+    else
+        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
+               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k);
+    return 0;
+}
+
+int pull_update(nvsm_model* m, bool entities, const AdamFullConsts& k) {
+    if (entities) TRY(build_buckets(m, m->cur->ids, m->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs));
+    else TRY(build_buckets(m, m->cur->features, m->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs));
+    const int dim = entities ? m->dd : m->dw;
+    if (vec4_ok(dim)) {
+        const int nch = (dim / 4 + 31) / 32;
+        if (nch <= 1) return launch_pull<4, 1>(m, entities, k);
+        if (nch <= 2) return launch_pull<4, 2>(m, entities, k);
+        if (nch <= 3) return launch_pull<4, 3>(m, entities, k);
+        if (nch <= 4) return launch_pull<4, 4>(m, entities, k);
+        return launch_pull<4, 8>(m, entities, k);
+    }
+    const int nch = (dim + 31) / 32;
+    if (nch <= 1) return launch_pull<1, 1>(m, entities, k);
+    if (nch <= 4) return launch_pull<1, 4>(m, entities, k);
+    if (nch <= 16) return launch_pull<1, 16>(m, entities, k);
+    return launch_pull<1, 32>(m, entities, k);
+}
+
 int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     float* theta = entities ? m->E : m->W;
     TableOpt& opt = entities ? m->optE : m->optW;
@@ -629,6 +712,12 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     const float bc = adam_bias_correction(c, opt.t);
     opt.t += 1;
     const int mode = m->cfg.adam_mode;
+    if (mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE && m->pull) {
+        AdamFullConsts k;
+        k.s1 = c.s1; k.lr1 = c.lr1; k.reg1 = (float)((1.0 - (double)c.b1) * (double)lambda);
+        k.s2 = c.s2; k.lr2 = c.lr2; k.lambda = lambda; k.lr = lr; k.bc = bc; k.eps = c.eps;
+        return pull_update(m, entities, k);
+    }
     if (mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE) {
         TRY(scatter(opt.agg, 1.0f, nullptr, 0.f));
         const float reg1 = (float)((1.0 - (double)c.b1) * (double)lambda);
@@ -816,10 +905,14 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->comm) nccl_api().CommDestroy(m->comm);
     float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
                    m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
-                   m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->gT, m->gb, m->gT_part, m->scratch};
+                   m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->stat_part, m->gT, m->gb, m->gT_part, m->scratch};
     for (float* p : fl)
         if (p) cudaFree(p);
     if (m->dsums) cudaFree(m->dsums);
+    int* il[] = {m->e_counts, m->e_offsets, m->e_refs, m->w_counts, m->w_offsets, m->w_refs, m->scan_tmp};
+    for (int* p : il)
+        if (p) cudaFree(p);
+    if (m->Y) cudaFree(m->Y);
     for (auto& s : m->slots) {
         if (s.features) cudaFree(s.features);
         if (s.fweights) cudaFree(s.fweights);
@@ -888,7 +981,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             const bool full = cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE;
             TRY(dev_alloc(&m->optW.m, V * dw)); TRY(dev_alloc(&m->optE.m, D * dd));
             TRY(dev_alloc(&m->optW.v, full ? V * dw : V)); TRY(dev_alloc(&m->optE.v, full ? D * dd : D));
-            if (full) { TRY(dev_alloc(&m->optW.agg, V * dw)); TRY(dev_alloc(&m->optE.agg, D * dd)); }
+            const bool can_pull = full && std::max(V, D) <= 1024L * 1024L && maxB * std::max<long>(m->R, m->n) < (1L << 31);
+            if (full && !can_pull) { TRY(dev_alloc(&m->optW.agg, V * dw)); TRY(dev_alloc(&m->optE.agg, D * dd)); }
             TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
             TRY(dev_alloc(&m->T_v, (size_t)dw * dd)); TRY(dev_alloc(&m->b_v, dd));
         }
@@ -899,10 +993,20 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->mean, dd)); TRY(dev_alloc(&m->invstd, dd));
         TRY(dev_alloc(&m->mean_dy, dd)); TRY(dev_alloc(&m->mean_dyx, dd));
         TRY(dev_alloc(&m->dsums, 5 * (size_t)dd + 1));
+        TRY(dev_alloc(&m->stat_part, (size_t)2 * m->num_sms * 2 * dd));
         TRY(dev_alloc(&m->gT, (size_t)dw * dd)); TRY(dev_alloc(&m->gb, dd));
         const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
         m->gt_splits = std::max(m->num_sms, (2 * m->num_sms + tiles - 1) / tiles);
         TRY(dev_alloc(&m->gT_part, (size_t)m->gt_splits * dw * dd, false));
+        m->pull = method == NVSM_ADAM && cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE &&
+                  V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
+        if (m->pull) {
+            TRY(dev_alloc(&m->Y, maxB * dd));
+            TRY(dev_alloc(&m->e_counts, D + 1)); TRY(dev_alloc(&m->e_offsets, D + 1)); TRY(dev_alloc(&m->e_refs, maxB * m->R));
+            TRY(dev_alloc(&m->w_counts, V + 1)); TRY(dev_alloc(&m->w_offsets, V + 1)); TRY(dev_alloc(&m->w_refs, maxB * m->n));
+            TRY(dev_alloc(&m->scan_tmp, 2 * 1024 + 2));
+            if (std::max(V, D) > 1024L * 1024L) m->pull = false;  // two-level scan limit
+        }
         m->slots.resize(m->cfg.num_batch_slots + 2);
         for (auto& s : m->slots) {
             TRY(dev_alloc(&s.features, maxB * m->n)); TRY(dev_alloc(&s.fweights, maxB * m->n));
@@ -1187,6 +1291,62 @@ int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const flo
     };
     const int rc = run();
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dP); cudaFree(dbias);
+    return rc;
+}
+
+// Device-resident timing of the tensor-core GEMM alone (scripts/bench_gemm.py).
+int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int splits, int with_stats, int iters,
+                       float* ms_out) {
+    if (!m || !ms_out) return fail("null argument");
+    CU(cudaSetDevice(m->device));
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    double* dS = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto run = [&]() -> int {
+        CU(cudaMalloc((void**)&dA, (size_t)M * K * 4)); CU(cudaMalloc((void**)&dB, (size_t)N * K * 4));
+        CU(cudaMalloc((void**)&dC, (size_t)M * N * 4 * std::max(1, splits))); CU(cudaMalloc((void**)&dS, (size_t)N * 16));
+        CU(cudaMemset(dA, 0, (size_t)M * K * 4)); CU(cudaMemset(dB, 0, (size_t)N * K * 4)); CU(cudaMemset(dS, 0, (size_t)N * 16));
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        for (int it = 0; it < iters + 3; ++it) {
+            if (it == 3) CU(cudaEventRecord(e0, m->stream));
+            TRY(run_gemm_tc(m, variant != 0, M, N, K, dA, dB, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr,
+                            with_stats ? dS : nullptr));
+        }
+        CU(cudaEventRecord(e1, m->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(ms_out, e0, e1));
+        *ms_out /= iters;
+        if (getenv("NVSM_TC_TRACE")) {
+            const int nct = ((M + 127) / 128) * std::max(1, splits);
+            unsigned long long* dT = nullptr;
+            CU(cudaMalloc((void**)&dT, (size_t)nct * 64));
+            CU(cudaMemset(dT, 0, (size_t)nct * 64));
+            g_tc_trace = dT;
+            const int rc2 = run_gemm_tc(m, variant != 0, M, N, K, dA, dB, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr, with_stats ? dS : nullptr);
+            g_tc_trace = nullptr;
+            if (rc2) return rc2;
+            CU(cudaStreamSynchronize(m->stream));
+            std::vector<unsigned long long> h((size_t)nct * 8);
+            CU(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(dT);
+            unsigned long long t0 = ~0ull;
+            for (int c = 0; c < nct; ++c) t0 = std::min(t0, h[c * 8]);
+            const int show[] = {0, 1, 2, nct / 2, nct - 1};
+            for (int c : show) {
+                if (c < 0 || c >= nct) continue;
+                printf("  cta %4d: start %6.2f setup +%5.2f accum_wait +%5.2f fence +%5.2f chunk0 +%5.2f chunk8 +%5.2f epi_done +%5.2f dealloc +%5.2f (us)\n", c,
+                       (h[c * 8] - t0) * 1e-3, (h[c * 8 + 1] - h[c * 8]) * 1e-3, (h[c * 8 + 2] - h[c * 8]) * 1e-3,
+                       (h[c * 8 + 3] - h[c * 8]) * 1e-3, (h[c * 8 + 4] - h[c * 8]) * 1e-3, (h[c * 8 + 5] - h[c * 8]) * 1e-3,
+                       (h[c * 8 + 6] - h[c * 8]) * 1e-3, (h[c * 8 + 7] - h[c * 8]) * 1e-3);
+            }
+            fflush(stdout);
+        }
+        return 0;
+    };
+    const int rc = run();
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     return rc;
 }
 

@@ -1,0 +1,152 @@
+// Pull-style ("gather, don't scatter") table update for full Adam
+// (DENSE_UPDATE_DENSE_VARIANCE, cpp/updates_adam.cu:199-213,251-283,310-328).
+//
+// full Adam touches every row of the table every step (both moments decay and the L2 term
+// acts on all rows), so the update is a dense pass anyway. Instead of scatter-adding the
+// sparse gradient into a table-sized buffer with atomics (reference: update_repr_kernel,
+// cpp/storage.cu:37-49) and then streaming that buffer back in, the batch's references are
+// bucketed by row (counting sort: histogram -> exclusive scan -> fill) and the dense pass
+// pulls each row's gradient from the L2-resident per-n-gram tensors while it already holds
+// theta / m / v of that row in registers:
+//   entities: agg[d] = sum_{c : id[c] = d} (+-mult[c]) * Y[c / R]        (cpp/objective.cu:381-401)
+//   words   : agg[w] = sum_{c : id[c] = w} fw[c] * gP[c / n]             (intermediate_results.cu:283-317)
+// No atomics on floats, no memset, one read and one write of theta / m / v per step.
+#pragma once
+
+#include "common.cuh"
+
+namespace nvsm {
+
+__global__ void __launch_bounds__(256) ref_count_kernel(const idx_t* __restrict__ ids, long total,
+                                                        int* __restrict__ counts) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < total) atomicAdd(counts + __ldg(ids + c), 1);
+}
+
+// Exclusive scan, three small launches: per-block scan of 1024 counts + block totals,
+// scan of the (<= 1024 * 1024 / 1024) block totals, add back.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict__ in, long n, int* __restrict__ out,
+                                                           int* __restrict__ block_sums) {
+    __shared__ int warp_tot[32];
+    const long i = (long)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int x = i < n ? in[i] : 0;
+    int v = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, t, o);
+            if (lane >= o) t += u;
+        }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int prefix = (w > 0 ? warp_tot[w - 1] : 0) + v - x;  // exclusive within the block
+    if (i < n) out[i] = prefix;
+    if (threadIdx.x == 1023 && block_sums) block_sums[blockIdx.x] = prefix + x;
+}
+
+__global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, long n, const int* __restrict__ block_prefix,
+                                                        long total_refs) {
+    const long i = (long)blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) out[i] += block_prefix[blockIdx.x];
+    if (i == 0) out[n] = (int)total_refs;  // sentinel: offsets[n] = number of references
+}
+
+// counts[] still holds the histogram; popping it hands out the slots of each bucket.
+__global__ void __launch_bounds__(256) ref_fill_kernel(const idx_t* __restrict__ ids, long total,
+                                                       const int* __restrict__ offsets, int* __restrict__ counts,
+                                                       int* __restrict__ refs) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const idx_t id = __ldg(ids + c);
+    const int pos = atomicSub(counts + id, 1) - 1;
+    refs[offsets[id] + pos] = (int)c;
+}
+
+struct AdamFullConsts {
+    float s1, lr1, reg1, s2, lr2, lambda, lr, bc, eps;
+};
+
+// One warp per table row. SRC rows (Y or gP) and the per-reference coefficient:
+//   ENTITY:  src row = ref / group, coef = (ref % group == 0 ? +1 : -1) * coefs[ref]   (group = R)
+//   WORD  :  src row = ref / group, coef = coefs[ref]                                  (group = n)
+template <int VEC, int NCH, bool ENTITY>
+__global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__ theta, float* __restrict__ m,
+                                                             float* __restrict__ v, long num_rows, int dim,
+                                                             const int* __restrict__ offsets,
+                                                             const int* __restrict__ refs,
+                                                             const float* __restrict__ coefs,
+                                                             const float* __restrict__ src, int group,
+                                                             const AdamFullConsts k) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim / VEC;
+    for (long row = warp0; row < num_rows; row += nwarps) {
+        const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        float agg[NCH][VEC];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+        for (int base = beg; base < end; base += 32) {
+            // lanes fetch up to 32 references of this row at once, then walk them together
+            const int cnt = min(32, end - base);
+            int my_src = 0;
+            float my_coef = 0.f;
+            if (lane < cnt) {
+                const int ref = __ldg(refs + base + lane);
+                my_src = ref / group;
+                const float cf = __ldg(coefs + ref);
+                my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
+            }
+            for (int t = 0; t < cnt; ++t) {
+                const int srow = __shfl_sync(kFull, my_src, t);
+                const float cf = __shfl_sync(kFull, my_coef, t);
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+                    if (c < nvec) {
+                        float x[VEC];
+                        load_vec_ro<VEC>(src + (long)srow * dim + c * VEC, x);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) agg[j][q] += cf * x[q];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            if (c < nvec) {
+                const long o = row * dim + c * VEC;
+                float th[VEC], mm[VEC], vv[VEC];
+                load_vec<VEC>(theta + o, th);
+                load_vec<VEC>(m + o, mm);
+                load_vec<VEC>(v + o, vv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const float ag = agg[j][q];
+                    const float g = ag + (-k.lambda * th[q]);
+                    mm[q] = (mm[q] * k.s1 + k.lr1 * ag) + (-k.reg1 * th[q]);
+                    vv[q] = vv[q] * k.s2 + (g * g) * k.lr2;
+                    th[q] = th[q] + ((mm[q] / (sqrtf(vv[q]) + k.eps)) * k.bc) * k.lr;
+                }
+                store_vec<VEC>(theta + o, th);
+                store_vec<VEC>(m + o, mm);
+                store_vec<VEC>(v + o, vv);
+            }
+        }
+    }
+}
+
+}  // namespace nvsm

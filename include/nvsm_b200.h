@@ -161,6 +161,11 @@ NVSM_API long nvsm_kernel_launches(nvsm_model* m); /* kernels launched by this m
 NVSM_API int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const float* A, const float* B,
                                float* C, float alpha, const float* bias, int splits);
 
+/* Micro-benchmark hook: average milliseconds of `iters` back-to-back launches of the
+ * tensor-core GEMM on device-resident (zero) operands. */
+NVSM_API int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int splits, int with_stats,
+                                int iters, float* ms_out);
+
 /* Multi-GPU (one process per GPU). The batch is sharded by n-gram row; the library
  * all-reduces batch-norm statistics and the dense gradients with NCCL (new: the reference
  * is single-GPU). id: 128 bytes from nvsm_comm_unique_id on rank 0, broadcast by the
