@@ -214,10 +214,8 @@ def run_ours(args, w, rank, world, local_rank):
     model.set_stream(stream.cuda_stream)
     rng = nv.RNG(1)
     model.initialize(rng)   # identical on every rank: same seed, same engine
-    if world > 1:
-        uid = [nv.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        model.comm_init(uid[0], world, rank)
+    from cunvsm_b200 import sharding
+    sharding.init_model_comm(model, dist, rank, world)
 
     # synthetic batches: every rank owns its own shard of n-gram rows
     raw = make_batches(w, B, 1234 + rank, NUM_BATCHES)
@@ -249,9 +247,7 @@ def run_ours(args, w, rank, world, local_rank):
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms = sharding.max_over_ranks(dist, ms, device="cuda")
         return ms, model.kernel_launches() - l0
 
     lr = w["lr"]
@@ -342,7 +338,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--update_method", default=None)
-    ap.add_argument("--gemm_mode", type=int, default=0)
+    ap.add_argument("--gemm_mode", type=int, default=1, help="0 fp32 SIMT, 1 tf32 tcgen05")
     ap.add_argument("--cpu_sample", type=int, default=5120)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()

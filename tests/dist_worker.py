@@ -1,0 +1,96 @@
+"""torchrun worker for tests/test_multi_gpu.py: N ranks, one GPU each, NCCL inside the library.
+
+Checks (batch-norm NVSM configuration, fp32 GEMMs):
+  * the sharded forward/backward reproduces the single-GPU loss, grad_transform and grad_bias of
+    the whole batch (global batch-norm statistics, 1/B with the global B);
+  * each rank's rows of grad_phrase / multipliers equal the matching rows of the single-GPU run;
+  * after update() the dense projection (T, b) is identical on every rank and equals the
+    single-GPU result, while the sparse tables received only the local rows' updates.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cunvsm_b200 as nv  # noqa: E402
+from cunvsm_b200 import sharding  # noqa: E402
+from tests.util import assert_close, make_batch  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gemm_mode = int(os.environ.get("NVSM_TEST_GEMM_MODE", "0"))
+    V, D, dw, dd, n, z, B = 3000, 2000, 300, 256, 10, 10, 4096
+    for method, mode, bn, nl in ((nv.SGD, 0, True, nv.HARD_TANH), (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE, True, nv.HARD_TANH),
+                                 (nv.ADAGRAD, 0, False, nv.TANH)):
+        desc = nv.ModelDesc(word_repr_size=dw, entity_repr_size=dd, batch_normalization=bn, nonlinearity=nl, clip_sigmoid=True)
+        tc_local = nv.TrainConfig(batch_size=B // world, window_size=n, num_random_entities=z, regularization_lambda=0.01,
+                                  update_method=method, adam_mode=mode)
+        tc_full = nv.TrainConfig(batch_size=B, window_size=n, num_random_entities=z, regularization_lambda=0.01,
+                                 update_method=method, adam_mode=mode)
+        dm = nv.Model(V, D, desc, tc_local, device=local, gemm_mode=gemm_mode)
+        dm.initialize(nv.RNG(1))
+        sharding.init_model_comm(dm, dist, rank, world)
+        ref = nv.Model(V, D, desc, tc_full, device=local, gemm_mode=gemm_mode)
+        ref.initialize(nv.RNG(1))
+
+        f, fw, labels, w = make_batch(np.random.default_rng(42), B, n, V, D, z)
+        ids = ref.generate_labels(labels, nv.RNG(777))
+        lo, hi = sharding.shard_range(B, rank, world)
+        sf, sfw, sl, sw, sids = sharding.shard_batch(f, fw, labels, w, ids, rank, world)
+
+        full_batch = nv.Batch(B, n).fill(f, labels, fw, w)
+        res_full = ref.compute_cost(full_batch, entity_ids=ids)
+        cost_full = res_full.get_cost()
+        ref.compute_gradients(res_full)
+
+        my_batch = nv.Batch(B // world, n).fill(sf, sl, sfw, sw)
+        res = dm.compute_cost(my_batch, entity_ids=sids)
+        cost = res.get_cost()
+        dm.compute_gradients(res)
+
+        tol = 2e-4 if gemm_mode == 0 else 2e-2
+        assert abs(cost - cost_full) <= tol * abs(cost_full), (cost, cost_full)
+        assert abs(res.scaled_regularization_lambda() - res_full.scaled_regularization_lambda()) < 1e-12
+        assert_close(dm.get_tensor("grad_transform"), ref.get_tensor("grad_transform"), tol, 1e-4 if gemm_mode == 0 else 2e-2, "gT")
+        assert_close(dm.get_tensor("grad_bias"), ref.get_tensor("grad_bias"), tol, 1e-4 if gemm_mode == 0 else 2e-2, "gb")
+        if bn:
+            assert_close(dm.get_tensor("bn_mean"), ref.get_tensor("bn_mean"), tol, 1e-4, "bn mean")
+            assert_close(dm.get_tensor("bn_invstd"), ref.get_tensor("bn_invstd"), tol, 1e-5, "bn invstd")
+        if gemm_mode == 0:
+            assert_close(dm.get_tensor("instance_multipliers"), ref.get_tensor("instance_multipliers").reshape(B, z + 1)[lo:hi], 1e-3, 1e-4, "mult")
+            assert_close(dm.get_tensor("grad_phrase_reprs"), ref.get_tensor("grad_phrase_reprs").reshape(B, dw)[lo:hi], 1e-3, 1e-4, "gP")
+
+        lr = 0.01
+        E0 = dm.get_tensor(nv.ENTITY_REPRS).copy()
+        dm.update(None, lr, res.scaled_regularization_lambda())
+        ref.update(None, lr, res_full.scaled_regularization_lambda())
+        if gemm_mode == 0:
+            assert_close(dm.get_tensor(nv.TRANSFORM), ref.get_tensor(nv.TRANSFORM), 1e-4, 1e-5, "T after update")
+            assert_close(dm.get_tensor(nv.BIAS), ref.get_tensor(nv.BIAS), 1e-4, 1e-4, "b after update")
+        # every rank holds the same dense projection
+        T = torch.from_numpy(dm.get_tensor(nv.TRANSFORM)).cuda()
+        Tmax, Tmin = T.clone(), T.clone()
+        dist.all_reduce(Tmax, op=dist.ReduceOp.MAX); dist.all_reduce(Tmin, op=dist.ReduceOp.MIN)
+        assert float((Tmax - Tmin).abs().max()) == 0.0
+        if method == nv.SGD:
+            # local sparse update: only documents referenced by THIS rank's rows moved (beyond the dense decay)
+            decay = 1.0 - res.scaled_regularization_lambda() * lr
+            moved = np.abs(dm.get_tensor(nv.ENTITY_REPRS).reshape(D, dd) - E0.reshape(D, dd) * np.float32(decay)).max(1) > 1e-7
+            assert set(np.nonzero(moved)[0]) <= set(np.unique(sids))
+        dm.close(); ref.close()
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_OK world=%d gemm_mode=%d" % (world, gemm_mode))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""-m gpu: the N > 1 path on real GPUs (needs >= 2 devices; skipped on a 1-GPU box).
+Launches tests/dist_worker.py under torch.distributed.run, one rank per GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_sharded_step_matches_single_gpu(gemm_mode):
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    env = dict(os.environ, NVSM_TEST_GEMM_MODE=str(gemm_mode))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + gemm_mode), os.path.join(ROOT, "tests", "dist_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MULTI_GPU_OK" in res.stdout
