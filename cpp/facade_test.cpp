@@ -1,0 +1,42 @@
+// Exercises the C++ façade the way the reference's own callers do (compute_cost ->
+// compute_gradients -> update -> get_cost, get_data, infer) and prints values the Python test
+// compares with the same sequence driven through ctypes.
+#include <cstdio>
+#include <memory>
+
+#include "cuNVSM/model.h"
+
+int main() {
+  lse::ModelDesc desc;
+  desc.set_word_repr_size(16); desc.set_entity_repr_size(8);
+  desc.mutable_transform_desc()->set_batch_normalization(true);
+  desc.mutable_transform_desc()->set_nonlinearity(lse::ModelDesc::TransformDesc::HARD_TANH);
+  desc.set_clip_sigmoid(true);
+  lse::TrainConfig tc;
+  tc.set_batch_size(256); tc.set_window_size(4); tc.set_num_random_entities(3); tc.set_regularization_lambda(0.01f);
+  tc.mutable_update_method()->set_type(lse::TrainConfig::ADAM);
+  tc.mutable_update_method()->mutable_adam_conf()->set_mode(lse::TrainConfig::UpdateMethodConf::AdamConf::DENSE_UPDATE_DENSE_VARIANCE);
+  RNG rng; rng.seed(5);
+  DefaultModel model(100, 60, desc, tc, 0, NVSM_GEMM_FP32);
+  model.initialize(&rng);
+  TextEntity::Batch batch(tc);
+  for (int i = 0; i < 256; ++i) {
+    std::vector<long> f = {i % 100, (i * 7) % 100, (i * 13 + 1) % 100, (i + 50) % 100};
+    batch.push_instance(f, {}, i % 60, 1.0f);
+  }
+  for (int step = 0; step < 3; ++step) {
+    std::unique_ptr<TextEntity::ForwardResult> result(model.compute_cost(batch, &rng));
+    std::unique_ptr<TextEntity::Gradients> gradients(model.compute_gradients(*result));
+    model.update(*gradients, 0.001f, result->scaled_regularization_lambda());
+    std::printf("cost %d %.9g\n", step, result->get_cost());
+  }
+  std::printf("rng %lu\n", nvsm_detail::rng_get_state(rng));
+  const auto data = model.get_data();
+  double cs = 0;
+  for (const auto& kv : data) for (float x : kv.second.data) cs += x;
+  std::printf("checksum %.9g\n", cs);
+  const auto out = model.infer({{1, 2, 3, 4}, {5, 6, 7, 8}}, 4);
+  std::printf("infer %zu %zu %.9g\n", out.rows, out.cols, (double)out.data[0]);
+  std::printf("params %zu\n", model.num_parameters());
+  return 0;
+}

@@ -1,0 +1,197 @@
+// cuNVSMTrainModel — training CLI with the reference's flag surface (reference: cpp/main.cu:15-76,
+// 623-768) driving the B200-native step through the Model façade (include/cuNVSM/model.h).
+//
+// The reference reads an Indri index; Indri is out of scope here, so the positional argument is
+// replaced by a seeded synthetic n-gram source (--synthetic_* flags). Everything else keeps the
+// reference's meaning: per-batch compute_cost / compute_gradients / update / get_cost
+// (iterate_data, cpp/main.cu:366-469), batches that are not a multiple of 1024 instances are
+// skipped (:392-398), default learning rates 0.01 (SGD/Adagrad) / 0.001 (Adam) (:710-721),
+// clip_sigmoid forced on (:645), --seed must be > 0 (:708), per-epoch batches/second logging
+// (:604-612) plus n-grams/second.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cuNVSM/model.h"
+
+namespace {
+
+struct Flags {
+  std::map<std::string, std::string> values;
+  Flags() {
+    values = {{"num_epochs", "100000"}, {"word_repr_size", "4"}, {"entity_repr_size", "4"}, {"batch_size", "1024"},
+              {"window_size", "8"}, {"num_random_entities", "1"}, {"seed", "0"}, {"regularization_lambda", "0.01"},
+              {"learning_rate", "0.0"}, {"update_method", ""}, {"weighting", "auto"}, {"feature_weighting", "uniform"},
+              {"bias_negative_samples", "false"}, {"nonlinearity", ""}, {"l2_phrase_normalization", "false"},
+              {"l2_entity_normalization", "false"}, {"batch_normalization", "false"}, {"compute_initial_cost", "false"},
+              {"check_gradients", "false"}, {"no_shuffle", "false"}, {"dump_initial_model", "false"}, {"dump_every", "0"},
+              {"entity_similarity_weight", "0.0"}, {"term_similarity_weight", "0.0"}, {"output", ""},
+              // replacements for the Indri positional argument
+              {"synthetic_num_words", "50000"}, {"synthetic_num_entities", "50000"}, {"synthetic_num_batches", "100"},
+              {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "tf32"}, {"v", "0"}};
+  }
+  void parse(int argc, char** argv) {
+    for (int i = 1; i < argc; ++i) {
+      std::string a = argv[i];
+      NVSM_CHECK(a.rfind("--", 0) == 0, ("unexpected argument " + a).c_str());
+      a = a.substr(2);
+      std::string key = a, val;
+      const size_t eq = a.find('=');
+      if (eq != std::string::npos) { key = a.substr(0, eq); val = a.substr(eq + 1); }
+      else if (key.rfind("no", 0) == 0 && values.count(key.substr(2)) && is_bool(key.substr(2))) { key = key.substr(2); val = "false"; }
+      else if (values.count(key) && is_bool(key)) { val = "true"; }
+      else { NVSM_CHECK(i + 1 < argc, ("missing value for --" + key).c_str()); val = argv[++i]; }
+      NVSM_CHECK(values.count(key), ("unknown flag --" + key).c_str());
+      values[key] = val;
+    }
+  }
+  bool is_bool(const std::string& k) const { const std::string& v = values.at(k); return v == "true" || v == "false"; }
+  std::string str(const std::string& k) const { return values.at(k); }
+  long i(const std::string& k) const { return std::stol(values.at(k)); }
+  double d(const std::string& k) const { return std::stod(values.at(k)); }
+  bool b(const std::string& k) const { return values.at(k) == "true" || values.at(k) == "1"; }
+};
+
+// Write the four parameter tensors as <output>_<suffix>.<name>.npy, row-major [objects, dim] — the
+// shapes the reference's HDF5 dump uses (cpp/hdf5.cu:26-53, lse_hdf5_inl.h:4-27).
+void dump_model(const DefaultModel& model, const std::string& output, const std::string& suffix) {
+  if (output.empty()) return;
+  for (const auto& kv : model.get_data()) {
+    const std::string path = output + "_" + suffix + "." + kv.first + ".npy";
+    std::ofstream f(path, std::ios::binary);
+    std::string hdr = "{'descr': '<f4', 'fortran_order': False, 'shape': (" + std::to_string(kv.second.cols) + ", " +
+                      std::to_string(kv.second.rows) + "), }";
+    while ((10 + hdr.size() + 1) % 64 != 0) hdr += ' ';
+    hdr += '\n';
+    const unsigned short len = static_cast<unsigned short>(hdr.size());
+    f.write("\x93NUMPY\x01\x00", 8);
+    f.write(reinterpret_cast<const char*>(&len), 2);
+    f.write(hdr.data(), hdr.size());
+    f.write(reinterpret_cast<const char*>(kv.second.data.data()), kv.second.data.size() * sizeof(float));
+  }
+  std::printf("Dumped model to %s_%s.*.npy\n", output.c_str(), suffix.c_str());
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Flags flags;
+  flags.parse(argc, argv);
+
+  const std::map<std::string, std::pair<lse::TrainConfig::UpdateMethod, lse::TrainConfig::UpdateMethodConf::AdamConf::AdamMode>>
+      UPDATE_METHODS = {  // cpp/main.cu:479-485
+          {"sgd", {lse::TrainConfig::SGD, lse::TrainConfig::UpdateMethodConf::AdamConf::NONE}},
+          {"adagrad", {lse::TrainConfig::ADAGRAD, lse::TrainConfig::UpdateMethodConf::AdamConf::NONE}},
+          {"sparse_adam", {lse::TrainConfig::ADAM, lse::TrainConfig::UpdateMethodConf::AdamConf::SPARSE}},
+          {"dense_adam", {lse::TrainConfig::ADAM, lse::TrainConfig::UpdateMethodConf::AdamConf::DENSE_UPDATE}},
+          {"full_adam", {lse::TrainConfig::ADAM, lse::TrainConfig::UpdateMethodConf::AdamConf::DENSE_UPDATE_DENSE_VARIANCE}}};
+  const std::map<std::string, lse::ModelDesc::TransformDesc::Nonlinearity> NONLINEARITIES = {
+      {"tanh", lse::ModelDesc::TransformDesc::TANH}, {"hard_tanh", lse::ModelDesc::TransformDesc::HARD_TANH}};
+
+  NVSM_CHECK(UPDATE_METHODS.count(flags.str("update_method")), "Please specify a valid --update_method.");
+  NVSM_CHECK(NONLINEARITIES.count(flags.str("nonlinearity")), "Please specify a valid --nonlinearity.");
+  NVSM_CHECK(flags.d("entity_similarity_weight") == 0.0 && flags.d("term_similarity_weight") == 0.0,
+             "the entity-entity / term-term mixture objectives are not part of this build");
+  NVSM_CHECK(!flags.b("check_gradients"), "--check_gradients is provided by the test-suite (tests/), not the CLI");
+
+  lse::ModelDesc model_desc;
+  model_desc.set_word_repr_size(flags.i("word_repr_size"));
+  model_desc.set_entity_repr_size(flags.i("entity_repr_size"));
+  model_desc.mutable_transform_desc()->set_batch_normalization(flags.b("batch_normalization"));
+  model_desc.mutable_transform_desc()->set_nonlinearity(NONLINEARITIES.at(flags.str("nonlinearity")));
+  model_desc.set_clip_sigmoid(true);
+  model_desc.set_bias_negative_samples(flags.b("bias_negative_samples"));
+  model_desc.set_l2_normalize_phrase_reprs(flags.b("l2_phrase_normalization"));
+  model_desc.set_l2_normalize_entity_reprs(flags.b("l2_entity_normalization"));
+
+  lse::TrainConfig train_config;
+  train_config.set_num_epochs(flags.i("num_epochs"));
+  train_config.set_batch_size(flags.i("batch_size"));
+  train_config.set_window_size(flags.i("window_size"));
+  train_config.set_num_random_entities(flags.i("num_random_entities"));
+  train_config.set_regularization_lambda(flags.d("regularization_lambda"));
+  train_config.set_learning_rate(flags.d("learning_rate"));
+  train_config.mutable_update_method()->set_type(UPDATE_METHODS.at(flags.str("update_method")).first);
+  train_config.mutable_update_method()->mutable_adam_conf()->set_mode(UPDATE_METHODS.at(flags.str("update_method")).second);
+  train_config.set_no_shuffle(flags.b("no_shuffle"));
+
+  NVSM_CHECK(flags.i("seed") > 0, "Please specify a --seed value.");
+  if (train_config.learning_rate() == 0.0) {
+    train_config.set_learning_rate(train_config.update_method().type() == lse::TrainConfig::ADAM ? 0.001 : 0.01);
+  }
+
+  RNG rng;
+  rng.seed(flags.i("seed"));
+
+  const size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
+  TextEntity::SyntheticSource data_source(V, D, flags.i("synthetic_num_batches"), flags.i("seed"), flags.d("synthetic_zipf"));
+  const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : NVSM_GEMM_TF32;
+
+  std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
+              model_desc.word_repr_size(), model_desc.entity_repr_size(), (int)model_desc.transform_desc().batch_normalization(),
+              flags.str("nonlinearity").c_str());
+  std::printf("Training: batch_size=%d window_size=%d num_random_entities=%d lambda=%g lr=%g update_method=%s |V|=%zu |D|=%zu\n",
+              train_config.batch_size(), train_config.window_size(), train_config.num_random_entities(),
+              train_config.regularization_lambda(), train_config.learning_rate(), flags.str("update_method").c_str(), V, D);
+
+  DefaultModel model(V, D, model_desc, train_config, flags.i("device"), gemm_mode);
+  model.initialize(&rng);
+  if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
+
+  TextEntity::Batch batch(train_config);
+  const long max_threads_per_block = 1024;  // Runtime::props().maxThreadsPerBlock in the reference
+  const bool verbose = flags.i("v") > 0;
+
+  auto iterate = [&](const bool backpropagate, size_t* num_batches, double* agg_cost, double* seconds) {
+    *num_batches = 0; *agg_cost = 0.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::unique_ptr<TextEntity::ForwardResult> previous;
+    while (data_source.has_next()) {
+      batch.clear();
+      data_source.next(&batch);
+      if (batch.num_instances() % max_threads_per_block != 0) {
+        std::fprintf(stderr, "Skipping Batch #%zu as it is not a multiple of %ld (%zu instances).\n", *num_batches,
+                     max_threads_per_block, batch.num_instances());
+      } else {
+        std::unique_ptr<TextEntity::ForwardResult> result(model.compute_cost(batch, &rng));
+        std::unique_ptr<TextEntity::Gradients> gradients(model.compute_gradients(*result));
+        if (backpropagate) model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
+        // read the previous batch's loss while this one runs (the reference synchronises every batch)
+        if (previous) {
+          const float c = previous->get_cost();
+          *agg_cost += c;
+          if (verbose) std::printf("Batch #%zu: cost=%g\n", *num_batches - 1, c);
+        }
+        previous = std::move(result);
+      }
+      if (flags.i("dump_every") > 0 && *num_batches > 0 && *num_batches % flags.i("dump_every") == 0)
+        dump_model(model, flags.str("output"), std::to_string(*num_batches));
+      ++*num_batches;
+    }
+    if (previous) *agg_cost += previous->get_cost();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  };
+
+  size_t nb; double cost, secs;
+  if (flags.b("compute_initial_cost")) {
+    data_source.reset();
+    iterate(false, &nb, &cost, &secs);
+    std::printf("Initial cost: %g\n", cost / nb);
+  }
+  size_t total_batches = 0; double total_secs = 0.0;
+  for (long epoch = 1; epoch <= train_config.num_epochs(); ++epoch) {
+    data_source.reset();
+    iterate(true, &nb, &cost, &secs);
+    total_batches += nb; total_secs += secs;
+    std::printf("Epoch #%ld: mean cost %g; %.2f batches/second, %.0f n-grams/second\n", epoch, cost / nb,
+                total_batches / total_secs, total_batches / total_secs * train_config.batch_size());
+    dump_model(model, flags.str("output"), std::to_string(epoch));
+  }
+  NVSM_ABORT_ON(nvsm_synchronize(model.handle()));
+  return 0;
+}

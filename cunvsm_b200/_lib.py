@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libnvsm_b200.so")
 
 # every symbol include/nvsm_b200.h declares
 SYMBOLS = [
-    "nvsm_last_error", "nvsm_version", "nvsm_create", "nvsm_destroy", "nvsm_set_stream", "nvsm_synchronize",
+    "nvsm_last_error", "nvsm_version", "nvsm_host_alloc", "nvsm_host_free", "nvsm_create", "nvsm_destroy", "nvsm_set_stream", "nvsm_synchronize",
     "nvsm_initialize", "nvsm_tensor_size", "nvsm_get_tensor", "nvsm_set_tensor", "nvsm_generate_labels",
     "nvsm_compute_cost", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost",
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
@@ -61,6 +61,8 @@ def load():
 
     f("nvsm_last_error", [], cs)
     f("nvsm_version", [])
+    f("nvsm_host_alloc", [ctypes.POINTER(vp), ctypes.c_ulong])
+    f("nvsm_host_free", [vp])
     f("nvsm_create", [ctypes.POINTER(NvsmConfig), ctypes.POINTER(vp)])
     f("nvsm_destroy", [vp], None)
     f("nvsm_set_stream", [vp, vp])

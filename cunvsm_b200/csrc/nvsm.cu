@@ -895,6 +895,17 @@ extern "C" {
 const char* nvsm_last_error(void) { return g_error.c_str(); }
 int nvsm_version(void) { return 100; }
 
+int nvsm_host_alloc(void** ptr, unsigned long bytes) {
+    if (!ptr) return fail("null argument");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int nvsm_host_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
 int nvsm_num_phases(void) { return PH_COUNT; }
 const char* nvsm_phase_name(int phase) { return (phase >= 0 && phase < PH_COUNT) ? kPhaseNames[phase] : ""; }
 

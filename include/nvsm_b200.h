@@ -72,6 +72,11 @@ typedef struct nvsm_config {
 NVSM_API const char* nvsm_last_error(void);
 NVSM_API int nvsm_version(void);
 
+/* Page-locked host memory for batches — TextEntity::Batch allocates its four arrays with
+ * cudaHostAlloc (cpp/data.cu:8-30); callers without the CUDA runtime use these. */
+NVSM_API int nvsm_host_alloc(void** ptr, unsigned long bytes);
+NVSM_API int nvsm_host_free(void* ptr);
+
 /* Model::Model / ~Model — include/cuNVSM/model.h:82-85, cpp/model.cu:6-35,95-103. */
 NVSM_API int nvsm_create(const nvsm_config* config, nvsm_model** out);
 NVSM_API void nvsm_destroy(nvsm_model* m);

@@ -1,0 +1,114 @@
+"""The C++ host side (include/cuNVSM/*.h façade + cpp/main.cpp CLI) over the C ABI."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "cpp")
+
+
+def _build():
+    from cunvsm_b200 import build as b
+    b.build()
+    subprocess.run(["make", "-C", CPP], check=True, capture_output=True)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every prototype in include/nvsm_b200.h is exported by libnvsm_b200.so and declared in the
+    ctypes binding (no compute calls: this runs without a GPU)."""
+    import re
+    from cunvsm_b200 import _lib
+    L = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "nvsm_b200.h")).read()
+    declared = set(re.findall(r"NVSM_API [\w\s\*]*?(nvsm_\w+)\(", hdr))
+    assert declared, "no prototypes parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.nvsm_version() >= 100
+    assert L.nvsm_num_phases() > 5 and L.nvsm_phase_name(1) == b"gather_mean"
+
+
+def test_host_sampler_is_bit_exact_with_oracle():
+    """nvsm_generate_labels (host, no GPU needed) against the oracle's restatement of
+    cpp/labels.cu:3-22 for several table sizes, including D where rejection is frequent."""
+    from cunvsm_b200 import _lib
+    from oracle import binding as O
+    L = _lib.load()
+    for D, z, B, seed in ((3, 10, 32, 10), (5000, 10, 100, 1), (50000, 10, 2000, 123), (1 << 30, 4, 500, 7),
+                          ((1 << 31) - 5, 3, 300, 99), (1, 2, 10, 5)):
+        labels = (np.arange(B, dtype=np.int64) * 7) % D
+        exp, st_exp = O.generate_labels(labels, z, D, seed)
+        out = np.zeros(B * (z + 1), dtype=np.int64)
+        st = ctypes.c_ulong(seed)
+        pl = ctypes.POINTER(ctypes.c_long)
+        assert L.nvsm_generate_labels(labels.ctypes.data_as(pl), B, z, D, ctypes.byref(st), out.ctypes.data_as(pl)) == 0
+        assert (out == exp).all() and st.value == st_exp
+
+
+def test_cpp_host_code_builds_and_fails_loudly_without_gpu():
+    _build()
+    assert os.path.exists(os.path.join(CPP, "cuNVSMTrainModel")) and os.path.exists(os.path.join(CPP, "facade_test"))
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    res = subprocess.run([os.path.join(CPP, "facade_test")], capture_output=True, text=True)
+    assert res.returncode != 0 and "no CUDA device" in res.stderr
+
+
+def test_cli_rejects_bad_flags():
+    _build()
+    cli = os.path.join(CPP, "cuNVSMTrainModel")
+    for args, msg in ((["--update_method", "bogus", "--nonlinearity", "tanh", "--seed", "1"], "valid --update_method"),
+                      (["--update_method", "sgd", "--nonlinearity", "relu", "--seed", "1"], "valid --nonlinearity"),
+                      (["--update_method", "sgd", "--nonlinearity", "tanh"], "--seed")):
+        res = subprocess.run([cli] + args, capture_output=True, text=True)
+        assert res.returncode != 0 and msg in res.stderr, res.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_facade_matches_python_driver():
+    """Same three full_adam steps through the C++ Model façade and through ctypes: identical costs
+    (same library, same RNG stream), identical parameter checksum."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "facade_test")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    lines = dict((" ".join(l.split()[:-1]), l.split()[-1]) for l in res.stdout.strip().splitlines())
+    import cunvsm_b200 as nv
+    desc = nv.ModelDesc(word_repr_size=16, entity_repr_size=8, batch_normalization=True, nonlinearity=nv.HARD_TANH, clip_sigmoid=True)
+    tc = nv.TrainConfig(batch_size=256, window_size=4, num_random_entities=3, regularization_lambda=0.01,
+                        update_method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE)
+    m = nv.Model(100, 60, desc, tc, gemm_mode=nv.GEMM_FP32)
+    rng = nv.RNG(5)
+    m.initialize(rng)
+    i = np.arange(256)
+    f = np.stack([i % 100, (i * 7) % 100, (i * 13 + 1) % 100, (i + 50) % 100], 1)
+    batch = nv.Batch(256, 4).fill(f, i % 60)
+    for step in range(3):
+        r = m.compute_cost(batch, rng)
+        m.compute_gradients(r)
+        m.update(None, 0.001, r.scaled_regularization_lambda())
+        assert abs(r.get_cost() - float(lines["cost %d" % step])) <= 2e-6 * abs(r.get_cost())
+    assert rng.state == int(lines["rng"])
+    cs = sum(float(v.astype(np.float64).sum()) for v in m.get_data().values())
+    assert abs(cs - float(lines["checksum"])) <= 1e-4 * abs(cs) + 1e-3
+    assert int(lines["params"]) == m.num_parameters()
+
+
+@pytest.mark.gpu
+def test_cli_trains_on_synthetic_source(tmp_path):
+    _build()
+    out = str(tmp_path / "model")
+    res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "64",
+                          "--entity_repr_size", "32", "--batch_size", "2048", "--window_size", "5", "--num_random_entities", "4",
+                          "--seed", "3", "--update_method", "full_adam", "--nonlinearity", "hard_tanh", "--batch_normalization",
+                          "--synthetic_num_words", "2000", "--synthetic_num_entities", "500", "--synthetic_num_batches", "20",
+                          "--output", out], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "Epoch #2" in res.stdout and "n-grams/second" in res.stdout
+    W = np.load(out + "_2.word_representations-representations.npy")
+    T = np.load(out + "_2.word_entity_mapping-transform.npy")
+    assert W.shape == (2000, 64) and T.shape == (64, 32) and np.isfinite(W).all()
