@@ -132,13 +132,24 @@ __global__ void __launch_bounds__(256) col_stats4_kernel(const float* __restrict
     }
 }
 
-__global__ void col_stats_reduce_kernel(const float* __restrict__ partials, int nblocks, int n,
-                                        double* __restrict__ sums) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+// sums[t] = sum over blocks of partials[b][t], in double. One warp-row of 32 columns x 8 block
+// slices per CTA so the ~300 partial rows are read with 8-way parallelism per column.
+__global__ void __launch_bounds__(256) col_stats_reduce_kernel(const float* __restrict__ partials, int nblocks, int n,
+                                                               double* __restrict__ sums) {
+    __shared__ double sm[8][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int slice = threadIdx.x >> 5;
     double a = 0.0;
-    for (int b = 0; b < nblocks; ++b) a += (double)partials[(long)b * n + t];
-    sums[t] = a;
+    if (col < n)
+        for (int b = slice; b < nblocks; b += 8) a += (double)__ldg(partials + (long)b * n + col);
+    sm[slice][threadIdx.x & 31] = a;
+    __syncthreads();
+    if (slice == 0 && col < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += sm[g][threadIdx.x];
+        sums[col] = t;
+    }
 }
 
 // mean / invstd from the (all-reduced) sums; biased variance, eps inside the sqrt.

@@ -87,6 +87,9 @@ struct nvsm_model {
     int device = 0, num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;      // reference buckets of the pull update are built here, under the forward pass
+    cudaEvent_t buckets_ready = nullptr, buckets_consumed = nullptr;
+    bool buckets_in_flight = false, buckets_ever_consumed = false;
     bool own_stream = false;
     long V, D;
     int dw, dd, n, z, R;
@@ -402,6 +405,8 @@ int dispatch_score(nvsm_model* m, const ScoreParams& sp) {
     return fail("entity_repr_size %d is not supported (max 1024 when a multiple of 4, else 512)", dd);
 }
 
+int start_bucket_build(nvsm_model* m, BatchSlot* s);
+
 int forward(nvsm_model* m, BatchSlot* s) {
     const long B = s->B;
     if (B <= 0) return fail("empty batch");
@@ -412,6 +417,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
     m->have_forward = false;
     m->have_gradients = false;
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
+    if (m->pull) TRY(start_bucket_build(m, s));
     const bool bn = m->cfg.batch_normalization != 0;
     const int dw = m->dw, dd = m->dd;
 
@@ -447,7 +453,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
             const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
             const int nblk = grid_for(m, B, 32, 2);   // <= 2 blocks per SM
             LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
-            LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 127) / 128, 128, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
+            LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
         }
         phase_end(m);
         TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true));
@@ -665,9 +671,30 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     return 0;
 }
 
+// The ids of a batch are known before the forward pass starts, so both bucket sets are built on
+// the auxiliary stream while the forward / backward kernels run on the main stream.
+int start_bucket_build(nvsm_model* m, BatchSlot* s) {
+    cudaStream_t main_stream = m->stream;
+    if (m->buckets_ever_consumed) CU(cudaStreamWaitEvent(m->aux_stream, m->buckets_consumed, 0));
+    CU(cudaStreamWaitEvent(m->aux_stream, s->ready, 0));
+    m->stream = m->aux_stream;   // LAUNCH targets m->stream
+    const bool prof = m->profiling;
+    m->profiling = false;
+    int rc = build_buckets(m, s->ids, s->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs);
+    if (rc == 0) rc = build_buckets(m, s->features, s->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs);
+    m->stream = main_stream;
+    m->profiling = prof;
+    if (rc) return rc;
+    CU(cudaEventRecord(m->buckets_ready, m->aux_stream));
+    m->buckets_in_flight = true;
+    return 0;
+}
+
 int pull_update(nvsm_model* m, bool entities, const AdamFullConsts& k) {
-    if (entities) TRY(build_buckets(m, m->cur->ids, m->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs));
-    else TRY(build_buckets(m, m->cur->features, m->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs));
+    if (entities) {
+        if (!m->buckets_in_flight) return fail("pull update without reference buckets");
+        CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
+    }
     const int dim = entities ? m->dd : m->dw;
     if (vec4_ok(dim)) {
         const int nch = (dim / 4 + 31) / 32;
@@ -785,6 +812,11 @@ int update(nvsm_model* m, float lr, float lambda) {
     phase_begin(m, PH_UPD_WORDS);
     TRY(update_table(m, false, lr, lambda));
     phase_end(m);
+    if (m->pull) {
+        CU(cudaEventRecord(m->buckets_consumed, m->stream));
+        m->buckets_ever_consumed = true;
+        m->buckets_in_flight = false;
+    }
     phase_begin(m, PH_UPD_TRANSFORM);
     TRY(update_transform(m, lr, lambda));
     phase_end(m);
@@ -938,6 +970,9 @@ void nvsm_destroy(nvsm_model* m) {
     for (auto e : m->loss_ev)
         if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+    if (m->buckets_ready) cudaEventDestroy(m->buckets_ready);
+    if (m->buckets_consumed) cudaEventDestroy(m->buckets_consumed);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -979,6 +1014,9 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         m->own_stream = true;
         CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->buckets_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->buckets_consumed, cudaEventDisableTiming));
         const long V = m->V, D = m->D, maxB = m->maxB;
         const int dw = m->dw, dd = m->dd;
         TRY(dev_alloc(&m->W, V * dw)); TRY(dev_alloc(&m->E, D * dd));
