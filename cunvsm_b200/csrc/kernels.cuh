@@ -386,14 +386,19 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
 // =====================================================================================
 // Per-column constants of the backward pass, once per step: grad_bias = sum(dy) (with and
 // without batch-norm, cpp/params.cu:510-520) and the two batch means BN backward needs.
+// `shifted_by_bias` (nullable): the ring score kernel accumulates sum dy * (xhat + bias); remove
+// the bias term here: sum dy * xhat = S2 - bias * S1.
 __global__ void bn_backward_prep_kernel(const double* __restrict__ col_sums, int dd, double batch,
-                                        float* __restrict__ gb, float* __restrict__ mean_dy,
-                                        float* __restrict__ mean_dyx) {
+                                        const float* __restrict__ shifted_by_bias, float* __restrict__ gb,
+                                        float* __restrict__ mean_dy, float* __restrict__ mean_dyx) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= dd) return;
-    gb[c] = (float)col_sums[c];
-    mean_dy[c] = (float)(col_sums[c] / batch);
-    mean_dyx[c] = (float)(col_sums[dd + c] / batch);
+    const double s1 = col_sums[c];
+    double s2 = col_sums[dd + c];
+    if (shifted_by_bias) s2 -= (double)shifted_by_bias[c] * s1;
+    gb[c] = (float)s1;
+    mean_dy[c] = (float)(s1 / batch);
+    mean_dyx[c] = (float)(s2 / batch);
 }
 
 template <int VEC>

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "pull_update.cuh"
+#include "score_ring.cuh"
 
 using namespace nvsm;
 
@@ -114,6 +115,8 @@ struct nvsm_model {
     float* Y = nullptr;  // post-activation projections, kept only for the pull-style (full Adam) update
     float *probs = nullptr, *mult = nullptr, *rowtmp = nullptr;
     float *mean = nullptr, *invstd = nullptr, *mean_dy = nullptr, *mean_dyx = nullptr;
+    float *bn_scale = nullptr, *bn_shift = nullptr;  // invstd, bias - mean * invstd (ring score kernel)
+    bool score_shifted = false;                       // backward column sums carry the bias term
     float* stat_part = nullptr;  // [2 * num_sms][2*dd] per-block partial column statistics
     double* dsums = nullptr;   // [2*dd fwd sums][dd var sums][2*dd bwd col sums][1 loss]
     float *gT = nullptr, *gb = nullptr, *gT_part = nullptr;
@@ -387,8 +390,57 @@ int launch_score(nvsm_model* m, const ScoreParams& sp) {
     return 0;
 }
 
+template <int NCH>
+int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t smem) {
+    static bool attr = false;
+    if (!attr) {
+        CU(cudaFuncSetAttribute(score_ring_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(score_ring_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    if (q.s.dd == NCH * 128) LAUNCH(m, (score_ring_kernel<NCH, true>), grid, q.warps * 32, smem, q);
+    else LAUNCH(m, (score_ring_kernel<NCH, false>), grid, q.warps * 32, smem, q);
+    return 0;
+}
+
+// Ring (cp.async.bulk) variant when the rows are 16-byte multiples and a >= 2-stage ring of
+// (R + 1) rows per warp fits in shared memory; returns -1 when it does not apply.
+int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
+    const int dd = sp.dd, R = sp.R;
+    if (!vec4_ok(dd) || R > 32 || dd > 1024 || getenv("NVSM_NO_RING")) return -1;
+    const size_t stage_bytes = (size_t)(R + 1) * dd * 4;
+    const size_t fixed = (size_t)(4 * dd + 2) * 4 + 8 * 4 * 8;
+    const size_t budget = 227 * 1024 - 1024;
+    int W = 8, S = 0;
+    const char* ew = getenv("NVSM_SCORE_W"); const char* es = getenv("NVSM_SCORE_S");
+    if (ew) W = std::max(1, std::min(8, atoi(ew)));
+    for (; W >= 2; W /= 2) {
+        S = (int)std::min<size_t>(4, (budget - fixed) / (W * stage_bytes));
+        if (S >= 2 || ew) break;
+    }
+    if (es) S = std::min(S, std::max(2, atoi(es)));
+    if (S < 2) return -1;
+    ScoreRingParams q;
+    q.s = sp; q.stages = S; q.warps = W; q.bn_scale = m->bn_scale; q.bn_shift = m->bn_shift;
+    const size_t smem = (size_t)W * S * stage_bytes + (size_t)(4 * dd + 2) * 4 + (size_t)W * S * 8;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (W * 32), (227 * 1024) / (smem + 1024)));
+    const int grid = (int)std::max<long>(1, std::min<long>((sp.B + W - 1) / W, (long)m->num_sms * per_sm));
+    const int nch = (dd / 4 + 31) / 32;
+    if (nch <= 1) return launch_score_ring<1>(m, q, grid, smem);
+    if (nch <= 2) return launch_score_ring<2>(m, q, grid, smem);
+    if (nch <= 3) return launch_score_ring<3>(m, q, grid, smem);
+    if (nch <= 4) return launch_score_ring<4>(m, q, grid, smem);
+    return launch_score_ring<8>(m, q, grid, smem);
+}
+
 int dispatch_score(nvsm_model* m, const ScoreParams& sp) {
     const int dd = sp.dd;
+    m->score_shifted = false;
+    {
+        const int rc = try_score_ring(m, sp);
+        if (rc == 0) { m->score_shifted = sp.act.use_bn != 0; return 0; }
+        if (rc > 0) return rc;
+    }
     if (vec4_ok(dd)) {
         const int nch = (dd / 4 + 31) / 32;
         if (nch <= 1) return launch_score<4, 1>(m, sp);
@@ -477,6 +529,8 @@ int forward(nvsm_model* m, BatchSlot* s) {
         phase_end(m);
     }
 
+    if (bn) LAUNCH(m, bn_affine_kernel, (dd + 127) / 128, 128, 0, m->mean, m->invstd, m->b, dd, m->bn_scale, m->bn_shift);
+
     // (4) scores, loss, multipliers and d cost / d pre-activation in one pass.
     phase_begin(m, PH_SCORE);
     {
@@ -524,8 +578,8 @@ int backward(nvsm_model* m) {
     const int dw = m->dw, dd = m->dd;
 
     phase_begin(m, PH_BN_BWD);
-    LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal, m->gb,
-           m->mean_dy, m->mean_dyx);
+    LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal,
+           m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy, m->mean_dyx);
     if (bn) {
         if (vec4_ok(dd)) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
@@ -948,7 +1002,7 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->comm) nccl_api().CommDestroy(m->comm);
     float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
                    m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
-                   m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->stat_part, m->gT, m->gb, m->gT_part, m->scratch};
+                   m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->bn_scale, m->bn_shift, m->stat_part, m->gT, m->gb, m->gT_part, m->scratch};
     for (float* p : fl)
         if (p) cudaFree(p);
     if (m->dsums) cudaFree(m->dsums);
@@ -1041,6 +1095,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->rowtmp, maxB));
         TRY(dev_alloc(&m->mean, dd)); TRY(dev_alloc(&m->invstd, dd));
         TRY(dev_alloc(&m->mean_dy, dd)); TRY(dev_alloc(&m->mean_dyx, dd));
+        TRY(dev_alloc(&m->bn_scale, dd)); TRY(dev_alloc(&m->bn_shift, dd));
         TRY(dev_alloc(&m->dsums, 5 * (size_t)dd + 1));
         TRY(dev_alloc(&m->stat_part, (size_t)2 * m->num_sms * 2 * dd));
         TRY(dev_alloc(&m->gT, (size_t)dw * dd)); TRY(dev_alloc(&m->gb, dd));
