@@ -40,30 +40,19 @@ constexpr uint32_t kGroupBytes = kBlockK * 32 * 4;       // one 32(MN) x 32(k) b
 
 struct Params {
     int M, N, K;           // problem: C[M, N] = A . B over K
-    int n_pad;             // N rounded up to a multiple of 16 (<= 512)
-    int n_half0, n_half1;  // the one or two UMMA N extents (multiples of 16, <= 256)
-    int b_boxes, b_box_rows;  // K-major B: TMA boxes per stage and rows per box
-    int kb_per_split;      // k-blocks (of 32) handled by one CTA along grid.y
+    int bn;                // tile N extent = UMMA N (multiple of 16, <= 256; MN-major B: multiple of 32)
+    int m_tiles, n_tiles;  // output tiles
+    int splits;            // split-K factor; tile index = (m_tile * n_tiles + n_tile) * splits + split
+    int kb_per_split;      // k-blocks (of 32) per split
     int stages;
     uint32_t stage_bytes;
-    uint32_t tmem_cols;    // power of two >= n_pad
+    uint32_t tmem_cols;    // power of two >= 2 * bn (two accumulator buffers)
     float* C;
     int ldc;
     long split_stride;     // elements between split-K partial outputs
     float alpha;
     const float* bias;     // nullable, per output column
-    int debug;             // bit0: skip global stores, bit1: skip MMAs, bit2: skip TMEM loads (timing experiments)
-    unsigned long long* trace;  // nullable: per-CTA globaltimer stamps (timing experiments)
-    double* col_stats;     // nullable: [2*N] += column sums and sums of squares of the stored C
-                           // (batch-norm statistics fused into the forward projection)
 };
-
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
-    return t;
-}
-#define NVSM_STAMP(slot) do { if (p.trace) p.trace[(long)(blockIdx.x + gridDim.x * blockIdx.y) * 8 + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,49 +141,51 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Column totals of a 32-row x 16-column register tile (one row per lane): recursive halving,
-// 16 shuffles. Afterwards v[0] of lane L is the total of column (L >> 1) & 15.
-__device__ __forceinline__ float column_totals16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-        const bool hi = lane & bit;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float keep = hi ? v[half + i] : v[i];
-            const float send = hi ? v[i] : v[half + i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-        }
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Persistent, warp-specialised GEMM: grid = min(#tiles, #SMs); every CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... The TMA producer runs ahead across tile boundaries
+// (the smem ring never drains), the MMA warp alternates between two TMEM accumulator buffers,
+// and the four epilogue warps drain buffer b of tile t while the MMAs of tile t+1 fill buffer
+// b ^ 1 (tmem_full / tmem_empty mbarriers).
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
-    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_stats[2 * 512];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBlockM;
     const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
-    const int kb0 = blockIdx.y * p.kb_per_split;
-    const int num_kb = max(0, min(p.kb_per_split, num_kb_total - kb0));
+    const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int stages = p.stages;
 
-    if (threadIdx.x == 0) NVSM_STAMP(0);
-    if (p.debug & 8) return;      // experiment: CTA launch throughput only
-    if (p.col_stats)
-        for (int t = threadIdx.x; t < 2 * p.n_pad; t += kThreads) s_stats[t] = 0.f;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&accum_bar), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 4);   // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -208,163 +199,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    if (threadIdx.x == 0) NVSM_STAMP(1);
-    const bool skip_main = p.debug & 16;   // experiment: setup + teardown only
 
-    if (skip_main) {
-    } else if (warp == 0) {
+    // tile -> (m0, n0, first k-block, number of k-blocks)
+    auto decode = [&](int t, int& m0, int& n0, int& kb0, int& nkb, int& split) {
+        split = t % p.splits;
+        const int mn = t / p.splits;
+        n0 = (mn % p.n_tiles) * p.bn;
+        m0 = (mn / p.n_tiles) * kBlockM;
+        kb0 = split * p.kb_per_split;
+        nkb = max(0, min(p.kb_per_split, num_kb_total - kb0));
+    };
+
+    if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                const uint32_t bar = smem_u32(&full_bar[s]);
-                const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
-                const uint32_t b_dst = a_dst + kATileBytes;
-                const int k0 = (kb0 + kb) * kBlockK;
-                mbar_expect_tx(bar, p.stage_bytes);
-                if constexpr (!A_MN) {
-                    tma_load_2d(a_dst, &tmA, bar, k0, m0);
-                } else {
+            uint32_t it = 0;   // running k-block counter across tiles
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m0, n0, kb0, nkb, split;
+                decode(t, m0, n0, kb0, nkb, split);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(smem_u32(&empty_bar[s]), ((it / stages) & 1u) ^ 1u);
+                    const uint32_t bar = smem_u32(&full_bar[s]);
+                    const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
+                    const uint32_t b_dst = a_dst + kATileBytes;
+                    const int k0 = (kb0 + kb) * kBlockK;
+                    mbar_expect_tx(bar, p.stage_bytes);
+                    if constexpr (!A_MN) {
+                        tma_load_2d(a_dst, &tmA, bar, k0, m0);
+                    } else {
 #pragma unroll
-                    for (int g = 0; g < kBlockM / 32; ++g) tma_load_2d(a_dst + g * kGroupBytes, &tmA, bar, m0 + 32 * g, k0);
-                }
-                if constexpr (!B_MN) {
-                    for (int bx = 0; bx < p.b_boxes; ++bx)
-                        tma_load_2d(b_dst + (uint32_t)bx * p.b_box_rows * 128u, &tmB, bar, k0, bx * p.b_box_rows);
-                } else {
-                    for (int g = 0; g < p.n_pad / 32; ++g) tma_load_2d(b_dst + g * kGroupBytes, &tmB, bar, 32 * g, k0);
+                        for (int g = 0; g < kBlockM / 32; ++g) tma_load_2d(a_dst + g * kGroupBytes, &tmA, bar, m0 + 32 * g, k0);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(b_dst, &tmB, bar, k0, n0);
+                    } else {
+                        for (int g = 0; g < p.bn / 32; ++g) tma_load_2d(b_dst + g * kGroupBytes, &tmB, bar, n0 + 32 * g, k0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc0 = make_idesc(p.n_half0, A_MN, B_MN);
-            const uint32_t idesc1 = make_idesc(p.n_half1 > 0 ? p.n_half1 : 16, A_MN, B_MN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
+            const uint32_t idesc = make_idesc(p.bn, A_MN, B_MN);
+            uint32_t it = 0, lt = 0;   // k-block counter, local tile counter
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+                int m0, n0, kb0, nkb, split;
+                decode(t, m0, n0, kb0, nkb, split);
+                const uint32_t buf = lt & 1u;
+                mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((lt >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-
-                const uint32_t a_base = smem_base + (uint32_t)s * p.stage_bytes;
-                const uint32_t b_base = a_base + kATileBytes;
+                const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % stages;
+                    mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_base + (uint32_t)s * p.stage_bytes;
+                    const uint32_t b_base = a_base + kATileBytes;
 #pragma unroll
-                for (int j = 0; j < kBlockK / kUmmaK; ++j) {
-                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-                    // K-major: 32 B further along the swizzled 128-byte row per K = 8.
-                    // MN-major: 8 k-rows = two 4-row atoms (SBO = 512 B apart) per K = 8.
-                    const uint64_t a_desc = A_MN ? make_desc(a_base + j * 1024u, kGroupBytes, 512u, 1u)
-                                                 : make_desc(a_base + j * 32u, 16u, 1024u, 2u);
-                    const uint64_t b_desc0 = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
-                                                  : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
-                    if (!(p.debug & 2)) umma_tf32(tmem_base, a_desc, b_desc0, idesc0, acc);
-                    if (p.n_half1 > 0) {
-                        const uint32_t off = B_MN ? (uint32_t)(p.n_half0 / 32) * kGroupBytes : (uint32_t)p.n_half0 * 128u;
-                        const uint64_t b_desc1 = B_MN ? make_desc(b_base + off + j * 1024u, kGroupBytes, 512u, 1u)
-                                                      : make_desc(b_base + off + j * 32u, 16u, 1024u, 2u);
-                        umma_tf32(tmem_base + (uint32_t)p.n_half0, a_desc, b_desc1, idesc1, acc);
+                    for (int j = 0; j < kBlockK / kUmmaK; ++j) {
+                        // K-major: 32 B further along the swizzled 128-byte row per K = 8.
+                        // MN-major: 8 k-rows = two 4-row atoms (SBO = 512 B apart) per K = 8.
+                        const uint64_t a_desc = A_MN ? make_desc(a_base + j * 1024u, kGroupBytes, 512u, 1u)
+                                                     : make_desc(a_base + j * 32u, 16u, 1024u, 2u);
+                        const uint64_t b_desc = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
+                                                     : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
+                        umma_tf32(tacc, a_desc, b_desc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                     }
+                    umma_commit(smem_u32(&empty_bar[s]));       // frees the smem stage when these MMAs retire
                 }
-                umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage when these MMAs retire
+                umma_commit(smem_u32(&tmem_full_bar[buf]));     // accumulator of this tile complete
             }
-            umma_commit(smem_u32(&accum_bar));          // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> global, overlapped with the next tile's MMAs =====
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;
-        float* crow = p.C + (long)blockIdx.y * p.split_stride + (long)m * p.ldc;
-        if (num_kb > 0) {
-            mbar_wait(smem_u32(&accum_bar), 0);
-            if (warp == 2 && lane == 0) NVSM_STAMP(2);
-            tc_fence_after();
-        }
-        if (warp == 2 && lane == 0) NVSM_STAMP(3);
-        // hoist everything the loop needs out of constant memory once
         const float alpha = p.alpha;
         const float* __restrict__ bias = p.bias;
-        const int Nv = p.N, n_pad = p.n_pad;
-        const bool row_ok = m < p.M;
-        const bool do_store = row_ok && !(p.debug & 1);
-        const bool do_ld = num_kb > 0 && !(p.debug & 4);
+        const int Nv = p.N;
         const bool vec_ok = (p.ldc & 3) == 0;
-        const bool stats = p.col_stats != nullptr;
-        for (int c0 = 0; c0 < n_pad; c0 += 16) {
-            float v[16];
-            if (do_ld) {
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+            int m0, n0, kb0, nkb, split;
+            decode(t, m0, n0, kb0, nkb, split);
+            const uint32_t buf = lt & 1u;
+            const int m = m0 + q * 32 + lane;
+            const bool row_ok = m < p.M;
+            float* crow = p.C + (long)split * p.split_stride + (long)m * p.ldc;
+            const uint32_t tacc = tmem_base + buf * (uint32_t)p.bn + ((uint32_t)(q * 32) << 16);
+            if (nkb > 0) {
+                mbar_wait(smem_u32(&tmem_full_bar[buf]), (lt >> 1) & 1u);
+                tc_fence_after();
             }
-            const bool full = c0 + 16 <= Nv;
-            float bv[16];
+            const int ncols = min(p.bn, Nv - n0);                 // valid columns of this tile
+            const int nchunks = (min(p.bn, max(ncols, 0)) + 15) / 16;
+            uint32_t rcur[16], rnext[16];
+            if (nkb > 0 && nchunks > 0) { tmem_ld16_nowait(tacc, rcur); tmem_ld_wait(); }
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int c0 = n0 + ch * 16;
+                if (nkb > 0 && ch + 1 < nchunks) tmem_ld16_nowait(tacc + (uint32_t)(ch + 1) * 16u, rnext);   // in flight during the stores
+                float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) bv[i] = 0.f;
-            if (bias) {
-                if (full) {
+                for (int i = 0; i < 16; ++i) v[i] = nkb > 0 ? __uint_as_float(rcur[i]) : 0.f;
+                const bool full = c0 + 16 <= Nv;
+                float bv[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                        bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+                for (int i = 0; i < 16; ++i) bv[i] = 0.f;
+                if (bias) {
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 tb = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                            bv[i] = tb.x; bv[i + 1] = tb.y; bv[i + 2] = tb.z; bv[i + 3] = tb.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < Nv) bv[i] = __ldg(bias + c0 + i);
                     }
-                } else {
+                }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < Nv) bv[i] = __ldg(bias + c0 + i);
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, v[i], bv[i]);
+                if (row_ok) {
+                    if (full && vec_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(crow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < Nv) crow[c0 + i] = v[i];
+                    }
+                }
+                if (nkb > 0 && ch + 1 < nchunks) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) rcur[i] = rnext[i];
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaf(alpha, v[i], bv[i]);
-            if (do_store) {
-                if (full && vec_ok) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<float4*>(crow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < Nv) crow[c0 + i] = v[i];
-                }
-            }
-            if (stats) {
-                // rows / columns outside the problem must contribute zeros
-                float sq[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = (row_ok && (full || c0 + i < Nv)) ? v[i] : 0.f;
-                    sq[i] = v[i] * v[i];
-                }
-                const float tot = column_totals16(v, lane);
-                const float tot2 = column_totals16(sq, lane);
-                if ((lane & 1) == 0) {
-                    const int col = c0 + ((lane >> 1) & 15);
-                    atomicAdd(&s_stats[col], tot);
-                    atomicAdd(&s_stats[n_pad + col], tot2);
-                }
-            }
-            if (warp == 2 && lane == 0 && c0 == 0) NVSM_STAMP(4);
-            if (warp == 2 && lane == 0 && c0 == 128) NVSM_STAMP(5);
+            // this warp no longer reads the buffer: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
         }
     }
-    if (warp == 2 && lane == 0) NVSM_STAMP(6);
     tc_fence_before();
     __syncthreads();
-    if (p.col_stats) {
-        for (int t = threadIdx.x; t < 2 * p.n_pad; t += kThreads) {
-            const int which = t / p.n_pad, col = t % p.n_pad;
-            if (col < p.N) atomicAdd(p.col_stats + (long)which * p.N + col, (double)s_stats[t]);
-        }
-    }
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-        if (lane == 0) NVSM_STAMP(7);
     }
 }
 

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
                                                           const idx_t* __restrict__ ids,
                                                           const float* __restrict__ wts,
                                                           long num_out, int window,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, int ld_out) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = acc[v] / fwin;
-            store_vec<VEC>(out + o * dim + c * VEC, acc);
+            store_vec<VEC>(out + o * ld_out + c * VEC, acc);
         }
     }
 }

@@ -126,6 +126,8 @@ struct nvsm_model {
     int *e_counts = nullptr, *e_offsets = nullptr, *e_refs = nullptr;
     int *w_counts = nullptr, *w_offsets = nullptr, *w_refs = nullptr;
     int* scan_tmp = nullptr;  // block totals of the two-level scan
+    int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
+                          // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
     bool use_tc = false;  // projection GEMMs on tcgen05 (gemm_mode != FP32 and shapes allow)
     float* scratch = nullptr;  // inspection buffer max(B*R*dd, ...) allocated on demand
     size_t scratch_bytes = 0;
@@ -291,9 +293,7 @@ int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer,
 }
 
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), with headroom.
-constexpr uint32_t kTcMaxDynSmem = 232448u - 6144u;
-
-unsigned long long* g_tc_trace = nullptr;  // set by nvsm_bench_gemm_tc for timing experiments
+constexpr uint32_t kTcMaxDynSmem = 232448u - 2048u;
 
 bool tc_shapes_ok(int dw, int dd) {
     // TMA needs 16-byte row strides; grad_transform's MN-major B tile needs dd % 32 == 0.
@@ -304,46 +304,38 @@ bool tc_shapes_ok(int dw, int dd) {
 //   mn_major == false: A is [M, K] row-major, Bm is [N, K] row-major      (both K-major)
 //   mn_major == true : A is [K, M] row-major, Bm is [K, N] row-major      (both MN-major)
 // splits > 1 writes `splits` partial products to C + z * split_stride.
-int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, const float* Bm, float* C,
-                int ldc, int splits, long split_stride, float alpha, const float* bias, int* splits_out = nullptr,
-                double* col_stats = nullptr) {
+int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
+                float* C, int ldc, int splits, long split_stride, float alpha, const float* bias,
+                int* splits_out = nullptr) {
     tc::Params p;
     p.M = M; p.N = N; p.K = K;
-    p.n_pad = mn_major ? (N + 31) / 32 * 32 : (N + 15) / 16 * 16;
-    if (p.n_pad > 512) return fail("tensor-core GEMM: N=%d too wide", N);
-    if (p.n_pad <= 256) { p.n_half0 = p.n_pad; p.n_half1 = 0; }
-    else {
-        const int unit = mn_major ? 32 : 16;
-        p.n_half0 = ((p.n_pad / 2) + unit - 1) / unit * unit;
-        p.n_half1 = p.n_pad - p.n_half0;
-    }
-    p.b_boxes = p.n_pad > 256 ? 2 : 1;
-    p.b_box_rows = p.n_pad / p.b_boxes;
-    if (!mn_major && (p.b_box_rows % 8 != 0)) return fail("tensor-core GEMM: unsupported N=%d", N);
+    const int unit = mn_major ? 32 : 16;
+    const int n_pad = (N + unit - 1) / unit * unit;
+    p.n_tiles = (n_pad + 255) / 256;
+    p.bn = ((n_pad + p.n_tiles - 1) / p.n_tiles + unit - 1) / unit * unit;   // <= 256
+    p.m_tiles = (M + tc::kBlockM - 1) / tc::kBlockM;
     const int num_kb = (K + tc::kBlockK - 1) / tc::kBlockK;
     splits = std::max(1, std::min(splits, num_kb));
     p.kb_per_split = (num_kb + splits - 1) / splits;
-    const int grid_y = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-    p.stage_bytes = tc::kATileBytes + (uint32_t)p.n_pad * 128u;
-    p.stages = (int)std::min<uint32_t>(6u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.stage_bytes = tc::kATileBytes + (uint32_t)p.bn * 128u;
+    p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
+    { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
     if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
     p.tmem_cols = 32;
-    while ((int)p.tmem_cols < p.n_pad) p.tmem_cols <<= 1;
+    while ((int)p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
     p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
-    p.col_stats = col_stats;
-    p.trace = g_tc_trace;
-    { const char* dbg = getenv("NVSM_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-    { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
     CUtensorMap tmA, tmB;
     if (!mn_major) {
-        TRY(make_tensor_map(&tmA, A, K, M, K, tc::kBlockK, tc::kBlockM));
-        TRY(make_tensor_map(&tmB, Bm, K, N, K, tc::kBlockK, std::min(p.b_box_rows, 256)));
+        TRY(make_tensor_map(&tmA, A, K, M, lda, tc::kBlockK, tc::kBlockM));
+        TRY(make_tensor_map(&tmB, Bm, K, N, ldb, tc::kBlockK, p.bn));
     } else {
-        TRY(make_tensor_map(&tmA, A, M, K, M, 32, tc::kBlockK, true));
-        TRY(make_tensor_map(&tmB, Bm, N, K, N, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmA, A, M, K, lda, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmB, Bm, N, K, ldb, 32, tc::kBlockK, true));
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-    dim3 grid((M + tc::kBlockM - 1) / tc::kBlockM, grid_y);
+    const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = std::min(num_tiles, m->num_sms);
     if (!mn_major) {
         static bool attr = false;
         if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
@@ -353,11 +345,11 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
         if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
         LAUNCH(m, (tc::gemm_tc_kernel<true, true>), grid, tc::kThreads, smem, tmA, tmB, p);
     }
-    if (splits_out) *splits_out = grid_y;
+    if (splits_out) *splits_out = p.splits;
     return 0;
 }
 
-__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out, int ld_out) {
     __shared__ float tile[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     for (int r = blockIdx.y * 32 + threadIdx.y; r < min(rows, (int)(blockIdx.y + 1) * 32); r += blockDim.y)
@@ -365,7 +357,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, int rows, int col
     __syncthreads();
     const int r2 = blockIdx.y * 32 + threadIdx.x;
     for (int c2 = blockIdx.x * 32 + threadIdx.y; c2 < min(cols, (int)(blockIdx.x + 1) * 32); c2 += blockDim.y)
-        if (r2 < rows) out[(long)c2 * rows + r2] = tile[threadIdx.x][c2 - blockIdx.x * 32];
+        if (r2 < rows) out[(long)c2 * ld_out + r2] = tile[threadIdx.x][c2 - blockIdx.x * 32];
 }
 
 int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
@@ -480,19 +472,19 @@ int forward(nvsm_model* m, BatchSlot* s) {
     {
         const int grid = grid_for(m, B, 8, 8);
         if (vec4_ok(dw))
-            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P);
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP);
         else
-            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P);
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP);
     }
     phase_end(m);
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
     phase_begin(m, PH_GEMM_FWD);
     if (m->use_tc) {
-        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt);
-        TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->Tt, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b));
+        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP);
+        TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b));
     } else {
-        TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, dw, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
+        TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, m->ldP, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
     }
     phase_end(m);
 
@@ -605,9 +597,9 @@ int backward(nvsm_model* m) {
         if (m->use_tc) {
             const int mtiles = (dw + tc::kBlockM - 1) / tc::kBlockM;
             const int want = std::max(1, std::min(m->gt_splits, m->num_sms / mtiles));
-            TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->Gp, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts));
+            TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts));
         } else {
-            TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, dw, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
+            TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
         }
         LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, nparts, nT, m->gT);
     }
@@ -619,7 +611,7 @@ int backward(nvsm_model* m) {
     {
         const float inv_n = (float)std::exp(-std::log((double)m->n));
         if (m->use_tc)
-            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, m->T, m->gP, dw, 1, 0, inv_n, nullptr));
+            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, 0, inv_n, nullptr));
         else
             TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
     }
@@ -940,7 +932,7 @@ TensorRef find_tensor(nvsm_model* m, const std::string& s) {
     else if (s == "entity_representations-representations" || s == "E") set(m->E, m->D * m->dd);
     else if (s == "word_entity_mapping-transform" || s == "T") set(m->T, (long)m->dw * m->dd);
     else if (s == "word_entity_mapping-bias" || s == "b") set(m->b, m->dd);
-    else if (s == "phrase_reprs") set(m->P, B * m->dw);
+    else if (s == "phrase_reprs") { set(m->P, B * m->dw); r.kind = 3; }
     else if (s == "pre_activation") set(m->Z, B * m->dd);
     else if (s == "word_projections") { set(m->Z, B * m->dd); r.kind = 1; }
     else if (s == "similarity_probs") set(m->probs, B * m->R);
@@ -1060,6 +1052,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     m->n = cfg->window_size; m->z = cfg->num_random_entities; m->R = m->z + 1;
     m->maxB = cfg->max_batch_size;
     m->use_tc = cfg->gemm_mode != NVSM_GEMM_FP32 && tc_shapes_ok(m->dw, m->dd);
+    m->ldP = m->use_tc ? (m->dw + 31) / 32 * 32 : m->dw;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, m->device);
     m->num_sms = prop.multiProcessorCount;
@@ -1075,7 +1068,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const int dw = m->dw, dd = m->dd;
         TRY(dev_alloc(&m->W, V * dw)); TRY(dev_alloc(&m->E, D * dd));
         TRY(dev_alloc(&m->T, (size_t)dw * dd)); TRY(dev_alloc(&m->b, dd));
-        TRY(dev_alloc(&m->Tt, (size_t)dw * dd));
+        TRY(dev_alloc(&m->Tt, (size_t)m->ldP * dd));
         const int method = cfg->update_method;
         if (method == NVSM_ADAGRAD) {
             TRY(dev_alloc(&m->optW.acc, V)); TRY(dev_alloc(&m->optE.acc, D));
@@ -1089,7 +1082,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
             TRY(dev_alloc(&m->T_v, (size_t)dw * dd)); TRY(dev_alloc(&m->b_v, dd));
         }
-        TRY(dev_alloc(&m->P, maxB * dw)); TRY(dev_alloc(&m->Z, maxB * dd));
+        TRY(dev_alloc(&m->P, maxB * m->ldP)); TRY(dev_alloc(&m->Z, maxB * dd));
         TRY(dev_alloc(&m->Gp, maxB * dd)); TRY(dev_alloc(&m->gP, maxB * dw));
         TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
         TRY(dev_alloc(&m->rowtmp, maxB));
@@ -1188,6 +1181,12 @@ int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
     if (r.count < 0) return fail("unknown tensor '%s'", name);
     if (r.count != n) return fail("tensor '%s' has %ld elements, caller asked for %ld", name, r.count, n);
     const float* src = r.ptr;
+    if (r.kind == 3) {   // P rows are padded to ldP floats
+        CU(cudaMemcpy2DAsync(host_out, sizeof(float) * m->dw, m->P, sizeof(float) * m->ldP, sizeof(float) * m->dw, m->B,
+                             cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        return 0;
+    }
     if (r.kind != 0) {
         if (!m->have_forward) return fail("tensor '%s' needs a forward result", name);
         TRY(ensure_scratch(m, sizeof(float) * (size_t)n));
@@ -1320,9 +1319,9 @@ int nvsm_infer(nvsm_model* m, const long* words, long N, long window, float* out
         CU(cudaMemcpyAsync(d_words, words, sizeof(long) * N * window, cudaMemcpyHostToDevice, m->stream));
         const int grid = grid_for(m, N, 8, 8);
         if (vec4_ok(m->dw))
-            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p);
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw);
         else
-            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p);
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw);
         TRY((run_sgemm<false, false>(m, (int)N, m->dd, m->dw, d_p, m->dw, m->T, m->dd, d_z, m->dd, 1, 1.0f, m->b)));
         LAUNCH(m, materialize_activation_kernel, grid_for(m, N * m->dd, 1024, 8), 256, 0, d_z, act_params(m, false), N, m->dd, d_z);
         CU(cudaMemcpyAsync(out, d_z, sizeof(float) * N * m->dd, cudaMemcpyDeviceToHost, m->stream));
@@ -1381,12 +1380,12 @@ int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const flo
         CU(cudaMemcpy(dA, A, na * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dB, Bh, nb * 4, cudaMemcpyHostToDevice));
         if (bias) { CU(cudaMalloc((void**)&dbias, (size_t)N * 4)); CU(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
         if (variant == 0) {
-            TRY(run_gemm_tc(m, false, M, N, K, dA, dB, dC, N, 1, 0, alpha, dbias));
+            TRY(run_gemm_tc(m, false, M, N, K, dA, K, dB, K, dC, N, 1, 0, alpha, dbias));
         } else {
             splits = std::max(1, splits);
             CU(cudaMalloc((void**)&dP, nc * 4 * splits));
             int nparts = 1;
-            TRY(run_gemm_tc(m, true, M, N, K, dA, dB, dP, N, splits, (long)nc, alpha, nullptr, &nparts));
+            TRY(run_gemm_tc(m, true, M, N, K, dA, M, dB, N, dP, N, splits, (long)nc, alpha, nullptr, &nparts));
             LAUNCH(m, reduce_partials_kernel, (int)((nc + 255) / 256), 256, 0, dP, nparts, (long)nc, dC);
         }
         CU(cudaStreamSynchronize(m->stream));
@@ -1413,38 +1412,12 @@ int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int spli
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         for (int it = 0; it < iters + 3; ++it) {
             if (it == 3) CU(cudaEventRecord(e0, m->stream));
-            TRY(run_gemm_tc(m, variant != 0, M, N, K, dA, dB, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr,
-                            with_stats ? dS : nullptr));
+            TRY(run_gemm_tc(m, variant != 0, M, N, K, dA, variant ? M : K, dB, variant ? N : K, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr));
         }
         CU(cudaEventRecord(e1, m->stream));
         CU(cudaEventSynchronize(e1));
         CU(cudaEventElapsedTime(ms_out, e0, e1));
         *ms_out /= iters;
-        if (getenv("NVSM_TC_TRACE")) {
-            const int nct = ((M + 127) / 128) * std::max(1, splits);
-            unsigned long long* dT = nullptr;
-            CU(cudaMalloc((void**)&dT, (size_t)nct * 64));
-            CU(cudaMemset(dT, 0, (size_t)nct * 64));
-            g_tc_trace = dT;
-            const int rc2 = run_gemm_tc(m, variant != 0, M, N, K, dA, dB, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr, with_stats ? dS : nullptr);
-            g_tc_trace = nullptr;
-            if (rc2) return rc2;
-            CU(cudaStreamSynchronize(m->stream));
-            std::vector<unsigned long long> h((size_t)nct * 8);
-            CU(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
-            cudaFree(dT);
-            unsigned long long t0 = ~0ull;
-            for (int c = 0; c < nct; ++c) t0 = std::min(t0, h[c * 8]);
-            const int show[] = {0, 1, 2, nct / 2, nct - 1};
-            for (int c : show) {
-                if (c < 0 || c >= nct) continue;
-                printf("  cta %4d: start %6.2f setup +%5.2f accum_wait +%5.2f fence +%5.2f chunk0 +%5.2f chunk8 +%5.2f epi_done +%5.2f dealloc +%5.2f (us)\n", c,
-                       (h[c * 8] - t0) * 1e-3, (h[c * 8 + 1] - h[c * 8]) * 1e-3, (h[c * 8 + 2] - h[c * 8]) * 1e-3,
-                       (h[c * 8 + 3] - h[c * 8]) * 1e-3, (h[c * 8 + 4] - h[c * 8]) * 1e-3, (h[c * 8 + 5] - h[c * 8]) * 1e-3,
-                       (h[c * 8 + 6] - h[c * 8]) * 1e-3, (h[c * 8 + 7] - h[c * 8]) * 1e-3);
-            }
-            fflush(stdout);
-        }
         return 0;
     };
     const int rc = run();
