@@ -55,6 +55,16 @@ __device__ __forceinline__ void red_add_vec(float* p, const float (&v)[VEC]) {
     }
 }
 
+// Round-to-nearest fp32 -> tf32 (10-bit mantissa), returned as an fp32 whose low 13 bits are zero.
+// tcgen05 kind::tf32 TRUNCATES the operands it reads (measured: scripts/probe_tf32_rounding.py), a
+// systematic toward-zero bias; operands that only feed the GEMMs are therefore pre-rounded by
+// their producers, which makes the hardware conversion exact and the error unbiased.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

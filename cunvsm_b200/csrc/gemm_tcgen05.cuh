@@ -161,9 +161,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // (the smem ring never drains), the MMA warp alternates between two TMEM accumulator buffers,
 // and the four epilogue warps drain buffer b of tile t while the MMAs of tile t+1 fill buffer
 // b ^ 1 (tmem_full / tmem_empty mbarriers).
-template <bool A_MN, bool B_MN>
+// SPLIT = 3xTF32: every operand arrives as hi = rn_tf32(x) and lo = x - hi (two arrays written by the
+// producers); per k-step the accumulator receives hi.hi + lo.hi + hi.lo, which restores fp32-level
+// accuracy (the dropped lo.lo term is ~2^-22 relative) at three tensor-core instructions per step.
+template <bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8];
     __shared__ __align__(8) uint64_t empty_bar[8];
@@ -176,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int stages = p.stages;
+    const uint32_t lo_off = kATileBytes + (uint32_t)p.bn * 128u;   // SPLIT: [A_hi][B_hi][A_lo][B_lo] per stage
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -215,6 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            if constexpr (SPLIT) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+            }
             uint32_t it = 0;   // running k-block counter across tiles
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m0, n0, kb0, nkb, split;
@@ -237,6 +246,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_2d(b_dst, &tmB, bar, k0, n0);
                     } else {
                         for (int g = 0; g < p.bn / 32; ++g) tma_load_2d(b_dst + g * kGroupBytes, &tmB, bar, n0 + 32 * g, k0);
+                    }
+                    if constexpr (SPLIT) {
+                        if constexpr (!A_MN) {
+                            tma_load_2d(a_dst + lo_off, &tmAlo, bar, k0, m0);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < kBlockM / 32; ++g)
+                                tma_load_2d(a_dst + lo_off + g * kGroupBytes, &tmAlo, bar, m0 + 32 * g, k0);
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d(b_dst + lo_off, &tmBlo, bar, k0, n0);
+                        } else {
+                            for (int g = 0; g < p.bn / 32; ++g)
+                                tma_load_2d(b_dst + lo_off + g * kGroupBytes, &tmBlo, bar, n0 + 32 * g, k0);
+                        }
                     }
                 }
             }
@@ -268,6 +292,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t b_desc = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
                                                      : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
                         umma_tf32(tacc, a_desc, b_desc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        if constexpr (SPLIT) {
+                            const uint64_t a_lo = A_MN ? make_desc(a_base + lo_off + j * 1024u, kGroupBytes, 512u, 1u)
+                                                       : make_desc(a_base + lo_off + j * 32u, 16u, 1024u, 2u);
+                            const uint64_t b_lo = B_MN ? make_desc(b_base + lo_off + j * 1024u, kGroupBytes, 512u, 1u)
+                                                       : make_desc(b_base + lo_off + j * 32u, 16u, 1024u, 2u);
+                            umma_tf32(tacc, a_lo, b_desc, idesc, 1u);
+                            umma_tf32(tacc, a_desc, b_lo, idesc, 1u);
+                        }
                     }
                     umma_commit(smem_u32(&empty_bar[s]));       // frees the smem stage when these MMAs retire
                 }

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
                                                           const idx_t* __restrict__ ids,
                                                           const float* __restrict__ wts,
                                                           long num_out, int window,
-                                                          float* __restrict__ out, int ld_out) {
+                                                          float* __restrict__ out, int ld_out, int tf32,
+                                                          float* __restrict__ out_lo) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -48,8 +49,18 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
                 for (int v = 0; v < VEC; ++v) acc[v] += wt * x[v];
             }
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = acc[v] / fwin;
+            float lo[VEC];
+            for (int v = 0; v < VEC; ++v) {
+                acc[v] = acc[v] / fwin;
+                lo[v] = 0.f;
+                if (tf32) {                              // P only feeds the tensor-core GEMMs
+                    const float hi = round_tf32(acc[v]);
+                    lo[v] = acc[v] - hi;                 // exact; second operand of the 3xTF32 split
+                    acc[v] = hi;
+                }
+            }
             store_vec<VEC>(out + o * ld_out + c * VEC, acc);
+            if (out_lo) store_vec<VEC>(out_lo + o * ld_out + c * VEC, lo);
         }
     }
 }
@@ -227,6 +238,8 @@ struct ScoreParams {
     float* mult;           // [B*R]
     float* Gp;             // [B, dd]
     float* Y;              // [B, dd] post-activation (nullable; kept for the pull-style update)
+    int tf32_gp;           // round Gp to tf32 (tensor-core GEMMs, no batch-norm: Gp is dX)
+    float* Gp_lo;          // nullable: Gp - rn_tf32(Gp) for the 3xTF32 GEMMs (no batch-norm)
     double* loss_acc;      // [1]  sum_c wbc_c log p_c
     double* col_sums;      // [2*dd]: sum_i dy, sum_i dy * xhat
 };
@@ -357,6 +370,12 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
                 cs[j][v] += dy[v];
                 cx[j][v] += dy[v] * xh[j][v];
             }
+            if (p.tf32_gp) {
+                float lo[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { const float hi = round_tf32(dy[v]); lo[v] = dy[v] - hi; dy[v] = hi; }
+                if (p.Gp_lo && c < nvec) store_vec<VEC>(p.Gp_lo + i * dd + c * VEC, lo);
+            }
             if (c < nvec) store_vec<VEC>(p.Gp + i * dd + c * VEC, dy);
         }
     }
@@ -406,12 +425,13 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(float* __restrict__ Gp
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ invstd,
                                                           const float* __restrict__ mean_dy,
-                                                          const float* __restrict__ mean_dyx, long rows, int dd) {
+                                                          const float* __restrict__ mean_dyx, long rows, int dd,
+                                                          int tf32, float* __restrict__ lo_out) {
     const int nvec = dd / VEC;
     const long total = rows * nvec;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const int c = (int)(t % nvec) * VEC;
-        float g[VEC], z[VEC];
+        float g[VEC], z[VEC], lo[VEC];
         load_vec<VEC>(Gp + t * VEC, g);
         load_vec_ro<VEC>(Z + t * VEC, z);
 #pragma unroll
@@ -419,8 +439,15 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(float* __restrict__ Gp
             const float is = __ldg(invstd + c + v);
             const float xh = (z[v] - __ldg(mean + c + v)) * is;
             g[v] = is * (g[v] - __ldg(mean_dy + c + v) - xh * __ldg(mean_dyx + c + v));
+            lo[v] = 0.f;
+            if (tf32) {                          // dX only feeds the tensor-core GEMMs
+                const float hi = round_tf32(g[v]);
+                lo[v] = g[v] - hi;
+                g[v] = hi;
+            }
         }
         store_vec<VEC>(Gp + t * VEC, g);
+        if (lo_out) store_vec<VEC>(lo_out + t * VEC, lo);
     }
 }
 
@@ -789,5 +816,14 @@ __global__ void __launch_bounds__(256) materialize_activation_kernel(const float
 }
 
 __global__ void increment_kernel(float* p, float eps) { *p += eps; }
+
+// x -> rn_tf32(x) in place, lo = x - rn_tf32(x) (test hook for the 3xTF32 GEMM).
+__global__ void split_tf32_kernel(float* __restrict__ x, float* __restrict__ lo, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float v = x[i], hi = round_tf32(v);
+        x[i] = hi;
+        lo[i] = v - hi;
+    }
+}
 
 }  // namespace nvsm

@@ -98,6 +98,8 @@ struct nvsm_model {
 
     // parameters
     float *W = nullptr, *E = nullptr, *T = nullptr, *b = nullptr;
+    float *P_lo = nullptr, *Gp_lo = nullptr, *Tt_lo = nullptr, *Tr_lo = nullptr;  // x - rn_tf32(x) operands (3xTF32)
+    float* Tr = nullptr;  // T rounded to tf32 [dw, dd]: B operand of the grad_phrase tensor-core GEMM
     float* Tt = nullptr;  // T transposed [dd, dw]: K-major B operand of the forward tensor-core GEMM
     TableOpt optW, optE;
     float *T_a = nullptr, *b_a = nullptr, *T_v = nullptr, *b_v = nullptr;  // transform acc/m, v
@@ -306,58 +308,82 @@ bool tc_shapes_ok(int dw, int dd) {
 // splits > 1 writes `splits` partial products to C + z * split_stride.
 int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
                 float* C, int ldc, int splits, long split_stride, float alpha, const float* bias,
-                int* splits_out = nullptr) {
+                int* splits_out = nullptr, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+    const bool split3 = A_lo != nullptr && B_lo != nullptr;
     tc::Params p;
     p.M = M; p.N = N; p.K = K;
     const int unit = mn_major ? 32 : 16;
     const int n_pad = (N + unit - 1) / unit * unit;
-    p.n_tiles = (n_pad + 255) / 256;
+    const int max_bn = split3 ? 128 : 256;   // 3xTF32 stages hold hi and lo tiles: keep them at 64 KB
+    p.n_tiles = (n_pad + max_bn - 1) / max_bn;
     p.bn = ((n_pad + p.n_tiles - 1) / p.n_tiles + unit - 1) / unit * unit;   // <= 256
     p.m_tiles = (M + tc::kBlockM - 1) / tc::kBlockM;
     const int num_kb = (K + tc::kBlockK - 1) / tc::kBlockK;
     splits = std::max(1, std::min(splits, num_kb));
     p.kb_per_split = (num_kb + splits - 1) / splits;
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-    p.stage_bytes = tc::kATileBytes + (uint32_t)p.bn * 128u;
+    p.stage_bytes = (tc::kATileBytes + (uint32_t)p.bn * 128u) * (split3 ? 2u : 1u);
     p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
     { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
     if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
     p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmAlo, tmBlo;
     if (!mn_major) {
         TRY(make_tensor_map(&tmA, A, K, M, lda, tc::kBlockK, tc::kBlockM));
         TRY(make_tensor_map(&tmB, Bm, K, N, ldb, tc::kBlockK, p.bn));
+        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, K, M, lda, tc::kBlockK, tc::kBlockM));
+        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, K, N, ldb, tc::kBlockK, p.bn));
     } else {
         TRY(make_tensor_map(&tmA, A, M, K, lda, 32, tc::kBlockK, true));
         TRY(make_tensor_map(&tmB, Bm, N, K, ldb, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, M, K, lda, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, N, K, ldb, 32, tc::kBlockK, true));
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(num_tiles, m->num_sms);
-    if (!mn_major) {
-        static bool attr = false;
-        if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
-        LAUNCH(m, (tc::gemm_tc_kernel<false, false>), grid, tc::kThreads, smem, tmA, tmB, p);
-    } else {
-        static bool attr = false;
-        if (!attr) { CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcMaxDynSmem)); attr = true; }
-        LAUNCH(m, (tc::gemm_tc_kernel<true, true>), grid, tc::kThreads, smem, tmA, tmB, p);
+    static bool attr = false;
+    if (!attr) {
+        const int mx = (int)kTcMaxDynSmem;
+        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr = true;
     }
+    if (!mn_major && !split3) LAUNCH(m, (tc::gemm_tc_kernel<false, false, false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+    else if (!mn_major) LAUNCH(m, (tc::gemm_tc_kernel<false, false, true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+    else if (!split3) LAUNCH(m, (tc::gemm_tc_kernel<true, true, false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+    else LAUNCH(m, (tc::gemm_tc_kernel<true, true, true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
     if (splits_out) *splits_out = p.splits;
     return 0;
 }
 
-__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out, int ld_out) {
+// out[c][r] = rn_tf32(in[r][c]) (K-major B operand of the forward GEMM); copy[r][c] = rn_tf32(in[r][c])
+// (K-major B operand of the grad_phrase GEMM).
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out, int ld_out,
+                                 float* __restrict__ copy, float* __restrict__ out_lo, float* __restrict__ copy_lo) {
+    __shared__ float tile_lo[32][33];
     __shared__ float tile[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     for (int r = blockIdx.y * 32 + threadIdx.y; r < min(rows, (int)(blockIdx.y + 1) * 32); r += blockDim.y)
-        if (c < cols) tile[r - blockIdx.y * 32][threadIdx.x] = in[(long)r * cols + c];
+        if (c < cols) {
+            const float raw = in[(long)r * cols + c];
+            const float x = round_tf32(raw);
+            tile[r - blockIdx.y * 32][threadIdx.x] = x;
+            tile_lo[r - blockIdx.y * 32][threadIdx.x] = raw - x;
+            copy[(long)r * cols + c] = x;
+            if (copy_lo) copy_lo[(long)r * cols + c] = raw - x;
+        }
     __syncthreads();
     const int r2 = blockIdx.y * 32 + threadIdx.x;
     for (int c2 = blockIdx.x * 32 + threadIdx.y; c2 < min(cols, (int)(blockIdx.x + 1) * 32); c2 += blockDim.y)
-        if (r2 < rows) out[(long)c2 * ld_out + r2] = tile[threadIdx.x][c2 - blockIdx.x * 32];
+        if (r2 < rows) {
+            out[(long)c2 * ld_out + r2] = tile[threadIdx.x][c2 - blockIdx.x * 32];
+            if (out_lo) out_lo[(long)c2 * ld_out + r2] = tile_lo[threadIdx.x][c2 - blockIdx.x * 32];
+        }
 }
 
 int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
@@ -472,17 +498,18 @@ int forward(nvsm_model* m, BatchSlot* s) {
     {
         const int grid = grid_for(m, B, 8, 8);
         if (vec4_ok(dw))
-            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP);
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP, m->use_tc ? 1 : 0, m->P_lo);
         else
-            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP);
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP, m->use_tc ? 1 : 0, m->P_lo);
     }
     phase_end(m);
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
     phase_begin(m, PH_GEMM_FWD);
     if (m->use_tc) {
-        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP);
-        TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b));
+        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP, m->Tr, m->Tt_lo, m->Tr_lo);
+        TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b, nullptr,
+                        m->P_lo, m->Tt_lo));
     } else {
         TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, m->ldP, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
     }
@@ -544,6 +571,8 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.bsn = (float)std::exp(-std::log((double)m->Bglobal));
         sp.act = act_params(m, bn);
         sp.probs = m->probs; sp.mult = m->mult; sp.Gp = m->Gp; sp.Y = m->Y;
+        sp.tf32_gp = (m->use_tc && !bn) ? 1 : 0;
+        sp.Gp_lo = bn ? nullptr : m->Gp_lo;
         sp.loss_acc = m->loss_acc(); sp.col_sums = m->bwd_sums();
         TRY(dispatch_score(m, sp));
     }
@@ -575,10 +604,10 @@ int backward(nvsm_model* m) {
     if (bn) {
         if (vec4_ok(dd)) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
-            LAUNCH(m, bn_backward_kernel<4>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd);
+            LAUNCH(m, bn_backward_kernel<4>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
         } else {
             const int grid = grid_for(m, B * dd, 256 * 4, 8);
-            LAUNCH(m, bn_backward_kernel<1>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd);
+            LAUNCH(m, bn_backward_kernel<1>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
         }
     }
     phase_end(m);
@@ -597,7 +626,8 @@ int backward(nvsm_model* m) {
         if (m->use_tc) {
             const int mtiles = (dw + tc::kBlockM - 1) / tc::kBlockM;
             const int want = std::max(1, std::min(m->gt_splits, m->num_sms / mtiles));
-            TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts));
+            TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts,
+                            m->P_lo, m->Gp_lo));
         } else {
             TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
         }
@@ -611,7 +641,7 @@ int backward(nvsm_model* m) {
     {
         const float inv_n = (float)std::exp(-std::log((double)m->n));
         if (m->use_tc)
-            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, 0, inv_n, nullptr));
+            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->Tr, dd, m->gP, dw, 1, 0, inv_n, nullptr, nullptr, m->Gp_lo, m->Tr_lo));
         else
             TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
     }
@@ -992,7 +1022,7 @@ void nvsm_destroy(nvsm_model* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->comm) nccl_api().CommDestroy(m->comm);
-    float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
+    float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->Tr, m->P_lo, m->Gp_lo, m->Tt_lo, m->Tr_lo, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
                    m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
                    m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->bn_scale, m->bn_shift, m->stat_part, m->gT, m->gb, m->gT_part, m->scratch};
     for (float* p : fl)
@@ -1036,7 +1066,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     if (cfg->update_method == NVSM_ADAM && (cfg->adam_mode < NVSM_ADAM_SPARSE || cfg->adam_mode > NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE)) return fail("Invalid mode configuration.");
     if (cfg->num_random_entities < 0) return fail("num_random_entities must be >= 0");
     if (cfg->max_batch_size <= 0 || cfg->window_size <= 0) return fail("max_batch_size and window_size must be > 0");
-    if (cfg->gemm_mode != NVSM_GEMM_FP32 && cfg->gemm_mode != NVSM_GEMM_TF32) return fail("gemm_mode %d is not available in this build", cfg->gemm_mode);
+    if (cfg->gemm_mode < NVSM_GEMM_FP32 || cfg->gemm_mode > NVSM_GEMM_3XTF32) return fail("invalid gemm_mode %d", cfg->gemm_mode);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("no CUDA device: libnvsm_b200 has no CPU fallback");
@@ -1068,7 +1098,11 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const int dw = m->dw, dd = m->dd;
         TRY(dev_alloc(&m->W, V * dw)); TRY(dev_alloc(&m->E, D * dd));
         TRY(dev_alloc(&m->T, (size_t)dw * dd)); TRY(dev_alloc(&m->b, dd));
-        TRY(dev_alloc(&m->Tt, (size_t)m->ldP * dd));
+        TRY(dev_alloc(&m->Tt, (size_t)m->ldP * dd)); TRY(dev_alloc(&m->Tr, (size_t)dw * dd));
+        if (m->use_tc && cfg->gemm_mode == NVSM_GEMM_3XTF32) {
+            TRY(dev_alloc(&m->P_lo, maxB * m->ldP)); TRY(dev_alloc(&m->Gp_lo, maxB * dd));
+            TRY(dev_alloc(&m->Tt_lo, (size_t)m->ldP * dd)); TRY(dev_alloc(&m->Tr_lo, (size_t)dw * dd));
+        }
         const int method = cfg->update_method;
         if (method == NVSM_ADAGRAD) {
             TRY(dev_alloc(&m->optW.acc, V)); TRY(dev_alloc(&m->optE.acc, D));
@@ -1185,6 +1219,13 @@ int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
         CU(cudaMemcpy2DAsync(host_out, sizeof(float) * m->dw, m->P, sizeof(float) * m->ldP, sizeof(float) * m->dw, m->B,
                              cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
+        if (m->P_lo) {   // 3xTF32: P = hi + lo
+            std::vector<float> lo((size_t)n);
+            CU(cudaMemcpy2DAsync(lo.data(), sizeof(float) * m->dw, m->P_lo, sizeof(float) * m->ldP, sizeof(float) * m->dw, m->B,
+                                 cudaMemcpyDeviceToHost, m->stream));
+            CU(cudaStreamSynchronize(m->stream));
+            for (long i = 0; i < n; ++i) host_out[i] += lo[i];
+        }
         return 0;
     }
     if (r.kind != 0) {
@@ -1319,9 +1360,9 @@ int nvsm_infer(nvsm_model* m, const long* words, long N, long window, float* out
         CU(cudaMemcpyAsync(d_words, words, sizeof(long) * N * window, cudaMemcpyHostToDevice, m->stream));
         const int grid = grid_for(m, N, 8, 8);
         if (vec4_ok(m->dw))
-            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw);
+            LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw, 0, (float*)nullptr);
         else
-            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw);
+            LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, m->dw, d_words, (const float*)nullptr, N, (int)window, d_p, m->dw, 0, (float*)nullptr);
         TRY((run_sgemm<false, false>(m, (int)N, m->dd, m->dw, d_p, m->dw, m->T, m->dd, d_z, m->dd, 1, 1.0f, m->b)));
         LAUNCH(m, materialize_activation_kernel, grid_for(m, N * m->dd, 1024, 8), 256, 0, d_z, act_params(m, false), N, m->dd, d_z);
         CU(cudaMemcpyAsync(out, d_z, sizeof(float) * N * m->dd, cudaMemcpyDeviceToHost, m->stream));
@@ -1379,13 +1420,22 @@ int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const flo
         CU(cudaMalloc((void**)&dA, na * 4)); CU(cudaMalloc((void**)&dB, nb * 4)); CU(cudaMalloc((void**)&dC, nc * 4));
         CU(cudaMemcpy(dA, A, na * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dB, Bh, nb * 4, cudaMemcpyHostToDevice));
         if (bias) { CU(cudaMalloc((void**)&dbias, (size_t)N * 4)); CU(cudaMemcpy(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice)); }
+        float *dAlo = nullptr, *dBlo = nullptr;
+        const bool split3 = variant >= 2;
+        variant &= 1;
+        if (split3) {
+            CU(cudaMalloc((void**)&dAlo, na * 4)); CU(cudaMalloc((void**)&dBlo, nb * 4));
+            LAUNCH(m, split_tf32_kernel, 512, 256, 0, dA, dAlo, (long)na);
+            LAUNCH(m, split_tf32_kernel, 512, 256, 0, dB, dBlo, (long)nb);
+        }
+        struct Free { float *a, *b; ~Free() { cudaFree(a); cudaFree(b); } } fr{dAlo, dBlo};
         if (variant == 0) {
-            TRY(run_gemm_tc(m, false, M, N, K, dA, K, dB, K, dC, N, 1, 0, alpha, dbias));
+            TRY(run_gemm_tc(m, false, M, N, K, dA, K, dB, K, dC, N, 1, 0, alpha, dbias, nullptr, dAlo, dBlo));
         } else {
             splits = std::max(1, splits);
             CU(cudaMalloc((void**)&dP, nc * 4 * splits));
             int nparts = 1;
-            TRY(run_gemm_tc(m, true, M, N, K, dA, M, dB, N, dP, N, splits, (long)nc, alpha, nullptr, &nparts));
+            TRY(run_gemm_tc(m, true, M, N, K, dA, M, dB, N, dP, N, splits, (long)nc, alpha, nullptr, &nparts, dAlo, dBlo));
             LAUNCH(m, reduce_partials_kernel, (int)((nc + 255) / 256), 256, 0, dP, nparts, (long)nc, dC);
         }
         CU(cudaStreamSynchronize(m->stream));

@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
                 cs[k][v] += dy[v];
                 cx[k][v] += dy[v] * tt[k][v];   // sum dy * (xhat + bias); the bias term is removed by the caller
             }
+            if (p.tf32_gp) {
+                float lo[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { const float hi = round_tf32(dy[v]); lo[v] = dy[v] - hi; dy[v] = hi; }
+                if (p.Gp_lo && (FULL || c4 < dd)) store_vec<VEC>(p.Gp_lo + i * dd + c4, lo);
+            }
             if (FULL || c4 < dd) store_vec<VEC>(p.Gp + i * dd + c4, dy);
         }
         // rotate the instance-weight queue; all lanes are done with stage s before it is refilled

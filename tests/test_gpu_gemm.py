@@ -23,7 +23,7 @@ def model():
 def gemm(model, variant, A, B, alpha=1.0, bias=None, splits=1):
     pf = ctypes.POINTER(ctypes.c_float)
     A = np.ascontiguousarray(A, dtype=np.float32); B = np.ascontiguousarray(B, dtype=np.float32)
-    if variant == 0:
+    if variant in (0, 2):
         M, K = A.shape; N = B.shape[0]
     else:
         K, M = A.shape; N = B.shape[1]
@@ -73,3 +73,21 @@ def test_tf32_error_bound_random(model):
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     err = np.abs(C - ref).max()
     assert err <= 2e-3 * np.sqrt(300) * 3, err
+
+
+@pytest.mark.parametrize("variant,M,N,K,splits", [(2, 512, 256, 300, 1), (2, 1000, 300, 256, 1), (3, 300, 256, 4096, 8), (3, 300, 256, 51200, 49)])
+def test_3xtf32_reaches_fp32_accuracy(model, variant, M, N, K, splits):
+    """3xTF32 (hi.hi + lo.hi + hi.lo): error must be at the fp32 level (1e-6 relative to the
+    sum of |a||b|), ~1000x below single-pass TF32."""
+    rng = np.random.default_rng(3)
+    if variant == 2:
+        A = rng.standard_normal((M, K)).astype(np.float32); B = rng.standard_normal((N, K)).astype(np.float32)
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        mag = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    else:
+        A = rng.standard_normal((K, M)).astype(np.float32); B = rng.standard_normal((K, N)).astype(np.float32)
+        ref = A.astype(np.float64).T @ B.astype(np.float64)
+        mag = np.abs(A).astype(np.float64).T @ np.abs(B).astype(np.float64)
+    C = gemm(model, variant, A, B, splits=splits)
+    rel = (np.abs(C - ref) / mag).max()
+    assert rel <= 2e-6, rel

@@ -134,7 +134,7 @@ def test_forward_backward_tf32_tensor_core_gemms(name):
     gm, om, rng = twin_models(**c, gemm_mode=nv.GEMM_TF32)
     _, _, cost, ocost = run_forward_backward(gm, om, rng, B, n, V, D, z)
     assert abs(cost - ocost) <= 2e-3 * abs(ocost)
-    assert_close(gm.get_tensor("phrase_reprs"), om.get("P"), RTOL, what="P")
+    assert_close(gm.get_tensor("phrase_reprs"), om.get("P"), 6e-4, what="P")   # stored rounded to tf32 (2^-11)
     assert_close(gm.get_tensor("word_projections"), om.get("Y"), 5e-3, 5e-3, what="Y")
     assert_close(gm.get_tensor("similarity_probs"), om.get("probs"), 5e-3, 2e-3, what="probs")
     for g, o in (("instance_multipliers", "mult"), ("grad_transform", "gT"), ("grad_bias", "gb"),
