@@ -9,8 +9,9 @@ ids, Glorot-initialised tables from minstd_rand0(seed 1), negatives from the ref
 sampler.
 
   value : steps on batches already resident in HBM (10 staged batches, cycled), CUDA events.
-  e2e   : the same steps through nvsm_train_step with pinned HOST buffers (H2D of ids / weights
-          every step inside the timed region, loss read back every step, one step lagged).
+  e2e   : the same steps through nvsm_step_sampled with pinned HOST buffers (H2D of word ids, weights
+          and positive labels every step inside the timed region, negatives drawn by the bit-exact
+          device sampler inside the step, loss read back every step, one step lagged).
   --impl reference : the CPU restatement of the reference (oracle port, OpenMP, all host
           threads) on a bounded sample of the same workload. The reference itself has no CPU
           path and cannot be built without its un-vendored device_matrix dependency.
@@ -171,7 +172,7 @@ def cpu_port_run(w, steps, warmup, sample_B):
 def run_reference(args, w, rank):
     if rank != 0:
         return
-    sample_B = args.cpu_sample
+    sample_B = min(args.cpu_sample, w["B"])
     r = cpu_port_run(w, args.steps, max(args.warmup, 1), sample_B)
     sample = ("%d n-grams/step (1/%d of the %d batch), full-size tables, float32, sampler+forward+backward+update; "
               "%s build" % (sample_B, max(1, w["B"] // sample_B), w["B"], "-march=native" if r["native"] else "portable"))
@@ -254,8 +255,10 @@ def run_ours(args, w, rank, world, local_rank):
     staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
 
     def host_fed(it):
+        # the reference-facing call on HOST buffers: features / weights / positive labels go up every step,
+        # the z negatives per instance are drawn on the device (bit-exact with the reference's host sampler)
         k = it % NUM_BATCHES
-        model.train_step(batches[k], ids_np[k], lr)
+        model.step_sampled(batches[k], lr)
         if it > 0:
             model.last_cost(1)  # loss of the previous step: D2H read every step, one step lagged
 
@@ -268,6 +271,7 @@ def run_ours(args, w, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     final_cost = model.last_cost()
 
+    model.sampler_seed(srng)
     for it in range(max(3, min(args.warmup, 5))):
         host_fed(it)
     ms_e2e, _ = timed(host_fed, args.steps)
@@ -281,6 +285,22 @@ def run_ours(args, w, rank, world, local_rank):
         staged(it)
     phases = {k: v / prof_steps for k, v in model.phase_ms().items()}
     model.set_profiling(False)
+
+    alt = None
+    if args.gemm_mode == 2 and not args.no_alt:
+        # the same timed loop with single-pass TF32 GEMMs (looser parity, see tests/test_gpu_loss_curve.py)
+        model.close()
+        model = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=1, num_batch_slots=NUM_BATCHES)
+        model.set_stream(stream.cuda_stream)
+        model.initialize(nv.RNG(1))
+        sharding.init_model_comm(model, dist, rank, world)
+        for s_ in range(NUM_BATCHES):
+            model.stage_batch(s_, batches[s_], ids_np[s_])
+        staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
+        for it in range(args.warmup):
+            staged(it)
+        ms_alt, _ = timed(staged, args.steps)
+        alt = {"gemm": "tf32_tcgen05", "value": B * world * args.steps / (ms_alt * 1e-3), "ms_per_step": ms_alt / args.steps}
 
     if rank == 0:
         peaks = {}
@@ -296,16 +316,22 @@ def run_ours(args, w, rank, world, local_rank):
         dom_ms = cand[dom]
         achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         total_alg = sum(alg.values()) * B
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(args.workload, {}).get(dom)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
                     "step_algorithmic_gbs": total_alg / (ms / args.steps * 1e-3) / 1e9,
                     "phase_ms": {k: round(v, 4) for k, v in phases.items()}}
-        h2d = int(B * w["n"] * 8 + B * w["n"] * 4 + B * (w["z"] + 1) * 8 + B * 4)
+        h2d = int(B * w["n"] * 8 + B * w["n"] * 4 + B * 8 + B * 4)
         ngrams = B * world * args.steps
         cpu = None
         if not args.no_cpu_baseline:
-            r = cpu_port_run(w, 2, 1, args.cpu_sample)
+            r = cpu_port_run(w, 2, 1, min(args.cpu_sample, w["B"]))
             cpu = {"value": r["value"], "unit": "n-grams/s", "cores": r["cores"], "kind": "port",
                    "sample": "%d n-grams/step x 2 steps of the same workload (full-size tables), float32 oracle, "
                              "sampler+forward+backward+update, %s build" % (args.cpu_sample, "-march=native" if r["native"] else "portable")}
@@ -318,11 +344,12 @@ def run_ours(args, w, rank, world, local_rank):
                        "l2": "working set (tables + moments + per-step tensors, > 1 GB) exceeds the 126 MB L2; "
                              "%d distinct batches cycled" % NUM_BATCHES,
                        "sparse_tables": "replicated, per-rank local updates" if world > 1 else "single GPU",
-                       "negatives": "pre-sampled by the bit-exact host sampler outside the timed region"},
+                       "negatives": "value: pre-sampled (bit-exact host sampler) and staged with the batch; e2e: drawn "
+                                    "inside the timed step by the bit-exact device sampler"},
             "e2e": {"value": ngrams / (ms_e2e * 1e-3), "unit": "n-grams/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "final_cost": final_cost,
+            "final_cost": final_cost, "alt_single_pass_tf32": alt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -338,9 +365,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--update_method", default=None)
-    ap.add_argument("--gemm_mode", type=int, default=1, help="0 fp32 SIMT, 1 tf32 tcgen05")
+    ap.add_argument("--gemm_mode", type=int, default=2, help="0 fp32 SIMT, 1 tf32 tcgen05, 2 3xtf32 tcgen05 (default: fp32-level parity)")
     ap.add_argument("--cpu_sample", type=int, default=5120)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_alt", action="store_true", help="skip the extra single-pass TF32 measurement")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.update_method:

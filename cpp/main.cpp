@@ -33,7 +33,7 @@ struct Flags {
               {"entity_similarity_weight", "0.0"}, {"term_similarity_weight", "0.0"}, {"output", ""},
               // replacements for the Indri positional argument
               {"synthetic_num_words", "50000"}, {"synthetic_num_entities", "50000"}, {"synthetic_num_batches", "100"},
-              {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "tf32"}, {"v", "0"}};
+              {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "3xtf32"}, {"host_sampler", "false"}, {"v", "0"}};
   }
   void parse(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
@@ -130,7 +130,7 @@ int main(int argc, char** argv) {
 
   const size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
   TextEntity::SyntheticSource data_source(V, D, flags.i("synthetic_num_batches"), flags.i("seed"), flags.d("synthetic_zipf"));
-  const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : NVSM_GEMM_TF32;
+  const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
 
   std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
               model_desc.word_repr_size(), model_desc.entity_repr_size(), (int)model_desc.transform_desc().batch_normalization(),
@@ -141,6 +141,9 @@ int main(int argc, char** argv) {
 
   DefaultModel model(V, D, model_desc, train_config, flags.i("device"), gemm_mode);
   model.initialize(&rng);
+  // negatives: the reference draws them on the host training thread (cpp/labels.cu:3-22, ~3.6 ms per
+  // 51200-batch); by default the same stream is produced on the device, --host_sampler restores the loop.
+  if (!flags.b("host_sampler")) model.use_device_sampler(&rng);
   if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
 
   TextEntity::Batch batch(train_config);
@@ -193,5 +196,6 @@ int main(int argc, char** argv) {
     dump_model(model, flags.str("output"), std::to_string(epoch));
   }
   NVSM_ABORT_ON(nvsm_synchronize(model.handle()));
+  model.sync_rng(&rng);
   return 0;
 }

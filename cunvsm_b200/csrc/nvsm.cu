@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "pull_update.cuh"
+#include "sampler.cuh"
 #include "score_ring.cuh"
 
 using namespace nvsm;
@@ -65,6 +66,7 @@ struct BatchSlot {
     idx_t* features = nullptr;   // [maxB*n]
     float* fweights = nullptr;   // [maxB*n]
     idx_t* ids = nullptr;        // [maxB*R]
+    idx_t* labels = nullptr;     // [maxB] positive ids (device sampler input)
     float* weights = nullptr;    // [maxB]
     long B = 0;
     cudaEvent_t ready = nullptr;     // H2D done
@@ -150,6 +152,13 @@ struct nvsm_model {
     double phase_ms[PH_COUNT] = {0};
     int open_phase = -1;
     cudaEvent_t open_ev = nullptr;
+
+    // device sampler (sampler.cuh): engine state double-buffered on the device
+    unsigned int* rng_dev = nullptr;   // [2]
+    int rng_cur = 0;
+    bool rng_seeded = false;
+    int *smp_counts = nullptr, *smp_offsets = nullptr, *smp_scan = nullptr, *smp_error = nullptr;
+    long smp_capacity = 0;             // candidate chunks allocated
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -314,7 +323,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.M = M; p.N = N; p.K = K;
     const int unit = mn_major ? 32 : 16;
     const int n_pad = (N + unit - 1) / unit * unit;
-    const int max_bn = split3 ? 128 : 256;   // 3xTF32 stages hold hi and lo tiles: keep them at 64 KB
+    const int max_bn = 256;   // (3xTF32: two 96 KB stages measured faster than three 64 KB stages with bn = 128)
     p.n_tiles = (n_pad + max_bn - 1) / max_bn;
     p.bn = ((n_pad + p.n_tiles - 1) / p.n_tiles + unit - 1) / unit * unit;   // <= 256
     p.m_tiles = (M + tc::kBlockM - 1) / tc::kBlockM;
@@ -493,7 +502,9 @@ int forward(nvsm_model* m, BatchSlot* s) {
 
     CU(cudaMemsetAsync(m->dsums, 0, (5 * (size_t)dd + 1) * sizeof(double), m->stream));
 
-    // (1) phrase representations: weighted mean of the word rows.
+    // (1) phrase representations: weighted mean of the word rows. (A cp.async-ring variant like
+    // score_ring_kernel and a fully unrolled window were both measured slower: the gather has almost
+    // no arithmetic per row, so plain loads at high occupancy win.)
     phase_begin(m, PH_GATHER);
     {
         const int grid = grid_for(m, B, 8, 8);
@@ -904,6 +915,80 @@ int update(nvsm_model* m, float lr, float lambda) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// device sampler
+// ------------------------------------------------------------------------------------
+// Candidates needed for N draws: N plus the expected rejections with a wide safety margin.
+long sampler_candidates(long N, long D) {
+    const unsigned long urngrange = 2147483645ul;
+    const unsigned long scaling = urngrange / (unsigned long)D, past = (unsigned long)D * scaling;
+    const double p_rej = (double)(urngrange + 1 - past) / (double)(urngrange + 1);
+    const double expect = (double)N * p_rej / std::max(1e-9, 1.0 - p_rej);
+    long T = N + (long)(expect * 1.5 + 8.0 * std::sqrt(expect + 1.0)) + 1024;
+    return (T + kSamplerChunk - 1) / kSamplerChunk * kSamplerChunk;
+}
+
+int ensure_sampler(nvsm_model* m) {
+    if (!m->rng_dev) {
+        TRY(dev_alloc(&m->rng_dev, 2));
+        TRY(dev_alloc(&m->smp_error, 1));
+        TRY(dev_alloc(&m->smp_scan, 2 * 1024 + 2));
+    }
+    const long chunks = sampler_candidates(m->maxB * std::max(1, m->z), m->D) / kSamplerChunk;
+    if (chunks > m->smp_capacity) {
+        if (m->smp_counts) cudaFree(m->smp_counts);
+        if (m->smp_offsets) cudaFree(m->smp_offsets);
+        m->smp_counts = m->smp_offsets = nullptr;
+        TRY(dev_alloc(&m->smp_counts, chunks + 1));
+        TRY(dev_alloc(&m->smp_offsets, chunks + 1));
+        m->smp_capacity = chunks;
+    }
+    return 0;
+}
+
+// ids[slot] <- labels[slot] + z device-sampled negatives per instance; advances the device engine state.
+int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B, int z, long D) {
+    if (!m->rng_seeded) return fail("device sampler used before nvsm_sampler_seed");
+    if (D <= 0 || D >= 2147483646L) return fail("device sampler supports 0 < num_entities < 2^31 - 2");
+    if (z == 0) {
+        LAUNCH(m, sampler_copy_labels_kernel, (int)((B + 255) / 256), 256, 0, labels, B, ids);
+        return 0;
+    }
+    SamplerParams p;
+    p.state_in = m->rng_dev + m->rng_cur;
+    p.state_out = m->rng_dev + (m->rng_cur ^ 1);
+    p.num_draws = B * z;
+    p.num_candidates = sampler_candidates(p.num_draws, D);
+    p.scaling = (unsigned int)(2147483645ul / (unsigned long)D);
+    p.past = (unsigned int)((unsigned long)D * p.scaling);
+    p.z = z; p.R = z + 1;
+    p.labels = labels; p.ids = ids;
+    p.counts = m->smp_counts; p.offsets = m->smp_offsets; p.error_flag = m->smp_error;
+    const long nchunks = p.num_candidates / kSamplerChunk;
+    if (nchunks > 1024L * 1024L) return fail("device sampler: batch too large");
+    if (nchunks > m->smp_capacity) {
+        CU(cudaStreamSynchronize(m->stream));
+        if (m->smp_counts) cudaFree(m->smp_counts);
+        if (m->smp_offsets) cudaFree(m->smp_offsets);
+        m->smp_counts = m->smp_offsets = nullptr;
+        TRY(dev_alloc(&m->smp_counts, nchunks + 1));
+        TRY(dev_alloc(&m->smp_offsets, nchunks + 1));
+        m->smp_capacity = nchunks;
+        p.counts = m->smp_counts; p.offsets = m->smp_offsets;
+    }
+    const int grid = (int)((nchunks + 255) / 256);
+    LAUNCH(m, sampler_count_kernel, grid, 256, 0, p);
+    const int nb = (int)((nchunks + 1023) / 1024);
+    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, m->smp_counts, nchunks, m->smp_offsets, m->smp_scan);
+    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->smp_scan, (long)nb, m->smp_scan + 1024, (int*)nullptr);
+    LAUNCH(m, scan_add_kernel, nb, 1024, 0, m->smp_offsets, nchunks, m->smp_scan + 1024, 0L);
+    LAUNCH(m, sampler_total_kernel, 1, 1, 0, m->smp_counts, m->smp_offsets, nchunks);
+    LAUNCH(m, sampler_fill_kernel, std::max(grid, (int)((B + 255) / 256)), 256, 0, p);
+    m->rng_cur ^= 1;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------
 // batches
 // ------------------------------------------------------------------------------------
@@ -1032,10 +1117,15 @@ void nvsm_destroy(nvsm_model* m) {
     for (int* p : il)
         if (p) cudaFree(p);
     if (m->Y) cudaFree(m->Y);
+    if (m->rng_dev) cudaFree(m->rng_dev);
+    int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
+    for (int* p : sl)
+        if (p) cudaFree(p);
     for (auto& s : m->slots) {
         if (s.features) cudaFree(s.features);
         if (s.fweights) cudaFree(s.fweights);
         if (s.ids) cudaFree(s.ids);
+        if (s.labels) cudaFree(s.labels);
         if (s.weights) cudaFree(s.weights);
         if (s.ready) cudaEventDestroy(s.ready);
         if (s.consumed) cudaEventDestroy(s.consumed);
@@ -1141,7 +1231,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         m->slots.resize(m->cfg.num_batch_slots + 2);
         for (auto& s : m->slots) {
             TRY(dev_alloc(&s.features, maxB * m->n)); TRY(dev_alloc(&s.fweights, maxB * m->n));
-            TRY(dev_alloc(&s.ids, maxB * m->R)); TRY(dev_alloc(&s.weights, maxB));
+            TRY(dev_alloc(&s.ids, maxB * m->R)); TRY(dev_alloc(&s.weights, maxB)); TRY(dev_alloc(&s.labels, maxB));
             CU(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
         }
@@ -1321,6 +1411,96 @@ int nvsm_train_step(nvsm_model* m, const long* features, const float* fw, const 
     TRY(forward(m, s));
     TRY(backward(m));
     return update(m, lr, nvsm_scaled_regularization_lambda(m));
+}
+
+// Device-resident std::minstd_rand0 state for the device sampler.
+int nvsm_sampler_seed(nvsm_model* m, unsigned long state) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    TRY(ensure_sampler(m));
+    unsigned int x = (unsigned int)(state % 2147483647ul);
+    if (x == 0) x = 1;   // std::linear_congruential_engine::seed
+    CU(cudaMemcpyAsync(m->rng_dev + m->rng_cur, &x, sizeof(x), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemsetAsync(m->smp_error, 0, sizeof(int), m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    m->rng_seeded = true;
+    return 0;
+}
+
+int nvsm_sampler_state(nvsm_model* m, unsigned long* state) {
+    if (!m || !state) return fail("null argument");
+    if (!m->rng_seeded) return fail("device sampler is not seeded");
+    CU(cudaSetDevice(m->device));
+    unsigned int x = 0;
+    int err = 0;
+    CU(cudaMemcpyAsync(&x, m->rng_dev + m->rng_cur, sizeof(x), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaMemcpyAsync(&err, m->smp_error, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    if (err) return fail("device sampler ran out of candidates (rejection rate far above expectation)");
+    *state = x;
+    return 0;
+}
+
+// Upload features / weights / positive labels, draw the negatives on the device, and (train != 0) run
+// the whole step. Equivalent to nvsm_generate_labels + nvsm_train_step with the engine state kept on
+// the device between steps.
+int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, const long* labels, const float* w,
+                      long B, float lr, int train) {
+    if (!m) return fail("null model");
+    if (!features || !fw || !labels || !w) return fail("null batch pointer");
+    if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
+    CU(cudaSetDevice(m->device));
+    TRY(ensure_sampler(m));
+    BatchSlot* s = next_live_slot(m);
+    cudaStream_t cs = m->copy_stream;
+    if (s->in_use) { CU(cudaEventRecord(s->consumed, m->stream)); s->ever_consumed = true; }
+    if (s->ever_consumed) CU(cudaStreamWaitEvent(cs, s->consumed, 0));
+    s->in_use = false;
+    CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->labels, labels, sizeof(long) * B, cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(s->ready, cs));
+    s->B = B;
+    CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
+    TRY(sample_labels_device(m, s->labels, s->ids, s->B, m->z, m->D));
+    CU(cudaEventRecord(s->ready, m->stream));   // "ready" now also covers the sampled ids (bucket build waits on it)
+    TRY(forward(m, s));
+    if (!train) return 0;
+    TRY(backward(m));
+    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+}
+
+// Stand-alone device sampling for arbitrary (z, num_objects): host labels in, host ids out.
+int nvsm_generate_labels_device(nvsm_model* m, const long* labels, long num_labels, long z, long num_objects,
+                                unsigned long* rng_state, long* out) {
+    if (!m || !labels || !rng_state || !out) return fail("null argument");
+    if (num_labels <= 0 || z < 0) return fail("invalid sampler arguments");
+    TRY(nvsm_sampler_seed(m, *rng_state));
+    idx_t *d_labels = nullptr, *d_ids = nullptr;
+    const long R = z + 1;
+    CU(cudaMalloc((void**)&d_labels, sizeof(long) * num_labels));
+    CU(cudaMalloc((void**)&d_ids, sizeof(long) * num_labels * R));
+    auto run = [&]() -> int {
+        CU(cudaMemcpyAsync(d_labels, labels, sizeof(long) * num_labels, cudaMemcpyHostToDevice, m->stream));
+        TRY(sample_labels_device(m, d_labels, d_ids, num_labels, (int)z, num_objects));
+        CU(cudaMemcpyAsync(out, d_ids, sizeof(long) * num_labels * R, cudaMemcpyDeviceToHost, m->stream));
+        return nvsm_sampler_state(m, rng_state);
+    };
+    const int rc = run();
+    cudaFree(d_labels); cudaFree(d_ids);
+    return rc;
+}
+
+// Read back the entity ids (positives + sampled negatives) of the running forward result.
+int nvsm_get_entity_ids(nvsm_model* m, long* out, long n) {
+    if (!m || !out) return fail("null argument");
+    if (!m->cur) return fail("no forward result");
+    if (n != m->B * m->R) return fail("entity id count mismatch: have %ld, asked %ld", m->B * m->R, n);
+    CU(cudaSetDevice(m->device));
+    CU(cudaMemcpyAsync(out, m->cur->ids, sizeof(long) * n, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return 0;
 }
 
 int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float* fw, const long* ids,

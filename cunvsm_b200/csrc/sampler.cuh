@@ -1,0 +1,101 @@
+// Device-side negative sampler, bit-exact with the reference's host loop
+// (UniformLabelGenerator::generate, cpp/labels.cu:3-22 -> generate_random_indexes,
+// include/cuNVSM/cuda_utils.h:24-33): for every instance, the positive label followed by z draws of
+// std::uniform_int_distribution<long>(0, D-1) on the shared std::minstd_rand0.
+//
+// libstdc++'s distribution on this engine (range [1, 2^31-2], not a power of two) is the classic
+// down-scaling loop:   scaling = 2147483645 / D;  past = D * scaling;
+//                      do ret = rng() - 1; while (ret >= past);   return ret / scaling;
+// i.e. a stream of candidates with (rare) rejections. minstd_rand0 is the Lehmer generator
+// x_{k+1} = 16807 x_k mod (2^31-1), so candidate k is a^(k+1) x_0 mod m: every thread jumps to the
+// start of its chunk with a modular power, walks the chunk, and a prefix sum over the per-chunk
+// accept counts compacts the accepted candidates into draw order. The engine state after the call is
+// the candidate that produced the last accepted draw — exactly where the host loop would stop.
+#pragma once
+
+#include "common.cuh"
+
+namespace nvsm {
+
+constexpr unsigned long long kLehmerM = 2147483647ull;   // 2^31 - 1
+constexpr unsigned long long kLehmerA = 16807ull;
+constexpr int kSamplerChunk = 64;                         // candidates per thread
+
+__device__ __forceinline__ unsigned int lehmer_mulmod(unsigned long long a, unsigned long long b) {
+    unsigned long long p = a * b;                         // < 2^62
+    p = (p & kLehmerM) + (p >> 31);
+    p = (p & kLehmerM) + (p >> 31);
+    return (unsigned int)(p >= kLehmerM ? p - kLehmerM : p);
+}
+
+__device__ __forceinline__ unsigned int lehmer_pow(unsigned long long e) {   // a^e mod m
+    unsigned int result = 1, base = (unsigned int)kLehmerA;
+    while (e) {
+        if (e & 1ull) result = lehmer_mulmod(result, base);
+        base = lehmer_mulmod(base, base);
+        e >>= 1;
+    }
+    return result;
+}
+
+struct SamplerParams {
+    const unsigned int* state_in;   // x_0
+    unsigned int* state_out;        // state after the last consumed candidate
+    long num_draws;                 // N = B * z
+    long num_candidates;            // T >= N + rejections (multiple of kSamplerChunk)
+    unsigned int scaling, past;
+    int z, R;
+    const idx_t* labels;            // [B]
+    idx_t* ids;                     // [B * R]
+    int* counts;                    // [T / chunk] accepted per chunk
+    const int* offsets;             // exclusive scan of counts (+ total at [nchunks])
+    int* error_flag;                // set when T was too small (caller falls back to the host sampler)
+};
+
+__global__ void __launch_bounds__(256) sampler_count_kernel(const SamplerParams p) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nchunks = p.num_candidates / kSamplerChunk;
+    if (t >= nchunks) return;
+    unsigned int x = lehmer_mulmod(lehmer_pow((unsigned long long)t * kSamplerChunk), *p.state_in);
+    int c = 0;
+#pragma unroll 8
+    for (int k = 0; k < kSamplerChunk; ++k) {
+        x = lehmer_mulmod(x, kLehmerA);
+        c += (x - 1u) < p.past;
+    }
+    p.counts[t] = c;
+}
+
+__global__ void __launch_bounds__(256) sampler_fill_kernel(const SamplerParams p) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nchunks = p.num_candidates / kSamplerChunk;
+    // positives
+    const long B = p.num_draws / max(p.z, 1);
+    for (long i = t; i < (p.z > 0 ? B : 0); i += (long)gridDim.x * blockDim.x) p.ids[i * p.R] = p.labels[i];
+    if (t >= nchunks) return;
+    long g = p.offsets[t];
+    if (t == nchunks - 1 && p.offsets[nchunks] < p.num_draws) *p.error_flag = 1;
+    if (g >= p.num_draws) return;
+    unsigned int x = lehmer_mulmod(lehmer_pow((unsigned long long)t * kSamplerChunk), *p.state_in);
+    for (int k = 0; k < kSamplerChunk && g < p.num_draws; ++k) {
+        x = lehmer_mulmod(x, kLehmerA);
+        const unsigned int ret = x - 1u;
+        if (ret < p.past) {
+            p.ids[(g / p.z) * p.R + 1 + (g % p.z)] = (idx_t)(ret / p.scaling);
+            if (g == p.num_draws - 1) *p.state_out = x;
+            ++g;
+        }
+    }
+}
+
+// offsets[nchunks] = total accepted (scan_add_kernel wrote its own `total` argument there)
+__global__ void sampler_total_kernel(const int* __restrict__ counts, int* __restrict__ offsets, long nchunks) {
+    offsets[nchunks] = offsets[nchunks - 1] + counts[nchunks - 1];
+}
+
+__global__ void sampler_copy_labels_kernel(const idx_t* __restrict__ labels, long B, idx_t* __restrict__ ids) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) ids[i] = labels[i];   // z == 0: R == 1
+}
+
+}  // namespace nvsm

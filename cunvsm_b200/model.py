@@ -307,6 +307,40 @@ class Model:
         check(self.L.nvsm_train_step(self.h, _pl(batch.features_), _pf(batch.feature_weights_), _pl(entity_ids),
                                      _pf(batch.weights_), B, learning_rate))
 
+    # --- device sampler ---------------------------------------------------------------------
+    def sampler_seed(self, rng):
+        """Move the engine state to the device (nvsm_sampler_seed)."""
+        check(self.L.nvsm_sampler_seed(self.h, rng.state))
+
+    def sampler_state(self):
+        st = ctypes.c_ulong()
+        check(self.L.nvsm_sampler_state(self.h, ctypes.byref(st)))
+        return st.value
+
+    def step_sampled(self, batch, learning_rate, train=True):
+        """Upload the batch, draw the negatives on the device (bit-exact with the host sampler) and run
+        compute_cost (+ compute_gradients + update when train). No synchronisation."""
+        self._keepalive = (batch,)
+        check(self.L.nvsm_step_sampled(self.h, _pl(batch.features_), _pf(batch.feature_weights_), _pl(batch.labels_),
+                                       _pf(batch.weights_), batch.num_instances_, learning_rate, int(train)))
+
+    def generate_labels_device(self, labels, rng, z=None, num_objects=None):
+        """nvsm_generate_labels on the device (bit-exact): returns ids [B*(z+1)], advances rng."""
+        labels = np.ascontiguousarray(labels, dtype=np.int64)
+        z = self.train_config.num_random_entities if z is None else z
+        D = self.num_entities if num_objects is None else num_objects
+        out = np.zeros(labels.size * (z + 1), dtype=np.int64)
+        st = ctypes.c_ulong(rng.state)
+        check(self.L.nvsm_generate_labels_device(self.h, _pl(labels), labels.size, z, D, ctypes.byref(st), _pl(out)))
+        rng.state = st.value
+        return out
+
+    def entity_ids(self, num_instances):
+        n = num_instances * (self.train_config.num_random_entities + 1)
+        out = np.zeros(n, dtype=np.int64)
+        check(self.L.nvsm_get_entity_ids(self.h, _pl(out), n))
+        return out
+
     def stage_batch(self, slot, batch, entity_ids):
         entity_ids = np.ascontiguousarray(entity_ids, dtype=np.int64)
         check(self.L.nvsm_stage_batch(self.h, slot, _pl(batch.features_), _pf(batch.feature_weights_),

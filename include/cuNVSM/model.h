@@ -161,11 +161,31 @@ class Model {
            static_cast<size_t>(desc_.word_repr_size()) * desc_.entity_repr_size() + desc_.entity_repr_size();
   }
 
+  // Optional: keep the std::minstd_rand0 state on the device and draw the negatives there (bit-exact
+  // with the host loop). While enabled, compute_cost ignores its RNG* argument; sync_rng() writes the
+  // device engine state back into the caller's RNG (synchronises).
+  void use_device_sampler(RNG* const rng) {
+    NVSM_ABORT_ON(nvsm_sampler_seed(handle_, nvsm_detail::rng_get_state(*rng)));
+    device_sampler_ = true;
+  }
+  void sync_rng(RNG* const rng) {
+    if (!device_sampler_) return;
+    unsigned long st = 0;
+    NVSM_ABORT_ON(nvsm_sampler_state(handle_, &st));
+    nvsm_detail::rng_set_state(rng, st);
+  }
+
   // reference: Model::compute_cost, cpp/objective.cu:30-313. Negatives are drawn from `rng` on the
   // host exactly like UniformLabelGenerator (cpp/labels.cu:3-22).
   ForwardResult* compute_cost(const Batch& batch, RNG* const rng) const {
     const size_t B = batch.num_instances(), R = train_config_.num_random_entities() + 1;
     NVSM_CHECK(batch.window_size() == static_cast<size_t>(train_config_.window_size()), "window size mismatch");
+    if (device_sampler_) {
+      NVSM_ABORT_ON(nvsm_step_sampled(handle_, batch.features(), batch.feature_weights(), batch.labels(), batch.weights(),
+                                      B, 0.0f, /*train=*/0));
+      ++forward_counter_;
+      return new ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
+    }
     entity_ids_.resize(B * R);
     unsigned long st = nvsm_detail::rng_get_state(*rng);
     NVSM_ABORT_ON(nvsm_generate_labels(batch.labels(), B, train_config_.num_random_entities(), num_entities_, &st,
@@ -243,6 +263,7 @@ class Model {
   const size_t num_words_, num_entities_;
   nvsm_model* handle_ = nullptr;
   bool initialized_ = false;
+  bool device_sampler_ = false;
   mutable std::vector<long> entity_ids_;
   mutable long forward_counter_ = 0;
 };

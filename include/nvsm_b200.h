@@ -138,6 +138,22 @@ NVSM_API int nvsm_train_step(nvsm_model* m, const long* features, const float* f
                     const long* entity_ids, const float* weights, long num_instances,
                     float learning_rate);
 
+/* Device-side negative sampler, bit-exact with nvsm_generate_labels (same std::minstd_rand0 stream,
+ * same libstdc++ uniform_int_distribution rejections): the engine state lives on the device between
+ * steps. nvsm_step_sampled = upload features / feature_weights / labels / weights (HOST buffers),
+ * draw the z negatives per instance on the device, compute_cost and — when train != 0 —
+ * compute_gradients + update (lambda / B). No synchronisation. */
+NVSM_API int nvsm_sampler_seed(nvsm_model* m, unsigned long rng_state);
+NVSM_API int nvsm_sampler_state(nvsm_model* m, unsigned long* rng_state);   /* synchronises */
+NVSM_API int nvsm_step_sampled(nvsm_model* m, const long* features, const float* feature_weights,
+                               const long* labels, const float* weights, long num_instances,
+                               float learning_rate, int train);
+NVSM_API int nvsm_get_entity_ids(nvsm_model* m, long* out, long n);         /* ids of the running step */
+/* nvsm_generate_labels on the device: host labels in, host ids out, *rng_state advanced. */
+NVSM_API int nvsm_generate_labels_device(nvsm_model* m, const long* labels, long num_labels,
+                                         long num_negative_labels, long num_objects,
+                                         unsigned long* rng_state, long* out);
+
 /* Device-resident batches: copy a host batch into slot `slot` once, then run steps on it
  * without host traffic. */
 NVSM_API int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float* feature_weights,

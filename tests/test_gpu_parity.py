@@ -319,3 +319,64 @@ def test_full_size_c2_full_adam_runs_and_learns():
         costs.append(m.last_cost())
     assert np.isfinite(costs).all()
     assert costs[-1] < costs[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-side sampler: bit-exact with the reference's host loop (cpp/labels.cu:3-22)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,z,B,seed", [(3, 10, 32, 10), (50000, 10, 51200, 1), (1000000, 32, 4096, 77), (200, 4, 4096, 5),
+                                        (7, 0, 100, 4), (1, 5, 64, 2)])
+def test_device_sampler_bit_exact(D, z, B, seed):
+    """ids and engine state after three consecutive batches (engine state kept on the device) equal the
+    oracle's serial std::uniform_int_distribution<long> draws."""
+    n = 2
+    desc = nv.ModelDesc(word_repr_size=4, entity_repr_size=4, clip_sigmoid=True)
+    tc = nv.TrainConfig(batch_size=B, window_size=n, num_random_entities=z)
+    m = nv.Model(10, D, desc, tc)
+    rng = nv.RNG(seed)
+    m.sampler_seed(rng)
+    state = rng.state
+    nrng = np.random.default_rng(seed)
+    for step in range(3):
+        labels = nrng.integers(0, D, size=B, dtype=np.int64)
+        batch = nv.Batch(B, n).fill(np.zeros((B, n)), labels)
+        m.step_sampled(batch, 0.0, train=False)
+        got = m.entity_ids(B)
+        exp, state = O.generate_labels(labels, z, D, state)
+        assert (got == exp).all(), "step %d" % step
+        assert m.sampler_state() == state
+
+
+@pytest.mark.parametrize("D,z,B,seed", [(1 << 30, 3, 20000, 9), (1500000000, 2, 40000, 3), (2147483645, 1, 30000, 11),
+                                        (1073741825, 4, 10000, 6), (50000, 10, 51200, 2)])
+def test_device_sampler_large_range(D, z, B, seed):
+    """Stand-alone device sampling for ranges where libstdc++'s rejection loop fires often
+    (D = 1.5e9 rejects ~30%, D = 2^30 + 1 rejects ~50% of the candidates)."""
+    m = nv.Model(4, 4, nv.ModelDesc(word_repr_size=4, entity_repr_size=4), nv.TrainConfig(batch_size=8, window_size=1))
+    labels = np.random.default_rng(seed).integers(0, D, size=B, dtype=np.int64)
+    rng = nv.RNG(seed)
+    got = m.generate_labels_device(labels, rng, z=z, num_objects=D)
+    exp, state = O.generate_labels(labels, z, D, seed)
+    assert (got == exp).all()
+    assert rng.state == state
+
+
+def test_device_sampled_step_equals_host_sampled_step():
+    """nvsm_step_sampled == nvsm_generate_labels + nvsm_train_step (same ids => same costs, same tables)."""
+    c = dict(V=400, D=300, dw=32, dd=32, n=4, z=6, B=1024, nonlinearity=nv.HARD_TANH, bn=True,
+             method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE)
+    a, _, rng_a = twin_models(**c)
+    b, _, rng_b = twin_models(**c)
+    assert rng_a.state == rng_b.state
+    b.sampler_seed(rng_b)
+    nrng = np.random.default_rng(1)
+    for step in range(4):
+        f, fw, labels, w = make_batch(nrng, c["B"], c["n"], c["V"], c["D"], c["z"])
+        batch = nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w)
+        ids = a.generate_labels(labels, rng_a)
+        a.train_step(batch, ids, 0.001)
+        b.step_sampled(batch, 0.001)
+        assert (b.entity_ids(c["B"]) == ids).all()
+        assert abs(a.last_cost() - b.last_cost()) <= 1e-6 * abs(a.last_cost())
+    assert b.sampler_state() == rng_a.state
+    assert_close(b.get_tensor(nv.ENTITY_REPRS), a.get_tensor(nv.ENTITY_REPRS), 1e-5, 1e-6)
