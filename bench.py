@@ -324,6 +324,11 @@ def run_ours(args, w, rank, world, local_rank):
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    # achieved counts ALGORITHMIC bytes (every referenced row gathered once and read-modify-written
+                    # once); rows are referenced ~10x per step and the tables fit the 126 MB L2, so most of that is
+                    # served by L2 and frac can exceed 1. dram_gbs is the ncu-measured DRAM traffic over the same time.
+                    "dram_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if (traffic and dom_ms > 0) else None,
+                    "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if (traffic and dom_ms > 0) else None,
                     "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
                     "step_algorithmic_gbs": total_alg / (ms / args.steps * 1e-3) / 1e9,
                     "phase_ms": {k: round(v, 4) for k, v in phases.items()}}

@@ -86,5 +86,34 @@ def full(src, dst):
             f.write("| %s | %s |\n" % (short(r[k]), " | ".join(vals)))
 
 
+PHASE_OF = [("gather_mean", "gather_mean"), ("score_", "score_loss_bwd"), ("adam_full_pull_kernel<4, 2, 1>", "update_entities"),
+            ("adam_full_pull_kernel<4, 3, 0>", "update_words"), ("entity_scatter", "update_entities"),
+            ("word_scatter", "update_words"), ("bn_backward_kernel", "bn_backward"), ("gemm_tc_kernel<1, 1", "gemm_grad_transform")]
+
+
+def traffic(src, dst, workload="C2"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of the dominant kernel of each
+    bench phase -> profiles/traffic.json (read by bench.py for roofline.traffic)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, rows = rows[0], rows[1], rows[2:]
+    k, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    acc = {}
+    for r in rows:
+        name = short(r[k])
+        for pat, phase in PHASE_OF:
+            if pat in name:
+                b = (to_mb(r[ir].replace(",", ""), units[ir]) + to_mb(r[iw].replace(",", ""), units[iw])) * 1e6
+                acc.setdefault(phase, []).append(b)
+                break
+    data = json.load(open(dst)) if os.path.exists(dst) else {}
+    data[workload] = {ph: int(sum(v) / len(v)) for ph, v in acc.items()}
+    data["_source"] = "ncu --set full --clock-control none capture %s (per launch, bytes)" % os.path.basename(src)
+    json.dump(data, open(dst, "w"), indent=1)
+    print(data)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
