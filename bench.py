@@ -43,6 +43,10 @@ WORKLOADS = {
     "C3": dict(name="NVSM hard_tanh+BN B=51200 V=200k D=500k d_w=300 d_d=256 n=10 z=16 adagrad",
                V=200000, D=500000, dw=300, dd=256, n=10, z=16, B=51200, nonlinearity="hard_tanh", bn=True,
                update_method="adagrad", lr=1e-2, lam=1e-2, bias_neg=False),
+    # configs[4] — LSE with bias_negative_samples, large document table (per-GPU batch 4096).
+    "C5": dict(name="LSE tanh bias_negative_samples B=4096 V=100k D=1M d=128 n=10 z=32 sgd",
+               V=100000, D=1000000, dw=128, dd=128, n=10, z=32, B=4096, nonlinearity="tanh", bn=False,
+               update_method="sgd", lr=1e-2, lam=1e-2, bias_neg=True),
     # configs[0] — the reference's own small LSE case.
     "C1": dict(name="LSE tanh B=4096 V=2k D=200 d=64 n=10 z=4", V=2000, D=200, dw=64, dd=64, n=10, z=4, B=4096,
                nonlinearity="tanh", bn=False, update_method="sgd", lr=1e-2, lam=1e-2, bias_neg=False),

@@ -140,8 +140,9 @@ void repr_storage_update(F* repr, size_t num_objects, size_t dim,
                          const std::vector<SparseGrad<F>>& descs, F lr, F lambda) {
     if (lambda > 0.0) {
         const F s = 1.0 - (lambda * lr);
-        const size_t n = num_objects * dim;
-        for (size_t i = 0; i < n; ++i) repr[i] *= s;
+        const long n = (long)(num_objects * dim);
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < n; ++i) repr[i] *= s;
     }
     for (const SparseGrad<F>& d : descs) {
         for (size_t x = 0; x < d.num_grads; ++x)
@@ -158,7 +159,8 @@ void repr_storage_update(F* repr, size_t num_objects, size_t dim,
 template <typename F, typename Op>
 void update_dense(F* param, size_t n, const F* grad, F lr, F lambda, Op op) {
     const F s = 1.0 - lambda * lr;
-    for (size_t i = 0; i < n; ++i) param[i] = param[i] * s + op(grad[i]) * lr;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) param[i] = param[i] * s + op(grad[i]) * lr;
 }
 template <typename F> struct Identity { F operator()(F x) const { return x; } };
 template <typename F> struct Square { F operator()(F x) const { return x * x; } };
@@ -331,7 +333,8 @@ struct RepresentationsUpdater {
         repr_storage_update(m.data(), num_objects, dim, descs, F(1.0 - beta1), F(1.0));
         if (!sgd_reg) {
             const F l = (1.0 - beta1) * lambda;
-            for (size_t i = 0; i < num_objects * dim; ++i) m[i] += -l * repr[i];
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)(num_objects * dim); ++i) m[i] += -l * repr[i];
         }
         if (sgd_reg) {
             std::vector<std::vector<F>> keep;
@@ -344,21 +347,26 @@ struct RepresentationsUpdater {
         } else {
             std::vector<F> agg(num_objects * dim, 0);
             repr_storage_update(agg.data(), num_objects, dim, descs, F(1.0), F(0.0));
-            for (size_t i = 0; i < agg.size(); ++i) agg[i] += -lambda * repr[i];
-            for (size_t i = 0; i < agg.size(); ++i) agg[i] = agg[i] * agg[i];
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)agg.size(); ++i) {
+                agg[i] += -lambda * repr[i];
+                agg[i] = agg[i] * agg[i];
+            }
             update_dense(v.data(), v.size(), agg.data(), F(1.0 - beta2), F(1.0), Identity<F>());
         }
         const F bc = std::sqrt(1.0 - std::pow(beta2, t)) / (1.0 - std::pow(beta1, t));
         t += 1;
         if (adam_mode == DENSE_UPDATE) {
             const F s = 1.0 - lambda * lr;
-            for (size_t o = 0; o < num_objects; ++o)
+#pragma omp parallel for schedule(static)
+            for (long o = 0; o < (long)num_objects; ++o)
                 for (size_t k = 0; k < dim; ++k) {
                     const F g = (m[o * dim + k] / (std::sqrt(v[o]) + epsilon)) * bc;
                     repr[o * dim + k] = repr[o * dim + k] * s + g * lr;
                 }
         } else if (adam_mode == DENSE_UPDATE_DENSE_VARIANCE) {
-            for (size_t i = 0; i < num_objects * dim; ++i) {
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)(num_objects * dim); ++i) {
                 const F g = (m[i] / (std::sqrt(v[i]) + epsilon)) * bc;
                 repr[i] = repr[i] * F(1.0) + g * lr;
             }
@@ -539,10 +547,12 @@ struct Model {
         }
         // Transform::backward.
         if (cfg.nonlinearity == TANH) {
-            for (size_t i = 0; i < B * dd; ++i) Gp[i] = (1.0 - Y[i] * Y[i]) * Gp[i];
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)(B * dd); ++i) Gp[i] = (1.0 - Y[i] * Y[i]) * Gp[i];
         } else {
             const Clip<F> clip(-1.0, 1.0);
-            for (size_t i = 0; i < B * dd; ++i) Gp[i] = clip.deriv(Y[i]) * Gp[i];
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)(B * dd); ++i) Gp[i] = clip.deriv(Y[i]) * Gp[i];
         }
         gb.assign(dd, 0);
         if (!cfg.batch_normalization) {
