@@ -226,7 +226,7 @@ def run_reference(args, w, rank):
                             "global_batch": B,
                             "reference_build": "unmodified /root/reference/cpp/*.cu, nvcc -O3 -use_fast_math float32 NDEBUG, "
                                                "cuBLAS SGEMM + cuDNN batch-norm, over oracle/ref_shim's reconstruction of "
-                                               "the un-vendored device_matrix (one Thrust/CUDA kernel per op, stream-ordered "
+                                               "the un-vendored device_matrix (one Thrust/CUDA kernel per op, size-bucketed caching "
                                                "pool for cnmem)"},
                     cpu_baseline={"value": r["value"], "unit": "n-grams/s", "cores": 1, "kind": "reference", "sample": sample},
                     e2e={"value": r["value"], "unit": "n-grams/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

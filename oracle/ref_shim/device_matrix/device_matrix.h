@@ -2,7 +2,7 @@
 // `third_party/device_matrix-CMakeLists.txt:6-8`, GIT_TAG master, source NOT under /root/reference)
 // that the reference's training step calls. Written from the reference's call sites and tests
 // (SURVEY.md Appendix A); one straightforward Thrust / CUDA kernel or cuBLAS call per operation,
-// column-major storage, stream-ordered pool allocation standing in for cnmem.
+// column-major storage, a size-bucketed caching pool standing in for cnmem.
 //
 // TEST INFRASTRUCTURE: exists only so the UNMODIFIED reference sources compile into
 // oracle/_ref/libcunvsm_ref_{f32,f64}.so (oracle/ref_shim/Makefile). Nothing under cunvsm_b200/
@@ -18,6 +18,8 @@
 #include <initializer_list>
 #include <iostream>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <type_traits>
 #include <utility>
@@ -195,6 +197,60 @@ class ScopedProfiler {
   explicit ScopedProfiler(const char* const) {}
 };
 
+// Device memory pool standing in for cnmem (the allocator device_matrix links, CMakeLists.txt:49,78 of the
+// reference): blocks are cached by size and handed back without touching the driver, so the steady-state step
+// performs no cudaMalloc / cudaFree. All work is ordered on one stream, which makes immediate reuse safe.
+class MemoryPool {
+ public:
+  static MemoryPool* getInstance() {
+      static MemoryPool* const instance = new MemoryPool;  // leaked on purpose: outlives every static matrix.
+      return instance;
+  }
+
+  void* allocate(const size_t bytes) {
+      const size_t rounded = ((bytes > 0 ? bytes : 1) + 511) / 512 * 512;
+      {
+          ::std::lock_guard< ::std::mutex> guard(mutex_);
+          ::std::vector<void*>& bucket = free_[rounded];
+          if (!bucket.empty()) {
+              void* const ptr = bucket.back();
+              bucket.pop_back();
+              return ptr;
+          }
+      }
+      void* ptr = nullptr;
+      cudaError_t status = cudaMalloc(&ptr, rounded);
+      if (status != cudaSuccess) {
+          cudaGetLastError();
+          release_cached();
+          status = cudaMalloc(&ptr, rounded);
+      }
+      CCE(status);
+      return ptr;
+  }
+
+  void deallocate(void* const ptr, const size_t bytes) {
+      const size_t rounded = ((bytes > 0 ? bytes : 1) + 511) / 512 * 512;
+      ::std::lock_guard< ::std::mutex> guard(mutex_);
+      free_[rounded].push_back(ptr);
+  }
+
+ private:
+  MemoryPool() {}
+
+  void release_cached() {
+      ::std::lock_guard< ::std::mutex> guard(mutex_);
+      cudaDeviceSynchronize();
+      for (::std::map<size_t, ::std::vector<void*> >::iterator it = free_.begin(); it != free_.end(); ++it) {
+          for (size_t i = 0; i < it->second.size(); ++i) cudaFree(it->second[i]);
+          it->second.clear();
+      }
+  }
+
+  ::std::mutex mutex_;
+  ::std::map<size_t, ::std::vector<void*> > free_;
+};
+
 template <typename FloatT>
 class Runtime {
  public:
@@ -212,11 +268,6 @@ class Runtime {
       CCE(cudaGetDevice(&device));
       CCE(cudaGetDeviceProperties(&props_, device));
       CCBE(cublasCreate(&handle_));
-      // Stream-ordered pool that keeps freed blocks (cnmem's behaviour): no cudaMalloc on the step.
-      cudaMemPool_t pool;
-      CCE(cudaDeviceGetDefaultMemPool(&pool, device));
-      unsigned long long threshold = ~0ull;
-      CCE(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   }
 
   cudaDeviceProp props_;
@@ -241,14 +292,12 @@ class device_matrix {
 
   device_matrix(const size_t rows, const size_t cols, const cudaStream_t stream)
       : rows_(rows), cols_(cols), stream_(stream), data_(nullptr) {
-      Runtime<float>::getInstance();  // pool configuration.
-      CCE(cudaMallocAsync(reinterpret_cast<void**>(&data_),
-                          ::std::max<size_t>(size(), 1) * sizeof(FloatT), stream_));
+      data_ = static_cast<FloatT*>(MemoryPool::getInstance()->allocate(size() * sizeof(FloatT)));
   }
 
   ~device_matrix() {
       if (data_ != nullptr) {
-          cudaFreeAsync(data_, stream_);
+          MemoryPool::getInstance()->deallocate(data_, size() * sizeof(FloatT));
       }
   }
 

@@ -30,7 +30,8 @@ KEEP = [
 def short(name):
     name = re.sub(r"^void ", "", name)
     name = re.sub(r"\(.*$", "", name)
-    return name.replace("nvsm::", "")
+    name = name.replace("nvsm::", "")
+    return name if len(name) <= 120 else name[:117] + "..."
 
 
 def to_mb(value, unit):
