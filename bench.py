@@ -274,7 +274,7 @@ def run_ours(args, w, rank, world, local_rank):
     rng = nv.RNG(1)
     model.initialize(rng)   # identical on every rank: same seed, same engine
     from cunvsm_b200 import sharding
-    sharding.init_model_comm(model, dist, rank, world)
+    sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0)
 
     # synthetic batches: every rank owns its own shard of n-gram rows
     raw = make_batches(w, B, 1234 + rank, NUM_BATCHES)
@@ -351,7 +351,7 @@ def run_ours(args, w, rank, world, local_rank):
         model = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=1, num_batch_slots=NUM_BATCHES)
         model.set_stream(stream.cuda_stream)
         model.initialize(nv.RNG(1))
-        sharding.init_model_comm(model, dist, rank, world)
+        sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0)
         for s_ in range(NUM_BATCHES):
             model.stage_batch(s_, batches[s_], ids_np[s_])
         staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
@@ -406,7 +406,8 @@ def run_ours(args, w, rank, world, local_rank):
                        "global_batch": B * world, "gemm": ["fp32_simt", "tf32_tcgen05", "3xtf32_tcgen05"][args.gemm_mode],
                        "l2": "working set (tables + moments + per-step tensors, > 1 GB) exceeds the 126 MB L2; "
                              "%d distinct batches cycled" % NUM_BATCHES,
-                       "sparse_tables": "replicated, per-rank local updates" if world > 1 else "single GPU",
+                       "sparse_tables": ("single GPU" if world == 1 else "replicated, per-rank local updates" if args.sparse_sync == "local"
+                                         else "replicated, rows all-gathered: every replica applies the global update"),
                        "negatives": "value: pre-sampled (bit-exact host sampler) and staged with the batch; e2e: drawn "
                                     "inside the timed step by the bit-exact device sampler"},
             "e2e": {"value": ngrams / (ms_e2e * 1e-3), "unit": "n-grams/s", "h2d_bytes_per_step": h2d,
@@ -433,6 +434,9 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--reference_kind", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: auto = the reference's own CUDA step (oracle/_ref) when built, else the CPU port")
+    ap.add_argument("--sparse_sync", default="local", choices=["local", "allgather"],
+                    help="N>1: local = per-rank sparse updates (north-star prescription, default); allgather = exact "
+                         "single-GPU trajectory (every replica applies all rows' updates)")
     ap.add_argument("--no_alt", action="store_true", help="skip the extra single-pass TF32 measurement")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

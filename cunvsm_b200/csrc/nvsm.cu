@@ -163,6 +163,11 @@ struct nvsm_model {
     // multi-GPU
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
+    // NVSM_SPARSE_ALLGATHER: every rank applies the table updates of ALL rows (exact single-GPU trajectory).
+    int sparse_mode = NVSM_SPARSE_LOCAL;
+    BatchSlot ag_slot;                  // gathered features / weights / ids of the global batch
+    float *ag_mult = nullptr, *ag_act = nullptr, *ag_gP = nullptr, *ag_rowtmp = nullptr;
+    int *ag_e_refs = nullptr, *ag_w_refs = nullptr;
 
     double* fwd_sums() { return dsums; }
     double* var_sums() { return dsums + 2 * dd; }
@@ -406,6 +411,14 @@ int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
     return 0;
 }
 
+int allgather_bytes(nvsm_model* m, const void* src, void* dst, size_t bytes_per_rank) {
+    int rc = nccl_api().AllGather(src, dst, bytes_per_rank, kNcclInt8, m->comm, (void*)m->stream);
+    if (rc != 0) return fail("ncclAllGather: %s", nccl_api().GetErrorString(rc));
+    return 0;
+}
+
+bool exact_sparse(const nvsm_model* m) { return m->nranks > 1 && m->sparse_mode == NVSM_SPARSE_ALLGATHER; }
+
 // ------------------------------------------------------------------------------------
 // forward: Model::compute_cost on a device-resident batch
 // ------------------------------------------------------------------------------------
@@ -496,7 +509,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
     m->have_forward = false;
     m->have_gradients = false;
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
-    if (m->pull) TRY(start_bucket_build(m, s));
+    if (m->pull && !exact_sparse(m)) TRY(start_bucket_build(m, s));  // (gathered ids only exist at update time)
     const bool bn = m->cfg.batch_normalization != 0;
     const int dw = m->dw, dd = m->dd;
 
@@ -890,15 +903,65 @@ int update_transform(nvsm_model* m, float lr, float lambda) {
     return 0;
 }
 
+// NVSM_SPARSE_ALLGATHER (SURVEY.md 8e "parity mode"): gather every rank's rows of (entity ids, multipliers,
+// activations, word ids, word weights, grad_phrase) so that each replica applies the table updates of the whole
+// global batch. Returns with the model's per-step pointers redirected to the gathered copies; `saved` restores them.
+struct LocalView {
+    BatchSlot* cur; long B; float *mult, *Z, *Y, *gP, *rowtmp; int *e_refs, *w_refs;
+};
+
+int gather_global_batch(nvsm_model* m, LocalView* saved) {
+    const long B = m->B, W = m->nranks;
+    BatchSlot* s = m->cur;
+    phase_begin(m, PH_ALLREDUCE);
+    TRY(allgather_bytes(m, s->ids, m->ag_slot.ids, sizeof(idx_t) * B * m->R));
+    TRY(allgather_bytes(m, m->mult, m->ag_mult, sizeof(float) * B * m->R));
+    TRY(allgather_bytes(m, m->pull ? m->Y : m->Z, m->ag_act, sizeof(float) * B * m->dd));
+    TRY(allgather_bytes(m, s->features, m->ag_slot.features, sizeof(idx_t) * B * m->n));
+    TRY(allgather_bytes(m, s->fweights, m->ag_slot.fweights, sizeof(float) * B * m->n));
+    TRY(allgather_bytes(m, m->gP, m->ag_gP, sizeof(float) * B * m->dw));
+    phase_end(m);
+    *saved = LocalView{m->cur, m->B, m->mult, m->Z, m->Y, m->gP, m->rowtmp, m->e_refs, m->w_refs};
+    m->ag_slot.B = B * W;
+    m->cur = &m->ag_slot; m->B = B * W;
+    m->mult = m->ag_mult; m->Z = m->ag_act; m->Y = m->ag_act; m->gP = m->ag_gP; m->rowtmp = m->ag_rowtmp;
+    m->e_refs = m->ag_e_refs; m->w_refs = m->ag_w_refs;
+    return 0;
+}
+
+void restore_local_view(nvsm_model* m, const LocalView& v) {
+    m->cur = v.cur; m->B = v.B; m->mult = v.mult; m->Z = v.Z; m->Y = v.Y; m->gP = v.gP; m->rowtmp = v.rowtmp;
+    m->e_refs = v.e_refs; m->w_refs = v.w_refs;
+}
+
 int update(nvsm_model* m, float lr, float lambda) {
     if (!m->have_gradients) return fail("update called without gradients");
     if (lr < 0.f || lambda < 0.f) return fail("learning rate and lambda must be >= 0");
+    const bool exact = exact_sparse(m);
+    LocalView local{};
+    if (exact) {
+        TRY(gather_global_batch(m, &local));
+        if (m->pull) {  // buckets over the gathered ids, on the main stream
+            phase_begin(m, PH_UPD_ENTITIES);
+            int rc = build_buckets(m, m->cur->ids, m->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs);
+            if (rc == 0) rc = build_buckets(m, m->cur->features, m->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs);
+            phase_end(m);
+            if (rc) { restore_local_view(m, local); return rc; }
+            CU(cudaEventRecord(m->buckets_ready, m->stream));
+            m->buckets_in_flight = true;
+        }
+    }
+    int rc = 0;
     phase_begin(m, PH_UPD_ENTITIES);
-    TRY(update_table(m, true, lr, lambda));
+    rc = update_table(m, true, lr, lambda);
     phase_end(m);
-    phase_begin(m, PH_UPD_WORDS);
-    TRY(update_table(m, false, lr, lambda));
-    phase_end(m);
+    if (rc == 0) {
+        phase_begin(m, PH_UPD_WORDS);
+        rc = update_table(m, false, lr, lambda);
+        phase_end(m);
+    }
+    if (exact) restore_local_view(m, local);
+    if (rc) return rc;
     if (m->pull) {
         CU(cudaEventRecord(m->buckets_consumed, m->stream));
         m->buckets_ever_consumed = true;
@@ -1117,6 +1180,11 @@ void nvsm_destroy(nvsm_model* m) {
     for (int* p : il)
         if (p) cudaFree(p);
     if (m->Y) cudaFree(m->Y);
+    void* ag[] = {m->ag_slot.ids, m->ag_slot.features, m->ag_slot.fweights, m->ag_mult, m->ag_act, m->ag_gP, m->ag_rowtmp,
+                  m->ag_e_refs, m->ag_w_refs};
+    for (void* p : ag)
+        if (p) cudaFree(p);
+    m->ag_slot.ids = nullptr; m->ag_slot.features = nullptr; m->ag_slot.fweights = nullptr;
     if (m->rng_dev) cudaFree(m->rng_dev);
     int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
     for (int* p : sl)
@@ -1681,6 +1749,22 @@ int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank) {
     if (rc != 0) return fail("ncclCommInitRank: %s", nccl_api().GetErrorString(rc));
     m->nranks = num_ranks;
     m->rank = rank;
+    return 0;
+}
+
+int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode) {
+    if (!m) return fail("null argument");
+    if (mode != NVSM_SPARSE_LOCAL && mode != NVSM_SPARSE_ALLGATHER) return fail("unknown sparse mode %d", mode);
+    if (mode == NVSM_SPARSE_ALLGATHER && m->nranks > 1 && !m->ag_mult) {
+        CU(cudaSetDevice(m->device));
+        const size_t G = (size_t)m->maxB * m->nranks;
+        TRY(dev_alloc(&m->ag_slot.ids, G * m->R)); TRY(dev_alloc(&m->ag_slot.features, G * m->n));
+        TRY(dev_alloc(&m->ag_slot.fweights, G * m->n));
+        TRY(dev_alloc(&m->ag_mult, G * m->R)); TRY(dev_alloc(&m->ag_act, G * m->dd)); TRY(dev_alloc(&m->ag_gP, G * m->dw));
+        TRY(dev_alloc(&m->ag_rowtmp, G));
+        if (m->pull) { TRY(dev_alloc(&m->ag_e_refs, G * m->R)); TRY(dev_alloc(&m->ag_w_refs, G * m->n)); }
+    }
+    m->sparse_mode = mode;
     return 0;
 }
 

@@ -29,6 +29,8 @@ UPDATE_METHODS = {
 }
 NONLINEARITIES = {"tanh": TANH, "hard_tanh": HARD_TANH}
 
+SPARSE_LOCAL, SPARSE_ALLGATHER = 0, 1
+
 WORD_REPRS = "word_representations-representations"
 ENTITY_REPRS = "entity_representations-representations"
 TRANSFORM = "word_entity_mapping-transform"
@@ -389,6 +391,11 @@ class Model:
 
     def comm_init(self, unique_id, num_ranks, rank):
         check(self.L.nvsm_comm_init(self.h, unique_id, num_ranks, rank))
+
+    def comm_set_sparse_mode(self, mode):
+        """SPARSE_LOCAL: per-rank local table updates; SPARSE_ALLGATHER: every replica applies the updates of
+        the whole global batch (the single-GPU trajectory)."""
+        check(self.L.nvsm_comm_set_sparse_mode(self.h, mode))
 
 
 def comm_unique_id():

@@ -39,13 +39,16 @@ def broadcast_unique_id(dist, make_id, rank, src=0):
     return bytes(uid)
 
 
-def init_model_comm(model, dist, rank, world):
-    """Attach an NCCL communicator to `model` (no-op for a single rank)."""
+def init_model_comm(model, dist, rank, world, sparse_mode=0):
+    """Attach an NCCL communicator to `model` (no-op for a single rank). sparse_mode: 0 = per-rank local
+    updates of the replicated tables, 1 = all-gather the rows so every replica applies the global update."""
     if world <= 1:
         return
     from .model import comm_unique_id
     uid = broadcast_unique_id(dist, comm_unique_id, rank)
     model.comm_init(uid, world, rank)
+    if sparse_mode:
+        model.comm_set_sparse_mode(sparse_mode)
 
 
 def max_over_ranks(dist, value, device=None):

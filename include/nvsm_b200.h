@@ -43,6 +43,8 @@ enum { NVSM_SGD = 0, NVSM_ADAGRAD = 1, NVSM_ADAM = 2 };
 enum { NVSM_ADAM_SPARSE = 1, NVSM_ADAM_DENSE_UPDATE = 2, NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE = 3 };
 /* projection GEMM arithmetic */
 enum { NVSM_GEMM_FP32 = 0, NVSM_GEMM_TF32 = 1, NVSM_GEMM_3XTF32 = 2 };
+/* Multi-GPU treatment of the sparse tables (nvsm_comm_set_sparse_mode). */
+enum { NVSM_SPARSE_LOCAL = 0, NVSM_SPARSE_ALLGATHER = 1 };
 
 /* lse::ModelDesc + lse::TrainConfig (proto/nvsm.proto:7-71) flattened; replaces the
  * arguments of Model::Model (include/cuNVSM/model.h:82-85). */
@@ -194,6 +196,14 @@ NVSM_API int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K,
  * sum over ranks. */
 NVSM_API int nvsm_comm_unique_id(char* id_out_128);
 NVSM_API int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank);
+
+/* How the replicated word / entity tables are updated when num_ranks > 1 (new: the reference is
+ * single-GPU). NVSM_SPARSE_LOCAL (default): each rank applies only the updates of its
+ * own rows, no exchange, replicas drift apart. NVSM_SPARSE_ALLGATHER: the ranks all-gather their rows of
+ * (entity ids, multipliers, activations, word ids, word weights, grad_phrase) with ncclAllGather and every
+ * replica applies the updates of the whole global batch, i.e. N GPUs follow the trajectory of
+ * Model::update (cpp/model.cu:187-220) on the global batch. Call after nvsm_comm_init. */
+NVSM_API int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode);
 
 #ifdef __cplusplus
 }

@@ -22,11 +22,56 @@ from cunvsm_b200 import sharding  # noqa: E402
 from tests.util import assert_close, make_batch  # noqa: E402
 
 
+def exact_mode(rank, world, local, gemm_mode):
+    V, D, dw, dd, n, z, B = 3000, 2000, 300, 256, 10, 10, 4096
+    combos = ((nv.SGD, 0, True, nv.HARD_TANH), (nv.ADAGRAD, 0, False, nv.TANH), (nv.ADAM, nv.SPARSE, True, nv.HARD_TANH),
+              (nv.ADAM, nv.DENSE_UPDATE, False, nv.TANH), (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE, True, nv.HARD_TANH))
+    for method, mode, bn, nl in combos:
+        desc = nv.ModelDesc(word_repr_size=dw, entity_repr_size=dd, batch_normalization=bn, nonlinearity=nl, clip_sigmoid=True)
+        mk = lambda bs: nv.TrainConfig(batch_size=bs, window_size=n, num_random_entities=z, regularization_lambda=0.01,
+                                       update_method=method, adam_mode=mode)
+        dm = nv.Model(V, D, desc, mk(B // world), device=local, gemm_mode=gemm_mode)
+        dm.initialize(nv.RNG(1))
+        sharding.init_model_comm(dm, dist, rank, world, sparse_mode=nv.SPARSE_ALLGATHER)
+        ref = nv.Model(V, D, desc, mk(B), device=local, gemm_mode=gemm_mode)
+        ref.initialize(nv.RNG(1))
+        nrng, srng, lr = np.random.default_rng(42), nv.RNG(777), 0.01
+        for step in range(3):
+            f, fw, labels, w = make_batch(nrng, B, n, V, D, z)
+            ids = ref.generate_labels(labels, srng)
+            sf, sfw, sl, sw, sids = sharding.shard_batch(f, fw, labels, w, ids, rank, world)
+            res_full = ref.compute_cost(nv.Batch(B, n).fill(f, labels, fw, w), entity_ids=ids)
+            ref.backprop(res_full, lr)
+            res = dm.compute_cost(nv.Batch(B // world, n).fill(sf, sl, sfw, sw), entity_ids=sids)
+            dm.backprop(res, lr)
+            tol = 2e-4 if gemm_mode == 0 else 2e-2
+            assert abs(res.get_cost() - res_full.get_cost()) <= tol * abs(res_full.get_cost()), (method, mode, step)
+        # Adam steps are ~lr whatever the gradient's size: absolute floor of a fraction of lr for those modes.
+        floor = 1e-5 if method != nv.ADAM else 1e-3
+        rt = 5e-4 if gemm_mode == 0 else 2e-2
+        for name in (nv.ENTITY_REPRS, nv.WORD_REPRS, nv.TRANSFORM, nv.BIAS):
+            assert_close(dm.get_tensor(name), ref.get_tensor(name), rt, floor if gemm_mode == 0 else 2e-2,
+                         "%s after 3 all-gather steps (method %d mode %d)" % (name, method, mode))
+        # the replicas must not have drifted apart beyond fp32 summation order
+        E = torch.from_numpy(dm.get_tensor(nv.ENTITY_REPRS)).cuda()
+        Emax, Emin = E.clone(), E.clone()
+        dist.all_reduce(Emax, op=dist.ReduceOp.MAX); dist.all_reduce(Emin, op=dist.ReduceOp.MIN)
+        assert float((Emax - Emin).abs().max()) <= (1e-6 if method != nv.ADAM else 1e-4), float((Emax - Emin).abs().max())
+        dm.close(); ref.close()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gemm_mode = int(os.environ.get("NVSM_TEST_GEMM_MODE", "0"))
+    if int(os.environ.get("NVSM_TEST_SPARSE_MODE", "0")) == 1:
+        exact_mode(rank, world, local, gemm_mode)
+        dist.barrier()
+        if rank == 0:
+            print("MULTI_GPU_OK world=%d gemm_mode=%d sparse=allgather" % (world, gemm_mode))
+        dist.destroy_process_group()
+        return
     V, D, dw, dd, n, z, B = 3000, 2000, 300, 256, 10, 10, 4096
     for method, mode, bn, nl in ((nv.SGD, 0, True, nv.HARD_TANH), (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE, True, nv.HARD_TANH),
                                  (nv.ADAGRAD, 0, False, nv.TANH)):

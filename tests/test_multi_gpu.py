@@ -27,3 +27,15 @@ def test_sharded_step_matches_single_gpu(gemm_mode):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout
+
+
+def test_allgather_sparse_mode_matches_single_gpu_trajectory():
+    """NVSM_SPARSE_ALLGATHER: 2 ranks x 3 steps == 1 GPU x 3 steps on the whole batch, all five optimisers."""
+    if _ngpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    env = dict(os.environ, NVSM_TEST_GEMM_MODE="0", NVSM_TEST_SPARSE_MODE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29610", os.path.join(ROOT, "tests", "dist_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "MULTI_GPU_OK" in res.stdout and "sparse=allgather" in res.stdout
