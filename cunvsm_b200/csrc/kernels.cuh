@@ -65,6 +65,106 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
     }
 }
 
+// Single-pass variant for dim % 4 == 0 and dim <= 512 floats: a group of LG lanes (power of two, <= 32) owns
+// one n-gram; lane sl < L of the group keeps K float4 column groups (c = sl + j L) in registers, so every
+// table row is visited ONCE (K independent 16-byte loads per lane per word) instead of once per 32-column
+// pass, and the window's ids / weights are loaded once per n-gram (one lane each) and broadcast with
+// shuffles. ncu on the pass-per-32-columns kernel above (C2, d_w = 300): 942 warp instructions per n-gram,
+// issue slots 49 % busy, i.e. issue-bound, the third pass running 11 of 32 lanes; this layout needs ~270.
+// Division by the window follows the reference's release build (-use_fast_math => __fdividef,
+// CMakeLists.txt:71-73 of the reference).
+template <int K, int LG>
+__global__ void __launch_bounds__(256) gather_mean_lanes_kernel(const float* __restrict__ table, int dim,
+                                                                const idx_t* __restrict__ ids,
+                                                                const float* __restrict__ wts,
+                                                                long num_out, int window, int L,
+                                                                float* __restrict__ out, int ld_out, int tf32,
+                                                                float* __restrict__ out_lo) {
+    constexpr int kGroups = kWarp / LG;
+    constexpr int U = 5;   // words in flight per lane: U * K independent 16-byte loads
+    const int lane = threadIdx.x & 31;
+    const int sl = lane & (LG - 1);
+    const int grp = lane / LG;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim >> 2;
+    const float fwin = (float)window;
+    const float4* __restrict__ tab4 = reinterpret_cast<const float4*>(table);
+    // Lanes beyond the row (and groups beyond the batch) read clamped, valid addresses and skip the store:
+    // the load / FMA loop stays branch-free, which lets all U * K loads issue back to back.
+    int cj[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) cj[j] = min(sl + j * L, nvec - 1);
+    for (long o0 = warp0 * kGroups; o0 < num_out; o0 += nwarps * kGroups) {
+        const long o = min(o0 + grp, num_out - 1);
+        float4 acc[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w0 = 0; w0 < window; w0 += LG) {
+            const int chunk = min(LG, window - w0);
+            // one lane per word: vector offset of its row and its weight
+            unsigned my_row = 0;
+            float my_wt = 0.f;
+            if (sl < chunk) {
+                my_row = (unsigned)(__ldg(ids + o * window + w0 + sl) * nvec);
+                my_wt = wts ? __ldg(wts + o * window + w0 + sl) : 1.0f;
+            }
+            int w = 0;
+            for (; w + U <= chunk; w += U) {
+                float4 x[U][K];
+                float wt[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned row = __shfl_sync(kFull, my_row, w + u, LG);
+                    wt[u] = __shfl_sync(kFull, my_wt, w + u, LG);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) x[u][j] = __ldg(tab4 + row + cj[j]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        acc[j].x = fmaf(wt[u], x[u][j].x, acc[j].x); acc[j].y = fmaf(wt[u], x[u][j].y, acc[j].y);
+                        acc[j].z = fmaf(wt[u], x[u][j].z, acc[j].z); acc[j].w = fmaf(wt[u], x[u][j].w, acc[j].w);
+                    }
+                }
+            }
+            for (; w < chunk; ++w) {
+                const unsigned row = __shfl_sync(kFull, my_row, w, LG);
+                const float wt1 = __shfl_sync(kFull, my_wt, w, LG);
+                float4 x1[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) x1[j] = __ldg(tab4 + row + cj[j]);
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    acc[j].x = fmaf(wt1, x1[j].x, acc[j].x); acc[j].y = fmaf(wt1, x1[j].y, acc[j].y);
+                    acc[j].z = fmaf(wt1, x1[j].z, acc[j].z); acc[j].w = fmaf(wt1, x1[j].w, acc[j].w);
+                }
+            }
+        }
+        if (sl < L && o0 + grp < num_out) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int c = sl + j * L;
+                if (c >= nvec) continue;
+                float a[4] = {__fdividef(acc[j].x, fwin), __fdividef(acc[j].y, fwin), __fdividef(acc[j].z, fwin),
+                              __fdividef(acc[j].w, fwin)};
+                float lo[4] = {0.f, 0.f, 0.f, 0.f};
+                if (tf32) {   // P only feeds the tensor-core GEMMs: hi = rn_tf32(x), lo = x - hi (exact)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float hi = round_tf32(a[v]);
+                        lo[v] = a[v] - hi;
+                        a[v] = hi;
+                    }
+                }
+                store_vec<4>(out + o * ld_out + c * 4, a);
+                if (out_lo) store_vec<4>(out_lo + o * ld_out + c * 4, lo);
+            }
+        }
+    }
+}
+
 // =====================================================================================
 // col_stats: sums[c] += sum_i Z[i, c], sums[dd + c] += sum_i Z[i, c]^2 (double).
 // First half of cudnnBatchNormalizationForwardTraining, per-activation mode

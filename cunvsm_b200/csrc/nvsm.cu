@@ -443,8 +443,11 @@ int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t 
     return 0;
 }
 
-// Ring (cp.async.bulk) variant when the rows are 16-byte multiples and a >= 2-stage ring of
-// (R + 1) rows per warp fits in shared memory; returns -1 when it does not apply.
+// Staged (cp.async) variant when the rows are 16-byte multiples; returns -1 when it does not apply.
+// Policy: one stage per warp and as many warps per SM as shared memory allows (two 8-warp blocks for the NVSM
+// shape) -- measured on C2: 16 warps/SM x 1 stage 92.9 us vs 8 warps/SM x 2-stage prefetch ring 124.6 us; the
+// per-n-gram work is a dependent LDS -> FMA -> shuffle chain, so extra warps hide more than a deeper ring does.
+// The >= 2-stage ring is kept for stages so large that fewer than 8 single-stage warps fit.
 int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
     const int dd = sp.dd, R = sp.R;
     if (!vec4_ok(dd) || R > 32 || dd > 1024 || getenv("NVSM_NO_RING")) return -1;
@@ -454,12 +457,22 @@ int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
     int W = 8, S = 0;
     const char* ew = getenv("NVSM_SCORE_W"); const char* es = getenv("NVSM_SCORE_S");
     if (ew) W = std::max(1, std::min(8, atoi(ew)));
-    for (; W >= 2; W /= 2) {
-        S = (int)std::min<size_t>(4, (budget - fixed) / (W * stage_bytes));
-        if (S >= 2 || ew) break;
+    if (!ew && !es) {
+        // single stage: blocks of W warps, as many blocks per SM as fit
+        for (W = 8; W >= 2; W /= 2) {
+            const size_t blocks = budget / (W * stage_bytes + fixed + 1024);
+            if (blocks * W >= 8) { S = 1; break; }
+        }
+        if (S == 0) W = 8;
     }
-    if (es) S = std::min(S, std::max(2, atoi(es)));
-    if (S < 2) return -1;
+    if (S == 0) {
+        for (; W >= 2; W /= 2) {
+            S = (int)std::min<size_t>(4, (budget - fixed) / (W * stage_bytes));
+            if (S >= 2 || ew) break;
+        }
+        if (es) S = std::min(S, std::max(1, atoi(es)));
+    }
+    if (S < 1) return -1;
     ScoreRingParams q;
     q.s = sp; q.stages = S; q.warps = W; q.bn_scale = m->bn_scale; q.bn_shift = m->bn_shift;
     const size_t smem = (size_t)W * S * stage_bytes + (size_t)(4 * dd + 2) * 4 + (size_t)W * S * 8;
@@ -521,7 +534,24 @@ int forward(nvsm_model* m, BatchSlot* s) {
     phase_begin(m, PH_GATHER);
     {
         const int grid = grid_for(m, B, 8, 8);
-        if (vec4_ok(dw))
+        const int nvec = dw / 4;
+        if (vec4_ok(dw) && nvec <= 128 && (long)m->V * nvec < (1L << 32)) {
+            // K float4 per lane, L active lanes per n-gram, LG = group width (power of two)
+            const int K = (nvec + 31) / 32, L = (nvec + K - 1) / K;
+            int LG = 1;
+            while (LG < L) LG <<= 1;
+            const int tf = m->use_tc ? 1 : 0;
+#define NVSM_GATHER(KK, GG) LAUNCH(m, (gather_mean_lanes_kernel<KK, GG>), grid_for(m, B / (32 / GG) + 1, 8, 8), 256, 0, m->W, dw, \
+                                   s->features, s->fweights, B, m->n, L, m->P, m->ldP, tf, m->P_lo)
+            if (K == 1 && LG <= 4) NVSM_GATHER(1, 4);
+            else if (K == 1 && LG == 8) NVSM_GATHER(1, 8);
+            else if (K == 1 && LG == 16) NVSM_GATHER(1, 16);
+            else if (K == 1) NVSM_GATHER(1, 32);
+            else if (K == 2) NVSM_GATHER(2, 32);
+            else if (K == 3) NVSM_GATHER(3, 32);
+            else NVSM_GATHER(4, 32);
+#undef NVSM_GATHER
+        } else if (vec4_ok(dw))
             LAUNCH(m, gather_mean_kernel<4>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP, m->use_tc ? 1 : 0, m->P_lo);
         else
             LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP, m->use_tc ? 1 : 0, m->P_lo);

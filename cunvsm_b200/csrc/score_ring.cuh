@@ -1,6 +1,6 @@
 // score_ring_kernel — the fused score / NCE loss / backward-through-dot kernel (see
 // kernels.cuh:score_kernel for the arithmetic and the reference citations) with the row traffic
-// moved off the register file: every warp owns a ring of `S` shared-memory stages, one stage = the
+// moved off the register file: every warp owns `S` shared-memory stages (S = 1 by default, see try_score_ring), one stage = the
 // pre-activation row Z[i] plus the R entity rows E[id[i,0..R)] of one n-gram, filled with 16-byte
 // cp.async (LDGSTS) copies, one commit group per n-gram. While the warp works on n-gram j from
 // stage j % S, the copies of n-grams j+1 .. j+S-1 are in flight, and the ids / instance weight of
@@ -145,14 +145,15 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     for (long j = 0; j < my_count; ++j) {
         const long i = warp0 + j * nwarps;
         // keep the ring full: n-gram j+S-1 goes into the stage consumed at iteration j-1
-        if (S == 2) iw_q[1] = niw; else if (S == 3) iw_q[2] = niw; else iw_q[3] = niw;
+        if (S == 1) iw_q[0] = niw; else if (S == 2) iw_q[1] = niw; else if (S == 3) iw_q[2] = niw; else iw_q[3] = niw;
         issue(j + S - 1, nid0);
         fetch_meta(j + S, nid0, niw);
 
         const int s = (int)(j % S);
         // groups j .. j+S-1 are outstanding: wait until at most S-1 remain, then make every lane's
         // copies visible to the whole warp
-        if (S == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (S == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (S == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else if (S == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
         else asm volatile("cp.async.wait_group 3;" ::: "memory");
         __syncwarp();

@@ -180,3 +180,37 @@ def test_cuda_tensor_core_path_matches_reference_nvsm_shape():
         err = np.linalg.norm(delta - delta_ref) / max(np.linalg.norm(delta_ref), 1e-30)
         assert err <= 1e-2, (rname, err)
         assert np.abs(delta - delta_ref).max() <= 0.05 * 5 * 1e-3, (rname, np.abs(delta - delta_ref).max())
+
+
+@pytest.mark.parametrize("gemm_mode", [nv.GEMM_FP32, nv.GEMM_3XTF32], ids=["fp32", "3xtf32"])
+def test_loss_curve_matches_reference_1000_steps(gemm_mode):
+    """North-star bar: the loss curve of the sm_100a path stays within 1e-3 of the REFERENCE's (float32 release
+    build, its own host sampler, cuBLAS SGEMM + cuDNN batch-norm) over 1000 steps of the NVSM recipe
+    (batch-norm + hard_tanh, full Adam, lambda 0.01, lr 1e-3) from the same seed."""
+    c = dict(V=5000, D=20000, dw=64, dd=64, n=6, z=5, B=2048, nonlinearity=nv.HARD_TANH, bn=True, clip=True,
+             bias_neg=False)
+    method = (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)
+    rm = ref_model(c, method, np.float32)
+    gm = cuda_model(c, method, gemm_mode=gemm_mode)
+    rng = nv.RNG(7)
+    gm.initialize(rng)
+    nrng = np.random.default_rng(0)
+    batches = []
+    for _ in range(40):
+        f, fw, labels, w = make_batch(nrng, c["B"], c["n"], c["V"], c["D"], c["z"], weighted=False)
+        labels = (f[:, 0] * 4 + f[:, 1] % 4) % c["D"]      # learnable: the document depends on the first two words
+        batches.append((rm.new_batch().fill(f, labels, fw, w), nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w)))
+    lr, g_costs, r_costs = 1e-3, [], []
+    for step in range(1000):
+        rb, gb = batches[step % len(batches)]
+        r_costs.append(rm.step(rb, lr))
+        res = gm.compute_cost(gb, rng)
+        gm.backprop(res, lr)
+        g_costs.append(res.get_cost())
+    assert rng.state == rm.rng_state, "both samplers consumed the engine identically for 1000 steps"
+    g, r = np.array(g_costs), np.array(r_costs)
+    assert r[-1] < r[0] - 0.05, "the run must actually learn"
+    dev = np.abs(g - r)
+    print("gemm_mode %d: reference loss %.4f -> %.4f, max |cuda - reference| = %.2e (first 100: %.2e, 500: %.2e)" % (
+        gemm_mode, r[0], r[-1], dev.max(), dev[:100].max(), dev[:500].max()))
+    assert dev.max() <= 1e-3, dev.max()
