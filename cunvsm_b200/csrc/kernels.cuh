@@ -342,6 +342,11 @@ struct ScoreParams {
     float* Gp_lo;          // nullable: Gp - rn_tf32(Gp) for the 3xTF32 GEMMs (no batch-norm)
     double* loss_acc;      // [1]  sum_c wbc_c log p_c
     double* col_sums;      // [2*dd]: sum_i dy, sum_i dy * xhat
+    // l2_normalize_entity_reprs (Normalizer::forward on the gathered rows, cpp/objective.cu:170-176,
+    // cpp/cuda_utils.cu:12-46): scores use e / |e|. Non-null => on; per reference the norm |e| and the
+    // normalised dot product e.y / |e| are kept for the backward pass (cpp/cuda_utils.cu:69-127).
+    float* enorm;          // [B*R] nullable
+    float* escore;         // [B*R] nullable
 };
 
 // Reduce four per-lane partial sums across the warp with 6 shuffles (instead of 20): after the
@@ -425,8 +430,27 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) dot[rr] += y[j][v] * e[rr][j][v];
             // every lane finishes the scalar chain of ONE row (slot (lane >> 3) & 3)
-            const float d = warp_sum4_transposed(dot[0], dot[1], dot[2], dot[3], lane);
+            float d = warp_sum4_transposed(dot[0], dot[1], dot[2], dot[3], lane);
             const int r = r0 + my_slot;
+            float inv_norm = 1.0f;
+            if (p.enorm) {   // Normalizer::forward: the row enters the dot product as e / |e|
+                float nsq[RB];
+#pragma unroll
+                for (int rr = 0; rr < RB; ++rr) {
+                    nsq[rr] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) nsq[rr] += e[rr][j][v] * e[rr][j][v];
+                }
+                const float nrm = sqrtf(warp_sum4_transposed(nsq[0], nsq[1], nsq[2], nsq[3], lane));
+                inv_norm = 1.0f / nrm;
+                d = d / nrm;
+                if (r < p.R && slot_leader) {
+                    p.enorm[i * p.R + r] = nrm;
+                    p.escore[i * p.R + r] = d;
+                }
+            }
             float coef = 0.f;
             if (r < p.R) {
                 const float sign = r == 0 ? 1.0f : -1.0f;
@@ -448,7 +472,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
                     p.probs[i * p.R + r] = prob;
                     p.mult[i * p.R + r] = m;
                 }
-                coef = sign * m;
+                coef = (sign * m) * inv_norm;   // d cost / d projection goes through the normalised row
             }
 #pragma unroll
             for (int rr = 0; rr < RB; ++rr) {
@@ -704,13 +728,110 @@ __global__ void __launch_bounds__(256) row_meansq_kernel(const float* __restrict
     }
 }
 
+// With entity normalisation the column is (mult / |e|) * (y - s e / |e|), s = e.y / |e| (mult already holds
+// mult / |e|): mean_k of its square = mult^2 * (mean_k y^2 - s^2 / dd).
 __global__ void entity_scalar_scatter_kernel(const idx_t* __restrict__ ids, const float* __restrict__ mult,
                                              const float* __restrict__ ysq, long total, int R, float scale,
-                                             float* __restrict__ acc) {
+                                             float* __restrict__ acc, const float* __restrict__ escore,
+                                             float inv_dim) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= total) return;
     const float m = mult[c];
-    atomicAdd(acc + ids[c], scale * (m * m * ysq[c / R]));
+    float q = ysq[c / R];
+    if (escore) { const float sc = escore[c]; q = fmaxf(q - sc * sc * inv_dim, 0.f); }
+    atomicAdd(acc + ids[c], scale * (m * m * q));
+}
+
+// =====================================================================================
+// L2 Normalizer (cpp/cuda_utils.cu:3-141; golden vectors cpp/cuda_utils_tests.cu:51-92).
+//   forward : out[:, c] = in[:, c] / |in[:, c]|                          (per instance = per row here)
+//   backward: gin = gout / n - x (x . gout) / n^3 = (gout - xhat (xhat . gout)) / n
+// =====================================================================================
+// Phrase side, forward: rows of P (hi + lo when the tensor-core split is on) are normalised in place.
+__global__ void __launch_bounds__(256) row_l2_normalize_kernel(float* __restrict__ P, float* __restrict__ P_lo,
+                                                               long rows, int dim, int ld, int tf32,
+                                                               float* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long i = warp0; i < rows; i += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < dim; c += kWarp) {
+            const float x = P[i * ld + c] + (P_lo ? P_lo[i * ld + c] : 0.f);
+            s += x * x;
+        }
+        const float nrm = sqrtf(warp_sum(s));
+        if (lane == 0) norms[i] = nrm;
+        for (int c = lane; c < dim; c += kWarp) {
+            float x = (P[i * ld + c] + (P_lo ? P_lo[i * ld + c] : 0.f)) / nrm;
+            float lo = 0.f;
+            if (tf32) { const float hi = round_tf32(x); lo = x - hi; x = hi; }
+            P[i * ld + c] = x;
+            if (P_lo) P_lo[i * ld + c] = lo;
+        }
+    }
+}
+
+// Phrase side, backward, in place over grad_phrase [rows, dim] (xhat = the normalised P kept by the forward).
+__global__ void __launch_bounds__(256) row_l2_normalize_backward_kernel(float* __restrict__ G, int ldg,
+                                                                        const float* __restrict__ P,
+                                                                        const float* __restrict__ P_lo, int ld,
+                                                                        const float* __restrict__ norms, long rows,
+                                                                        int dim) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long i = warp0; i < rows; i += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < dim; c += kWarp) {
+            const float xh = P[i * ld + c] + (P_lo ? P_lo[i * ld + c] : 0.f);
+            s += xh * G[i * ldg + c];
+        }
+        const float dot = warp_sum(s);
+        const float nrm = norms[i];
+        for (int c = lane; c < dim; c += kWarp) {
+            const float xh = P[i * ld + c] + (P_lo ? P_lo[i * ld + c] : 0.f);
+            G[i * ldg + c] = (G[i * ldg + c] - xh * dot) / nrm;
+        }
+    }
+}
+
+// Entity side. Per reference c = (i, r) with row d = ids[c], n = |E_d|, s = E_d . y_i / n:
+//   grad column = (+-mult / n) * y_i  -  (+-mult * s / n^2) * E_d
+// The first term is the ordinary scatter with mult_eff = mult / n; the second is a per-row multiple of the row
+// itself: kself[d] = sum_c +-mult_c s_c / n_c^2, applied by the *_self kernels below against the pre-update E.
+__global__ void entity_norm_prep_kernel(const idx_t* __restrict__ ids, const float* __restrict__ mult,
+                                        const float* __restrict__ enorm, const float* __restrict__ escore,
+                                        long total, int R, float* __restrict__ mult_eff,
+                                        float* __restrict__ kself) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= total) return;
+    const float n = enorm[c], m = mult[c];
+    mult_eff[c] = m / n;
+    const float signed_m = (c % R) != 0 ? -m : m;
+    atomicAdd(kself + ids[c], signed_m * escore[c] / (n * n));
+}
+
+// theta[d, :] *= decay - lr * kself[d] * (acc ? 1 / sqrt(acc[d] + eps) : 1)   (dense decay + self term of SGD / Adagrad)
+__global__ void __launch_bounds__(256) scale_rows_self_kernel(float* __restrict__ theta, long num_rows, int dim,
+                                                              float decay, float lr, const float* __restrict__ kself,
+                                                              const float* __restrict__ acc, float eps) {
+    const long total = num_rows * dim;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long d = t / dim;
+        float k = kself[d];
+        if (acc) k = k / sqrtf(acc[d] + eps);
+        theta[t] = theta[t] * decay - (lr * k) * theta[t];
+    }
+}
+
+// target[d, :] += coef * kself[d] * source[d, :]
+__global__ void __launch_bounds__(256) row_self_axpy_kernel(float* __restrict__ target, const float* __restrict__ source,
+                                                            long num_rows, int dim, float coef,
+                                                            const float* __restrict__ kself) {
+    const long total = num_rows * dim;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x)
+        target[t] += (coef * kself[t / dim]) * source[t];
 }
 
 __global__ void word_scalar_scatter_kernel(const idx_t* __restrict__ ids, const float* __restrict__ fw,
@@ -890,17 +1011,28 @@ __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUp
 }
 
 // Dense-ify grad_entity for inspection: out[c, :] = +-mult[c] * y[i(c), :].
+// With entity normalisation (enorm != null): +-(mult / n) * (y - s E_d / n).
 __global__ void __launch_bounds__(256) materialize_grad_entity_kernel(const float* __restrict__ Z, const ActParams act,
                                                                       const float* __restrict__ mult, long total_cols,
-                                                                      int R, int dd, float* __restrict__ out) {
+                                                                      int R, int dd, float* __restrict__ out,
+                                                                      const float* __restrict__ E,
+                                                                      const idx_t* __restrict__ ids,
+                                                                      const float* __restrict__ enorm,
+                                                                      const float* __restrict__ escore) {
     const long total = total_cols * dd;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const long c = t / dd;
         const int k = (int)(t % dd);
         const long i = c / R;
         float xh;
-        const float y = act_forward(act, Z[i * dd + k], k, xh);
-        const float g = y * mult[c];
+        float y = act_forward(act, Z[i * dd + k], k, xh);
+        float m = mult[c];
+        if (enorm) {
+            const float n = enorm[c];
+            y = y - escore[c] * E[ids[c] * dd + k] / n;
+            m = m / n;
+        }
+        const float g = y * m;
         out[t] = (c % R) != 0 ? -g : g;
     }
 }

@@ -160,6 +160,12 @@ struct nvsm_model {
     int *smp_counts = nullptr, *smp_offsets = nullptr, *smp_scan = nullptr, *smp_error = nullptr;
     long smp_capacity = 0;             // candidate chunks allocated
 
+    // L2 Normalizer (cpp/cuda_utils.cu:3-141): per-n-gram norms of P; per-reference |E_d| and normalised score;
+    // effective multipliers mult / |E_d| and the per-row self coefficient of the entity gradient
+    bool l2_phrase = false, l2_entity = false;
+    float *p_norms = nullptr, *enorm = nullptr, *escore = nullptr, *mult_eff = nullptr, *kself = nullptr;
+    bool entity_prep_done = false;
+
     // multi-GPU
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
@@ -167,6 +173,7 @@ struct nvsm_model {
     int sparse_mode = NVSM_SPARSE_LOCAL;
     BatchSlot ag_slot;                  // gathered features / weights / ids of the global batch
     float *ag_mult = nullptr, *ag_act = nullptr, *ag_gP = nullptr, *ag_rowtmp = nullptr;
+    float* ag_escore = nullptr;
     int *ag_e_refs = nullptr, *ag_w_refs = nullptr;
 
     double* fwd_sums() { return dsums; }
@@ -451,6 +458,7 @@ int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t 
 int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
     const int dd = sp.dd, R = sp.R;
     if (!vec4_ok(dd) || R > 32 || dd > 1024 || getenv("NVSM_NO_RING")) return -1;
+    if (sp.enorm) return -1;   // entity normalisation lives in the register variant (score_kernel)
     const size_t stage_bytes = (size_t)(R + 1) * dd * 4;
     const size_t fixed = (size_t)(4 * dd + 2) * 4 + 8 * 4 * 8;
     const size_t budget = 227 * 1024 - 1024;
@@ -556,6 +564,8 @@ int forward(nvsm_model* m, BatchSlot* s) {
         else
             LAUNCH(m, gather_mean_kernel<1>, grid, 256, 0, m->W, dw, s->features, s->fweights, B, m->n, m->P, m->ldP, m->use_tc ? 1 : 0, m->P_lo);
     }
+    if (m->l2_phrase)   // Normalizer::forward on the phrase representations, in place (cpp/objective.cu:134-140)
+        LAUNCH(m, row_l2_normalize_kernel, grid_for(m, B, 8, 8), 256, 0, m->P, m->P_lo, B, dw, m->ldP, m->use_tc ? 1 : 0, m->p_norms);
     phase_end(m);
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
@@ -628,6 +638,9 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.tf32_gp = (m->use_tc && !bn) ? 1 : 0;
         sp.Gp_lo = bn ? nullptr : m->Gp_lo;
         sp.loss_acc = m->loss_acc(); sp.col_sums = m->bwd_sums();
+        sp.enorm = m->l2_entity ? m->enorm : nullptr;
+        sp.escore = m->l2_entity ? m->escore : nullptr;
+        m->entity_prep_done = false;
         TRY(dispatch_score(m, sp));
     }
     phase_end(m);
@@ -699,6 +712,9 @@ int backward(nvsm_model* m) {
         else
             TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
     }
+    if (m->l2_phrase)   // Normalizer::backward on grad_phrase (cpp/objective.cu:461-468); linear, so 1/n commutes
+        LAUNCH(m, row_l2_normalize_backward_kernel, grid_for(m, B, 8, 8), 256, 0, m->gP, dw, m->P, m->P_lo, m->ldP,
+               m->p_norms, B, dw);
     phase_end(m);
     m->have_gradients = true;
     return 0;
@@ -760,7 +776,7 @@ int scatter_entity_meansq(nvsm_model* m, float* acc, float scale) {
            act_params(m, m->cfg.batch_normalization != 0), m->B, m->dd, inv_dim, m->rowtmp);
     const long total = m->B * m->R;
     LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, m->mult, m->rowtmp,
-           total, m->R, scale, acc);
+           total, m->R, scale, acc, m->l2_entity ? (const float*)m->escore : (const float*)nullptr, inv_dim);
     return 0;
 }
 
@@ -794,10 +810,10 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
     if (entities)
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k);
+               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, m->l2_entity ? (const float*)m->kself : (const float*)nullptr);
     else
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k);
+               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr);
     return 0;
 }
 
@@ -854,8 +870,18 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
         return entities ? scatter_entity_meansq(m, acc, scale) : scatter_word_meansq(m, acc, scale);
     };
     // RepresentationsStorage::update (cpp/storage.cu:51-102): dense decay, then scatter.
+    const bool self = entities && m->l2_entity;   // gradient carries - kself[d] * E_d (entity normalisation)
+    auto self_axpy = [&](float* target, float coef) -> int {
+        LAUNCH(m, row_self_axpy_kernel, grid_for(m, count, 256 * 4, 8), 256, 0, target, (const float*)theta, N, dim, coef,
+               (const float*)m->kself);
+        return 0;
+    };
     auto sgd = [&](const float* acc, float eps) -> int {
-        if (lambda > 0.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
+        const float decay = lambda > 0.0f ? (float)(1.0 - (double)(lambda * lr)) : 1.0f;
+        if (self)
+            LAUNCH(m, scale_rows_self_kernel, grid_for(m, count, 256 * 4, 8), 256, 0, theta, N, dim, decay, lr,
+                   (const float*)m->kself, acc, eps);
+        else if (lambda > 0.0f) TRY(scale_table(m, theta, count, decay));
         return scatter(theta, lr, acc, eps);
     };
     const int method = m->cfg.update_method;
@@ -877,6 +903,7 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     }
     if (mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE) {
         TRY(scatter(opt.agg, 1.0f, nullptr, 0.f));
+        if (self) TRY(self_axpy(opt.agg, -1.0f));
         const float reg1 = (float)((1.0 - (double)c.b1) * (double)lambda);
         const int grid = grid_for(m, count / 4 + 1, 256, 8);
         LAUNCH(m, adam_full_kernel, grid, 256, 0, theta, opt.m, opt.v, opt.agg, count, c.s1, c.lr1, reg1, c.s2,
@@ -886,6 +913,7 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     // SPARSE and DENSE_UPDATE share the moment updates: m dense decay + scatter, scalar v.
     TRY(scale_table(m, opt.m, count, c.s1));
     TRY(scatter(opt.m, c.lr1, nullptr, 0.f));
+    if (self) TRY(self_axpy(opt.m, -c.lr1));
     TRY(scale_table(m, opt.v, N, c.s2));
     TRY(scatter_meansq(opt.v, c.lr2));
     if (mode == NVSM_ADAM_DENSE_UPDATE) {
@@ -937,7 +965,7 @@ int update_transform(nvsm_model* m, float lr, float lambda) {
 // activations, word ids, word weights, grad_phrase) so that each replica applies the table updates of the whole
 // global batch. Returns with the model's per-step pointers redirected to the gathered copies; `saved` restores them.
 struct LocalView {
-    BatchSlot* cur; long B; float *mult, *Z, *Y, *gP, *rowtmp; int *e_refs, *w_refs;
+    BatchSlot* cur; long B; float *mult, *Z, *Y, *gP, *rowtmp, *escore; int *e_refs, *w_refs;
 };
 
 int gather_global_batch(nvsm_model* m, LocalView* saved) {
@@ -950,8 +978,10 @@ int gather_global_batch(nvsm_model* m, LocalView* saved) {
     TRY(allgather_bytes(m, s->features, m->ag_slot.features, sizeof(idx_t) * B * m->n));
     TRY(allgather_bytes(m, s->fweights, m->ag_slot.fweights, sizeof(float) * B * m->n));
     TRY(allgather_bytes(m, m->gP, m->ag_gP, sizeof(float) * B * m->dw));
+    if (m->l2_entity) TRY(allgather_bytes(m, m->escore, m->ag_escore, sizeof(float) * B * m->R));
     phase_end(m);
-    *saved = LocalView{m->cur, m->B, m->mult, m->Z, m->Y, m->gP, m->rowtmp, m->e_refs, m->w_refs};
+    *saved = LocalView{m->cur, m->B, m->mult, m->Z, m->Y, m->gP, m->rowtmp, m->escore, m->e_refs, m->w_refs};
+    if (m->l2_entity) m->escore = m->ag_escore;
     m->ag_slot.B = B * W;
     m->cur = &m->ag_slot; m->B = B * W;
     m->mult = m->ag_mult; m->Z = m->ag_act; m->Y = m->ag_act; m->gP = m->ag_gP; m->rowtmp = m->ag_rowtmp;
@@ -961,7 +991,7 @@ int gather_global_batch(nvsm_model* m, LocalView* saved) {
 
 void restore_local_view(nvsm_model* m, const LocalView& v) {
     m->cur = v.cur; m->B = v.B; m->mult = v.mult; m->Z = v.Z; m->Y = v.Y; m->gP = v.gP; m->rowtmp = v.rowtmp;
-    m->e_refs = v.e_refs; m->w_refs = v.w_refs;
+    m->escore = v.escore; m->e_refs = v.e_refs; m->w_refs = v.w_refs;
 }
 
 int update(nvsm_model* m, float lr, float lambda) {
@@ -969,14 +999,26 @@ int update(nvsm_model* m, float lr, float lambda) {
     if (lr < 0.f || lambda < 0.f) return fail("learning rate and lambda must be >= 0");
     const bool exact = exact_sparse(m);
     LocalView local{};
+    float* const mult_orig = m->mult;
+    if (m->l2_entity) {
+        // Normalizer::backward of the entity rows, split into an effective multiplier and a per-row self term
+        phase_begin(m, PH_UPD_ENTITIES);
+        CU(cudaMemsetAsync(m->kself, 0, sizeof(float) * m->D, m->stream));
+        const long total = m->B * m->R;
+        LAUNCH(m, entity_norm_prep_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, (const float*)m->mult,
+               (const float*)m->enorm, (const float*)m->escore, total, m->R, m->mult_eff, m->kself);
+        phase_end(m);
+        if (exact) TRY(allreduce(m, m->kself, (size_t)m->D, false));
+        m->mult = m->mult_eff;
+    }
     if (exact) {
-        TRY(gather_global_batch(m, &local));
+        if (int grc = gather_global_batch(m, &local)) { m->mult = mult_orig; return grc; }
         if (m->pull) {  // buckets over the gathered ids, on the main stream
             phase_begin(m, PH_UPD_ENTITIES);
             int rc = build_buckets(m, m->cur->ids, m->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs);
             if (rc == 0) rc = build_buckets(m, m->cur->features, m->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs);
             phase_end(m);
-            if (rc) { restore_local_view(m, local); return rc; }
+            if (rc) { restore_local_view(m, local); m->mult = mult_orig; return rc; }
             CU(cudaEventRecord(m->buckets_ready, m->stream));
             m->buckets_in_flight = true;
         }
@@ -991,6 +1033,7 @@ int update(nvsm_model* m, float lr, float lambda) {
         phase_end(m);
     }
     if (exact) restore_local_view(m, local);
+    m->mult = mult_orig;
     if (rc) return rc;
     if (m->pull) {
         CU(cudaEventRecord(m->buckets_consumed, m->stream));
@@ -1211,7 +1254,7 @@ void nvsm_destroy(nvsm_model* m) {
         if (p) cudaFree(p);
     if (m->Y) cudaFree(m->Y);
     void* ag[] = {m->ag_slot.ids, m->ag_slot.features, m->ag_slot.fweights, m->ag_mult, m->ag_act, m->ag_gP, m->ag_rowtmp,
-                  m->ag_e_refs, m->ag_w_refs};
+                  m->ag_e_refs, m->ag_w_refs, m->ag_escore, m->p_norms, m->enorm, m->escore, m->mult_eff, m->kself};
     for (void* p : ag)
         if (p) cudaFree(p);
     m->ag_slot.ids = nullptr; m->ag_slot.features = nullptr; m->ag_slot.fweights = nullptr;
@@ -1249,7 +1292,6 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     if (cfg->word_repr_size > 1024 || cfg->entity_repr_size > 1024) return fail("representation sizes above 1024 are not supported");
     if (cfg->entity_repr_size % 4 != 0 && cfg->entity_repr_size > 512) return fail("entity_repr_size must be a multiple of 4 above 512");
     if (cfg->nonlinearity != NVSM_TANH && cfg->nonlinearity != NVSM_HARD_TANH) return fail("nonlinearity %d not implemented.", cfg->nonlinearity);
-    if (cfg->l2_normalize_phrase_reprs || cfg->l2_normalize_entity_reprs) return fail("l2 normalisation of representations is not implemented in this build");
     if (cfg->update_method < NVSM_SGD || cfg->update_method > NVSM_ADAM) return fail("invalid update_method %d", cfg->update_method);
     if (cfg->update_method == NVSM_ADAM && (cfg->adam_mode < NVSM_ADAM_SPARSE || cfg->adam_mode > NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE)) return fail("Invalid mode configuration.");
     if (cfg->num_random_entities < 0) return fail("num_random_entities must be >= 0");
@@ -1299,7 +1341,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             const bool full = cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE;
             TRY(dev_alloc(&m->optW.m, V * dw)); TRY(dev_alloc(&m->optE.m, D * dd));
             TRY(dev_alloc(&m->optW.v, full ? V * dw : V)); TRY(dev_alloc(&m->optE.v, full ? D * dd : D));
-            const bool can_pull = full && std::max(V, D) <= 1024L * 1024L && maxB * std::max<long>(m->R, m->n) < (1L << 31);
+            const bool can_pull = full && std::max(V, D) <= 1024L * 1024L && maxB * std::max<long>(m->R, m->n) < (1L << 31) &&
+                                  !getenv("NVSM_NO_PULL");   // test knob: exercise the scatter + dense full-Adam path
             if (full && !can_pull) { TRY(dev_alloc(&m->optW.agg, V * dw)); TRY(dev_alloc(&m->optE.agg, D * dd)); }
             TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
             TRY(dev_alloc(&m->T_v, (size_t)dw * dd)); TRY(dev_alloc(&m->b_v, dd));
@@ -1308,6 +1351,13 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->Gp, maxB * dd)); TRY(dev_alloc(&m->gP, maxB * dw));
         TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
         TRY(dev_alloc(&m->rowtmp, maxB));
+        m->l2_phrase = cfg->l2_normalize_phrase_reprs != 0;
+        m->l2_entity = cfg->l2_normalize_entity_reprs != 0;
+        if (m->l2_phrase) TRY(dev_alloc(&m->p_norms, maxB));
+        if (m->l2_entity) {
+            TRY(dev_alloc(&m->enorm, maxB * m->R)); TRY(dev_alloc(&m->escore, maxB * m->R));
+            TRY(dev_alloc(&m->mult_eff, maxB * m->R)); TRY(dev_alloc(&m->kself, m->D));
+        }
         TRY(dev_alloc(&m->mean, dd)); TRY(dev_alloc(&m->invstd, dd));
         TRY(dev_alloc(&m->mean_dy, dd)); TRY(dev_alloc(&m->mean_dyx, dd));
         TRY(dev_alloc(&m->bn_scale, dd)); TRY(dev_alloc(&m->bn_shift, dd));
@@ -1424,7 +1474,9 @@ int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
         if (r.kind == 1)
             LAUNCH(m, materialize_activation_kernel, grid, 256, 0, m->Z, act, m->B, m->dd, m->scratch);
         else
-            LAUNCH(m, materialize_grad_entity_kernel, grid, 256, 0, m->Z, act, m->mult, m->B * m->R, m->R, m->dd, m->scratch);
+            LAUNCH(m, materialize_grad_entity_kernel, grid, 256, 0, m->Z, act, m->mult, m->B * m->R, m->R, m->dd, m->scratch,
+                   (const float*)m->E, (const idx_t*)m->cur->ids, m->l2_entity ? (const float*)m->enorm : (const float*)nullptr,
+                   m->l2_entity ? (const float*)m->escore : (const float*)nullptr);
         src = m->scratch;
     }
     CU(cudaMemcpyAsync(host_out, src, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, m->stream));
@@ -1793,6 +1845,7 @@ int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode) {
         TRY(dev_alloc(&m->ag_mult, G * m->R)); TRY(dev_alloc(&m->ag_act, G * m->dd)); TRY(dev_alloc(&m->ag_gP, G * m->dw));
         TRY(dev_alloc(&m->ag_rowtmp, G));
         if (m->pull) { TRY(dev_alloc(&m->ag_e_refs, G * m->R)); TRY(dev_alloc(&m->ag_w_refs, G * m->n)); }
+        if (m->l2_entity) TRY(dev_alloc(&m->ag_escore, G * m->R));
     }
     m->sparse_mode = mode;
     return 0;

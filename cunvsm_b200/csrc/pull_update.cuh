@@ -86,13 +86,16 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
                                                              const int* __restrict__ refs,
                                                              const float* __restrict__ coefs,
                                                              const float* __restrict__ src, int group,
-                                                             const AdamFullConsts k) {
+                                                             const AdamFullConsts k,
+                                                             const float* __restrict__ self_k) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim / VEC;
     for (long row = warp0; row < num_rows; row += nwarps) {
         const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        // entity normalisation: the gradient carries - self_k[row] * theta[row] (entity_norm_prep_kernel)
+        const float ks = self_k ? __ldg(self_k + row) : 0.f;
         float agg[NCH][VEC];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
                 load_vec<VEC>(v + o, vv);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float ag = agg[j][q];
+                    const float ag = agg[j][q] - ks * th[q];
                     const float g = ag + (-k.lambda * th[q]);
                     mm[q] = (mm[q] * k.s1 + k.lr1 * ag) + (-k.reg1 * th[q]);
                     vv[q] = vv[q] * k.s2 + (g * g) * k.lr2;

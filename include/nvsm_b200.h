@@ -57,8 +57,8 @@ typedef struct nvsm_config {
     int batch_normalization;      /* ModelDesc.TransformDesc.batch_normalization */
     int clip_sigmoid;             /* forced on by the CLI, cpp/main.cu:645 */
     int bias_negative_samples;
-    int l2_normalize_phrase_reprs; /* not implemented: must be 0 */
-    int l2_normalize_entity_reprs; /* not implemented: must be 0 */
+    int l2_normalize_phrase_reprs; /* Normalizer on the phrase representations, cpp/objective.cu:96-99,134-140,461-468 */
+    int l2_normalize_entity_reprs; /* Normalizer on the gathered entity rows, cpp/objective.cu:101-104,170-176,403-409 */
     int update_method;            /* NVSM_SGD | NVSM_ADAGRAD | NVSM_ADAM */
     int adam_mode;                /* NVSM_ADAM_* when update_method == NVSM_ADAM */
     int num_random_entities;      /* z */
