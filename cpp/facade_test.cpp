@@ -3,6 +3,7 @@
 // compares with the same sequence driven through ctypes.
 #include <cstdio>
 #include <memory>
+#include <tuple>
 
 #include "cuNVSM/model.h"
 
@@ -38,5 +39,29 @@ int main() {
   const auto out = model.infer({{1, 2, 3, 4}, {5, 6, 7, 8}}, 4);
   std::printf("infer %zu %zu %.9g\n", out.rows, out.cols, (double)out.data[0]);
   std::printf("params %zu\n", model.num_parameters());
+
+  // TextEntityEntityEntity mixture (reference: train<TextEntityEntityEntity::Objective>, cpp/main.cu:734-741)
+  {
+    lse::TrainConfig mtc = tc;
+    mtc.set_text_entity_weight(0.75f); mtc.set_entity_entity_weight(0.25f);
+    RNG mrng; mrng.seed(5);
+    Model<TextEntityEntityEntity::Objective> mix(100, 60, desc, mtc, 0, NVSM_GEMM_FP32);
+    mix.initialize(&mrng);
+    std::tuple<TextEntity::Batch, EntityEntity::Batch> both(mtc, mtc);   // element-wise converting construction
+    for (int i = 0; i < 256; ++i) {
+      std::vector<long> f = {i % 100, (i * 7) % 100, (i * 13 + 1) % 100, (i + 50) % 100};
+      std::get<0>(both).push_instance(f, {}, i % 60, 1.0f);
+      std::get<1>(both).push_instance(std::make_tuple((long)(i % 60), (long)((i * 11 + 3) % 60), 1.0f + (i % 3)));
+    }
+    for (int step = 0; step < 3; ++step) {
+      std::unique_ptr<MultiForwardResult> result(mix.compute_cost(both, &mrng));
+      std::unique_ptr<TextEntity::Gradients> gradients(mix.compute_gradients(*result));
+      mix.update(*gradients, 0.001f, result->scaled_regularization_lambda());
+      std::printf("mixcost %d %.9g\n", step, result->get_cost());
+    }
+    double mcs = 0;
+    for (const auto& kv : mix.get_data()) for (float x : kv.second.data) mcs += x;
+    std::printf("mixchecksum %.9g\n", mcs);
+  }
   return 0;
 }

@@ -59,7 +59,8 @@ struct Flags {
 
 // Write the four parameter tensors as <output>_<suffix>.<name>.npy, row-major [objects, dim] — the
 // shapes the reference's HDF5 dump uses (cpp/hdf5.cu:26-53, lse_hdf5_inl.h:4-27).
-void dump_model(const DefaultModel& model, const std::string& output, const std::string& suffix) {
+template <typename ModelT>
+void dump_model(const ModelT& model, const std::string& output, const std::string& suffix) {
   if (output.empty()) return;
   for (const auto& kv : model.get_data()) {
     const std::string path = output + "_" + suffix + "." + kv.first + ".npy";
@@ -75,6 +76,155 @@ void dump_model(const DefaultModel& model, const std::string& output, const std:
     f.write(reinterpret_cast<const char*>(kv.second.data.data()), kv.second.data.size() * sizeof(float));
   }
   std::printf("Dumped model to %s_%s.*.npy\n", output.c_str(), suffix.c_str());
+}
+
+
+// Seeded synthetic similarity source (stands in for RepresentationSimilarity::DataSource over a similarity file,
+// cpp/data.cu:225-345): `num_batches` full batches of uniform random id pairs with unit weights per epoch.
+class SimilaritySource {
+ public:
+  SimilaritySource(size_t num_objects, size_t num_batches, unsigned long seed)
+      : num_objects_(num_objects), num_batches_(num_batches), seed_(seed), emitted_(0), rng_(seed) {}
+  void reset() { emitted_ = 0; rng_.seed(seed_); }
+  bool has_next() const { return emitted_ < num_batches_; }
+  void next(RepresentationSimilarity::Batch* batch) {
+    std::uniform_int_distribution<long> pick(0, static_cast<long>(num_objects_) - 1);
+    while (!batch->full()) batch->push_instance(std::make_tuple(pick(rng_), pick(rng_), 1.0f));
+    ++emitted_;
+  }
+ private:
+  const size_t num_objects_, num_batches_;
+  const unsigned long seed_;
+  size_t emitted_;
+  std::mt19937_64 rng_;
+};
+
+struct Sources {
+  TextEntity::SyntheticSource* text;
+  SimilaritySource* pairs;
+};
+
+// BatchHandler of the reference (cpp/main.cu:159-228): uniform access to the batch type of every objective.
+template <typename ObjectiveT>
+struct BatchOps;
+
+template <>
+struct BatchOps<TextEntity::Objective> {
+  typedef TextEntity::Batch BatchT;
+  static const bool has_text = true, pairs_over_entities = true;
+  static BatchT* make(const lse::TrainConfig& tc) { return new BatchT(tc); }
+  static void clear(BatchT* b) { b->clear(); }
+  static void next(Sources& s, BatchT* b) { s.text->next(b); }
+  static bool has_next(Sources& s) { return s.text->has_next(); }
+  static void reset(Sources& s) { s.text->reset(); }
+  static size_t num_instances(const BatchT& b) { return b.num_instances(); }
+};
+
+template <int K>
+struct BatchOps<RepresentationSimilarity::ObjectiveT<K>> {
+  typedef RepresentationSimilarity::Batch BatchT;
+  static const bool has_text = false, pairs_over_entities = (K == NVSM_OBJECTIVE_ENTITY_ENTITY);
+  static BatchT* make(const lse::TrainConfig& tc) { return new BatchT(tc); }
+  static void clear(BatchT* b) { b->clear(); }
+  static void next(Sources& s, BatchT* b) { s.pairs->next(b); }
+  static bool has_next(Sources& s) { return s.pairs->has_next(); }
+  static void reset(Sources& s) { s.pairs->reset(); }
+  static size_t num_instances(const BatchT& b) { return b.num_instances(); }
+};
+
+template <int K>
+struct BatchOps<MixtureObjectiveT<K>> {
+  typedef std::tuple<TextEntity::Batch, RepresentationSimilarity::Batch> BatchT;
+  static const bool has_text = true, pairs_over_entities = (K == NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY);
+  static BatchT* make(const lse::TrainConfig& tc) { return new BatchT(tc, tc); }
+  static void clear(BatchT* b) { std::get<0>(*b).clear(); std::get<1>(*b).clear(); }
+  static void next(Sources& s, BatchT* b) { s.text->next(&std::get<0>(*b)); s.pairs->next(&std::get<1>(*b)); }
+  static bool has_next(Sources& s) { return s.text->has_next() && s.pairs->has_next(); }   // MultiSource semantics
+  static void reset(Sources& s) { s.text->reset(); s.pairs->reset(); }
+  static size_t num_instances(const BatchT& b) { return std::get<0>(b).num_instances(); }
+};
+
+// train<ObjectiveT> of the reference (cpp/main.cu:471-621)
+template <typename ObjectiveT>
+int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::TrainConfig& train_config_in) {
+  typedef BatchOps<ObjectiveT> Ops;
+  lse::TrainConfig train_config = train_config_in;
+  RNG rng;
+  rng.seed(flags.i("seed"));
+
+  const size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
+  TextEntity::SyntheticSource data_source(V, D, flags.i("synthetic_num_batches"), flags.i("seed"), flags.d("synthetic_zipf"));
+  const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
+
+  std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
+              model_desc.word_repr_size(), model_desc.entity_repr_size(), (int)model_desc.transform_desc().batch_normalization(),
+              flags.str("nonlinearity").c_str());
+  std::printf("Training: batch_size=%d window_size=%d num_random_entities=%d lambda=%g lr=%g update_method=%s |V|=%zu |D|=%zu\n",
+              train_config.batch_size(), train_config.window_size(), train_config.num_random_entities(),
+              train_config.regularization_lambda(), train_config.learning_rate(), flags.str("update_method").c_str(), V, D);
+
+  Model<ObjectiveT> model(V, D, model_desc, train_config, flags.i("device"), gemm_mode);
+  model.initialize(&rng);
+  // negatives: the reference draws them on the host training thread (cpp/labels.cu:3-22, ~3.6 ms per
+  // 51200-batch); by default the same stream is produced on the device, --host_sampler restores the loop.
+  if (!flags.b("host_sampler") && Ops::has_text) model.use_device_sampler(&rng);
+  if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
+
+  SimilaritySource similarity_source(Ops::pairs_over_entities ? D : V, flags.i("synthetic_num_batches"), flags.i("seed") + 17);
+  Sources sources{&data_source, &similarity_source};
+  std::unique_ptr<typename Ops::BatchT> batch_ptr(Ops::make(train_config));
+  typename Ops::BatchT& batch = *batch_ptr;
+  const long max_threads_per_block = 1024;  // Runtime::props().maxThreadsPerBlock in the reference
+  const bool verbose = flags.i("v") > 0;
+
+  auto iterate = [&](const bool backpropagate, size_t* num_batches, double* agg_cost, double* seconds) {
+    *num_batches = 0; *agg_cost = 0.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::unique_ptr<typename ObjectiveT::ForwardResultType> previous;
+    while (Ops::has_next(sources)) {
+      Ops::clear(&batch);
+      Ops::next(sources, &batch);
+      if (Ops::num_instances(batch) % max_threads_per_block != 0) {
+        std::fprintf(stderr, "Skipping Batch #%zu as it is not a multiple of %ld (%zu instances).\n", *num_batches,
+                     max_threads_per_block, Ops::num_instances(batch));
+      } else {
+        std::unique_ptr<typename ObjectiveT::ForwardResultType> result(model.compute_cost(batch, &rng));
+        std::unique_ptr<TextEntity::Gradients> gradients(model.compute_gradients(*result));
+        if (backpropagate) model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
+        // read the previous batch's loss while this one runs (the reference synchronises every batch)
+        if (previous) {
+          const float c = previous->get_cost();
+          *agg_cost += c;
+          if (verbose) std::printf("Batch #%zu: cost=%g\n", *num_batches - 1, c);
+        }
+        previous = std::move(result);
+      }
+      if (flags.i("dump_every") > 0 && *num_batches > 0 && *num_batches % flags.i("dump_every") == 0)
+        dump_model(model, flags.str("output"), std::to_string(*num_batches));
+      ++*num_batches;
+    }
+    if (previous) *agg_cost += previous->get_cost();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  };
+
+  size_t nb; double cost, secs;
+  if (flags.b("compute_initial_cost")) {
+    Ops::reset(sources);
+    iterate(false, &nb, &cost, &secs);
+    std::printf("Initial cost: %g\n", cost / nb);
+  }
+  size_t total_batches = 0; double total_secs = 0.0;
+  for (long epoch = 1; epoch <= train_config.num_epochs(); ++epoch) {
+    Ops::reset(sources);
+    iterate(true, &nb, &cost, &secs);
+    total_batches += nb; total_secs += secs;
+    std::printf("Epoch #%ld: mean cost %g; %.2f batches/second, %.0f n-grams/second\n", epoch, cost / nb,
+                total_batches / total_secs, total_batches / total_secs * train_config.batch_size());
+    dump_model(model, flags.str("output"), std::to_string(epoch));
+  }
+  NVSM_ABORT_ON(nvsm_synchronize(model.handle()));
+  model.sync_rng(&rng);
+  return 0;
 }
 
 }  // namespace
@@ -95,8 +245,9 @@ int main(int argc, char** argv) {
 
   NVSM_CHECK(UPDATE_METHODS.count(flags.str("update_method")), "Please specify a valid --update_method.");
   NVSM_CHECK(NONLINEARITIES.count(flags.str("nonlinearity")), "Please specify a valid --nonlinearity.");
-  NVSM_CHECK(flags.d("entity_similarity_weight") == 0.0 && flags.d("term_similarity_weight") == 0.0,
-             "the entity-entity / term-term mixture objectives are not part of this build");
+  // cpp/main.cu:698-706
+  NVSM_CHECK(flags.d("entity_similarity_weight") >= 0.0 && flags.d("entity_similarity_weight") <= 1.0, "--entity_similarity_weight must be in [0, 1]");
+  NVSM_CHECK(flags.d("term_similarity_weight") >= 0.0 && flags.d("term_similarity_weight") <= 1.0, "--term_similarity_weight must be in [0, 1]");
   NVSM_CHECK(!flags.b("check_gradients"), "--check_gradients is provided by the test-suite (tests/), not the CLI");
 
   lse::ModelDesc model_desc;
@@ -119,83 +270,17 @@ int main(int argc, char** argv) {
   train_config.mutable_update_method()->set_type(UPDATE_METHODS.at(flags.str("update_method")).first);
   train_config.mutable_update_method()->mutable_adam_conf()->set_mode(UPDATE_METHODS.at(flags.str("update_method")).second);
   train_config.set_no_shuffle(flags.b("no_shuffle"));
+  train_config.set_text_entity_weight(1.0 - flags.d("entity_similarity_weight") - flags.d("term_similarity_weight"));
+  train_config.set_entity_entity_weight(flags.d("entity_similarity_weight"));
+  train_config.set_term_term_weight(flags.d("term_similarity_weight"));
 
   NVSM_CHECK(flags.i("seed") > 0, "Please specify a --seed value.");
   if (train_config.learning_rate() == 0.0) {
     train_config.set_learning_rate(train_config.update_method().type() == lse::TrainConfig::ADAM ? 0.001 : 0.01);
   }
 
-  RNG rng;
-  rng.seed(flags.i("seed"));
-
-  const size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
-  TextEntity::SyntheticSource data_source(V, D, flags.i("synthetic_num_batches"), flags.i("seed"), flags.d("synthetic_zipf"));
-  const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
-
-  std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
-              model_desc.word_repr_size(), model_desc.entity_repr_size(), (int)model_desc.transform_desc().batch_normalization(),
-              flags.str("nonlinearity").c_str());
-  std::printf("Training: batch_size=%d window_size=%d num_random_entities=%d lambda=%g lr=%g update_method=%s |V|=%zu |D|=%zu\n",
-              train_config.batch_size(), train_config.window_size(), train_config.num_random_entities(),
-              train_config.regularization_lambda(), train_config.learning_rate(), flags.str("update_method").c_str(), V, D);
-
-  DefaultModel model(V, D, model_desc, train_config, flags.i("device"), gemm_mode);
-  model.initialize(&rng);
-  // negatives: the reference draws them on the host training thread (cpp/labels.cu:3-22, ~3.6 ms per
-  // 51200-batch); by default the same stream is produced on the device, --host_sampler restores the loop.
-  if (!flags.b("host_sampler")) model.use_device_sampler(&rng);
-  if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
-
-  TextEntity::Batch batch(train_config);
-  const long max_threads_per_block = 1024;  // Runtime::props().maxThreadsPerBlock in the reference
-  const bool verbose = flags.i("v") > 0;
-
-  auto iterate = [&](const bool backpropagate, size_t* num_batches, double* agg_cost, double* seconds) {
-    *num_batches = 0; *agg_cost = 0.0;
-    const auto t0 = std::chrono::steady_clock::now();
-    std::unique_ptr<TextEntity::ForwardResult> previous;
-    while (data_source.has_next()) {
-      batch.clear();
-      data_source.next(&batch);
-      if (batch.num_instances() % max_threads_per_block != 0) {
-        std::fprintf(stderr, "Skipping Batch #%zu as it is not a multiple of %ld (%zu instances).\n", *num_batches,
-                     max_threads_per_block, batch.num_instances());
-      } else {
-        std::unique_ptr<TextEntity::ForwardResult> result(model.compute_cost(batch, &rng));
-        std::unique_ptr<TextEntity::Gradients> gradients(model.compute_gradients(*result));
-        if (backpropagate) model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
-        // read the previous batch's loss while this one runs (the reference synchronises every batch)
-        if (previous) {
-          const float c = previous->get_cost();
-          *agg_cost += c;
-          if (verbose) std::printf("Batch #%zu: cost=%g\n", *num_batches - 1, c);
-        }
-        previous = std::move(result);
-      }
-      if (flags.i("dump_every") > 0 && *num_batches > 0 && *num_batches % flags.i("dump_every") == 0)
-        dump_model(model, flags.str("output"), std::to_string(*num_batches));
-      ++*num_batches;
-    }
-    if (previous) *agg_cost += previous->get_cost();
-    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  };
-
-  size_t nb; double cost, secs;
-  if (flags.b("compute_initial_cost")) {
-    data_source.reset();
-    iterate(false, &nb, &cost, &secs);
-    std::printf("Initial cost: %g\n", cost / nb);
-  }
-  size_t total_batches = 0; double total_secs = 0.0;
-  for (long epoch = 1; epoch <= train_config.num_epochs(); ++epoch) {
-    data_source.reset();
-    iterate(true, &nb, &cost, &secs);
-    total_batches += nb; total_secs += secs;
-    std::printf("Epoch #%ld: mean cost %g; %.2f batches/second, %.0f n-grams/second\n", epoch, cost / nb,
-                total_batches / total_secs, total_batches / total_secs * train_config.batch_size());
-    dump_model(model, flags.str("output"), std::to_string(epoch));
-  }
-  NVSM_ABORT_ON(nvsm_synchronize(model.handle()));
-  model.sync_rng(&rng);
-  return 0;
+  // objective selection, cpp/main.cu:729-757
+  if (train_config.entity_entity_weight() > 0.0) return train<TextEntityEntityEntity::Objective>(flags, model_desc, train_config);
+  if (train_config.term_term_weight() > 0.0) return train<TextEntityTermTerm::Objective>(flags, model_desc, train_config);
+  return train<TextEntity::Objective>(flags, model_desc, train_config);
 }

@@ -17,7 +17,8 @@ SYMBOLS = [
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
-    "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_sampler_seed", "nvsm_sampler_state",
+    "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
+    "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_sampler_seed", "nvsm_sampler_state",
     "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device",
 ]
 
@@ -33,7 +34,8 @@ class NvsmConfig(ctypes.Structure):
         ("num_random_entities", ctypes.c_int), ("max_batch_size", ctypes.c_int),
         ("window_size", ctypes.c_int), ("regularization_lambda", ctypes.c_float),
         ("device", ctypes.c_int), ("gemm_mode", ctypes.c_int), ("num_batch_slots", ctypes.c_int),
-        ("reserved", ctypes.c_int * 7),
+        ("objective", ctypes.c_int), ("text_entity_weight", ctypes.c_float), ("similarity_weight", ctypes.c_float),
+        ("max_similarity_batch_size", ctypes.c_int), ("reserved", ctypes.c_int * 3),
     ]
 
 
@@ -101,6 +103,9 @@ def load():
     f("nvsm_comm_unique_id", [ctypes.c_char_p])
     f("nvsm_comm_init", [vp, ctypes.c_char_p, ci, ci])
     f("nvsm_comm_set_sparse_mode", [vp, ci])
+    f("nvsm_similarity_compute_cost", [vp, pl, pf, cl])
+    f("nvsm_similarity_get_cost", [vp, pf])
+    f("nvsm_similarity_scaled_regularization_lambda", [vp], cf)
     _lib = L
     return L
 

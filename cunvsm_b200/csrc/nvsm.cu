@@ -24,6 +24,7 @@
 #include "pull_update.cuh"
 #include "sampler.cuh"
 #include "score_ring.cuh"
+#include "similarity.cuh"
 
 using namespace nvsm;
 
@@ -165,6 +166,16 @@ struct nvsm_model {
     bool l2_phrase = false, l2_entity = false;
     float *p_norms = nullptr, *enorm = nullptr, *escore = nullptr, *mult_eff = nullptr, *kself = nullptr;
     bool entity_prep_done = false;
+
+    // RepresentationSimilarity objective (similarity.cuh): pairs over the entity or the word table
+    bool has_text = true, has_pair = false, pair_entities = false;
+    float text_scale = 1.0f, pair_scale = 1.0f;   // w_k / sum_k w_k of the mixtures
+    long maxN = 0, pair_N = 0;
+    idx_t* pair_ids = nullptr;
+    float *pair_w = nullptr, *pair_probs = nullptr, *pair_mult = nullptr, *pair_G = nullptr, *pair_msq = nullptr;
+    double* pair_loss = nullptr;        // device [1]
+    double* pair_loss_host = nullptr;   // pinned [1]
+    bool have_pair_forward = false;
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -523,6 +534,7 @@ int start_bucket_build(nvsm_model* m, BatchSlot* s);
 int forward(nvsm_model* m, BatchSlot* s) {
     const long B = s->B;
     if (B <= 0) return fail("empty batch");
+    if (!m->has_text) return fail("this handle was created for a RepresentationSimilarity objective: use nvsm_similarity_compute_cost");
     m->cur = s;
     s->in_use = true;
     m->B = B;
@@ -632,7 +644,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.sig_lo_cmp = fceil(slo); sp.sig_lo_val = (float)slo;
         sp.sig_hi_cmp = ffloor(shi); sp.sig_hi_val = (float)shi;
         sp.der_lo_cmp = ffloor(dlo); sp.der_hi_cmp = fceil(dhi);
-        sp.bsn = (float)std::exp(-std::log((double)m->Bglobal));
+        sp.bsn = (float)std::exp(-std::log((double)m->Bglobal)) * m->text_scale;   // mixture weight folded into the multipliers
         sp.act = act_params(m, bn);
         sp.probs = m->probs; sp.mult = m->mult; sp.Gp = m->Gp; sp.Y = m->Y;
         sp.tf32_gp = (m->use_tc && !bn) ? 1 : 0;
@@ -863,11 +875,32 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     const long N = entities ? m->D : m->V;
     const int dim = entities ? m->dd : m->dw;
     const long count = N * dim;
-    auto scatter = [&](float* target, float scale, const float* acc, float eps) {
-        return entities ? scatter_entities(m, target, scale, acc, eps) : scatter_words(m, target, scale, acc, eps);
+    // gradient descriptors of this table (CompositeGradients::get_representations_gradient): the TextEntity one
+    // and / or the RepresentationSimilarity one (window 1, no weights)
+    const bool text = m->has_text;
+    const bool pair = m->has_pair && m->pair_entities == entities;
+    if (!text && !pair) return 0;   // "No gradient": the reference skips the table (cpp/params.cu:301-304)
+    const long pairM = 2 * m->pair_N;
+    auto pair_scatter = [&](float* target, float scale, const float* acc, float eps) -> int {
+        const int grid = grid_for(m, pairM, 8, 8);
+        if (vec4_ok(dim)) LAUNCH(m, rows_scatter_kernel<4>, grid, 256, 0, (const float*)m->pair_G, (const idx_t*)m->pair_ids, pairM, dim, target, scale, acc, eps);
+        else LAUNCH(m, rows_scatter_kernel<1>, grid, 256, 0, (const float*)m->pair_G, (const idx_t*)m->pair_ids, pairM, dim, target, scale, acc, eps);
+        return 0;
     };
-    auto scatter_meansq = [&](float* acc, float scale) {
-        return entities ? scatter_entity_meansq(m, acc, scale) : scatter_word_meansq(m, acc, scale);
+    auto scatter = [&](float* target, float scale, const float* acc, float eps) -> int {
+        if (text) TRY(entities ? scatter_entities(m, target, scale, acc, eps) : scatter_words(m, target, scale, acc, eps));
+        if (pair) TRY(pair_scatter(target, scale, acc, eps));
+        return 0;
+    };
+    auto scatter_meansq = [&](float* acc, float scale) -> int {
+        if (text) TRY(entities ? scatter_entity_meansq(m, acc, scale) : scatter_word_meansq(m, acc, scale));
+        if (pair) {
+            const float inv_dim = (float)std::exp(-std::log((double)dim));
+            LAUNCH(m, row_meansq_kernel, grid_for(m, pairM, 8, 8), 256, 0, (const float*)m->pair_G, pairM, dim, inv_dim, m->pair_msq);
+            LAUNCH(m, rows_scalar_scatter_kernel, (int)((pairM + 255) / 256), 256, 0, (const idx_t*)m->pair_ids,
+                   (const float*)m->pair_msq, pairM, scale, acc);
+        }
+        return 0;
     };
     // RepresentationsStorage::update (cpp/storage.cu:51-102): dense decay, then scatter.
     const bool self = entities && m->l2_entity;   // gradient carries - kself[d] * E_d (entity normalisation)
@@ -886,6 +919,9 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     };
     const int method = m->cfg.update_method;
     if (method == NVSM_SGD) return sgd(nullptr, 0.f);
+    if (text && pair && (method == NVSM_ADAGRAD || (method == NVSM_ADAM && m->cfg.adam_mode == NVSM_ADAM_SPARSE)))
+        return fail("Adagrad / sparse Adam do not implement multiple gradients (cpp/updates_adagrad.cu:108-109, "
+                    "cpp/updates_adam.cu:339-340): use sgd, dense_adam or full_adam with a mixture objective");
     if (method == NVSM_ADAGRAD) {  // cpp/updates_adagrad.cu:99-179
         TRY(scatter_meansq(opt.acc, 1.0f));
         return sgd(opt.acc, 1e-6f);
@@ -924,6 +960,14 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
     }
     // SPARSE: window-averaged step, applied through the SGD scatter with dense decay.
     if (lambda > 0.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
+    if (pair) {   // single descriptor, window 1: same per-reference step as the entity side
+        const int grid = grid_for(m, pairM, 8, 8);
+        if (vec4_ok(dim))
+            LAUNCH(m, adam_sparse_entity_kernel<4>, grid, 256, 0, (const idx_t*)m->pair_ids, pairM, dim, opt.m, opt.v, bc, c.eps, lr, theta);
+        else
+            LAUNCH(m, adam_sparse_entity_kernel<1>, grid, 256, 0, (const idx_t*)m->pair_ids, pairM, dim, opt.m, opt.v, bc, c.eps, lr, theta);
+        return 0;
+    }
     if (entities) {
         const long total = m->B * m->R;
         const int grid = grid_for(m, total, 8, 8);
@@ -996,6 +1040,16 @@ void restore_local_view(nvsm_model* m, const LocalView& v) {
 
 int update(nvsm_model* m, float lr, float lambda) {
     if (!m->have_gradients) return fail("update called without gradients");
+    if (m->has_pair && !m->have_pair_forward) return fail("this objective needs nvsm_similarity_compute_cost before update");
+    if (!m->has_text) {   // EntityEntity / TermTerm: one table, nothing else (the reference skips gradient-less params)
+        if (lr < 0.f || lambda < 0.f) return fail("learning rate and lambda must be >= 0");
+        phase_begin(m, m->pair_entities ? PH_UPD_ENTITIES : PH_UPD_WORDS);
+        const int prc = update_table(m, m->pair_entities, lr, lambda);
+        phase_end(m);
+        m->have_gradients = false;
+        m->have_pair_forward = false;
+        return prc;
+    }
     if (lr < 0.f || lambda < 0.f) return fail("learning rate and lambda must be >= 0");
     const bool exact = exact_sparse(m);
     LocalView local{};
@@ -1048,6 +1102,7 @@ int update(nvsm_model* m, float lr, float lambda) {
     m->cur->ever_consumed = true;
     m->cur->in_use = false;
     m->have_gradients = false;  // grad_phrase may have been overwritten (sparse Adam)
+    m->have_pair_forward = false;
     return 0;
 }
 
@@ -1193,6 +1248,9 @@ TensorRef find_tensor(nvsm_model* m, const std::string& s) {
     else if (s == "grad_phrase_reprs") set(m->gP, B * m->dw);
     else if (s == "grad_projection") set(m->Gp, B * m->dd);
     else if (s == "grad_entity_repr") { set(m->Z, B * m->R * m->dd); r.kind = 2; }
+    else if (s == "similarity_pair_probs") set(m->pair_probs, m->pair_N);
+    else if (s == "similarity_multipliers") set(m->pair_mult, m->pair_N);
+    else if (s == "grad_similarity") set(m->pair_G, 2 * m->pair_N * (m->pair_entities ? m->dd : m->dw));
     else if (s == "bn_mean") set(m->mean, m->dd);
     else if (s == "bn_invstd") set(m->invstd, m->dd);
     else if (s == "word_representations-m") set(m->optW.m, m->V * m->dw);
@@ -1258,6 +1316,10 @@ void nvsm_destroy(nvsm_model* m) {
     for (void* p : ag)
         if (p) cudaFree(p);
     m->ag_slot.ids = nullptr; m->ag_slot.features = nullptr; m->ag_slot.fweights = nullptr;
+    void* pr[] = {m->pair_ids, m->pair_w, m->pair_probs, m->pair_mult, m->pair_G, m->pair_msq, m->pair_loss};
+    for (void* p : pr)
+        if (p) cudaFree(p);
+    if (m->pair_loss_host) cudaFreeHost(m->pair_loss_host);
     if (m->rng_dev) cudaFree(m->rng_dev);
     int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
     for (int* p : sl)
@@ -1342,7 +1404,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             TRY(dev_alloc(&m->optW.m, V * dw)); TRY(dev_alloc(&m->optE.m, D * dd));
             TRY(dev_alloc(&m->optW.v, full ? V * dw : V)); TRY(dev_alloc(&m->optE.v, full ? D * dd : D));
             const bool can_pull = full && std::max(V, D) <= 1024L * 1024L && maxB * std::max<long>(m->R, m->n) < (1L << 31) &&
-                                  !getenv("NVSM_NO_PULL");   // test knob: exercise the scatter + dense full-Adam path
+                                  !getenv("NVSM_NO_PULL") &&   // test knob: exercise the scatter + dense full-Adam path
+                                  cfg->objective == NVSM_OBJECTIVE_TEXT_ENTITY;   // pair gradients go through the scatter path
             if (full && !can_pull) { TRY(dev_alloc(&m->optW.agg, V * dw)); TRY(dev_alloc(&m->optE.agg, D * dd)); }
             TRY(dev_alloc(&m->T_a, (size_t)dw * dd)); TRY(dev_alloc(&m->b_a, dd));
             TRY(dev_alloc(&m->T_v, (size_t)dw * dd)); TRY(dev_alloc(&m->b_v, dd));
@@ -1351,6 +1414,30 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->Gp, maxB * dd)); TRY(dev_alloc(&m->gP, maxB * dw));
         TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
         TRY(dev_alloc(&m->rowtmp, maxB));
+        {
+            const int obj = cfg->objective;
+            if (obj < NVSM_OBJECTIVE_TEXT_ENTITY || obj > NVSM_OBJECTIVE_TEXT_ENTITY_TERM_TERM) return fail("unknown objective %d", obj);
+            m->has_text = obj == NVSM_OBJECTIVE_TEXT_ENTITY || obj >= NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY;
+            m->has_pair = obj != NVSM_OBJECTIVE_TEXT_ENTITY;
+            m->pair_entities = obj == NVSM_OBJECTIVE_ENTITY_ENTITY || obj == NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY;
+            if (m->has_text && m->has_pair) {
+                // TextEntity*::Objective CHECKs both weights != 0 (cpp/objective.cu:709-710,758-759)
+                const float wt = cfg->text_entity_weight, ws = cfg->similarity_weight;
+                if (wt == 0.f || ws == 0.f) return fail("mixture objectives need non-zero text_entity_weight and similarity_weight");
+                m->text_scale = wt / (wt + ws);
+                m->pair_scale = ws / (wt + ws);
+            }
+            if (m->has_pair) {
+                m->maxN = cfg->max_similarity_batch_size > 0 ? cfg->max_similarity_batch_size : maxB;
+                const int pdim = m->pair_entities ? dd : dw;
+                TRY(dev_alloc(&m->pair_ids, 2 * m->maxN)); TRY(dev_alloc(&m->pair_w, m->maxN));
+                TRY(dev_alloc(&m->pair_probs, m->maxN)); TRY(dev_alloc(&m->pair_mult, m->maxN));
+                TRY(dev_alloc(&m->pair_G, 2 * m->maxN * pdim)); TRY(dev_alloc(&m->pair_msq, 2 * m->maxN));
+                TRY(dev_alloc(&m->pair_loss, 1));
+                CU(cudaHostAlloc((void**)&m->pair_loss_host, sizeof(double), cudaHostAllocDefault));
+                *m->pair_loss_host = 0.0;
+            }
+        }
         m->l2_phrase = cfg->l2_normalize_phrase_reprs != 0;
         m->l2_entity = cfg->l2_normalize_entity_reprs != 0;
         if (m->l2_phrase) TRY(dev_alloc(&m->p_norms, maxB));
@@ -1368,6 +1455,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         m->gt_splits = std::max(m->num_sms, (2 * m->num_sms + tiles - 1) / tiles);
         TRY(dev_alloc(&m->gT_part, (size_t)m->gt_splits * dw * dd, false));
         m->pull = method == NVSM_ADAM && cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE &&
+                  m->optE.agg == nullptr /* see can_pull above */ &&
                   V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
         if (m->pull) {
             TRY(dev_alloc(&m->Y, maxB * dd));
@@ -1522,7 +1610,74 @@ int nvsm_compute_cost(nvsm_model* m, const long* features, const float* fw, cons
 int nvsm_compute_gradients(nvsm_model* m) {
     if (!m) return fail("null model");
     CU(cudaSetDevice(m->device));
+    if (m->has_pair && !m->have_pair_forward) return fail("compute_gradients: the similarity objective has no forward result");
+    if (!m->has_text) {   // the pair gradients were written by the fused forward / backward kernel
+        m->have_gradients = true;
+        return 0;
+    }
     return backward(m);
+}
+
+int nvsm_similarity_compute_cost(nvsm_model* m, const long* pair_ids, const float* weights, long num_pairs) {
+    if (!m || !pair_ids || !weights) return fail("null argument");
+    if (!m->has_pair) return fail("this handle has no RepresentationSimilarity objective (nvsm_config.objective)");
+    if (num_pairs <= 0 || num_pairs > m->maxN) return fail("num_pairs %ld outside (0, %ld]", num_pairs, m->maxN);
+    CU(cudaSetDevice(m->device));
+    const long limit = m->pair_entities ? m->D : m->V;
+    for (long i = 0; i < 2 * num_pairs; ++i)
+        if (pair_ids[i] < 0 || pair_ids[i] >= limit) return fail("pair id %ld out of range at %ld", pair_ids[i], i);
+    CU(cudaMemcpyAsync(m->pair_ids, pair_ids, sizeof(idx_t) * 2 * num_pairs, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemcpyAsync(m->pair_w, weights, sizeof(float) * num_pairs, cudaMemcpyHostToDevice, m->stream));
+    CU(cudaMemsetAsync(m->pair_loss, 0, sizeof(double), m->stream));
+    m->pair_N = num_pairs;
+    PairParams p;
+    p.table = m->pair_entities ? m->E : m->W;
+    p.dim = m->pair_entities ? m->dd : m->dw;
+    p.ids = m->pair_ids; p.w = m->pair_w; p.N = num_pairs;
+    const float ef = m->cfg.clip_sigmoid ? 1e-7f : 0.0f, eb = m->cfg.clip_sigmoid ? 1e-6f : 0.0f;
+    auto fceil = [](double d) { float f = (float)d; if ((double)f < d) f = std::nextafter(f, INFINITY); return f; };
+    auto ffloor = [](double d) { float f = (float)d; if ((double)f > d) f = std::nextafter(f, -INFINITY); return f; };
+    p.sig_lo_cmp = fceil((double)ef); p.sig_lo_val = (float)(double)ef;
+    p.sig_hi_cmp = ffloor(1.0 - (double)ef); p.sig_hi_val = (float)(1.0 - (double)ef);
+    p.der_lo_cmp = ffloor((double)eb); p.der_hi_cmp = fceil(1.0 - (double)eb);
+    p.bsn = (float)std::exp(-std::log((double)num_pairs));
+    p.scale = m->pair_scale;
+    p.probs = m->pair_probs; p.mult = m->pair_mult; p.G = m->pair_G; p.loss_acc = m->pair_loss;
+    const int grid = grid_for(m, num_pairs, 8, 8);
+    phase_begin(m, PH_SCORE);
+    if (vec4_ok(p.dim)) {
+        const int nch = (p.dim / 4 + 31) / 32;
+        if (nch <= 1) LAUNCH(m, (pair_forward_backward_kernel<4, 1>), grid, 256, 0, p);
+        else if (nch <= 2) LAUNCH(m, (pair_forward_backward_kernel<4, 2>), grid, 256, 0, p);
+        else if (nch <= 4) LAUNCH(m, (pair_forward_backward_kernel<4, 4>), grid, 256, 0, p);
+        else if (nch <= 8) LAUNCH(m, (pair_forward_backward_kernel<4, 8>), grid, 256, 0, p);
+        else { phase_end(m); return fail("representation size %d too large for the similarity kernel", p.dim); }
+    } else {
+        const int nch = (p.dim + 31) / 32;
+        if (nch <= 4) LAUNCH(m, (pair_forward_backward_kernel<1, 4>), grid, 256, 0, p);
+        else if (nch <= 16) LAUNCH(m, (pair_forward_backward_kernel<1, 16>), grid, 256, 0, p);
+        else if (nch <= 32) LAUNCH(m, (pair_forward_backward_kernel<1, 32>), grid, 256, 0, p);
+        else { phase_end(m); return fail("representation size %d too large for the similarity kernel", p.dim); }
+    }
+    phase_end(m);
+    CU(cudaMemcpyAsync(m->pair_loss_host, m->pair_loss, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    m->have_pair_forward = true;
+    m->have_gradients = false;
+    return 0;
+}
+
+int nvsm_similarity_get_cost(nvsm_model* m, float* cost) {
+    if (!m || !cost) return fail("null argument");
+    if (!m->has_pair || m->pair_N <= 0) return fail("no similarity forward result");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->stream));
+    *cost = (float)(-(*m->pair_loss_host) / (double)m->pair_N);   // cpp/intermediate_results.cu:80-124
+    return 0;
+}
+
+float nvsm_similarity_scaled_regularization_lambda(nvsm_model* m) {
+    if (!m || m->pair_N <= 0) return 0.f;
+    return m->cfg.regularization_lambda / (float)m->pair_N;
 }
 
 int nvsm_update(nvsm_model* m, float lr, float lambda) {
@@ -1837,6 +1992,7 @@ int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank) {
 int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode) {
     if (!m) return fail("null argument");
     if (mode != NVSM_SPARSE_LOCAL && mode != NVSM_SPARSE_ALLGATHER) return fail("unknown sparse mode %d", mode);
+    if (mode == NVSM_SPARSE_ALLGATHER && m->has_pair) return fail("NVSM_SPARSE_ALLGATHER is implemented for the TextEntity objective only");
     if (mode == NVSM_SPARSE_ALLGATHER && m->nranks > 1 && !m->ag_mult) {
         CU(cudaSetDevice(m->device));
         const size_t G = (size_t)m->maxB * m->nranks;

@@ -30,6 +30,8 @@ UPDATE_METHODS = {
 NONLINEARITIES = {"tanh": TANH, "hard_tanh": HARD_TANH}
 
 SPARSE_LOCAL, SPARSE_ALLGATHER = 0, 1
+# Model<...::Objective> instantiations of the reference (cpp/model.cu:222-228)
+TEXT_ENTITY, ENTITY_ENTITY, TERM_TERM, TEXT_ENTITY_ENTITY_ENTITY, TEXT_ENTITY_TERM_TERM = 0, 1, 2, 3, 4
 
 WORD_REPRS = "word_representations-representations"
 ENTITY_REPRS = "entity_representations-representations"
@@ -60,6 +62,9 @@ class TrainConfig:
     learning_rate: float = 0.0
     update_method: int = SGD
     adam_mode: int = SPARSE
+    text_entity_weight: float = 1.0
+    entity_entity_weight: float = 0.0
+    term_term_weight: float = 0.0
     num_epochs: int = 1
 
 
@@ -174,6 +179,61 @@ class ForwardResult:
         return self._model.get_tensor("similarity_probs")
 
 
+class SimilarityBatch:
+    """RepresentationSimilarity::Batch (include/cuNVSM/data.h:560-614): features_ [2*batch] pair ids, weights_ [batch]."""
+
+    def __init__(self, batch_size):
+        self.batch_size_ = int(batch_size)
+        self.features_, keep_f = _pinned((2 * self.batch_size_,), np.int64)
+        self.weights_, keep_w = _pinned((self.batch_size_,), np.float32)
+        self._keep = [keep_f, keep_w]
+        self.num_instances_ = 0
+
+    def fill(self, pairs, weights=None):
+        pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+        N = pairs.shape[0]
+        assert N <= self.batch_size_
+        self.features_[:2 * N] = pairs.ravel()
+        self.weights_[:N] = 1.0 if weights is None else np.asarray(weights, dtype=np.float32)
+        self.num_instances_ = N
+        return self
+
+    def num_instances(self):
+        return self.num_instances_
+
+
+class SimilarityForwardResult:
+    """RepresentationSimilarity::ForwardResult: get_cost / scaled_regularization_lambda / get_similarity_probs."""
+
+    def __init__(self, model, num_instances):
+        self.model, self.num_instances = model, num_instances
+
+    def get_cost(self):
+        c = ctypes.c_float()
+        check(self.model.L.nvsm_similarity_get_cost(self.model.h, ctypes.byref(c)))
+        return float(c.value)
+
+    def scaled_regularization_lambda(self):
+        return float(self.model.L.nvsm_similarity_scaled_regularization_lambda(self.model.h))
+
+    def get_similarity_probs(self):
+        return self.model.get_tensor("similarity_pair_probs")
+
+
+class MultiForwardResult:
+    """MultiForwardResultBase (cpp/intermediate_results.cu:186-240): plain averages over the constituents."""
+
+    def __init__(self, *results):
+        self.results = results
+
+    def get_cost(self):
+        return float(np.float32(sum(np.float32(r.get_cost()) for r in self.results)) / np.float32(len(self.results)))
+
+    def scaled_regularization_lambda(self):
+        return float(np.float32(sum(np.float32(r.scaled_regularization_lambda()) for r in self.results))
+                     / np.float32(len(self.results)))
+
+
 class Gradients:
     def __init__(self, model):
         self._model = model
@@ -186,7 +246,7 @@ class Model:
     """Model<TextEntity::Objective> (include/cuNVSM/model.h:76-130) over the C ABI."""
 
     def __init__(self, num_words, num_entities, desc, train_config, device=0, gemm_mode=GEMM_FP32,
-                 num_batch_slots=1, max_batch_size=None):
+                 num_batch_slots=1, max_batch_size=None, objective=TEXT_ENTITY, max_similarity_batch_size=None):
         self.L = _lib.load()
         self.desc, self.train_config = desc, train_config
         self.num_words, self.num_entities = int(num_words), int(num_entities)
@@ -205,6 +265,11 @@ class Model:
         cfg.window_size = train_config.window_size
         cfg.regularization_lambda = train_config.regularization_lambda
         cfg.device, cfg.gemm_mode, cfg.num_batch_slots = device, gemm_mode, num_batch_slots
+        self.objective = cfg.objective = objective
+        cfg.text_entity_weight = train_config.text_entity_weight
+        cfg.similarity_weight = (train_config.entity_entity_weight if objective in (ENTITY_ENTITY, TEXT_ENTITY_ENTITY_ENTITY)
+                                 else train_config.term_term_weight)
+        cfg.max_similarity_batch_size = int(max_similarity_batch_size or train_config.batch_size)
         self.cfg = cfg
         self.h = ctypes.c_void_p()
         check(self.L.nvsm_create(ctypes.byref(cfg), ctypes.byref(self.h)))
@@ -288,6 +353,21 @@ class Model:
     def compute_gradients(self, result=None):
         check(self.L.nvsm_compute_gradients(self.h))
         return Gradients(self)
+
+    # --- RepresentationSimilarity objective (EntityEntity / TermTerm and the mixtures) ----------
+    def similarity_compute_cost(self, batch):
+        """RepresentationSimilarity::Objective::compute_cost (cpp/objective.cu:487-573) on a SimilarityBatch."""
+        N = batch.num_instances_
+        self._keepalive_pairs = batch
+        check(self.L.nvsm_similarity_compute_cost(self.h, _pl(batch.features_), _pf(batch.weights_), N))
+        return SimilarityForwardResult(self, N)
+
+    def compute_cost_mixture(self, text_batch, similarity_batch, rng=None, entity_ids=None):
+        """TextEntity{EntityEntity,TermTerm}::Objective::compute_cost (cpp/objective.cu:713-724,762-773): both
+        constituents on their own batch; the result averages their costs and scaled lambdas."""
+        text = self.compute_cost(text_batch, rng, entity_ids)
+        sim = self.similarity_compute_cost(similarity_batch)
+        return MultiForwardResult(text, sim)
 
     def update(self, gradients, learning_rate, scaled_regularization_lambda):
         check(self.L.nvsm_update(self.h, learning_rate, scaled_regularization_lambda))

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <tuple>
 #include <vector>
 
 #include "../nvsm_b200.h"
@@ -56,6 +57,8 @@ class Batch : public BatchInterface {
     clear();
   }
   explicit Batch(const lse::TrainConfig& train_config) : Batch(train_config.batch_size(), train_config.window_size()) {}
+  // Forward constructor (reference: include/cuNVSM/data.h:120-121), for std::tuple<Batch...> of the mixtures.
+  Batch(const std::tuple<size_t, size_t>& args) : Batch(std::get<0>(args), std::get<1>(args)) {}
   virtual ~Batch() {
     nvsm_host_free(features_); nvsm_host_free(feature_weights_); nvsm_host_free(labels_); nvsm_host_free(weights_);
   }
@@ -159,5 +162,59 @@ class SyntheticSource : public DataSourceBase {
 };
 
 }  // namespace TextEntity
+
+// reference: RepresentationSimilarity::Batch, include/cuNVSM/data.h:551-614 / cpp/data.cu:157-222 — pairs of object
+// ids (features_[2 i], features_[2 i + 1]) with one weight per pair, pinned host memory.
+namespace RepresentationSimilarity {
+
+typedef std::tuple<ObjectIdxType, ObjectIdxType, WeightType> InstanceT;
+
+class Batch : public BatchInterface {
+ public:
+  explicit Batch(const size_t batch_size) : batch_size_(batch_size), num_instances_(0) {
+    NVSM_CHECK(batch_size_ > 0, "batch size must be positive");
+    void* raw = nullptr;
+    NVSM_CHECK(nvsm_host_alloc(&raw, batch_size_ * 2 * sizeof(ObjectIdxType)) == 0, nvsm_last_error());
+    features_ = static_cast<ObjectIdxType*>(raw);
+    NVSM_CHECK(nvsm_host_alloc(&raw, batch_size_ * sizeof(WeightType)) == 0, nvsm_last_error());
+    weights_ = static_cast<WeightType*>(raw);
+  }
+  explicit Batch(const lse::TrainConfig& train_config) : Batch(static_cast<size_t>(train_config.batch_size())) {}
+  Batch(const size_t batch_size, const size_t /* window_size, ignored like the reference */) : Batch(batch_size) {}
+  Batch(const std::tuple<size_t>& args) : Batch(std::get<0>(args)) {}
+  virtual ~Batch() { nvsm_host_free(features_); nvsm_host_free(weights_); }
+  Batch(const Batch&) = delete;
+  Batch& operator=(const Batch&) = delete;
+
+  virtual void clear() override { num_instances_ = 0; }
+  virtual bool full() const override { return num_instances_ == batch_size_; }
+  virtual bool empty() const override { return num_instances_ == 0; }
+  virtual size_t num_instances() const override { return num_instances_; }
+  virtual size_t maximum_size() const override { return batch_size_; }
+
+  // RepresentationSimilarity::DataSource::next (cpp/data.cu:316-334)
+  bool push_instance(const InstanceT& instance) {
+    if (full()) return false;
+    features_[2 * num_instances_] = std::get<0>(instance);
+    features_[2 * num_instances_ + 1] = std::get<1>(instance);
+    weights_[num_instances_] = std::get<2>(instance);
+    ++num_instances_;
+    return true;
+  }
+
+  const ObjectIdxType* features() const { return features_; }
+  const WeightType* weights() const { return weights_; }
+
+ private:
+  const size_t batch_size_;
+  ObjectIdxType* features_ = nullptr;
+  WeightType* weights_ = nullptr;
+  size_t num_instances_;
+};
+
+}  // namespace RepresentationSimilarity
+
+namespace EntityEntity { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; }
+namespace TermTerm { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; }
 
 #endif  // CUNVSM_B200_DATA_H

@@ -43,6 +43,7 @@ class Typedefs {
 
 template <typename ObjectiveT>
 class Model;
+class MultiForwardResult;
 
 namespace TextEntity {
 
@@ -77,6 +78,7 @@ class ForwardResult {
   mutable FloatT cost_ = 0;
   mutable bool have_cost_ = false;
   template <typename O> friend class ::Model;
+  friend class ::MultiForwardResult;
 };
 
 // reference: Gradients / SingleGradients (intermediate_results.h:45-110)
@@ -91,9 +93,9 @@ class Gradients {
     return out;
   }
  private:
-  explicit Gradients(nvsm_model* m, const ForwardResult* r) : model_(m), result_(r) {}
+  explicit Gradients(nvsm_model* m, const void* r) : model_(m), result_(r) {}
   nvsm_model* model_;
-  const ForwardResult* result_;
+  const void* result_;   // the forward result these gradients belong to (must outlive them, like the reference)
   template <typename O> friend class ::Model;
 };
 
@@ -106,9 +108,104 @@ class Objective {
   typedef Batch BatchType;
   typedef ForwardResult ForwardResultType;
   typedef Gradients GradientsType;
+  static const int kObjective = NVSM_OBJECTIVE_TEXT_ENTITY;
+  template <typename ModelT>
+  static ForwardResultType* compute_cost(const ModelT* model, const BatchType& batch, RNG* const rng) {
+    return model->text_forward(batch, rng);
+  }
 };
 
 }  // namespace TextEntity
+
+namespace RepresentationSimilarity {
+
+// reference: RepresentationSimilarity::ForwardResult, intermediate_results.h:311-361
+class ForwardResult {
+ public:
+  typedef Typedefs::FloatT FloatT;
+  FloatT get_cost() const {
+    if (!have_cost_) { NVSM_ABORT_ON(nvsm_similarity_get_cost(model_, &cost_)); have_cost_ = true; }
+    return cost_;
+  }
+  FloatT scaled_regularization_lambda() const { return lambda_; }
+  std::vector<FloatT> get_similarity_probs() const {
+    const long n = nvsm_tensor_size(model_, "similarity_pair_probs");
+    std::vector<FloatT> out(n);
+    NVSM_ABORT_ON(nvsm_get_tensor(model_, "similarity_pair_probs", out.data(), n));
+    return out;
+  }
+  long age() const { return 0; }
+
+ private:
+  ForwardResult(nvsm_model* m, FloatT lambda) : model_(m), lambda_(lambda) {}
+  nvsm_model* model_;
+  FloatT lambda_;
+  mutable FloatT cost_ = 0;
+  mutable bool have_cost_ = false;
+  template <typename O> friend class ::Model;
+};
+
+template <int kObjectiveId>
+class ObjectiveT {
+ public:
+  typedef Typedefs::WordIdxType WordIdxType;
+  typedef Typedefs::EntityIdxType EntityIdxType;
+  typedef Typedefs::FloatT FloatT;
+  typedef Batch BatchType;
+  typedef ForwardResult ForwardResultType;
+  typedef TextEntity::Gradients GradientsType;
+  static const int kObjective = kObjectiveId;
+  template <typename ModelT>
+  static ForwardResultType* compute_cost(const ModelT* model, const BatchType& batch, RNG* const) {
+    return model->pair_forward(batch);
+  }
+};
+
+}  // namespace RepresentationSimilarity
+
+// reference: EntityEntity::Objective / TermTerm::Objective, objective.h:134-162
+namespace EntityEntity { typedef RepresentationSimilarity::ObjectiveT<NVSM_OBJECTIVE_ENTITY_ENTITY> Objective; }
+namespace TermTerm { typedef RepresentationSimilarity::ObjectiveT<NVSM_OBJECTIVE_TERM_TERM> Objective; }
+
+// reference: MultiForwardResultBase, intermediate_results.h:167-195 / cpp/intermediate_results.cu:186-240 — cost and
+// scaled lambda are the plain averages over the constituents.
+class MultiForwardResult {
+ public:
+  typedef Typedefs::FloatT FloatT;
+  FloatT get_cost() const { return (text_->get_cost() + pair_->get_cost()) / 2; }
+  FloatT scaled_regularization_lambda() const {
+    return (text_->scaled_regularization_lambda() + pair_->scaled_regularization_lambda()) / 2;
+  }
+  long age() const { return text_->age(); }
+  const TextEntity::ForwardResult& text() const { return *text_; }
+  const RepresentationSimilarity::ForwardResult& similarity() const { return *pair_; }
+
+ private:
+  MultiForwardResult(TextEntity::ForwardResult* t, RepresentationSimilarity::ForwardResult* p) : text_(t), pair_(p) {}
+  std::unique_ptr<TextEntity::ForwardResult> text_;
+  std::unique_ptr<RepresentationSimilarity::ForwardResult> pair_;
+  template <typename O> friend class ::Model;
+};
+
+// reference: TextEntityEntityEntity::Objective / TextEntityTermTerm::Objective, objective.h:164-238 — both
+// constituents on their own batch, gradients merged with weights w_k / sum_k w_k.
+template <int kObjectiveId>
+class MixtureObjectiveT {
+ public:
+  typedef Typedefs::WordIdxType WordIdxType;
+  typedef Typedefs::EntityIdxType EntityIdxType;
+  typedef Typedefs::FloatT FloatT;
+  typedef std::tuple<TextEntity::Batch, RepresentationSimilarity::Batch> BatchType;
+  typedef MultiForwardResult ForwardResultType;
+  typedef TextEntity::Gradients GradientsType;
+  static const int kObjective = kObjectiveId;
+  template <typename ModelT>
+  static ForwardResultType* compute_cost(const ModelT* model, const BatchType& batch, RNG* const rng) {
+    return model->mixture_forward(std::get<0>(batch), std::get<1>(batch), rng);
+  }
+};
+namespace TextEntityEntityEntity { typedef MixtureObjectiveT<NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY> Objective; }
+namespace TextEntityTermTerm { typedef MixtureObjectiveT<NVSM_OBJECTIVE_TEXT_ENTITY_TERM_TERM> Objective; }
 
 template <typename ObjectiveT>
 class Model {
@@ -142,6 +239,11 @@ class Model {
     c.window_size = train_config.window_size();
     c.regularization_lambda = train_config.regularization_lambda();
     c.device = device; c.gemm_mode = gemm_mode; c.num_batch_slots = 1;
+    c.objective = ObjectiveT::kObjective;
+    c.text_entity_weight = train_config.text_entity_weight();
+    c.similarity_weight = (c.objective == NVSM_OBJECTIVE_ENTITY_ENTITY || c.objective == NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY)
+                              ? train_config.entity_entity_weight() : train_config.term_term_weight();
+    c.max_similarity_batch_size = train_config.batch_size();
     NVSM_ABORT_ON(nvsm_create(&c, &handle_));
   }
   virtual ~Model() { nvsm_destroy(handle_); }
@@ -175,16 +277,21 @@ class Model {
     nvsm_detail::rng_set_state(rng, st);
   }
 
-  // reference: Model::compute_cost, cpp/objective.cu:30-313. Negatives are drawn from `rng` on the
-  // host exactly like UniformLabelGenerator (cpp/labels.cu:3-22).
+  // reference: Model::compute_cost (cpp/model.cu:136-143) -> ObjectiveT::compute_cost
   ForwardResult* compute_cost(const Batch& batch, RNG* const rng) const {
+    return ObjectiveT::compute_cost(this, batch, rng);
+  }
+
+  // TextEntity::Objective::compute_cost, cpp/objective.cu:30-313. Negatives are drawn from `rng` on the
+  // host exactly like UniformLabelGenerator (cpp/labels.cu:3-22).
+  TextEntity::ForwardResult* text_forward(const TextEntity::Batch& batch, RNG* const rng) const {
     const size_t B = batch.num_instances(), R = train_config_.num_random_entities() + 1;
     NVSM_CHECK(batch.window_size() == static_cast<size_t>(train_config_.window_size()), "window size mismatch");
     if (device_sampler_) {
       NVSM_ABORT_ON(nvsm_step_sampled(handle_, batch.features(), batch.feature_weights(), batch.labels(), batch.weights(),
                                       B, 0.0f, /*train=*/0));
       ++forward_counter_;
-      return new ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
+      return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
     }
     entity_ids_.resize(B * R);
     unsigned long st = nvsm_detail::rng_get_state(*rng);
@@ -194,7 +301,20 @@ class Model {
     NVSM_ABORT_ON(nvsm_compute_cost(handle_, batch.features(), batch.feature_weights(), entity_ids_.data(),
                                     batch.weights(), B));
     ++forward_counter_;
-    return new ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
+    return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
+  }
+
+  // RepresentationSimilarity::Objective::compute_cost, cpp/objective.cu:487-573
+  RepresentationSimilarity::ForwardResult* pair_forward(const RepresentationSimilarity::Batch& batch) const {
+    NVSM_ABORT_ON(nvsm_similarity_compute_cost(handle_, batch.features(), batch.weights(), batch.num_instances()));
+    return new RepresentationSimilarity::ForwardResult(handle_, nvsm_similarity_scaled_regularization_lambda(handle_));
+  }
+
+  // TextEntity{EntityEntity,TermTerm}::Objective::compute_cost, cpp/objective.cu:713-724,762-773
+  MultiForwardResult* mixture_forward(const TextEntity::Batch& text, const RepresentationSimilarity::Batch& pairs,
+                                      RNG* const rng) const {
+    TextEntity::ForwardResult* const t = text_forward(text, rng);
+    return new MultiForwardResult(t, pair_forward(pairs));
   }
 
   // reference: Model::compute_gradients, cpp/objective.cu:315-481

@@ -43,6 +43,10 @@ enum { NVSM_SGD = 0, NVSM_ADAGRAD = 1, NVSM_ADAM = 2 };
 enum { NVSM_ADAM_SPARSE = 1, NVSM_ADAM_DENSE_UPDATE = 2, NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE = 3 };
 /* projection GEMM arithmetic */
 enum { NVSM_GEMM_FP32 = 0, NVSM_GEMM_TF32 = 1, NVSM_GEMM_3XTF32 = 2 };
+/* Objectives of the reference (include/cuNVSM/objective.h): TextEntity (the NVSM/LSE step), the pairwise
+ * RepresentationSimilarity objective over the entity or the word table, and the two mixtures. */
+enum { NVSM_OBJECTIVE_TEXT_ENTITY = 0, NVSM_OBJECTIVE_ENTITY_ENTITY = 1, NVSM_OBJECTIVE_TERM_TERM = 2,
+       NVSM_OBJECTIVE_TEXT_ENTITY_ENTITY_ENTITY = 3, NVSM_OBJECTIVE_TEXT_ENTITY_TERM_TERM = 4 };
 /* Multi-GPU treatment of the sparse tables (nvsm_comm_set_sparse_mode). */
 enum { NVSM_SPARSE_LOCAL = 0, NVSM_SPARSE_ALLGATHER = 1 };
 
@@ -68,7 +72,11 @@ typedef struct nvsm_config {
     int device;                   /* CUDA device ordinal */
     int gemm_mode;                /* NVSM_GEMM_* */
     int num_batch_slots;          /* device-resident batch slots for nvsm_stage_batch (>= 1) */
-    int reserved[7];
+    int objective;                /* NVSM_OBJECTIVE_*: which Model<...::Objective> this handle is (cpp/model.cu:222-228) */
+    float text_entity_weight;     /* TrainConfig.text_entity_weight   (mixtures; cpp/main.cu:704-706) */
+    float similarity_weight;      /* TrainConfig.entity_entity_weight or .term_term_weight */
+    int max_similarity_batch_size; /* largest RepresentationSimilarity::Batch (pairs) a step will see */
+    int reserved[3];
 } nvsm_config;
 
 NVSM_API const char* nvsm_last_error(void);
@@ -188,6 +196,19 @@ NVSM_API int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, 
  * tensor-core GEMM on device-resident (zero) operands. */
 NVSM_API int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int splits, int with_stats,
                                 int iters, float* ms_out);
+
+/* RepresentationSimilarity::Objective::compute_cost + compute_gradients — cpp/objective.cu:487-672 — on a
+ * RepresentationSimilarity::Batch (include/cuNVSM/data.h:560-614): pair_ids [2*num_pairs] HOST (adjacent ids form a
+ * pair, rows of the entity table for *_ENTITY_ENTITY objectives, of the word table for *_TERM_TERM), weights
+ * [num_pairs] HOST. Only valid on handles created with such an objective. For the mixtures call it next to
+ * nvsm_compute_cost, then nvsm_compute_gradients and nvsm_update as usual: gradients are merged with the weights
+ * w_k / sum_k w_k (MergeGradientsFn, cpp/intermediate_results.cu:3-60), ForwardResult::get_cost and
+ * scaled_regularization_lambda of the mixture are the plain averages of the constituents' (:200-235).
+ * Readable afterwards: "similarity_pair_probs" [num_pairs], "similarity_multipliers" [num_pairs],
+ * "grad_similarity" [2*num_pairs, dim]. */
+NVSM_API int nvsm_similarity_compute_cost(nvsm_model* m, const long* pair_ids, const float* weights, long num_pairs);
+NVSM_API int nvsm_similarity_get_cost(nvsm_model* m, float* cost);
+NVSM_API float nvsm_similarity_scaled_regularization_lambda(nvsm_model* m);
 
 /* Multi-GPU (one process per GPU). The batch is sharded by n-gram row; the library
  * all-reduces batch-norm statistics and the dense gradients with NCCL (new: the reference

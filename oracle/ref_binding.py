@@ -54,6 +54,18 @@ def lib(dtype):
         "ref_update": ([vp, cd, cd], None),
         "ref_step": ([vp, vp, cd], cd),
         "ref_synchronize": ([], None),
+        "ref2_create": ([ci, cl, cl, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cd, cd, cd, cul], vp),
+        "ref2_destroy": ([vp], None),
+        "ref2_get_rng_state": ([vp], cul),
+        "ref2_tensor_size": ([vp, ctypes.c_char_p], cl),
+        "ref2_get_tensor": ([vp, ctypes.c_char_p, pf], ci),
+        "ref2_fill_text": ([vp, pl, pf, pl, pf, cl], None),
+        "ref2_fill_pairs": ([vp, pl, pf, cl], None),
+        "ref2_forward": ([vp], None),
+        "ref2_get_cost": ([vp], cd),
+        "ref2_scaled_regularization_lambda": ([vp], cd),
+        "ref2_compute_gradients": ([vp], None),
+        "ref2_update": ([vp, cd, cd], None),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(L, name)
@@ -162,3 +174,75 @@ class Model:
 
     def synchronize(self):
         self.L.ref_synchronize()
+
+
+ENTITY_ENTITY, TERM_TERM, TEXT_ENTITY_ENTITY_ENTITY, TEXT_ENTITY_TERM_TERM = 1, 2, 3, 4
+
+
+class ObjectiveModel:
+    """Model<EntityEntity / TermTerm / TextEntityEntityEntity / TextEntityTermTerm ::Objective> of the reference
+    (cpp/model.cu:222-228); owns its batch(es)."""
+
+    def __init__(self, objective, num_words, num_entities, word_repr_size, entity_repr_size, *, batch_size, window_size,
+                 num_random_entities, similarity_batch_size, nonlinearity=TANH, batch_normalization=False,
+                 clip_sigmoid=False, bias_negative_samples=False, update_method=SGD, adam_mode=SPARSE,
+                 regularization_lambda=0.0, text_entity_weight=1.0, similarity_weight=0.0, seed=1, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.L = lib(self.dtype)
+        self.window = window_size
+        self.h = self.L.ref2_create(objective, num_words, num_entities, word_repr_size, entity_repr_size, nonlinearity,
+                                    int(batch_normalization), int(clip_sigmoid), int(bias_negative_samples),
+                                    update_method, adam_mode, batch_size, window_size, num_random_entities,
+                                    similarity_batch_size, float(regularization_lambda), float(text_entity_weight),
+                                    float(similarity_weight), seed)
+        assert self.h, "unknown objective"
+
+    def __del__(self):
+        try:
+            self.L.ref2_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def rng_state(self):
+        return self.L.ref2_get_rng_state(self.h)
+
+    def _pf(self, a):
+        return a.ctypes.data_as(ctypes.POINTER(self.L._ct))
+
+    def fill_text(self, features, labels, feature_weights, weights):
+        f = np.ascontiguousarray(features, dtype=np.int64).ravel()
+        fw = np.ascontiguousarray(feature_weights, dtype=self.dtype).ravel()
+        lab = np.ascontiguousarray(labels, dtype=np.int64).ravel()
+        w = np.ascontiguousarray(weights, dtype=self.dtype).ravel()
+        pl = ctypes.POINTER(ctypes.c_long)
+        self.L.ref2_fill_text(self.h, f.ctypes.data_as(pl), self._pf(fw), lab.ctypes.data_as(pl), self._pf(w), lab.size)
+
+    def fill_pairs(self, pairs, weights):
+        ids = np.ascontiguousarray(pairs, dtype=np.int64).ravel()
+        w = np.ascontiguousarray(weights, dtype=self.dtype).ravel()
+        assert ids.size == 2 * w.size
+        self.L.ref2_fill_pairs(self.h, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_long)), self._pf(w), w.size)
+
+    def get(self, name):
+        n = self.L.ref2_tensor_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros(n, dtype=self.dtype)
+        assert self.L.ref2_get_tensor(self.h, name.encode(), self._pf(out)) == 0
+        return out
+
+    def forward(self):
+        self.L.ref2_forward(self.h)
+
+    def get_cost(self):
+        return self.L.ref2_get_cost(self.h)
+
+    def scaled_lambda(self):
+        return self.L.ref2_scaled_regularization_lambda(self.h)
+
+    def compute_gradients(self):
+        self.L.ref2_compute_gradients(self.h)
+
+    def update(self, lr, scaled_lambda):
+        self.L.ref2_update(self.h, lr, scaled_lambda)

@@ -96,6 +96,20 @@ def test_cpp_facade_matches_python_driver():
     cs = sum(float(v.astype(np.float64).sum()) for v in m.get_data().values())
     assert abs(cs - float(lines["checksum"])) <= 1e-4 * abs(cs) + 1e-3
     assert int(lines["params"]) == m.num_parameters()
+    # the TextEntityEntityEntity mixture through Model<TextEntityEntityEntity::Objective>
+    mtc = nv.TrainConfig(batch_size=256, window_size=4, num_random_entities=3, regularization_lambda=0.01,
+                         update_method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE, text_entity_weight=0.75,
+                         entity_entity_weight=0.25)
+    mm = nv.Model(100, 60, desc, mtc, gemm_mode=nv.GEMM_FP32, objective=nv.TEXT_ENTITY_ENTITY_ENTITY)
+    mrng = nv.RNG(5)
+    mm.initialize(mrng)
+    pairs = nv.SimilarityBatch(256).fill(np.stack([i % 60, (i * 11 + 3) % 60], 1), 1.0 + (i % 3))
+    for step in range(3):
+        r = mm.compute_cost_mixture(batch, pairs, mrng)
+        mm.backprop(r, 0.001)
+        assert abs(r.get_cost() - float(lines["mixcost %d" % step])) <= 2e-6 * abs(r.get_cost())
+    mcs = sum(float(v.astype(np.float64).sum()) for v in mm.get_data().values())
+    assert abs(mcs - float(lines["mixchecksum"])) <= 1e-4 * abs(mcs) + 1e-3
 
 
 @pytest.mark.gpu
@@ -112,3 +126,20 @@ def test_cli_trains_on_synthetic_source(tmp_path):
     W = np.load(out + "_2.word_representations-representations.npy")
     T = np.load(out + "_2.word_entity_mapping-transform.npy")
     assert W.shape == (2000, 64) and T.shape == (64, 32) and np.isfinite(W).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flag", ["--entity_similarity_weight", "--term_similarity_weight"])
+def test_cli_trains_mixture_objective(tmp_path, flag):
+    """cuNVSMTrainModel with a mixture weight selects TextEntityEntityEntity / TextEntityTermTerm (cpp/main.cu:729-757)."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "64",
+                          "--entity_repr_size", "32", "--batch_size", "1024", "--window_size", "5", "--num_random_entities", "4",
+                          "--seed", "3", "--update_method", "full_adam", "--nonlinearity", "tanh", flag, "0.25",
+                          "--synthetic_num_words", "2000", "--synthetic_num_entities", "500", "--synthetic_num_batches", "10"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "Epoch #2" in res.stdout
+    import re
+    costs = [float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)]
+    assert len(costs) == 2 and np.isfinite(costs).all() and costs[1] < costs[0]

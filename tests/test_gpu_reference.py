@@ -230,3 +230,113 @@ def test_loss_curve_matches_reference_1000_steps(gemm_mode):
     print("gemm_mode %d: reference loss %.4f -> %.4f, max |cuda - reference| = %.2e (first 100: %.2e, 500: %.2e)" % (
         gemm_mode, r[0], r[-1], dev.max(), dev[:100].max(), dev[:500].max()))
     assert dev.max() <= 1e-3, dev.max()
+
+
+# ---- 8f-1: RepresentationSimilarity objectives and the mixtures against the reference --------------------------------
+SIM_METHODS = [(nv.SGD, 0), (nv.ADAGRAD, 0), (nv.ADAM, nv.SPARSE), (nv.ADAM, nv.DENSE_UPDATE),
+               (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)]
+
+
+def _objective_models(objective, c, method, N, wt, ws, lam=0.01):
+    rm = R.ObjectiveModel(objective, c["V"], c["D"], c["dw"], c["dd"], batch_size=c["B"], window_size=c["n"],
+                          num_random_entities=c["z"], similarity_batch_size=N, nonlinearity=c["nonlinearity"],
+                          batch_normalization=c["bn"], clip_sigmoid=c["clip"], bias_negative_samples=c["bias_neg"],
+                          update_method=method[0], adam_mode=method[1], regularization_lambda=lam,
+                          text_entity_weight=wt, similarity_weight=ws, seed=7, dtype=np.float32)
+    desc = nv.ModelDesc(word_repr_size=c["dw"], entity_repr_size=c["dd"], batch_normalization=c["bn"],
+                        nonlinearity=c["nonlinearity"], clip_sigmoid=c["clip"], bias_negative_samples=c["bias_neg"])
+    ee = objective in (nv.ENTITY_ENTITY, nv.TEXT_ENTITY_ENTITY_ENTITY)
+    tc = nv.TrainConfig(batch_size=c["B"], window_size=c["n"], num_random_entities=c["z"], regularization_lambda=lam,
+                        update_method=method[0], adam_mode=method[1], text_entity_weight=wt,
+                        entity_entity_weight=ws if ee else 0.0, term_term_weight=0.0 if ee else ws)
+    gm = nv.Model(c["V"], c["D"], desc, tc, objective=objective, max_similarity_batch_size=N)
+    rng = nv.RNG(7)
+    gm.initialize(rng)
+    assert rng.state == rm.rng_state
+    for rname, _, gname in PARAMS:
+        np.testing.assert_array_equal(rm.get(rname), gm.get_tensor(gname), err_msg="init " + rname)
+    return rm, gm, rng
+
+
+def _check_params(gm, rm, method, lr, what):
+    for rname, _, gname in PARAMS:
+        ref_value = rm.get(rname)
+        floor = 1e-5 if method[0] != nv.ADAM else 2e-3 * lr / max(np.abs(ref_value).max(), 1e-30)
+        assert_close(gm.get_tensor(gname), ref_value, 5e-4, max(floor, 1e-5), "%s %s" % (rname, what))
+        gm.set_tensor(gname, ref_value)
+
+
+@pytest.mark.parametrize("objective", [nv.ENTITY_ENTITY, nv.TERM_TERM], ids=["entity_entity", "term_term"])
+@pytest.mark.parametrize("method", SIM_METHODS, ids=lambda m: "m%d_%d" % m)
+def test_similarity_objective_matches_reference(objective, method):
+    """Model<EntityEntity::Objective> / Model<TermTerm::Objective> (cpp/objective.cu:485-700): cost, pair
+    probabilities through the gradient columns, and the one updated table for three steps; the other parameters must
+    stay untouched (the reference skips gradient-less parameters, cpp/params.cu:301-304)."""
+    c = CASES[1]
+    N = 384
+    rm, gm, _ = _objective_models(objective, c, method, N, 1.0, 1.0)
+    nrng = np.random.default_rng(3)
+    limit = c["D"] if objective == nv.ENTITY_ENTITY else c["V"]
+    gname = "grad_entity_repr" if objective == nv.ENTITY_ENTITY else "grad_phrase_reprs"
+    lr = 0.05
+    for step in range(3):
+        pairs = nrng.integers(0, limit, size=(N, 2), dtype=np.int64)
+        w = nrng.uniform(0.0, 2.0, size=N).astype(np.float32)
+        rm.fill_pairs(pairs, w); rm.forward()
+        res = gm.similarity_compute_cost(nv.SimilarityBatch(N).fill(pairs, w))
+        rcost = rm.get_cost()
+        assert abs(res.get_cost() - rcost) <= 2e-4 * abs(rcost) + 1e-7
+        assert abs(res.scaled_regularization_lambda() - rm.scaled_lambda()) <= 1e-9
+        rm.compute_gradients(); gm.compute_gradients(res)
+        assert_close(gm.get_tensor("grad_similarity"), rm.get(gname), 2e-4, 1e-5, "pair gradient step %d" % step)
+        rm.update(lr, rm.scaled_lambda()); gm.update(None, lr, res.scaled_regularization_lambda())
+        _check_params(gm, rm, method, lr, "after step %d" % step)
+
+
+@pytest.mark.parametrize("objective", [nv.TEXT_ENTITY_ENTITY_ENTITY, nv.TEXT_ENTITY_TERM_TERM], ids=["te_ee", "te_tt"])
+@pytest.mark.parametrize("method", [(nv.SGD, 0), (nv.ADAM, nv.DENSE_UPDATE), (nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)],
+                         ids=lambda m: "m%d_%d" % m)
+@pytest.mark.parametrize("case", [1, 2])
+def test_mixture_objective_matches_reference(objective, method, case):
+    """TextEntityEntityEntity / TextEntityTermTerm (cpp/objective.cu:700-794): merged gradients with weights
+    w_k / sum w_k, averaged cost and lambda, every optimiser that supports multiple gradient descriptors."""
+    c = CASES[case]
+    N = 256
+    wt, ws = 0.7, 0.3
+    rm, gm, rng = _objective_models(objective, c, method, N, wt, ws)
+    nrng = np.random.default_rng(9)
+    limit = c["D"] if objective == nv.TEXT_ENTITY_ENTITY_ENTITY else c["V"]
+    lr = 0.05
+    for step in range(3):
+        f, fw, labels, w = make_batch(nrng, c["B"], c["n"], c["V"], c["D"], c["z"])
+        pairs = nrng.integers(0, limit, size=(N, 2), dtype=np.int64)
+        pw = nrng.uniform(0.0, 2.0, size=N).astype(np.float32)
+        rm.fill_text(f, labels, fw, w); rm.fill_pairs(pairs, pw); rm.forward()
+        res = gm.compute_cost_mixture(nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w), nv.SimilarityBatch(N).fill(pairs, pw), rng)
+        assert rng.state == rm.rng_state
+        rcost = rm.get_cost()
+        assert abs(res.get_cost() - rcost) <= 2e-4 * abs(rcost) + 1e-7
+        assert abs(res.scaled_regularization_lambda() - rm.scaled_lambda()) <= 1e-8
+        rm.compute_gradients(); gm.compute_gradients(res)
+        assert_close(gm.get_tensor("grad_transform"), rm.get("grad_transform"), 2e-4, 1e-5, "merged gT step %d" % step)
+        assert_close(gm.get_tensor("grad_bias"), rm.get("grad_bias"), 2e-4, 1e-5, "merged gb step %d" % step)
+        rm.update(lr, rm.scaled_lambda()); gm.update(None, lr, res.scaled_regularization_lambda())
+        _check_params(gm, rm, method, lr, "after step %d" % step)
+
+
+def test_mixture_rejects_single_descriptor_optimisers():
+    """Adagrad and sparse Adam abort on multiple gradient descriptors in the reference
+    (cpp/updates_adagrad.cu:108-109, cpp/updates_adam.cu:339-340); the library returns an error instead."""
+    c = CASES[0]
+    desc = nv.ModelDesc(word_repr_size=c["dw"], entity_repr_size=c["dd"], clip_sigmoid=True)
+    tc = nv.TrainConfig(batch_size=c["B"], window_size=c["n"], num_random_entities=c["z"], update_method=nv.ADAGRAD,
+                        text_entity_weight=0.5, entity_entity_weight=0.5)
+    gm = nv.Model(c["V"], c["D"], desc, tc, objective=nv.TEXT_ENTITY_ENTITY_ENTITY, max_similarity_batch_size=16)
+    rng = nv.RNG(7)
+    gm.initialize(rng)
+    f, fw, labels, w = make_batch(np.random.default_rng(0), c["B"], c["n"], c["V"], c["D"], c["z"])
+    res = gm.compute_cost_mixture(nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w),
+                                  nv.SimilarityBatch(16).fill(np.zeros((16, 2), np.int64) + [[1, 2]]), rng)
+    gm.compute_gradients(res)
+    with pytest.raises(nv.NvsmError):
+        gm.update(None, 0.01, res.scaled_regularization_lambda())
