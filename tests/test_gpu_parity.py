@@ -225,8 +225,12 @@ def test_staged_batch_equals_host_batch():
 
 
 def test_errors_are_reported_not_swallowed():
-    with pytest.raises(nv.NvsmError):
-        nv.Model(10, 10, nv.ModelDesc(l2_normalize_phrase_reprs=True), nv.TrainConfig())
+    with pytest.raises(nv.NvsmError):   # a mixture objective with a zero weight (CHECK_NE in cpp/objective.cu:709-710)
+        nv.Model(10, 10, nv.ModelDesc(), nv.TrainConfig(text_entity_weight=1.0, entity_entity_weight=0.0),
+                 objective=nv.TEXT_ENTITY_ENTITY_ENTITY)
+    with pytest.raises(nv.NvsmError):   # a pair forward on a plain TextEntity handle
+        nv.Model(10, 10, nv.ModelDesc(), nv.TrainConfig(batch_size=8, window_size=2)).similarity_compute_cost(
+            nv.SimilarityBatch(4).fill(np.zeros((4, 2))))
     m = nv.Model(10, 10, nv.ModelDesc(), nv.TrainConfig(batch_size=8, window_size=2))
     with pytest.raises(nv.NvsmError):
         m.compute_gradients()          # no forward result
