@@ -32,7 +32,7 @@ namespace nvsm {
 namespace tc {
 
 constexpr int kBlockM = 128;        // UMMA M (cta_group::1)
-constexpr int kBlockK = 32;         // fp32 elements per 128-byte swizzled row
+constexpr int kBlockK = 32;         // fp32 elements per 128-byte swizzled row (KB = 32); KB = 16 uses 64-byte rows
 constexpr int kUmmaK = 8;           // tf32 K per instruction
 constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = kBlockM * kBlockK * 4;  // 16 KB
@@ -45,6 +45,7 @@ struct Params {
     int splits;            // split-K factor; tile index = (m_tile * n_tiles + n_tile) * splits + split
     int kb_per_split;      // k-blocks (of 32) per split
     int stages;
+    int kb;                // k-block: fp32 elements along K per pipeline stage (16 or 32) = template KB
     uint32_t stage_bytes;
     uint32_t tmem_cols;    // power of two >= 2 * bn (two accumulator buffers)
     float* C;
@@ -164,7 +165,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // SPLIT = 3xTF32: every operand arrives as hi = rn_tf32(x) and lo = x - hi (two arrays written by the
 // producers); per k-step the accumulator receives hi.hi + lo.hi + hi.lo, which restores fp32-level
 // accuracy (the dropped lo.lo term is ~2^-22 relative) at three tensor-core instructions per step.
-template <bool A_MN, bool B_MN, bool SPLIT>
+// KB = k-block per pipeline stage: 32 fp32 (128-byte rows, SWIZZLE_128B) or 16 fp32 (64-byte rows, SWIZZLE_64B for
+// K-major operands; MN-major tiles simply hold 16 instead of 32 k-rows). Halving the k-block halves the stage and
+// doubles the ring depth in the same shared memory: the 3xTF32 stages are (A + B) x (hi + lo) = 96 KB at KB = 32,
+// i.e. a 2-deep ring that cannot cover the TMA latency (ncu: tensor pipe ~52 % busy, L2 ~50 %).
+template <bool A_MN, bool B_MN, bool SPLIT, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, const Params p) {
@@ -177,10 +182,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_kb_total = (p.K + kBlockK - 1) / kBlockK;
+    constexpr uint32_t kATile = kBlockM * KB * 4;        // A tile bytes per stage
+    constexpr uint32_t kGroup = KB * 32 * 4;             // one 32(MN) x KB(k) MN-major box
+    constexpr uint32_t kSboK = KB == 32 ? 1024u : 512u;  // K-major: 8-row atom of KB*4-byte rows
+    constexpr uint32_t kLayoutK = KB == 32 ? 2u : 4u;    // SWIZZLE_128B : SWIZZLE_64B
+    const int num_kb_total = (p.K + KB - 1) / KB;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int stages = p.stages;
-    const uint32_t lo_off = kATileBytes + (uint32_t)p.bn * 128u;   // SPLIT: [A_hi][B_hi][A_lo][B_lo] per stage
+    const uint32_t lo_off = kATile + (uint32_t)p.bn * (KB * 4u);   // SPLIT: [A_hi][B_hi][A_lo][B_lo] per stage
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -233,19 +242,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(smem_u32(&empty_bar[s]), ((it / stages) & 1u) ^ 1u);
                     const uint32_t bar = smem_u32(&full_bar[s]);
                     const uint32_t a_dst = smem_base + (uint32_t)s * p.stage_bytes;
-                    const uint32_t b_dst = a_dst + kATileBytes;
-                    const int k0 = (kb0 + kb) * kBlockK;
+                    const uint32_t b_dst = a_dst + kATile;
+                    const int k0 = (kb0 + kb) * KB;
                     mbar_expect_tx(bar, p.stage_bytes);
                     if constexpr (!A_MN) {
                         tma_load_2d(a_dst, &tmA, bar, k0, m0);
                     } else {
 #pragma unroll
-                        for (int g = 0; g < kBlockM / 32; ++g) tma_load_2d(a_dst + g * kGroupBytes, &tmA, bar, m0 + 32 * g, k0);
+                        for (int g = 0; g < kBlockM / 32; ++g) tma_load_2d(a_dst + g * kGroup, &tmA, bar, m0 + 32 * g, k0);
                     }
                     if constexpr (!B_MN) {
                         tma_load_2d(b_dst, &tmB, bar, k0, n0);
                     } else {
-                        for (int g = 0; g < p.bn / 32; ++g) tma_load_2d(b_dst + g * kGroupBytes, &tmB, bar, n0 + 32 * g, k0);
+                        for (int g = 0; g < p.bn / 32; ++g) tma_load_2d(b_dst + g * kGroup, &tmB, bar, n0 + 32 * g, k0);
                     }
                     if constexpr (SPLIT) {
                         if constexpr (!A_MN) {
@@ -253,13 +262,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
 #pragma unroll
                             for (int g = 0; g < kBlockM / 32; ++g)
-                                tma_load_2d(a_dst + lo_off + g * kGroupBytes, &tmAlo, bar, m0 + 32 * g, k0);
+                                tma_load_2d(a_dst + lo_off + g * kGroup, &tmAlo, bar, m0 + 32 * g, k0);
                         }
                         if constexpr (!B_MN) {
                             tma_load_2d(b_dst + lo_off, &tmBlo, bar, k0, n0);
                         } else {
                             for (int g = 0; g < p.bn / 32; ++g)
-                                tma_load_2d(b_dst + lo_off + g * kGroupBytes, &tmBlo, bar, n0 + 32 * g, k0);
+                                tma_load_2d(b_dst + lo_off + g * kGroup, &tmBlo, bar, n0 + 32 * g, k0);
                         }
                     }
                 }
@@ -282,21 +291,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(smem_u32(&full_bar[s]), (it / stages) & 1u);
                     tc_fence_after();
                     const uint32_t a_base = smem_base + (uint32_t)s * p.stage_bytes;
-                    const uint32_t b_base = a_base + kATileBytes;
+                    const uint32_t b_base = a_base + kATile;
 #pragma unroll
-                    for (int j = 0; j < kBlockK / kUmmaK; ++j) {
+                    for (int j = 0; j < KB / kUmmaK; ++j) {
                         // K-major: 32 B further along the swizzled 128-byte row per K = 8.
                         // MN-major: 8 k-rows = two 4-row atoms (SBO = 512 B apart) per K = 8.
-                        const uint64_t a_desc = A_MN ? make_desc(a_base + j * 1024u, kGroupBytes, 512u, 1u)
-                                                     : make_desc(a_base + j * 32u, 16u, 1024u, 2u);
-                        const uint64_t b_desc = B_MN ? make_desc(b_base + j * 1024u, kGroupBytes, 512u, 1u)
-                                                     : make_desc(b_base + j * 32u, 16u, 1024u, 2u);
+                        const uint64_t a_desc = A_MN ? make_desc(a_base + j * 1024u, kGroup, 512u, 1u)
+                                                     : make_desc(a_base + j * 32u, 16u, kSboK, kLayoutK);
+                        const uint64_t b_desc = B_MN ? make_desc(b_base + j * 1024u, kGroup, 512u, 1u)
+                                                     : make_desc(b_base + j * 32u, 16u, kSboK, kLayoutK);
                         umma_tf32(tacc, a_desc, b_desc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                         if constexpr (SPLIT) {
-                            const uint64_t a_lo = A_MN ? make_desc(a_base + lo_off + j * 1024u, kGroupBytes, 512u, 1u)
-                                                       : make_desc(a_base + lo_off + j * 32u, 16u, 1024u, 2u);
-                            const uint64_t b_lo = B_MN ? make_desc(b_base + lo_off + j * 1024u, kGroupBytes, 512u, 1u)
-                                                       : make_desc(b_base + lo_off + j * 32u, 16u, 1024u, 2u);
+                            const uint64_t a_lo = A_MN ? make_desc(a_base + lo_off + j * 1024u, kGroup, 512u, 1u)
+                                                       : make_desc(a_base + lo_off + j * 32u, 16u, kSboK, kLayoutK);
+                            const uint64_t b_lo = B_MN ? make_desc(b_base + lo_off + j * 1024u, kGroup, 512u, 1u)
+                                                       : make_desc(b_base + lo_off + j * 32u, 16u, kSboK, kLayoutK);
                             umma_tf32(tacc, a_lo, b_desc, idesc, 1u);
                             umma_tf32(tacc, a_desc, b_lo, idesc, 1u);
                         }

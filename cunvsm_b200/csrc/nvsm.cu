@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2cta.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "pull_update.cuh"
@@ -312,6 +313,9 @@ EncodeTiledFn encode_tiled_fn() {
 // 2-D fp32 row-major tensor [outer, inner] with a {box_inner, box_outer} box, 128B swizzle, zero OOB fill.
 int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer, long row_stride_elems,
                     int box_inner, int box_outer, bool atom32 = false) {
+    // K-major boxes: the swizzle span equals the box row (32 fp32 = 128 B, or 16 fp32 = 64 B at k-block 16)
+    const CUtensorMapSwizzle swz = atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                          : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail("cuTensorMapEncodeTiled is unavailable in this driver");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -319,7 +323,7 @@ int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer,
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) inner=%ld outer=%ld box=%dx%d", (int)r, inner, outer, box_inner, box_outer);
@@ -342,6 +346,49 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
                 float* C, int ldc, int splits, long split_stride, float alpha, const float* bias,
                 int* splits_out = nullptr, const float* A_lo = nullptr, const float* B_lo = nullptr) {
     const bool split3 = A_lo != nullptr && B_lo != nullptr;
+    {
+        // Two-SM (cta_group::2) kernel for the K-major, un-split GEMMs (forward, grad_phrase); see gemm_tcgen05_2cta.cuh.
+        // Default: on when one 256-wide tile covers N (the forward projection: B traffic per SM halves, measured
+        // 70.2 -> 62.3 us on C2); grad_phrase (N = 300 -> two 160-wide tiles) measured equal (56.2 vs 56.6 us) and
+        // stays on the single-SM kernel. NVSM_TC_2CTA=0 / 1 forces it off / on for every eligible GEMM.
+        const char* e = getenv("NVSM_TC_2CTA");
+        const bool want = e ? atoi(e) != 0 : (N > 160 && N <= 256);
+        if (want && !mn_major && splits <= 1 && m->num_sms >= 2) {
+            tc::Params p;
+            p.M = M; p.N = N; p.K = K;
+            const int n_pad = (N + 15) / 16 * 16;
+            p.n_tiles = (n_pad + 255) / 256;
+            p.bn = ((n_pad + p.n_tiles - 1) / p.n_tiles + 15) / 16 * 16;   // <= 256, bn / 2 a multiple of 8
+            p.m_tiles = (M + 255) / 256;
+            p.splits = 1; p.kb = 32;
+            p.kb_per_split = (K + tc::kBlockK - 1) / tc::kBlockK;
+            p.stage_bytes = (tc::kATileBytes + (uint32_t)(p.bn / 2) * 128u) * (split3 ? 2u : 1u);
+            p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
+            { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
+            if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
+            p.tmem_cols = 512;   // whole TMEM: both CTAs of the pair must get base 0
+            p.C = C; p.ldc = ldc; p.split_stride = 0; p.alpha = alpha; p.bias = bias;
+            CUtensorMap tmA, tmB, tmAlo, tmBlo;
+            TRY(make_tensor_map(&tmA, A, K, M, lda, tc::kBlockK, tc::kBlockM));
+            TRY(make_tensor_map(&tmB, Bm, K, N, ldb, tc::kBlockK, p.bn / 2));
+            TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, K, M, lda, tc::kBlockK, tc::kBlockM));
+            TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, K, N, ldb, tc::kBlockK, p.bn / 2));
+            const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+            const int num_tiles = p.m_tiles * p.n_tiles;
+            const int grid = 2 * std::min(num_tiles, m->num_sms / 2);
+            static bool attr2 = false;
+            if (!attr2) {
+                const int mx = (int)kTcMaxDynSmem;
+                CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+                CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+                attr2 = true;
+            }
+            if (split3) LAUNCH(m, (tc::gemm_tc2_kernel<true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+            else LAUNCH(m, (tc::gemm_tc2_kernel<false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+            if (splits_out) *splits_out = 1;
+            return 0;
+        }
+    }
     tc::Params p;
     p.M = M; p.N = N; p.K = K;
     const int unit = mn_major ? 32 : 16;
@@ -350,11 +397,15 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.n_tiles = (n_pad + max_bn - 1) / max_bn;
     p.bn = ((n_pad + p.n_tiles - 1) / p.n_tiles + unit - 1) / unit * unit;   // <= 256
     p.m_tiles = (M + tc::kBlockM - 1) / tc::kBlockM;
-    const int num_kb = (K + tc::kBlockK - 1) / tc::kBlockK;
+    // k-block per stage: 16 halves the stage (deeper ring, twice the TMA requests and barrier round trips); NVSM_TC_KB overrides
+    int kb = 32;   // measured on C2 (3xTF32): k-block 16 = 4-deep ring 72 / 88 / 68 us (fwd, gT, gP) vs k-block 32 = 2-deep 70 / 71 / 57 us
+    { const char* e = getenv("NVSM_TC_KB"); if (e && (atoi(e) == 16 || atoi(e) == 32)) kb = atoi(e); }
+    p.kb = kb;
+    const int num_kb = (K + kb - 1) / kb;
     splits = std::max(1, std::min(splits, num_kb));
     p.kb_per_split = (num_kb + splits - 1) / splits;
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-    p.stage_bytes = (tc::kATileBytes + (uint32_t)p.bn * 128u) * (split3 ? 2u : 1u);
+    p.stage_bytes = ((uint32_t)tc::kBlockM * kb * 4u + (uint32_t)p.bn * kb * 4u) * (split3 ? 2u : 1u);
     p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
     { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
     if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
@@ -363,15 +414,15 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
     CUtensorMap tmA, tmB, tmAlo, tmBlo;
     if (!mn_major) {
-        TRY(make_tensor_map(&tmA, A, K, M, lda, tc::kBlockK, tc::kBlockM));
-        TRY(make_tensor_map(&tmB, Bm, K, N, ldb, tc::kBlockK, p.bn));
-        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, K, M, lda, tc::kBlockK, tc::kBlockM));
-        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, K, N, ldb, tc::kBlockK, p.bn));
+        TRY(make_tensor_map(&tmA, A, K, M, lda, kb, tc::kBlockM));
+        TRY(make_tensor_map(&tmB, Bm, K, N, ldb, kb, p.bn));
+        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, K, M, lda, kb, tc::kBlockM));
+        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, K, N, ldb, kb, p.bn));
     } else {
-        TRY(make_tensor_map(&tmA, A, M, K, lda, 32, tc::kBlockK, true));
-        TRY(make_tensor_map(&tmB, Bm, N, K, ldb, 32, tc::kBlockK, true));
-        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, M, K, lda, 32, tc::kBlockK, true));
-        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, N, K, ldb, 32, tc::kBlockK, true));
+        TRY(make_tensor_map(&tmA, A, M, K, lda, 32, kb, true));
+        TRY(make_tensor_map(&tmB, Bm, N, K, ldb, 32, kb, true));
+        TRY(make_tensor_map(&tmAlo, split3 ? A_lo : A, M, K, lda, 32, kb, true));
+        TRY(make_tensor_map(&tmBlo, split3 ? B_lo : Bm, N, K, ldb, 32, kb, true));
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -379,16 +430,25 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     static bool attr = false;
     if (!attr) {
         const int mx = (int)kTcMaxDynSmem;
-        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+#define NVSM_TC_ATTR(A_, B_, S_, K_) CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<A_, B_, S_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+        NVSM_TC_ATTR(false, false, false, 32); NVSM_TC_ATTR(false, false, true, 32); NVSM_TC_ATTR(true, true, false, 32); NVSM_TC_ATTR(true, true, true, 32);
+        NVSM_TC_ATTR(false, false, false, 16); NVSM_TC_ATTR(false, false, true, 16); NVSM_TC_ATTR(true, true, false, 16); NVSM_TC_ATTR(true, true, true, 16);
+#undef NVSM_TC_ATTR
         attr = true;
     }
-    if (!mn_major && !split3) LAUNCH(m, (tc::gemm_tc_kernel<false, false, false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
-    else if (!mn_major) LAUNCH(m, (tc::gemm_tc_kernel<false, false, true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
-    else if (!split3) LAUNCH(m, (tc::gemm_tc_kernel<true, true, false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
-    else LAUNCH(m, (tc::gemm_tc_kernel<true, true, true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+#define NVSM_TC_LAUNCH(A_, B_, S_, K_) LAUNCH(m, (tc::gemm_tc_kernel<A_, B_, S_, K_>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p)
+    if (kb == 32) {
+        if (!mn_major && !split3) NVSM_TC_LAUNCH(false, false, false, 32);
+        else if (!mn_major) NVSM_TC_LAUNCH(false, false, true, 32);
+        else if (!split3) NVSM_TC_LAUNCH(true, true, false, 32);
+        else NVSM_TC_LAUNCH(true, true, true, 32);
+    } else {
+        if (!mn_major && !split3) NVSM_TC_LAUNCH(false, false, false, 16);
+        else if (!mn_major) NVSM_TC_LAUNCH(false, false, true, 16);
+        else if (!split3) NVSM_TC_LAUNCH(true, true, false, 16);
+        else NVSM_TC_LAUNCH(true, true, true, 16);
+    }
+#undef NVSM_TC_LAUNCH
     if (splits_out) *splits_out = p.splits;
     return 0;
 }
