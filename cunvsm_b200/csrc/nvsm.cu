@@ -94,6 +94,11 @@ struct nvsm_model {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;      // reference buckets of the pull update are built here, under the forward pass
     cudaEvent_t buckets_ready = nullptr, buckets_consumed = nullptr;
+    // fused steps: the entity-table update only needs the forward pass, so it runs on the auxiliary stream under
+    // batch-norm backward and the two backward GEMMs of the main stream (start_entity_update)
+    cudaEvent_t score_done = nullptr, entity_done = nullptr;
+    bool entity_async = false, entity_async_running = false;
+    float* rowtmp_e = nullptr;   // entity-side row scratch (the word side may run concurrently)
     bool buckets_in_flight = false, buckets_ever_consumed = false;
     bool own_stream = false;
     long V, D;
@@ -844,10 +849,11 @@ int scatter_words(nvsm_model* m, float* target, float scale, const float* acc, f
 // acc_E[id] += scale * mean_k grad_entity[k, c]^2
 int scatter_entity_meansq(nvsm_model* m, float* acc, float scale) {
     const float inv_dim = (float)std::exp(-std::log((double)m->dd));
+    float* const tmp = m->entity_async_running ? m->rowtmp_e : m->rowtmp;
     LAUNCH(m, row_meansq_act_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->Z,
-           act_params(m, m->cfg.batch_normalization != 0), m->B, m->dd, inv_dim, m->rowtmp);
+           act_params(m, m->cfg.batch_normalization != 0), m->B, m->dd, inv_dim, tmp);
     const long total = m->B * m->R;
-    LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, m->mult, m->rowtmp,
+    LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, m->mult, tmp,
            total, m->R, scale, acc, m->l2_entity ? (const float*)m->escore : (const float*)nullptr, inv_dim);
     return 0;
 }
@@ -909,10 +915,9 @@ int start_bucket_build(nvsm_model* m, BatchSlot* s) {
 }
 
 int pull_update(nvsm_model* m, bool entities, const AdamFullConsts& k) {
-    if (entities) {
-        if (!m->buckets_in_flight) return fail("pull update without reference buckets");
-        CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
-    }
+    // (both tables wait: with the asynchronous entity update the two run on different streams)
+    if (!m->buckets_in_flight) return fail("pull update without reference buckets");
+    CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
     const int dim = entities ? m->dd : m->dw;
     if (vec4_ok(dim)) {
         const int nch = (dim / 4 + 31) / 32;
@@ -1138,9 +1143,11 @@ int update(nvsm_model* m, float lr, float lambda) {
         }
     }
     int rc = 0;
-    phase_begin(m, PH_UPD_ENTITIES);
-    rc = update_table(m, true, lr, lambda);
-    phase_end(m);
+    if (!m->entity_async) {
+        phase_begin(m, PH_UPD_ENTITIES);
+        rc = update_table(m, true, lr, lambda);
+        phase_end(m);
+    }
     if (rc == 0) {
         phase_begin(m, PH_UPD_WORDS);
         rc = update_table(m, false, lr, lambda);
@@ -1157,6 +1164,10 @@ int update(nvsm_model* m, float lr, float lambda) {
     phase_begin(m, PH_UPD_TRANSFORM);
     TRY(update_transform(m, lr, lambda));
     phase_end(m);
+    if (m->entity_async) {   // join: everything after update() is ordered behind the entity update as well
+        CU(cudaStreamWaitEvent(m->stream, m->entity_done, 0));
+        m->entity_async = false;
+    }
     // The batch slot may be overwritten once everything enqueued so far has run.
     CU(cudaEventRecord(m->cur->consumed, m->stream));
     m->cur->ever_consumed = true;
@@ -1166,6 +1177,36 @@ int update(nvsm_model* m, float lr, float lambda) {
     return 0;
 }
 
+
+// Fused steps (forward, backward and update issued by one call): Model::update applies the entity gradients first
+// (cpp/model.cu:200-206) and those only depend on the forward pass (multipliers, activations, ids), so the entity
+// table is updated on the auxiliary stream while batch-norm backward and the grad_transform / grad_phrase GEMMs run on
+// the main stream. The bandwidth-bound update and the pipeline-bound GEMMs share the SMs; nothing they touch overlaps
+// (E, its moments, mult, Y | Gp, P, T, gT, gP). Same arithmetic, same order per table.
+int start_entity_update(nvsm_model* m, float lr, float lambda) {
+    if (m->profiling || exact_sparse(m) || m->l2_entity || m->has_pair || !m->has_text || getenv("NVSM_NO_OVERLAP")) return 0;
+    if (lr < 0.f || lambda < 0.f) return 0;   // update() reports it
+    CU(cudaEventRecord(m->score_done, m->stream));
+    CU(cudaStreamWaitEvent(m->aux_stream, m->score_done, 0));
+    cudaStream_t main_stream = m->stream;
+    m->stream = m->aux_stream;
+    m->entity_async_running = true;
+    const int rc = update_table(m, true, lr, lambda);
+    m->entity_async_running = false;
+    m->stream = main_stream;
+    if (rc) return rc;
+    CU(cudaEventRecord(m->entity_done, m->aux_stream));
+    m->entity_async = true;
+    return 0;
+}
+
+int fused_step(nvsm_model* m, BatchSlot* s, float lr) {
+    TRY(forward(m, s));
+    const float lambda = m->cfg.regularization_lambda / (float)m->Bglobal;
+    TRY(start_entity_update(m, lr, lambda));
+    TRY(backward(m));
+    return update(m, lr, lambda);
+}
 
 // ------------------------------------------------------------------------------------
 // device sampler
@@ -1400,6 +1441,9 @@ void nvsm_destroy(nvsm_model* m) {
         if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+    if (m->score_done) cudaEventDestroy(m->score_done);
+    if (m->entity_done) cudaEventDestroy(m->entity_done);
+    if (m->rowtmp_e) cudaFree(m->rowtmp_e);
     if (m->buckets_ready) cudaEventDestroy(m->buckets_ready);
     if (m->buckets_consumed) cudaEventDestroy(m->buckets_consumed);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
@@ -1444,6 +1488,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         m->own_stream = true;
         CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->score_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->entity_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buckets_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buckets_consumed, cudaEventDisableTiming));
         const long V = m->V, D = m->D, maxB = m->maxB;
@@ -1473,7 +1519,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->P, maxB * m->ldP)); TRY(dev_alloc(&m->Z, maxB * dd));
         TRY(dev_alloc(&m->Gp, maxB * dd)); TRY(dev_alloc(&m->gP, maxB * dw));
         TRY(dev_alloc(&m->probs, maxB * m->R)); TRY(dev_alloc(&m->mult, maxB * m->R));
-        TRY(dev_alloc(&m->rowtmp, maxB));
+        TRY(dev_alloc(&m->rowtmp, maxB)); TRY(dev_alloc(&m->rowtmp_e, maxB));
         {
             const int obj = cfg->objective;
             if (obj < NVSM_OBJECTIVE_TEXT_ENTITY || obj > NVSM_OBJECTIVE_TEXT_ENTITY_TERM_TERM) return fail("unknown objective %d", obj);
@@ -1773,9 +1819,7 @@ int nvsm_train_step(nvsm_model* m, const long* features, const float* fw, const 
     CU(cudaSetDevice(m->device));
     BatchSlot* s = next_live_slot(m);
     TRY(upload_batch(m, s, features, fw, ids, w, B, true));
-    TRY(forward(m, s));
-    TRY(backward(m));
-    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+    return fused_step(m, s, lr);
 }
 
 // Device-resident std::minstd_rand0 state for the device sampler.
@@ -1830,10 +1874,8 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
     TRY(sample_labels_device(m, s->labels, s->ids, s->B, m->z, m->D));
     CU(cudaEventRecord(s->ready, m->stream));   // "ready" now also covers the sampled ids (bucket build waits on it)
-    TRY(forward(m, s));
-    if (!train) return 0;
-    TRY(backward(m));
-    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+    if (!train) return forward(m, s);
+    return fused_step(m, s, lr);
 }
 
 // Stand-alone device sampling for arbitrary (z, num_objects): host labels in, host ids out.
@@ -1886,9 +1928,10 @@ int nvsm_compute_cost_staged(nvsm_model* m, int slot) {
 }
 
 int nvsm_train_step_staged(nvsm_model* m, int slot, float lr) {
-    TRY(nvsm_compute_cost_staged(m, slot));
-    TRY(backward(m));
-    return update(m, lr, nvsm_scaled_regularization_lambda(m));
+    if (!m) return fail("null model");
+    if (slot < 0 || slot >= m->cfg.num_batch_slots) return fail("slot %d out of range", slot);
+    CU(cudaSetDevice(m->device));
+    return fused_step(m, &m->slots[slot], lr);
 }
 
 int nvsm_infer(nvsm_model* m, const long* words, long N, long window, float* out) {
