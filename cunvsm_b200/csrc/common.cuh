@@ -33,6 +33,27 @@ __device__ __forceinline__ void load_vec_ro(const float* __restrict__ p, float (
     }
 }
 
+// Streaming (evict-first) access for data touched once per kernel, so that it does not push re-used lines
+// (gathered rows) out of L2.
+template <int VEC>
+__device__ __forceinline__ void load_vec_cs(const float* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = __ldcs(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec_cs(float* __restrict__ p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+        __stcs(p, v[0]);
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[VEC]) {
     if constexpr (VEC == 4) {
@@ -63,6 +84,20 @@ __device__ __forceinline__ float round_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+
+// sqrt / divide as the reference's release build compiles them (-use_fast_math => --prec-sqrt=false
+// --prec-div=false, CMakeLists.txt:71-73 of the reference): sqrt.approx / div.approx, one MUFU each instead of
+// the ~20-instruction IEEE sequences.
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) {
+    float r;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -746,7 +746,10 @@ int backward(nvsm_model* m) {
     LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal,
            m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy, m->mean_dyx);
     if (bn) {
-        if (vec4_ok(dd)) {
+        if (vec4_ok(dd) && 256 % (dd / 4) == 0) {
+            const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
+            LAUNCH(m, bn_backward_cols_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
+        } else if (vec4_ok(dd)) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
             LAUNCH(m, bn_backward_kernel<4>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
         } else {
