@@ -264,15 +264,57 @@ __global__ void __launch_bounds__(256) col_stats_reduce_kernel(const float* __re
 }
 
 // mean / invstd from the (all-reduced) sums; biased variance, eps inside the sqrt.
+// Also writes the affine form the staged score kernel consumes: scale = invstd, shift = bias - mean * invstd.
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int dd, double batch, double eps,
-                                   float* __restrict__ mean, float* __restrict__ invstd) {
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   const float* __restrict__ bias, float* __restrict__ scale, float* __restrict__ shift) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= dd) return;
     const double mu = sums[c] / batch;
     double var = sums[dd + c] / batch - mu * mu;
     if (var < 0.0) var = 0.0;
-    mean[c] = (float)mu;
-    invstd[c] = (float)(1.0 / sqrt(var + eps));
+    const float mf = (float)mu, isf = (float)(1.0 / sqrt(var + eps));
+    mean[c] = mf;
+    invstd[c] = isf;
+    scale[c] = isf;
+    shift[c] = bias[c] - mf * isf;
+}
+
+// Single-GPU: the partial reduction (col_stats_reduce_kernel) and the finalisation in one launch. One CTA owns 32
+// columns: 8 slices of the partial rows per column, sums and sums of squares together, double accumulation.
+__global__ void __launch_bounds__(1024) col_stats_reduce_finalize_kernel(const float* __restrict__ partials, int nblocks, int dd,
+                                                                         double batch, double eps, double* __restrict__ sums,
+                                                                         float* __restrict__ mean, float* __restrict__ invstd,
+                                                                         const float* __restrict__ bias,
+                                                                         float* __restrict__ scale, float* __restrict__ shift) {
+    constexpr int S = 32;   // slices of the partial rows per column (blockDim = 32 columns x S)
+    __shared__ double sm[2][S][32];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int slice = threadIdx.x >> 5;
+    double a = 0.0, q = 0.0;
+    if (col < dd)
+        for (int b = slice; b < nblocks; b += S) {
+            a += (double)__ldg(partials + (long)b * 2 * dd + col);
+            q += (double)__ldg(partials + (long)b * 2 * dd + dd + col);
+        }
+    sm[0][slice][threadIdx.x & 31] = a;
+    sm[1][slice][threadIdx.x & 31] = q;
+    __syncthreads();
+    if (slice == 0 && col < dd) {
+        double s = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int g = 0; g < S; ++g) { s += sm[0][g][threadIdx.x]; s2 += sm[1][g][threadIdx.x]; }
+        sums[col] = s;
+        sums[dd + col] = s2;
+        const double mu = s / batch;
+        double var = s2 / batch - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float mf = (float)mu, isf = (float)(1.0 / sqrt(var + eps));
+        mean[col] = mf;
+        invstd[col] = isf;
+        scale[col] = isf;
+        shift[col] = bias[col] - mf * isf;
+    }
 }
 
 // Numerically careful variant: second pass accumulating sum (x - mean)^2.
@@ -578,11 +620,15 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(float* __restrict__ Gp
 // Same arithmetic for dd % 4 == 0 with (dd / 4) dividing the block size: a thread keeps ONE float4 column group for
 // all of its rows, so the four per-column parameters live in registers instead of being re-read per element
 // (ncu on the kernel above: 18 loads per 2 stores, L1TEX 88 % busy, LSU queue throttling, DRAM at 58 %).
+// The per-column means of dy and dy * xhat come straight from the (all-reduced) double column sums of the score kernel
+// (what bn_backward_prep_kernel computes), and the first row of threads also publishes grad_bias / mean_dy / mean_dyx.
 __global__ void __launch_bounds__(256) bn_backward_cols_kernel(float* __restrict__ Gp, const float* __restrict__ Z,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ invstd,
-                                                               const float* __restrict__ mean_dy,
-                                                               const float* __restrict__ mean_dyx, long rows, int dd,
+                                                               const double* __restrict__ col_sums, double batch,
+                                                               const float* __restrict__ shifted_by_bias,
+                                                               float* __restrict__ gb, float* __restrict__ mean_dy,
+                                                               float* __restrict__ mean_dyx, long rows, int dd,
                                                                int tf32, float* __restrict__ lo_out) {
     const int nvec = dd >> 2;
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -590,7 +636,18 @@ __global__ void __launch_bounds__(256) bn_backward_cols_kernel(float* __restrict
     const int c = (int)(tid % nvec);
     const long row_stride = nthreads / nvec;
     const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + c), mu = __ldg(reinterpret_cast<const float4*>(mean) + c);
-    const float4 md = __ldg(reinterpret_cast<const float4*>(mean_dy) + c), mx = __ldg(reinterpret_cast<const float4*>(mean_dyx) + c);
+    float mdv[4], mxv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int col = 4 * c + v;
+        const double s1 = col_sums[col];
+        double s2 = col_sums[dd + col];
+        if (shifted_by_bias) s2 -= (double)__ldg(shifted_by_bias + col) * s1;
+        mdv[v] = (float)(s1 / batch);
+        mxv[v] = (float)(s2 / batch);
+        if (tid < nvec) { gb[col] = (float)s1; mean_dy[col] = mdv[v]; mean_dyx[col] = mxv[v]; }
+    }
+    const float4 md = make_float4(mdv[0], mdv[1], mdv[2], mdv[3]), mx = make_float4(mxv[0], mxv[1], mxv[2], mxv[3]);
     float4* __restrict__ G4 = reinterpret_cast<float4*>(Gp);
     const float4* __restrict__ Z4 = reinterpret_cast<const float4*>(Z);
     float4* __restrict__ L4 = reinterpret_cast<float4*>(lo_out);
@@ -1035,6 +1092,11 @@ struct TransformUpdateParams {
     float* aT; float* ab;   // adagrad acc / adam m
     float* vT; float* vb;   // adam v
     float s1, lr1, s2, lr2, bc, eps;
+    // fused in (single GPU): the split-K partial reduction of grad_transform (gT_out = sum_z part[z]) ...
+    const float* gT_part; int nparts; float* gT_out;
+    // ... and the tensor-core operand copies of the NEW T for the next step's GEMMs: Tr = rn_tf32(T) [dw, dd],
+    // Tt = its transpose [dd, ldT] (K-major B operand of the forward GEMM) and the 3xTF32 remainders
+    float* Tr; float* Tt; float* Tr_lo; float* Tt_lo; int dd; int ldT;
 };
 
 __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUpdateParams p) {
@@ -1043,7 +1105,25 @@ __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUp
         const bool is_bias = t >= p.nT;
         const long k = is_bias ? t - p.nT : t;
         float* th = is_bias ? p.b + k : p.T + k;
-        float g = is_bias ? p.gb[k] : p.gT[k];
+        float g;
+        if (is_bias) {
+            g = p.gb[k];
+        } else if (p.gT_part) {
+            // same summation order as reduce_partials_kernel; eight independent loads in flight
+            g = 0.f;
+            int z = 0;
+            for (; z + 8 <= p.nparts; z += 8) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = __ldg(p.gT_part + (long)(z + u) * p.nT + k);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) g += x[u];
+            }
+            for (; z < p.nparts; ++z) g += __ldg(p.gT_part + (long)z * p.nT + k);
+            p.gT_out[k] = g;
+        } else {
+            g = p.gT[k];
+        }
         const float lam = is_bias ? 0.f : p.lambda;
         if (p.method == 0) {
             *th = *th * (1.0f - lam * p.lr) + g * p.lr;
@@ -1063,6 +1143,13 @@ __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUp
             *vv = v;
             g = (m * p.bc) / (sqrtf(v) + p.eps);
             *th = *th + g * p.lr;
+        }
+        if (!is_bias && p.Tr) {
+            const float raw = *th, hi = round_tf32(raw);
+            const long r = k / p.dd, c = k - r * p.dd;
+            p.Tr[k] = hi;
+            p.Tt[c * p.ldT + r] = hi;
+            if (p.Tr_lo) { p.Tr_lo[k] = raw - hi; p.Tt_lo[c * p.ldT + r] = raw - hi; }
         }
     }
 }

@@ -132,6 +132,8 @@ struct nvsm_model {
     double* dsums = nullptr;   // [2*dd fwd sums][dd var sums][2*dd bwd col sums][1 loss]
     float *gT = nullptr, *gb = nullptr, *gT_part = nullptr;
     int gt_splits = 1;
+    int gt_nparts = 0;          // split-K partials of the running step's grad_transform
+    bool gt_reduced = true;     // gT holds their sum (single GPU: summed inside transform_update_kernel or on demand)
     // pull-style full Adam: per-step reference buckets (counting sort by row)
     bool pull = false;
     int *e_counts = nullptr, *e_offsets = nullptr, *e_refs = nullptr;
@@ -140,6 +142,7 @@ struct nvsm_model {
     int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
                           // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
     bool use_tc = false;  // projection GEMMs on tcgen05 (gemm_mode != FP32 and shapes allow)
+    bool t_copies_stale = true;   // Tt / Tr (+ lo) do not match T: refreshed by transform_update_kernel or the next forward
     float* scratch = nullptr;  // inspection buffer max(B*R*dd, ...) allocated on demand
     size_t scratch_bytes = 0;
     // loss read-back ring: every forward ends with an async D2H of its loss sum
@@ -648,7 +651,10 @@ int forward(nvsm_model* m, BatchSlot* s) {
     // (2) projection Z = P . T (+ b when batch-norm is off).
     phase_begin(m, PH_GEMM_FWD);
     if (m->use_tc) {
-        LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP, m->Tr, m->Tt_lo, m->Tr_lo);
+        if (m->t_copies_stale) {   // after initialize / set_tensor; update() keeps the copies current otherwise
+            LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP, m->Tr, m->Tt_lo, m->Tr_lo);
+            m->t_copies_stale = false;
+        }
         TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b, nullptr,
                         m->P_lo, m->Tt_lo));
     } else {
@@ -665,14 +671,21 @@ int forward(nvsm_model* m, BatchSlot* s) {
             const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
             const int nblk = grid_for(m, B, 32, 2);   // <= 2 blocks per SM
             LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
-            LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
+            if (m->nranks <= 1) {
+                LAUNCH(m, col_stats_reduce_finalize_kernel, (dd + 31) / 32, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                       1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift);
+            } else {
+                LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
+            }
         }
         phase_end(m);
-        TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true));
-        phase_begin(m, PH_BN_STATS);
-        LAUNCH(m, bn_finalize_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), dd, (double)m->Bglobal,
-               1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd);
-        phase_end(m);
+        if (m->nranks > 1) {
+            TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true));
+            phase_begin(m, PH_BN_STATS);
+            LAUNCH(m, bn_finalize_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), dd, (double)m->Bglobal,
+                   1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift);
+            phase_end(m);
+        }
     } else if (bn) {
         phase_begin(m, PH_BN_STATS);
         const int grid = grid_for(m, B, 64, 4);
@@ -689,7 +702,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
         phase_end(m);
     }
 
-    if (bn) LAUNCH(m, bn_affine_kernel, (dd + 127) / 128, 128, 0, m->mean, m->invstd, m->b, dd, m->bn_scale, m->bn_shift);
+    if (bn && !m->use_tc) LAUNCH(m, bn_affine_kernel, (dd + 127) / 128, 128, 0, m->mean, m->invstd, m->b, dd, m->bn_scale, m->bn_shift);
 
     // (4) scores, loss, multipliers and d cost / d pre-activation in one pass.
     phase_begin(m, PH_SCORE);
@@ -733,6 +746,14 @@ int forward(nvsm_model* m, BatchSlot* s) {
     return 0;
 }
 
+int reduce_gt_partials(nvsm_model* m) {
+    if (m->gt_reduced) return 0;
+    const long nT = (long)m->dw * m->dd;
+    LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, m->gt_nparts, nT, m->gT);
+    m->gt_reduced = true;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------
 // backward: Model::compute_gradients
 // ------------------------------------------------------------------------------------
@@ -743,12 +764,16 @@ int backward(nvsm_model* m) {
     const int dw = m->dw, dd = m->dd;
 
     phase_begin(m, PH_BN_BWD);
-    LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal,
-           m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy, m->mean_dyx);
+    const bool cols_kernel = bn && vec4_ok(dd) && 256 % (dd / 4) == 0;
+    if (!cols_kernel)
+        LAUNCH(m, bn_backward_prep_kernel, (dd + 127) / 128, 128, 0, m->bwd_sums(), dd, (double)m->Bglobal,
+               m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy, m->mean_dyx);
     if (bn) {
-        if (vec4_ok(dd) && 256 % (dd / 4) == 0) {
+        if (cols_kernel) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
-            LAUNCH(m, bn_backward_cols_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
+            LAUNCH(m, bn_backward_cols_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, (const double*)m->bwd_sums(),
+                   (double)m->Bglobal, m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy,
+                   m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
         } else if (vec4_ok(dd)) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
             LAUNCH(m, bn_backward_kernel<4>, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, m->mean_dy, m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
@@ -778,7 +803,9 @@ int backward(nvsm_model* m) {
         } else {
             TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
         }
-        LAUNCH(m, reduce_partials_kernel, (int)((nT + 255) / 256), 256, 0, m->gT_part, nparts, nT, m->gT);
+        m->gt_nparts = nparts;
+        m->gt_reduced = false;
+        if (m->nranks > 1 || getenv("NVSM_NO_FUSED_REDUCE")) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
     }
     phase_end(m);
     TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
@@ -1069,7 +1096,11 @@ int update_transform(nvsm_model* m, float lr, float lambda) {
         p.bc = adam_bias_correction(c, m->t_transform);
         m->t_transform += 1;
     }
-    LAUNCH(m, transform_update_kernel, (int)((p.nT + p.nb + 255) / 256), 256, 0, p);
+    p.gT_part = nullptr; p.nparts = 0; p.gT_out = m->gT;
+    if (!m->gt_reduced) { p.gT_part = m->gT_part; p.nparts = m->gt_nparts; m->gt_reduced = true; }
+    p.Tr = nullptr; p.Tt = nullptr; p.Tr_lo = nullptr; p.Tt_lo = nullptr; p.dd = m->dd; p.ldT = m->ldP;
+    if (m->use_tc) { p.Tr = m->Tr; p.Tt = m->Tt; p.Tr_lo = m->Tr_lo; p.Tt_lo = m->Tt_lo; m->t_copies_stale = false; }
+    LAUNCH(m, transform_update_kernel, (int)((p.nT + p.nb + 127) / 128), 128, 0, p);
     return 0;
 }
 
@@ -1632,6 +1663,7 @@ int nvsm_initialize(nvsm_model* m, unsigned long* rng_state) {
     TRY(glorot(m->W, m->dw, m->V));
     TRY(glorot(m->E, m->dd, m->D));
     TRY(glorot(m->T, m->dd, m->dw));
+    m->t_copies_stale = true;
     CU(cudaMemsetAsync(m->b, 0, sizeof(float) * m->dd, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     *rng_state = rng_state_of(rng);
@@ -1649,6 +1681,7 @@ int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
     TensorRef r = find_tensor(m, name);
     if (r.count < 0) return fail("unknown tensor '%s'", name);
     if (r.count != n) return fail("tensor '%s' has %ld elements, caller asked for %ld", name, r.count, n);
+    if (r.ptr == m->gT) TRY(reduce_gt_partials(m));   // single GPU: the partial sum is otherwise fused into the update
     const float* src = r.ptr;
     if (r.kind == 3) {   // P rows are padded to ldP floats
         CU(cudaMemcpy2DAsync(host_out, sizeof(float) * m->dw, m->P, sizeof(float) * m->ldP, sizeof(float) * m->dw, m->B,
@@ -1689,6 +1722,7 @@ int nvsm_set_tensor(nvsm_model* m, const char* name, const float* host_in, long 
     if (r.count != n) return fail("tensor '%s' has %ld elements, caller passed %ld", name, r.count, n);
     CU(cudaMemcpyAsync(r.ptr, host_in, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
     CU(cudaStreamSynchronize(m->stream));
+    m->t_copies_stale = true;   // (cheap to refresh; only T matters)
     return 0;
 }
 
@@ -1972,6 +2006,7 @@ int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx, float ep
     if (r.count < 0 || r.kind != 0) return fail("unknown tensor '%s'", name);
     if (idx < 0 || idx >= r.count) return fail("index %ld out of range for '%s'", idx, name);
     LAUNCH(m, increment_kernel, 1, 1, 0, r.ptr + idx, epsilon);
+    m->t_copies_stale = true;
     return 0;
 }
 
