@@ -1864,6 +1864,7 @@ int nvsm_sampler_seed(nvsm_model* m, unsigned long state) {
     if (!m) return fail("null model");
     CU(cudaSetDevice(m->device));
     TRY(ensure_sampler(m));
+    if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));
     unsigned int x = (unsigned int)(state % 2147483647ul);
     if (x == 0) x = 1;   // std::linear_congruential_engine::seed
     CU(cudaMemcpyAsync(m->rng_dev + m->rng_cur, &x, sizeof(x), cudaMemcpyHostToDevice, m->stream));
@@ -1879,6 +1880,7 @@ int nvsm_sampler_state(nvsm_model* m, unsigned long* state) {
     CU(cudaSetDevice(m->device));
     unsigned int x = 0;
     int err = 0;
+    if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));   // nvsm_step_sampled samples there
     CU(cudaMemcpyAsync(&x, m->rng_dev + m->rng_cur, sizeof(x), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaMemcpyAsync(&err, m->smp_error, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
@@ -1906,11 +1908,19 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s->labels, labels, sizeof(long) * B, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
-    CU(cudaEventRecord(s->ready, cs));
     s->B = B;
+    {
+        // The negatives of this batch are drawn on the copy stream right behind its H2D copies, i.e. under the
+        // previous step's kernels on the main stream (the engine state chains from call to call on that stream).
+        cudaStream_t main_stream = m->stream;
+        const bool prof = m->profiling;
+        m->stream = cs; m->profiling = false;
+        const int src = sample_labels_device(m, s->labels, s->ids, s->B, m->z, m->D);
+        m->stream = main_stream; m->profiling = prof;
+        if (src) return src;
+    }
+    CU(cudaEventRecord(s->ready, cs));   // "ready" covers the copies and the sampled ids (bucket build waits on it)
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
-    TRY(sample_labels_device(m, s->labels, s->ids, s->B, m->z, m->D));
-    CU(cudaEventRecord(s->ready, m->stream));   // "ready" now also covers the sampled ids (bucket build waits on it)
     if (!train) return forward(m, s);
     return fused_step(m, s, lr);
 }
