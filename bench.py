@@ -274,7 +274,8 @@ def run_ours(args, w, rank, world, local_rank):
     rng = nv.RNG(1)
     model.initialize(rng)   # identical on every rank: same seed, same engine
     from cunvsm_b200 import sharding
-    sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0)
+    sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0,
+                             peer_exchange=not args.no_peer)
 
     # synthetic batches: every rank owns its own shard of n-gram rows
     raw = make_batches(w, B, 1234 + rank, NUM_BATCHES)
@@ -351,7 +352,8 @@ def run_ours(args, w, rank, world, local_rank):
         model = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=1, num_batch_slots=NUM_BATCHES)
         model.set_stream(stream.cuda_stream)
         model.initialize(nv.RNG(1))
-        sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0)
+        sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0,
+                             peer_exchange=not args.no_peer)
         for s_ in range(NUM_BATCHES):
             model.stage_batch(s_, batches[s_], ids_np[s_])
         staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
@@ -360,6 +362,9 @@ def run_ours(args, w, rank, world, local_rank):
         ms_alt, _ = timed(staged, args.steps)
         alt = {"gemm": "tf32_tcgen05", "value": B * world * args.steps / (ms_alt * 1e-3), "ms_per_step": ms_alt / args.steps}
 
+    peer_ok = world > 1 and model.comm_peer_status()[0]
+    if world > 1 and model.comm_peer_status()[1]:
+        raise RuntimeError("NVLink peer exchange timed out waiting for a peer")
     if rank == 0:
         peaks = {}
         try:
@@ -414,6 +419,9 @@ def run_ours(args, w, rank, world, local_rank):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "final_cost": final_cost, "alt_single_pass_tf32": alt,
+            "collectives": (None if world == 1 else
+                            {"small_reductions": "nvlink peer exchange (peer_allreduce.cuh)" if peer_ok else "ncclAllReduce",
+                             "grad_transform": "ncclAllReduce on a side stream under grad_phrase + word update"}),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -437,6 +445,7 @@ def main():
     ap.add_argument("--sparse_sync", default="local", choices=["local", "allgather"],
                     help="N>1: local = per-rank sparse updates (north-star prescription, default); allgather = exact "
                          "single-GPU trajectory (every replica applies all rows' updates)")
+    ap.add_argument("--no_peer", action="store_true", help="N>1: small reductions through ncclAllReduce instead of the NVLink peer exchange")
     ap.add_argument("--no_alt", action="store_true", help="skip the extra single-pass TF32 measurement")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])

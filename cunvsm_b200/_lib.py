@@ -17,7 +17,7 @@ SYMBOLS = [
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
-    "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
+    "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_comm_peer_export", "nvsm_comm_peer_import", "nvsm_comm_peer_status", "nvsm_comm_peer_disable", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
     "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_sampler_seed", "nvsm_sampler_state",
     "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device",
 ]
@@ -103,6 +103,10 @@ def load():
     f("nvsm_comm_unique_id", [ctypes.c_char_p])
     f("nvsm_comm_init", [vp, ctypes.c_char_p, ci, ci])
     f("nvsm_comm_set_sparse_mode", [vp, ci])
+    f("nvsm_comm_peer_export", [vp, ctypes.c_char_p])
+    f("nvsm_comm_peer_import", [vp, ctypes.c_char_p])
+    f("nvsm_comm_peer_status", [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)])
+    f("nvsm_comm_peer_disable", [vp])
     f("nvsm_similarity_compute_cost", [vp, pl, pf, cl])
     f("nvsm_similarity_get_cost", [vp, pf])
     f("nvsm_similarity_scaled_regularization_lambda", [vp], cf)

@@ -22,6 +22,7 @@
 #include "gemm_tcgen05_2cta.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include "peer_allreduce.cuh"
 #include "pull_update.cuh"
 #include "sampler.cuh"
 #include "score_ring.cuh"
@@ -189,6 +190,17 @@ struct nvsm_model {
     // multi-GPU
     NcclComm comm = nullptr;
     int nranks = 1, rank = 0;
+    // small reductions over NVLink peer memory (peer_allreduce.cuh); NCCL is the fallback and carries grad_transform
+    bool peer_ready = false;
+    PeerXchg peer{};
+    double* peer_inbox = nullptr;                // this rank's inbox (exported with CUDA IPC)
+    unsigned long long* peer_flags = nullptr;
+    void* peer_mapped[2 * kPeerMaxRanks] = {nullptr};   // IPC mappings to close
+    unsigned long long peer_epoch[kPeerKinds] = {0, 0, 0, 0};
+    int* peer_error = nullptr;
+    cudaStream_t comm_stream = nullptr;          // grad_transform all-reduce, under grad_phrase and the word update
+    cudaEvent_t gt_ready = nullptr, gt_reduced_ev = nullptr;
+    bool gt_allreduce_pending = false;
     // NVSM_SPARSE_ALLGATHER: every rank applies the table updates of ALL rows (exact single-GPU trajectory).
     int sparse_mode = NVSM_SPARSE_LOCAL;
     BatchSlot ag_slot;                  // gathered features / weights / ids of the global batch
@@ -486,10 +498,17 @@ __global__ void transpose_kernel(const float* __restrict__ in, int rows, int col
         }
 }
 
-int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double) {
+// kind >= 0 names one of the kPeerKinds per-step reduction sites that may use the NVLink peer exchange.
+int allreduce(nvsm_model* m, void* buf, size_t count, bool is_double, int kind = -1) {
     if (m->nranks <= 1) return 0;
     phase_end(m);
     phase_begin(m, PH_ALLREDUCE);
+    if (m->peer_ready && is_double && kind >= 0 && kind < kPeerKinds && (long)count <= m->peer.slot_doubles) {
+        const unsigned long long epoch = ++m->peer_epoch[kind];
+        LAUNCH(m, peer_allreduce_kernel, 1, 256, 0, m->peer, (double*)buf, (int)count, kind, epoch, m->peer_error);
+        phase_end(m);
+        return 0;
+    }
     int rc = nccl_api().AllReduce(buf, buf, count, is_double ? kNcclFloat64 : kNcclFloat32, kNcclSum, m->comm,
                                   (void*)m->stream);
     phase_end(m);
@@ -680,7 +699,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
         }
         phase_end(m);
         if (m->nranks > 1) {
-            TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true));
+            TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true, 0));
             phase_begin(m, PH_BN_STATS);
             LAUNCH(m, bn_finalize_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), dd, (double)m->Bglobal,
                    1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift);
@@ -691,11 +710,11 @@ int forward(nvsm_model* m, BatchSlot* s) {
         const int grid = grid_for(m, B, 64, 4);
         LAUNCH(m, col_stats_kernel, grid, 256, 0, m->Z, B, dd, m->fwd_sums());
         phase_end(m);
-        TRY(allreduce(m, m->fwd_sums(), dd, true));
+        TRY(allreduce(m, m->fwd_sums(), dd, true, 1));
         phase_begin(m, PH_BN_STATS);
         LAUNCH(m, col_var_kernel, grid, 256, 0, m->Z, B, dd, m->fwd_sums(), (double)m->Bglobal, m->var_sums());
         phase_end(m);
-        TRY(allreduce(m, m->var_sums(), dd, true));
+        TRY(allreduce(m, m->var_sums(), dd, true, 2));
         phase_begin(m, PH_BN_STATS);
         LAUNCH(m, bn_finalize2_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), m->var_sums(), dd,
                (double)m->Bglobal, 1e-4 /* cpp/objective.cu:114 */, m->mean, m->invstd);
@@ -734,7 +753,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
         TRY(dispatch_score(m, sp));
     }
     phase_end(m);
-    TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true));
+    TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true, 3));
     {
         const int slot = (int)(m->forward_count % nvsm_model::kCostRing);
         CU(cudaMemcpyAsync(m->loss_host + slot, m->loss_acc(), sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -743,6 +762,15 @@ int forward(nvsm_model* m, BatchSlot* s) {
         m->forward_count++;
     }
     m->have_forward = true;
+    return 0;
+}
+
+// grad_transform's all-reduce may still be running on the communication stream (see backward()).
+int join_gt_allreduce(nvsm_model* m) {
+    if (m->gt_allreduce_pending) {
+        CU(cudaStreamWaitEvent(m->stream, m->gt_reduced_ev, 0));
+        m->gt_allreduce_pending = false;
+    }
     return 0;
 }
 
@@ -759,6 +787,7 @@ int reduce_gt_partials(nvsm_model* m) {
 // ------------------------------------------------------------------------------------
 int backward(nvsm_model* m) {
     if (!m->have_forward) return fail("compute_gradients called without a forward result");
+    TRY(join_gt_allreduce(m));
     const long B = m->B;
     const bool bn = m->cfg.batch_normalization != 0;
     const int dw = m->dw, dd = m->dd;
@@ -808,7 +837,20 @@ int backward(nvsm_model* m) {
         if (m->nranks > 1 || getenv("NVSM_NO_FUSED_REDUCE")) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
     }
     phase_end(m);
-    TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
+    if (m->nranks > 1) {
+        // grad_transform is only consumed by the projection update at the very end of the step: its all-reduce runs on
+        // the communication stream under the grad_phrase GEMM and the word update (joined in update_transform).
+        if (m->comm_stream && !m->profiling) {
+            CU(cudaEventRecord(m->gt_ready, m->stream));
+            CU(cudaStreamWaitEvent(m->comm_stream, m->gt_ready, 0));
+            const int arc = nccl_api().AllReduce(m->gT, m->gT, (size_t)dw * dd, kNcclFloat32, kNcclSum, m->comm, (void*)m->comm_stream);
+            if (arc != 0) return fail("ncclAllReduce: %s", nccl_api().GetErrorString(arc));
+            CU(cudaEventRecord(m->gt_reduced_ev, m->comm_stream));
+            m->gt_allreduce_pending = true;
+        } else {
+            TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
+        }
+    }
 
     // grad_phrase[B, dw] = dX . T^T, scaled by 1/n (cpp/objective.cu:453-476)
     phase_begin(m, PH_GEMM_GP);
@@ -1083,6 +1125,7 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
 }
 
 int update_transform(nvsm_model* m, float lr, float lambda) {
+    TRY(join_gt_allreduce(m));
     TransformUpdateParams p;
     p.T = m->T; p.b = m->b; p.gT = m->gT; p.gb = m->gb;
     p.nT = (long)m->dw * m->dd; p.nb = m->dd;
@@ -1436,6 +1479,14 @@ void nvsm_destroy(nvsm_model* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->comm) nccl_api().CommDestroy(m->comm);
+    for (void* p : m->peer_mapped)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (m->peer_inbox) cudaFree(m->peer_inbox);
+    if (m->peer_flags) cudaFree(m->peer_flags);
+    if (m->peer_error) cudaFree(m->peer_error);
+    if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    if (m->gt_ready) cudaEventDestroy(m->gt_ready);
+    if (m->gt_reduced_ev) cudaEventDestroy(m->gt_reduced_ev);
     float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->Tr, m->P_lo, m->Gp_lo, m->Tt_lo, m->Tr_lo, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
                    m->optE.acc, m->optE.agg, m->T_a, m->b_a, m->T_v, m->b_v, m->P, m->Z, m->Gp, m->gP, m->probs,
                    m->mult, m->rowtmp, m->mean, m->invstd, m->mean_dy, m->mean_dyx, m->bn_scale, m->bn_shift, m->stat_part, m->gT, m->gb, m->gT_part, m->scratch};
@@ -1681,7 +1732,7 @@ int nvsm_get_tensor(nvsm_model* m, const char* name, float* host_out, long n) {
     TensorRef r = find_tensor(m, name);
     if (r.count < 0) return fail("unknown tensor '%s'", name);
     if (r.count != n) return fail("tensor '%s' has %ld elements, caller asked for %ld", name, r.count, n);
-    if (r.ptr == m->gT) TRY(reduce_gt_partials(m));   // single GPU: the partial sum is otherwise fused into the update
+    if (r.ptr == m->gT) { TRY(reduce_gt_partials(m)); TRY(join_gt_allreduce(m)); }   // single GPU: the partial sum is otherwise fused into the update
     const float* src = r.ptr;
     if (r.kind == 3) {   // P rows are padded to ldP floats
         CU(cudaMemcpy2DAsync(host_out, sizeof(float) * m->dw, m->P, sizeof(float) * m->ldP, sizeof(float) * m->dw, m->B,
@@ -2137,6 +2188,76 @@ int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank) {
     if (rc != 0) return fail("ncclCommInitRank: %s", nccl_api().GetErrorString(rc));
     m->nranks = num_ranks;
     m->rank = rank;
+    if (!m->comm_stream) {
+        CU(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->gt_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// NVLink peer exchange for the small per-step reductions (peer_allreduce.cuh). Optional: without it they go through
+// ncclAllReduce. Protocol: after nvsm_comm_init every rank calls nvsm_comm_peer_export (128 bytes: two CUDA IPC memory
+// handles), the caller all-gathers the blobs (rank order) and hands them to nvsm_comm_peer_import on every rank.
+int nvsm_comm_peer_export(nvsm_model* m, char* handles_out_128) {
+    if (!m || !handles_out_128) return fail("null argument");
+    if (m->nranks < 2 || m->nranks > kPeerMaxRanks) return fail("peer exchange needs 2..%d ranks", kPeerMaxRanks);
+    CU(cudaSetDevice(m->device));
+    if (!m->peer_inbox) {
+        m->peer.nranks = m->nranks; m->peer.rank = m->rank;
+        m->peer.slot_doubles = 2 * m->dd + 8;
+        const size_t nslots = (size_t)kPeerKinds * 2 * m->nranks;
+        TRY(dev_alloc(&m->peer_inbox, nslots * m->peer.slot_doubles));
+        TRY(dev_alloc(&m->peer_flags, nslots));
+        TRY(dev_alloc(&m->peer_error, 1));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h[2];
+    CU(cudaIpcGetMemHandle(&h[0], m->peer_inbox));
+    CU(cudaIpcGetMemHandle(&h[1], m->peer_flags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handles_out_128, h, 128);
+    return 0;
+}
+
+int nvsm_comm_peer_import(nvsm_model* m, const char* all_handles) {
+    if (!m || !all_handles) return fail("null argument");
+    if (!m->peer_inbox) return fail("nvsm_comm_peer_import before nvsm_comm_peer_export");
+    CU(cudaSetDevice(m->device));
+    for (int p = 0; p < m->nranks; ++p) {
+        if (p == m->rank) {
+            m->peer.inbox[p] = m->peer_inbox;
+            m->peer.flags[p] = m->peer_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, all_handles + (size_t)p * 128, 128);
+        void *inbox = nullptr, *flags = nullptr;
+        CU(cudaIpcOpenMemHandle(&inbox, h[0], cudaIpcMemLazyEnablePeerAccess));
+        CU(cudaIpcOpenMemHandle(&flags, h[1], cudaIpcMemLazyEnablePeerAccess));
+        m->peer_mapped[2 * p] = inbox; m->peer_mapped[2 * p + 1] = flags;
+        m->peer.inbox[p] = (double*)inbox;
+        m->peer.flags[p] = (unsigned long long*)flags;
+    }
+    m->peer_ready = true;
+    return 0;
+}
+
+int nvsm_comm_peer_disable(nvsm_model* m) {
+    if (!m) return fail("null argument");
+    m->peer_ready = false;
+    return 0;
+}
+
+int nvsm_comm_peer_status(nvsm_model* m, int* ready, int* error) {
+    if (!m || !ready || !error) return fail("null argument");
+    *ready = m->peer_ready ? 1 : 0;
+    *error = 0;
+    if (m->peer_error) {
+        CU(cudaSetDevice(m->device));
+        CU(cudaStreamSynchronize(m->stream));
+        CU(cudaMemcpy(error, m->peer_error, sizeof(int), cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

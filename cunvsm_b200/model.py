@@ -472,6 +472,24 @@ class Model:
     def comm_init(self, unique_id, num_ranks, rank):
         check(self.L.nvsm_comm_init(self.h, unique_id, num_ranks, rank))
 
+    def comm_peer_export(self):
+        buf = ctypes.create_string_buffer(128)
+        check(self.L.nvsm_comm_peer_export(self.h, buf))
+        return buf.raw
+
+    def comm_peer_import(self, blobs):
+        """blobs: the 128-byte exports of all ranks, in rank order."""
+        data = b"".join(blobs)
+        check(self.L.nvsm_comm_peer_import(self.h, data))
+
+    def peer_ready_override_off(self):
+        check(self.L.nvsm_comm_peer_disable(self.h))
+
+    def comm_peer_status(self):
+        ready, err = ctypes.c_int(), ctypes.c_int()
+        check(self.L.nvsm_comm_peer_status(self.h, ctypes.byref(ready), ctypes.byref(err)))
+        return bool(ready.value), int(err.value)
+
     def comm_set_sparse_mode(self, mode):
         """SPARSE_LOCAL: per-rank local table updates; SPARSE_ALLGATHER: every replica applies the updates of
         the whole global batch (the single-GPU trajectory)."""

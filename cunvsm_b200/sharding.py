@@ -39,7 +39,7 @@ def broadcast_unique_id(dist, make_id, rank, src=0):
     return bytes(uid)
 
 
-def init_model_comm(model, dist, rank, world, sparse_mode=0):
+def init_model_comm(model, dist, rank, world, sparse_mode=0, peer_exchange=True):
     """Attach an NCCL communicator to `model` (no-op for a single rank). sparse_mode: 0 = per-rank local
     updates of the replicated tables, 1 = all-gather the rows so every replica applies the global update."""
     if world <= 1:
@@ -49,6 +49,31 @@ def init_model_comm(model, dist, rank, world, sparse_mode=0):
     model.comm_init(uid, world, rank)
     if sparse_mode:
         model.comm_set_sparse_mode(sparse_mode)
+    if peer_exchange:
+        init_peer_exchange(model, dist, world)
+
+
+def init_peer_exchange(model, dist, world):
+    """NVLink peer exchange for the small per-step reductions; every rank must take the same decision, so the
+    outcome of the IPC export / import is agreed on before anybody uses it (NCCL stays the fallback)."""
+    try:
+        blob = model.comm_peer_export()
+    except Exception:
+        blob = None
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob)
+    ok = all(isinstance(b, (bytes, bytearray)) and len(b) == 128 for b in blobs)
+    if ok:
+        try:
+            model.comm_peer_import([bytes(b) for b in blobs])
+        except Exception:
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        model.peer_ready_override_off()
+    dist.barrier()
+    return all(flags)
 
 
 def max_over_ranks(dist, value, device=None):

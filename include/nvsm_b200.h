@@ -218,6 +218,17 @@ NVSM_API float nvsm_similarity_scaled_regularization_lambda(nvsm_model* m);
 NVSM_API int nvsm_comm_unique_id(char* id_out_128);
 NVSM_API int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank);
 
+/* Optional NVLink peer exchange for the latency-bound per-step reductions (batch-norm sums, backward column sums +
+ * loss): a one-block kernel pushes each rank's few KB into the peers' inboxes over NVLink and sums them in rank
+ * order (cunvsm_b200/csrc/peer_allreduce.cuh), ~3 us instead of ~17 us per small ncclAllReduce. After
+ * nvsm_comm_init every rank exports 128 bytes (two CUDA IPC handles), the caller all-gathers the blobs in rank order
+ * and passes num_ranks * 128 bytes to nvsm_comm_peer_import. Without it the reductions use NCCL. grad_transform
+ * (d_w * d_d floats) always goes through ncclAllReduce, on a side stream under grad_phrase and the word update. */
+NVSM_API int nvsm_comm_peer_export(nvsm_model* m, char* handles_out_128);
+NVSM_API int nvsm_comm_peer_import(nvsm_model* m, const char* all_handles);
+NVSM_API int nvsm_comm_peer_disable(nvsm_model* m);   /* back to NCCL (every rank must take the same decision) */
+NVSM_API int nvsm_comm_peer_status(nvsm_model* m, int* ready, int* error);
+
 /* How the replicated word / entity tables are updated when num_ranks > 1 (new: the reference is
  * single-GPU). NVSM_SPARSE_LOCAL (default): each rank applies only the updates of its
  * own rows, no exchange, replicas drift apart. NVSM_SPARSE_ALLGATHER: the ranks all-gather their rows of

@@ -82,7 +82,9 @@ def main():
                                  update_method=method, adam_mode=mode)
         dm = nv.Model(V, D, desc, tc_local, device=local, gemm_mode=gemm_mode)
         dm.initialize(nv.RNG(1))
-        sharding.init_model_comm(dm, dist, rank, world)
+        sharding.init_model_comm(dm, dist, rank, world, peer_exchange=os.environ.get("NVSM_TEST_NO_PEER") is None)
+        if os.environ.get("NVSM_TEST_NO_PEER") is None:
+            assert dm.comm_peer_status() == (True, 0), "NVLink peer exchange must be up on a multi-GPU box"
         ref = nv.Model(V, D, desc, tc_full, device=local, gemm_mode=gemm_mode)
         ref.initialize(nv.RNG(1))
 
@@ -130,6 +132,7 @@ def main():
             decay = 1.0 - res.scaled_regularization_lambda() * lr
             moved = np.abs(dm.get_tensor(nv.ENTITY_REPRS).reshape(D, dd) - E0.reshape(D, dd) * np.float32(decay)).max(1) > 1e-7
             assert set(np.nonzero(moved)[0]) <= set(np.unique(sids))
+        assert dm.comm_peer_status()[1] == 0, "peer exchange timed out"
         dm.close(); ref.close()
     dist.barrier()
     if rank == 0:
