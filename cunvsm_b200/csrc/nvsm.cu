@@ -136,7 +136,8 @@ struct nvsm_model {
     int gt_nparts = 0;          // split-K partials of the running step's grad_transform
     bool gt_reduced = true;     // gT holds their sum (single GPU: summed inside transform_update_kernel or on demand)
     // pull-style full Adam: per-step reference buckets (counting sort by row)
-    bool pull = false;
+    bool pull = false;          // reference buckets are built every step (full Adam, SGD, Adagrad)
+    float* wcoef = nullptr;     // word-side Adagrad coefficients fw / sqrt(mean acc + eps) [maxB * n]
     int *e_counts = nullptr, *e_offsets = nullptr, *e_refs = nullptr;
     int *w_counts = nullptr, *w_offsets = nullptr, *w_refs = nullptr;
     int* scan_tmp = nullptr;  // block totals of the two-level scan
@@ -265,6 +266,8 @@ int collect_phases(nvsm_model* m) {
     m->pending.clear();
     return 0;
 }
+
+constexpr long kPullMinRows = 8192;   // pull-style SGD / Adagrad below this many table rows: atomics win
 
 int grid_for(const nvsm_model* m, long work_items, int items_per_block, int blocks_per_sm) {
     long need = (work_items + items_per_block - 1) / items_per_block;
@@ -967,6 +970,57 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     return 0;
 }
 
+template <int VEC, int NCH>
+int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool touch_all, float* acc, const float* ysq,
+                    const float* word_coefs) {
+    const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
+    if (entities)
+        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f);
+    else
+        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f);
+    return 0;
+}
+
+// SGD / Adagrad through the reference buckets (sgd_pull_kernel).
+int pull_sgd(nvsm_model* m, bool entities, float lr, float lambda) {
+    if (!m->buckets_in_flight) return fail("pull update without reference buckets");
+    CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
+    const bool adagrad = m->cfg.update_method == NVSM_ADAGRAD;
+    const float decay = lambda > 0.0f ? (float)(1.0 - (double)(lambda * lr)) : 1.0f;
+    const bool touch_all = lambda > 0.0f;
+    float* acc = nullptr;
+    const float* ysq = nullptr;
+    const float* word_coefs = m->cur->fweights;
+    if (adagrad && entities) {
+        float* const tmp = m->entity_async_running ? m->rowtmp_e : m->rowtmp;
+        const float inv_dim = (float)std::exp(-std::log((double)m->dd));
+        LAUNCH(m, row_meansq_act_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->Z, act_params(m, m->cfg.batch_normalization != 0),
+               m->B, m->dd, inv_dim, tmp);
+        acc = m->optE.acc; ysq = tmp;
+    } else if (adagrad) {
+        TRY(scatter_word_meansq(m, m->optW.acc, 1.0f));   // V scalars: atomics are fine here
+        LAUNCH(m, word_adagrad_coef_kernel, (int)((m->B + 255) / 256), 256, 0, (const idx_t*)m->cur->features,
+               (const float*)m->cur->fweights, (const float*)m->optW.acc, m->B, m->n, 1e-6f, m->wcoef);
+        word_coefs = m->wcoef;
+    }
+    const int dim = entities ? m->dd : m->dw;
+    if (vec4_ok(dim)) {
+        const int nch = (dim / 4 + 31) / 32;
+        if (nch <= 1) return launch_sgd_pull<4, 1>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+        if (nch <= 2) return launch_sgd_pull<4, 2>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+        if (nch <= 3) return launch_sgd_pull<4, 3>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+        if (nch <= 4) return launch_sgd_pull<4, 4>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+        return launch_sgd_pull<4, 8>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+    }
+    const int nch = (dim + 31) / 32;
+    if (nch <= 1) return launch_sgd_pull<1, 1>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+    if (nch <= 4) return launch_sgd_pull<1, 4>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+    if (nch <= 16) return launch_sgd_pull<1, 16>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+    return launch_sgd_pull<1, 32>(m, entities, decay, lr, touch_all, acc, ysq, word_coefs);
+}
+
 // The ids of a batch are known before the forward pass starts, so both bucket sets are built on
 // the auxiliary stream while the forward / backward kernels run on the main stream.
 int start_bucket_build(nvsm_model* m, BatchSlot* s) {
@@ -1055,6 +1109,9 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
         return scatter(theta, lr, acc, eps);
     };
     const int method = m->cfg.update_method;
+    if (m->pull && (method == NVSM_SGD || method == NVSM_ADAGRAD) && text && !pair && !self && N >= kPullMinRows &&
+        !(exact_sparse(m) && method == NVSM_ADAGRAD))   // (the gathered batch has no word-coefficient buffer)
+        return pull_sgd(m, entities, lr, lambda);
     if (method == NVSM_SGD) return sgd(nullptr, 0.f);
     if (text && pair && (method == NVSM_ADAGRAD || (method == NVSM_ADAM && m->cfg.adam_mode == NVSM_ADAM_SPARSE)))
         return fail("Adagrad / sparse Adam do not implement multiple gradients (cpp/updates_adagrad.cu:108-109, "
@@ -1497,6 +1554,7 @@ void nvsm_destroy(nvsm_model* m) {
     for (int* p : il)
         if (p) cudaFree(p);
     if (m->Y) cudaFree(m->Y);
+    if (m->wcoef) cudaFree(m->wcoef);
     void* ag[] = {m->ag_slot.ids, m->ag_slot.features, m->ag_slot.fweights, m->ag_mult, m->ag_act, m->ag_gP, m->ag_rowtmp,
                   m->ag_e_refs, m->ag_w_refs, m->ag_escore, m->p_norms, m->enorm, m->escore, m->mult_eff, m->kself};
     for (void* p : ag)
@@ -1645,14 +1703,21 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
         m->gt_splits = std::max(m->num_sms, (2 * m->num_sms + tiles - 1) / tiles);
         TRY(dev_alloc(&m->gT_part, (size_t)m->gt_splits * dw * dd, false));
-        m->pull = method == NVSM_ADAM && cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE &&
-                  m->optE.agg == nullptr /* see can_pull above */ &&
+        const bool full_adam_pull = method == NVSM_ADAM && cfg->adam_mode == NVSM_ADAM_DENSE_UPDATE_DENSE_VARIANCE &&
+                                    m->optE.agg == nullptr /* see can_pull above */;
+        // SGD / Adagrad: pull-style as well (no float atomics), for the plain TextEntity objective
+        // (one warp per table row: only worth it when there are enough rows to fill the machine; C1's 200-row entity
+        // table measured 12 -> 34 us through the pull path)
+        const bool sgd_pull = (method == NVSM_SGD || method == NVSM_ADAGRAD) && cfg->objective == NVSM_OBJECTIVE_TEXT_ENTITY &&
+                              !cfg->l2_normalize_entity_reprs && !getenv("NVSM_NO_PULL") && std::max(V, D) >= kPullMinRows;
+        m->pull = (full_adam_pull || sgd_pull) &&
                   V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
         if (m->pull) {
             TRY(dev_alloc(&m->Y, maxB * dd));
             TRY(dev_alloc(&m->e_counts, D + 1)); TRY(dev_alloc(&m->e_offsets, D + 1)); TRY(dev_alloc(&m->e_refs, maxB * m->R));
             TRY(dev_alloc(&m->w_counts, V + 1)); TRY(dev_alloc(&m->w_offsets, V + 1)); TRY(dev_alloc(&m->w_refs, maxB * m->n));
             TRY(dev_alloc(&m->scan_tmp, 2 * 1024 + 2));
+            if (method == NVSM_ADAGRAD) TRY(dev_alloc(&m->wcoef, maxB * m->n));
             if (std::max(V, D) > 1024L * 1024L) m->pull = false;  // two-level scan limit
         }
         m->slots.resize(m->cfg.num_batch_slots + 2);

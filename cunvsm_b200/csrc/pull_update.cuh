@@ -154,4 +154,94 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
     }
 }
 
+// Pull-style SGD / Adagrad (cpp/storage.cu:51-102, cpp/updates_adagrad.cu:99-179) over the same reference buckets:
+//   theta[row] = theta[row] * decay + lr * rs * sum_{refs of row} coef_ref * src[ref / group]
+// decay = 1 - lambda_s * lr is the reference's dense whole-table decay (touch_all != 0), otherwise rows without
+// references are not touched at all. Replaces one float atomic per element per reference (update_repr_kernel) by
+// reads of the L2-resident per-n-gram rows; every row is written once.
+//   entity Adagrad (acc != null): acc[row] += sum_refs coef^2 * ysq[ref / group]  (mean_k of the squared gradient
+//   column, window 1), rs = 1 / sqrt(acc[row] + eps) with the UPDATED accumulator, like adagrad_update_kernel.
+//   word Adagrad: the per-n-gram factor 1 / sqrt(mean_w acc[id_w] + eps) is folded into coefs by the caller.
+template <int VEC, int NCH, bool ENTITY>
+__global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta, long num_rows, int dim,
+                                                       const int* __restrict__ offsets, const int* __restrict__ refs,
+                                                       const float* __restrict__ coefs, const float* __restrict__ src,
+                                                       int group, float decay, float lr, int touch_all,
+                                                       float* __restrict__ acc, const float* __restrict__ ysq, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim / VEC;
+    for (long row = warp0; row < num_rows; row += nwarps) {
+        const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        if (beg == end && !touch_all) continue;
+        float agg[NCH][VEC];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+        float sq = 0.f;
+        for (int base = beg; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            int my_src = 0;
+            float my_coef = 0.f;
+            if (lane < cnt) {
+                const int ref = __ldg(refs + base + lane);
+                my_src = ref / group;
+                const float cf = __ldg(coefs + ref);
+                my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
+                if (acc) sq += cf * cf * __ldg(ysq + my_src);
+            }
+            for (int t = 0; t < cnt; ++t) {
+                const int srow = __shfl_sync(kFull, my_src, t);
+                const float cf = __shfl_sync(kFull, my_coef, t);
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+                    if (c < nvec) {
+                        float x[VEC];
+                        load_vec_ro<VEC>(src + (long)srow * dim + c * VEC, x);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) agg[j][q] += cf * x[q];
+                    }
+                }
+            }
+        }
+        float rs = 1.0f;
+        if (acc) {
+            sq = warp_sum(sq);
+            const float a = acc[row] + sq;
+            if (lane == 0 && beg != end) acc[row] = a;
+            rs = 1.0f / sqrtf(a + eps);
+        }
+        const float step = lr * rs;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            if (c < nvec) {
+                const long o = row * dim + c * VEC;
+                float th[VEC];
+                load_vec_cs<VEC>(theta + o, th);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) th[q] = th[q] * decay + step * agg[j][q];
+                store_vec_cs<VEC>(theta + o, th);
+            }
+        }
+    }
+}
+
+// Word-side Adagrad coefficients: wcoef[i * n + w] = fw[i, w] / sqrt(mean_w' acc[id[i, w']] + eps)
+// (adagrad_update_kernel with window n, cpp/updates_adagrad.cu:83-97; acc already holds this batch's contribution).
+__global__ void word_adagrad_coef_kernel(const idx_t* __restrict__ ids, const float* __restrict__ fw,
+                                         const float* __restrict__ acc, long B, int n, float eps,
+                                         float* __restrict__ wcoef) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float a = 0.f;
+    for (int w = 0; w < n; ++w) a += __ldg(acc + __ldg(ids + i * n + w));
+    a /= (float)n;
+    const float factor = 1.0f / sqrtf(a + eps);
+    for (int w = 0; w < n; ++w) wcoef[i * n + w] = __ldg(fw + i * n + w) * factor;
+}
+
 }  // namespace nvsm
