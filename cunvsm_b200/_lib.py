@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnvsm_b200.so")
+LIB_PATH = os.environ.get("NVSM_LIB_PATH") or os.path.join(HERE, "libnvsm_b200.so")   # (override: kernel-variant experiments)
 
 # every symbol include/nvsm_b200.h declares
 SYMBOLS = [

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc[v] += wt * x[v];
             }
-#pragma unroll
             float lo[VEC];
+#pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 acc[v] = acc[v] / fwin;
                 lo[v] = 0.f;
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
 // pass, and the window's ids / weights are loaded once per n-gram (one lane each) and broadcast with
 // shuffles. ncu on the pass-per-32-columns kernel above (C2, d_w = 300): 942 warp instructions per n-gram,
 // issue slots 49 % busy, i.e. issue-bound, the third pass running 11 of 32 lanes; this layout needs ~270.
+// U words are loaded back to back before their FMAs (NVSM_GATHER_U).
 // Division by the window follows the reference's release build (-use_fast_math => __fdividef,
 // CMakeLists.txt:71-73 of the reference).
 template <int K, int LG>
@@ -81,7 +82,10 @@ __global__ void __launch_bounds__(256) gather_mean_lanes_kernel(const float* __r
                                                                 float* __restrict__ out, int ld_out, int tf32,
                                                                 float* __restrict__ out_lo) {
     constexpr int kGroups = kWarp / LG;
-    constexpr int U = 5;   // words in flight per lane: U * K independent 16-byte loads
+#ifndef NVSM_GATHER_U
+#define NVSM_GATHER_U 2   // measured on C2 (us): U=1 83.2, 2 81.5, 3 90.9, 5 87.9, 10 117 -- occupancy beats loads in flight
+#endif
+    constexpr int U = NVSM_GATHER_U;   // words in flight per lane: U * K independent 16-byte loads
     const int lane = threadIdx.x & 31;
     const int sl = lane & (LG - 1);
     const int grp = lane / LG;

@@ -691,7 +691,9 @@ int forward(nvsm_model* m, BatchSlot* s) {
         phase_begin(m, PH_BN_STATS);
         {
             const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
-            const int nblk = grid_for(m, B, 32, 2);   // <= 2 blocks per SM
+            int bps = 4;   // blocks per SM (NVSM_STATS_BPS: experiment knob)
+            { const char* e = getenv("NVSM_STATS_BPS"); if (e) bps = std::max(1, std::min(8, atoi(e))); }
+            const int nblk = grid_for(m, B, 16, bps);
             LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
             if (m->nranks <= 1) {
                 LAUNCH(m, col_stats_reduce_finalize_kernel, (dd + 31) / 32, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
@@ -1698,7 +1700,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         TRY(dev_alloc(&m->mean_dy, dd)); TRY(dev_alloc(&m->mean_dyx, dd));
         TRY(dev_alloc(&m->bn_scale, dd)); TRY(dev_alloc(&m->bn_shift, dd));
         TRY(dev_alloc(&m->dsums, 5 * (size_t)dd + 1));
-        TRY(dev_alloc(&m->stat_part, (size_t)2 * m->num_sms * 2 * dd));
+        TRY(dev_alloc(&m->stat_part, (size_t)8 * m->num_sms * 2 * dd));
         TRY(dev_alloc(&m->gT, (size_t)dw * dd)); TRY(dev_alloc(&m->gb, dd));
         const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
         m->gt_splits = std::max(m->num_sms, (2 * m->num_sms + tiles - 1) / tiles);
