@@ -33,7 +33,10 @@ struct Flags {
               {"entity_similarity_weight", "0.0"}, {"term_similarity_weight", "0.0"}, {"output", ""},
               // replacements for the Indri positional argument
               {"synthetic_num_words", "50000"}, {"synthetic_num_entities", "50000"}, {"synthetic_num_batches", "100"},
-              {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "3xtf32"}, {"host_sampler", "false"}, {"v", "0"}};
+              {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "3xtf32"}, {"host_sampler", "false"}, {"v", "0"},
+              // pre-tokenised n-gram file (`<entity> <w_1> ... <w_n> [| weight]` per line) instead of the synthetic source,
+              // prefetched by an AsyncSource with this many pinned batches (the reference uses 10, cpp/main.cu:212-219)
+              {"ngram_file", ""}, {"num_concurrent_batches", "10"}};
   }
   void parse(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
@@ -100,7 +103,7 @@ class SimilaritySource {
 };
 
 struct Sources {
-  TextEntity::SyntheticSource* text;
+  DataSource<TextEntity::Batch>* text;
   SimilaritySource* pairs;
 };
 
@@ -152,8 +155,22 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   RNG rng;
   rng.seed(flags.i("seed"));
 
-  const size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
-  TextEntity::SyntheticSource data_source(V, D, flags.i("synthetic_num_batches"), flags.i("seed"), flags.d("synthetic_zipf"));
+  size_t V = flags.i("synthetic_num_words"), D = flags.i("synthetic_num_entities");
+  std::unique_ptr<DataSource<TextEntity::Batch>> data_source_ptr;
+  const bool file_source = !flags.str("ngram_file").empty();
+  if (file_source) {
+    // construct_data_source + wrap_source_async of the reference (cpp/main.cu:212-240), on an n-gram file
+    TextEntity::NGramFileSource* const file = new TextEntity::NGramFileSource(
+        flags.str("ngram_file"), train_config.window_size(), &rng, train_config.no_shuffle());
+    V = file->vocabulary_size(); D = file->corpus_size();
+    std::printf("n-gram file: %zu instances, |V|=%zu |D|=%zu\n", file->num_instances(), V, D);
+    data_source_ptr.reset(new AsyncSource<TextEntity::Batch>(flags.i("num_concurrent_batches"), train_config.batch_size(),
+                                                             train_config.window_size(), file));
+  } else {
+    data_source_ptr.reset(new TextEntity::SyntheticSource(V, D, flags.i("synthetic_num_batches"), flags.i("seed"),
+                                                          flags.d("synthetic_zipf")));
+  }
+  DataSource<TextEntity::Batch>& data_source = *data_source_ptr;
   const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
 
   std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
@@ -215,7 +232,12 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   }
   size_t total_batches = 0; double total_secs = 0.0;
   for (long epoch = 1; epoch <= train_config.num_epochs(); ++epoch) {
+    // the file source shuffles with the shared engine (cpp/data_indri.cpp:386-397): bring its state back from the
+    // device sampler first and hand it over again afterwards, so the stream matches the reference's single RNG
+    const bool device_rng = file_source && !flags.b("host_sampler") && Ops::has_text;
+    if (device_rng) model.sync_rng(&rng);
     Ops::reset(sources);
+    if (device_rng) model.use_device_sampler(&rng);
     iterate(true, &nb, &cost, &secs);
     total_batches += nb; total_secs += secs;
     std::printf("Epoch #%ld: mean cost %g; %.2f batches/second, %.0f n-grams/second\n", epoch, cost / nb,

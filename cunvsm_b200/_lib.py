@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("NVSM_LIB_PATH") or os.path.join(HERE, "libnvsm_b200.s
 SYMBOLS = [
     "nvsm_last_error", "nvsm_version", "nvsm_host_alloc", "nvsm_host_free", "nvsm_create", "nvsm_destroy", "nvsm_set_stream", "nvsm_synchronize",
     "nvsm_initialize", "nvsm_tensor_size", "nvsm_get_tensor", "nvsm_set_tensor", "nvsm_generate_labels",
-    "nvsm_compute_cost", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost",
+    "nvsm_compute_cost", "nvsm_wait_upload", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost",
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
@@ -76,6 +76,7 @@ def load():
     f("nvsm_set_tensor", [vp, cs, pf, cl])
     f("nvsm_generate_labels", [pl, cl, cl, cl, pul, pl])
     f("nvsm_compute_cost", [vp, pl, pf, pl, pf, cl])
+    f("nvsm_wait_upload", [vp])
     f("nvsm_compute_gradients", [vp])
     f("nvsm_update", [vp, cf, cf])
     f("nvsm_get_cost", [vp, pf])

@@ -2043,6 +2043,16 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     return fused_step(m, s, lr);
 }
 
+// Block the host until the H2D copies (and, in device-sampler mode, the sampling) of the running forward result's
+// batch have finished: after this the caller may overwrite / recycle the host buffers it passed in.
+int nvsm_wait_upload(nvsm_model* m) {
+    if (!m) return fail("null model");
+    if (!m->cur) return 0;
+    CU(cudaSetDevice(m->device));
+    CU(cudaEventSynchronize(m->cur->ready));
+    return 0;
+}
+
 // Stand-alone device sampling for arbitrary (z, num_objects): host labels in, host ids out.
 int nvsm_generate_labels_device(nvsm_model* m, const long* labels, long num_labels, long z, long num_objects,
                                 unsigned long* rng_state, long* out) {

@@ -2,14 +2,25 @@
 // TextEntity::Batch has the reference's layout (reference: include/cuNVSM/data.h:114-177,
 // cpp/data.cu:8-30,94-124): four page-locked arrays, instance-major,
 //   features_[B*n] (long), feature_weights_[B*n], labels_[B] (long), weights_[B].
-// The Indri-backed sources of the reference are out of scope; SyntheticSource generates seeded
-// uniform / Zipf n-grams with the same DataSource contract (has_next / next / reset / progress).
+// The Indri-backed sources of the reference are out of scope; SyntheticSource generates seeded uniform / Zipf n-grams
+// and NGramFileSource reads pre-tokenised n-grams, both with the DataSource contract (has_next / next / reset /
+// progress); AsyncSource is the reference's prefetching wrapper (cpp/data_async.cpp).
 #ifndef CUNVSM_B200_DATA_H
 #define CUNVSM_B200_DATA_H
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -29,6 +40,7 @@ class BatchInterface {
   virtual bool empty() const = 0;
   virtual size_t num_instances() const = 0;
   virtual size_t maximum_size() const = 0;
+  virtual void swap(BatchInterface* const other) = 0;   // reference: include/cuNVSM/data.h:57
 };
 
 template <typename BatchT>
@@ -102,6 +114,16 @@ class Batch : public BatchInterface {
   const WeightType* weights() const { return weights_; }
   void set_num_instances(size_t n) { NVSM_CHECK(n <= batch_size_, "too many instances"); num_instances_ = n; }
 
+  // reference: TextEntity::Batch::swap, cpp/data.cu:76-92 — exchanges the pinned arrays, no copy
+  virtual void swap(BatchInterface* const other) override {
+    Batch* const o = dynamic_cast<Batch*>(other);
+    NVSM_CHECK(o != nullptr, "swap with a different batch type");
+    NVSM_CHECK(batch_size_ == o->batch_size_ && window_size_ == o->window_size_, "swap needs equally sized batches");
+    std::swap(features_, o->features_); std::swap(feature_weights_, o->feature_weights_);
+    std::swap(labels_, o->labels_); std::swap(weights_, o->weights_);
+    std::swap(num_instances_, o->num_instances_);
+  }
+
  private:
   template <typename T>
   static void alloc(T** p, size_t count) {
@@ -161,7 +183,177 @@ class SyntheticSource : public DataSourceBase {
   std::vector<double> word_cdf_, entity_cdf_;
 };
 
+// Pre-tokenised n-gram file (stands in for IndriSource, cpp/data_indri.cpp, whose Indri index is out of scope):
+// one instance per line, `<entity_id> <word_id_1> ... <word_id_n>` with an optional `| <instance_weight>` tail;
+// lines starting with '#' are comments. Like IndriSource::reset (cpp/data_indri.cpp:386-397) every epoch walks the
+// instances in an order shuffled with the SHARED RNG (unless no_shuffle), so the engine consumption order
+// init -> shuffle -> negatives of the reference is kept. Only full batches are emitted (the CLI skips others).
+class NGramFileSource : public DataSourceBase {
+ public:
+  NGramFileSource(const std::string& path, const size_t window_size, RNG* const rng, const bool no_shuffle = false)
+      : window_size_(window_size), rng_(rng), no_shuffle_(no_shuffle), position_(0), max_word_(-1), max_entity_(-1) {
+    std::ifstream file(path);
+    NVSM_CHECK(file.good(), ("cannot open n-gram file " + path).c_str());
+    std::string line;
+    while (std::getline(file, line)) {
+      if (line.empty() || line[0] == '#') continue;
+      float weight = 1.0f;
+      const size_t bar = line.find('|');
+      if (bar != std::string::npos) { weight = std::stof(line.substr(bar + 1)); line = line.substr(0, bar); }
+      std::istringstream iss(line);
+      long entity = -1;
+      iss >> entity;
+      NVSM_CHECK(!iss.fail() && entity >= 0, "malformed n-gram line: entity id");
+      for (size_t w = 0; w < window_size_; ++w) {
+        long id = -1;
+        iss >> id;
+        NVSM_CHECK(!iss.fail() && id >= 0, "malformed n-gram line: fewer word ids than the window size");
+        words_.push_back(id);
+        max_word_ = std::max(max_word_, id);
+      }
+      entities_.push_back(entity);
+      weights_.push_back(weight);
+      max_entity_ = std::max(max_entity_, entity);
+    }
+    NVSM_CHECK(!entities_.empty(), "empty n-gram file");
+    order_.resize(entities_.size());
+    std::iota(order_.begin(), order_.end(), 0);
+  }
+  size_t num_instances() const { return entities_.size(); }
+  size_t vocabulary_size() const { return static_cast<size_t>(max_word_ + 1); }
+  size_t corpus_size() const { return static_cast<size_t>(max_entity_ + 1); }
+
+  virtual void reset() override {
+    position_ = 0;
+    std::iota(order_.begin(), order_.end(), 0);
+    if (!no_shuffle_ && rng_ != nullptr) std::shuffle(order_.begin(), order_.end(), *rng_);
+  }
+  // (batch size is only known at next(): ask "is there any instance left", like the reference's sources)
+  virtual bool has_next() const override { return position_ < order_.size(); }
+  virtual float32 progress() const override { return static_cast<float32>(position_) / order_.size(); }
+  virtual void next(Batch* const batch) override {
+    batch->clear();
+    NVSM_CHECK(batch->window_size() == window_size_, "batch window does not match the n-gram file");
+    const size_t B = std::min(batch->maximum_size(), order_.size() - position_);
+    for (size_t i = 0; i < B; ++i) {
+      const size_t k = order_[position_ + i];
+      std::copy(&words_[k * window_size_], &words_[(k + 1) * window_size_], &batch->features()[i * window_size_]);
+      std::fill(&batch->feature_weights()[i * window_size_], &batch->feature_weights()[(i + 1) * window_size_], 1.0f);
+      batch->labels()[i] = entities_[k];
+      batch->weights()[i] = weights_[k];
+    }
+    batch->set_num_instances(B);
+    position_ += B;
+  }
+
+ private:
+  const size_t window_size_;
+  RNG* const rng_;
+  const bool no_shuffle_;
+  size_t position_;
+  long max_word_, max_entity_;
+  std::vector<long> words_, entities_;
+  std::vector<float> weights_;
+  std::vector<size_t> order_;
+};
+
 }  // namespace TextEntity
+
+// reference: AsyncSource, include/cuNVSM/data.h:663-711 / cpp/data_async.cpp — a worker thread keeps
+// `num_concurrent_batches` pinned batches filled from the wrapped source; next() SWAPS the caller's empty batch with a
+// full buffer (no copy). reset() restarts the worker after resetting the source on the calling thread (which is where
+// the shared RNG is touched, as in the reference). Condition variables instead of the reference's yield-spinning
+// on boost::lockfree queues.
+template <typename BatchT>
+class AsyncSource : public DataSource<BatchT> {
+ public:
+  typedef BatchT BatchType;
+
+  // Takes ownership of `source`.
+  AsyncSource(const size_t num_concurrent_batches, const size_t batch_size, const size_t window_size,
+              DataSource<BatchT>* const source)
+      : source_(source), stop_(false), running_(false) {
+    NVSM_CHECK(num_concurrent_batches > 0, "need at least one buffer");
+    for (size_t i = 0; i < num_concurrent_batches; ++i) {
+      buffers_.emplace_back(new BatchT(batch_size, window_size));
+      empty_.push_back(buffers_.back().get());
+    }
+    start_worker();
+  }
+  virtual ~AsyncSource() { stop_worker(); }
+
+  virtual void reset() override {
+    stop_worker();
+    source_->reset();
+    for (BatchT* b : full_) { b->clear(); empty_.push_back(b); }   // drop batches prefetched from the old epoch
+    full_.clear();
+    start_worker();
+  }
+  virtual bool has_next() const override {
+    std::unique_lock<std::mutex> lock(mutex_);
+    cv_.wait(lock, [&] { return !full_.empty() || !running_; });
+    return !full_.empty();
+  }
+  virtual void next(BatchT* const batch) override {
+    NVSM_CHECK(batch->empty(), "AsyncSource::next needs an empty batch");
+    std::unique_lock<std::mutex> lock(mutex_);
+    cv_.wait(lock, [&] { return !full_.empty() || !running_; });
+    NVSM_CHECK(!full_.empty(), "AsyncSource::next called without has_next");
+    BatchT* const buffer = full_.front();
+    full_.pop_front();
+    batch->swap(buffer);
+    buffer->clear();
+    empty_.push_back(buffer);
+    cv_.notify_all();
+  }
+  virtual float32 progress() const override { return source_->progress(); }
+
+ private:
+  void start_worker() {
+    stop_ = false;
+    running_ = true;
+    thread_.reset(new std::thread([this] {
+      for (;;) {
+        BatchT* buffer = nullptr;
+        {
+          std::unique_lock<std::mutex> lock(mutex_);
+          cv_.wait(lock, [&] { return stop_ || !empty_.empty(); });
+          if (stop_ || !source_->has_next()) break;
+          buffer = empty_.front();
+          empty_.pop_front();
+        }
+        source_->next(buffer);   // outside the lock: this is the expensive part
+        {
+          std::lock_guard<std::mutex> lock(mutex_);
+          full_.push_back(buffer);
+        }
+        cv_.notify_all();
+      }
+      {
+        std::lock_guard<std::mutex> lock(mutex_);
+        running_ = false;
+      }
+      cv_.notify_all();
+    }));
+  }
+  void stop_worker() {
+    {
+      std::lock_guard<std::mutex> lock(mutex_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (thread_ && thread_->joinable()) thread_->join();
+    thread_.reset();
+  }
+
+  std::unique_ptr<DataSource<BatchT>> source_;
+  std::vector<std::unique_ptr<BatchT>> buffers_;
+  std::deque<BatchT*> empty_, full_;
+  mutable std::mutex mutex_;
+  mutable std::condition_variable cv_;
+  std::unique_ptr<std::thread> thread_;
+  bool stop_, running_;
+};
 
 // reference: RepresentationSimilarity::Batch, include/cuNVSM/data.h:551-614 / cpp/data.cu:157-222 — pairs of object
 // ids (features_[2 i], features_[2 i + 1]) with one weight per pair, pinned host memory.
@@ -204,6 +396,13 @@ class Batch : public BatchInterface {
 
   const ObjectIdxType* features() const { return features_; }
   const WeightType* weights() const { return weights_; }
+
+  virtual void swap(BatchInterface* const other) override {   // cpp/data.cu:196-210
+    Batch* const o = dynamic_cast<Batch*>(other);
+    NVSM_CHECK(o != nullptr && batch_size_ == o->batch_size_, "swap needs an equally sized batch of the same type");
+    std::swap(features_, o->features_); std::swap(weights_, o->weights_);
+    std::swap(num_instances_, o->num_instances_);
+  }
 
  private:
   const size_t batch_size_;

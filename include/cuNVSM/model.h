@@ -290,6 +290,7 @@ class Model {
     if (device_sampler_) {
       NVSM_ABORT_ON(nvsm_step_sampled(handle_, batch.features(), batch.feature_weights(), batch.labels(), batch.weights(),
                                       B, 0.0f, /*train=*/0));
+      NVSM_ABORT_ON(nvsm_wait_upload(handle_));   // the caller may recycle the batch (AsyncSource) once we return
       ++forward_counter_;
       return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
     }
@@ -300,6 +301,7 @@ class Model {
     nvsm_detail::rng_set_state(rng, st);
     NVSM_ABORT_ON(nvsm_compute_cost(handle_, batch.features(), batch.feature_weights(), entity_ids_.data(),
                                     batch.weights(), B));
+    NVSM_ABORT_ON(nvsm_wait_upload(handle_));     // (entity_ids_ is reused by the next call as well)
     ++forward_counter_;
     return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
   }
@@ -307,6 +309,7 @@ class Model {
   // RepresentationSimilarity::Objective::compute_cost, cpp/objective.cu:487-573
   RepresentationSimilarity::ForwardResult* pair_forward(const RepresentationSimilarity::Batch& batch) const {
     NVSM_ABORT_ON(nvsm_similarity_compute_cost(handle_, batch.features(), batch.weights(), batch.num_instances()));
+    NVSM_ABORT_ON(nvsm_synchronize(handle_));     // pair batches are copied on the compute stream: cheap, and recyclable after
     return new RepresentationSimilarity::ForwardResult(handle_, nvsm_similarity_scaled_regularization_lambda(handle_));
   }
 

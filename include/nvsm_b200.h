@@ -127,6 +127,11 @@ NVSM_API int nvsm_generate_labels(const long* labels, long num_labels, long num_
 NVSM_API int nvsm_compute_cost(nvsm_model* m, const long* features, const float* feature_weights,
                       const long* entity_ids, const float* weights, long num_instances);
 
+/* nvsm_compute_cost / nvsm_train_step / nvsm_step_sampled return once the H2D copies of their host arrays are
+ * ENQUEUED. A caller that recycles those arrays (AsyncSource swaps pinned batches, cpp/data_async.cpp) waits here
+ * first; the reference gets the same guarantee from the blocking get_cost() of every batch (cpp/main.cu:444). */
+NVSM_API int nvsm_wait_upload(nvsm_model* m);
+
 /* Model::compute_gradients — include/cuNVSM/model.h:109, cpp/objective.cu:315-481. */
 NVSM_API int nvsm_compute_gradients(nvsm_model* m);
 

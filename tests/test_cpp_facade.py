@@ -143,3 +143,34 @@ def test_cli_trains_mixture_objective(tmp_path, flag):
     import re
     costs = [float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)]
     assert len(costs) == 2 and np.isfinite(costs).all() and costs[1] < costs[0]
+
+
+@pytest.mark.gpu
+def test_cli_ngram_file_source_async_prefetch(tmp_path):
+    """NGramFileSource + AsyncSource (the reference's prefetch contract, cpp/data_async.cpp) behind the CLI: two epochs
+    over a pre-tokenised n-gram file, shuffled with the shared minstd_rand0 engine. The host-sampler run and the
+    device-sampler run consume that engine in the same order (init -> shuffle -> negatives), so their costs agree."""
+    _build()
+    rng = np.random.default_rng(0)
+    n, N, V, D = 4, 8192 + 300, 500, 120          # 8 full batches of 1024 + a partial one the CLI must skip
+    words = rng.integers(0, V, size=(N, n))
+    docs = (words[:, 0] * 3 + words[:, 1]) % D     # learnable
+    path = tmp_path / "ngrams.txt"
+    with open(path, "w") as f:
+        f.write("# entity w1 w2 w3 w4\n")
+        for i in range(N):
+            f.write("%d %s%s\n" % (docs[i], " ".join(map(str, words[i])), " | 1.5" if i % 7 == 0 else ""))
+    outs = []
+    for extra in (["--host_sampler"], []):
+        res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "32",
+                              "--entity_repr_size", "16", "--batch_size", "1024", "--window_size", str(n),
+                              "--num_random_entities", "3", "--seed", "11", "--update_method", "sgd", "--nonlinearity", "tanh",
+                              "--gemm", "fp32", "--ngram_file", str(path), "--num_concurrent_batches", "3"] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        assert "|V|=%d |D|=%d" % (words.max() + 1, docs.max() + 1) in res.stdout
+        assert res.stderr.count("Skipping Batch") == 2      # the partial batch of each epoch
+        import re
+        outs.append([float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)])
+    assert len(outs[0]) == 2 and np.isfinite(outs[0]).all()
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-6)   # identical batches, identical negatives
