@@ -162,8 +162,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
     // construct_data_source + wrap_source_async of the reference (cpp/main.cu:212-240), on an n-gram file
     TextEntity::NGramFileSource* const file = new TextEntity::NGramFileSource(
         flags.str("ngram_file"), train_config.window_size(), &rng, train_config.no_shuffle());
-    V = file->vocabulary_size(); D = file->corpus_size();
-    std::printf("n-gram file: %zu instances, |V|=%zu |D|=%zu\n", file->num_instances(), V, D);
+    std::printf("n-gram file: %zu instances\n", file->num_instances());
     data_source_ptr.reset(new AsyncSource<TextEntity::Batch>(flags.i("num_concurrent_batches"), train_config.batch_size(),
                                                              train_config.window_size(), file));
   } else {
@@ -171,6 +170,17 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
                                                           flags.d("synthetic_zipf")));
   }
   DataSource<TextEntity::Batch>& data_source = *data_source_ptr;
+  // Extract meta data through a generic interface: it sizes the model and is written next to the dumps
+  // (reference: cpp/main.cu:501-537; read back by py/nvsm/base.py:load_meta).
+  lse::Metadata meta;
+  data_source.extract_metadata(&meta);
+  V = meta.term_size(); D = meta.object_size();
+  NVSM_CHECK(V > 0 && D > 0, "the data source reports an empty vocabulary or corpus");
+  std::printf("Training statistics: vocabulary size=%zu, corpus size=%zu\n", V, D);
+  if (!flags.str("output").empty()) {
+    std::ofstream meta_file(flags.str("output") + "_meta", std::ios::binary);
+    NVSM_CHECK(meta.SerializeToOstream(&meta_file), "cannot write the _meta file");
+  }
   const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
 
   std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",

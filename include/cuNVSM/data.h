@@ -51,7 +51,28 @@ class DataSource {
   virtual void next(BatchT* const batch) = 0;
   virtual bool has_next() const = 0;
   virtual float32 progress() const = 0;
+  // reference: DataSourceInterface::extract_metadata, include/cuNVSM/data.h:75 (sources without a mapping leave it empty)
+  virtual void extract_metadata(lse::Metadata* const metadata) const { (void)metadata; }
 };
+
+namespace nvsm_detail {
+// Metadata of a source whose ids are already model ids: term i <-> i (with its frequency), object j <-> j.
+inline void identity_metadata(const size_t num_words, const size_t num_entities, const long* const term_frequency,
+                              const long total_terms, lse::Metadata* const metadata) {
+  for (size_t i = 0; i < num_words; ++i) {
+    lse::Metadata::TermInfo* const term = metadata->add_term();
+    term->set_index_term_id(static_cast<int>(i));
+    term->set_model_term_id(static_cast<int>(i));
+    term->set_term_frequency(term_frequency != nullptr ? static_cast<int>(term_frequency[i]) : 0);
+  }
+  metadata->set_total_terms(static_cast<int>(total_terms));
+  for (size_t j = 0; j < num_entities; ++j) {
+    lse::Metadata::ObjectInfo* const object = metadata->add_object();
+    object->set_model_object_id(static_cast<int>(j));
+    object->set_index_object_id(static_cast<int>(j));
+  }
+}
+}  // namespace nvsm_detail
 
 namespace TextEntity {
 
@@ -162,6 +183,10 @@ class SyntheticSource : public DataSourceBase {
     batch->set_num_instances(B);
     ++emitted_;
   }
+  // identity id mapping; synthetic ids carry no corpus statistics
+  virtual void extract_metadata(lse::Metadata* const metadata) const override {
+    nvsm_detail::identity_metadata(num_words_, num_entities_, nullptr, 0, metadata);
+  }
 
  private:
   void build_cdf(size_t n, std::vector<double>* cdf) const {
@@ -245,6 +270,14 @@ class NGramFileSource : public DataSourceBase {
     batch->set_num_instances(B);
     position_ += B;
   }
+  // reference: IndriSource::extract_metadata, cpp/data_indri.cpp:534-555. The file is pre-tokenised, so index ids ==
+  // model ids; term_frequency = occurrences of the word in the file, total_terms = all occurrences (what the
+  // self-information weighting of py/nvsm/base.py:query_representation divides by).
+  virtual void extract_metadata(lse::Metadata* const metadata) const override {
+    std::vector<long> frequency(vocabulary_size(), 0);
+    for (const long w : words_) ++frequency[w];
+    nvsm_detail::identity_metadata(vocabulary_size(), corpus_size(), frequency.data(), static_cast<long>(words_.size()), metadata);
+  }
 
  private:
   const size_t window_size_;
@@ -307,6 +340,7 @@ class AsyncSource : public DataSource<BatchT> {
     cv_.notify_all();
   }
   virtual float32 progress() const override { return source_->progress(); }
+  virtual void extract_metadata(lse::Metadata* const metadata) const override { source_->extract_metadata(metadata); }  // cpp/data_async.cpp
 
  private:
   void start_worker() {

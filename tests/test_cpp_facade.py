@@ -165,9 +165,18 @@ def test_cli_ngram_file_source_async_prefetch(tmp_path):
         res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "32",
                               "--entity_repr_size", "16", "--batch_size", "1024", "--window_size", str(n),
                               "--num_random_entities", "3", "--seed", "11", "--update_method", "sgd", "--nonlinearity", "tanh",
-                              "--gemm", "fp32", "--ngram_file", str(path), "--num_concurrent_batches", "3"] + extra,
+                              "--gemm", "fp32", "--ngram_file", str(path), "--num_concurrent_batches", "3",
+                              "--output", str(tmp_path / "model")] + extra,
                              capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr
+        # the `_meta` file of the reference (cpp/main.cu:527-537): term / object mapping + corpus statistics
+        meta = subprocess.run([os.path.join(CPP, "cuNVSMMeta"), "print", str(tmp_path / "model_meta")], check=True,
+                              capture_output=True, text=True).stdout.strip().split("\n")
+        assert meta[-1] == "total_terms %d" % (N * n)
+        assert sum(l.startswith("term ") for l in meta) == words.max() + 1
+        assert sum(l.startswith("object ") for l in meta) == docs.max() + 1
+        assert meta[7] == "term 7 7 %d" % (words == 7).sum()
+        os.remove(tmp_path / "model_meta")
         assert "|V|=%d |D|=%d" % (words.max() + 1, docs.max() + 1) in res.stdout
         assert res.stderr.count("Skipping Batch") == 2      # the partial batch of each epoch
         import re
