@@ -1197,6 +1197,25 @@ __global__ void __launch_bounds__(256) materialize_activation_kernel(const float
 
 __global__ void increment_kernel(float* p, float eps) { *p += eps; }
 
+// Ids outside their table would gather from and update memory that is not theirs (the reference only DCHECKs them,
+// include/cuNVSM/storage.h). One pass right behind the upload of a batch clamps such ids to row 0 and raises a flag
+// in mapped host memory (written only when something is wrong) that the host reports at its next synchronising call.
+__global__ void validate_ids_kernel(idx_t* __restrict__ words, long num_words, long word_limit,
+                                    idx_t* __restrict__ entities, long num_entities, long entity_limit,
+                                    volatile int* __restrict__ host_flags) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < num_words + num_entities; i += stride) {
+        const bool is_word = i < num_words;
+        idx_t* const p = is_word ? words + i : entities + (i - num_words);
+        const idx_t v = *p;
+        if (v < 0 || v >= (is_word ? word_limit : entity_limit)) {
+            *p = 0;
+            host_flags[is_word ? 0 : 1] = 1;
+            __threadfence_system();
+        }
+    }
+}
+
 // x -> rn_tf32(x) in place, lo = x - rn_tf32(x) (test hook for the 3xTF32 GEMM).
 __global__ void split_tf32_kernel(float* __restrict__ x, float* __restrict__ lo, long n) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {

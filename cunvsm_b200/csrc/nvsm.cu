@@ -154,6 +154,7 @@ struct nvsm_model {
     long loss_B[kCostRing] = {0};
     long forward_count = 0;
     bool have_forward = false, have_gradients = false;
+    int* id_flags = nullptr;      // mapped pinned [2]: a word id / an entity id of an uploaded batch was out of range
 
     // instrumentation
     long launches = 0;
@@ -1420,6 +1421,32 @@ int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B,
 // ------------------------------------------------------------------------------------
 // batches
 // ------------------------------------------------------------------------------------
+// Range-check (and clamp) the ids of a batch on the stream that uploaded them; see validate_ids_kernel.
+int validate_ids(nvsm_model* m, cudaStream_t on, idx_t* words, long num_words, idx_t* entities, long num_entities) {
+    cudaStream_t main_stream = m->stream;
+    m->stream = on;
+    const int grid = grid_for(m, num_words + num_entities, 4 * 256, 2);
+    int rc = [&]() -> int {
+        LAUNCH(m, validate_ids_kernel, grid, 256, 0, words, num_words, m->V, entities, num_entities, m->D, m->id_flags);
+        return 0;
+    }();
+    m->stream = main_stream;
+    return rc;
+}
+
+// Report (once) that a batch uploaded earlier carried out-of-range ids. Call after a synchronisation that covers
+// the upload: the flags live in mapped host memory.
+int check_id_flags(nvsm_model* m) {
+    if (!m->id_flags) return 0;
+    volatile int* f = m->id_flags;
+    const int bad_words = f[0], bad_entities = f[1];
+    if (!bad_words && !bad_entities) return 0;
+    f[0] = 0; f[1] = 0;
+    return fail("a batch contained %s outside [0, %ld) (clamped to 0; results of that step are meaningless)",
+                bad_words ? (bad_entities ? "word and entity ids" : "word ids") : "entity ids",
+                bad_words ? m->V : m->D);
+}
+
 int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float* fw, const long* ids,
                  const float* w, long B, bool use_copy_stream) {
     if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
@@ -1438,6 +1465,7 @@ int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float*
     CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s->ids, ids, sizeof(long) * B * m->R, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
+    TRY(validate_ids(m, cs, s->features, B * m->n, s->ids, B * m->R));
     if (cs == m->stream) phase_end(m);
     CU(cudaEventRecord(s->ready, cs));
     s->B = B;
@@ -1582,6 +1610,7 @@ void nvsm_destroy(nvsm_model* m) {
     for (auto& ev : m->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto e : m->ev_pool) cudaEventDestroy(e);
     if (m->loss_host) cudaFreeHost(m->loss_host);
+    if (m->id_flags) cudaFreeHost(m->id_flags);
     for (auto e : m->loss_ev)
         if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -1730,6 +1759,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
         }
         CU(cudaHostAlloc((void**)&m->loss_host, sizeof(double) * nvsm_model::kCostRing, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&m->id_flags, 2 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        m->id_flags[0] = m->id_flags[1] = 0;
         for (auto& e : m->loss_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         // score kernel: column-sum staging in dynamic shared memory
         CU(cudaDeviceSynchronize());
@@ -1760,7 +1791,7 @@ int nvsm_synchronize(nvsm_model* m) {
     CU(cudaSetDevice(m->device));
     CU(cudaStreamSynchronize(m->copy_stream));
     CU(cudaStreamSynchronize(m->stream));
-    return 0;
+    return check_id_flags(m);
 }
 
 int nvsm_initialize(nvsm_model* m, unsigned long* rng_state) {
@@ -1954,6 +1985,7 @@ int nvsm_read_cost(nvsm_model* m, int steps_back, float* cost) {
     CU(cudaSetDevice(m->device));
     const int slot = (int)((m->forward_count - 1 - steps_back) % nvsm_model::kCostRing);
     CU(cudaEventSynchronize(m->loss_ev[slot]));
+    TRY(check_id_flags(m));
     // cost = -(sum_c mass_c) / B   (cpp/intermediate_results.cu:94-120)
     float s = (float)m->loss_host[slot];
     s /= (float)m->loss_B[slot];
@@ -2027,6 +2059,7 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     CU(cudaMemcpyAsync(s->labels, labels, sizeof(long) * B, cudaMemcpyHostToDevice, cs));
     CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
     s->B = B;
+    TRY(validate_ids(m, cs, s->features, B * m->n, s->labels, B));   // the sampled negatives are in range by construction
     {
         // The negatives of this batch are drawn on the copy stream right behind its H2D copies, i.e. under the
         // previous step's kernels on the main stream (the engine state chains from call to call on that stream).
@@ -2050,7 +2083,7 @@ int nvsm_wait_upload(nvsm_model* m) {
     if (!m->cur) return 0;
     CU(cudaSetDevice(m->device));
     CU(cudaEventSynchronize(m->cur->ready));
-    return 0;
+    return check_id_flags(m);
 }
 
 // Stand-alone device sampling for arbitrary (z, num_objects): host labels in, host ids out.
@@ -2092,7 +2125,7 @@ int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float*
     CU(cudaSetDevice(m->device));
     TRY(upload_batch(m, &m->slots[slot], features, fw, ids, w, B, false));
     CU(cudaStreamSynchronize(m->stream));
-    return 0;
+    return check_id_flags(m);
 }
 
 int nvsm_compute_cost_staged(nvsm_model* m, int slot) {

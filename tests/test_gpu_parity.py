@@ -241,6 +241,38 @@ def test_errors_are_reported_not_swallowed():
         m.compute_cost(batch, nv.RNG(1))  # larger than max_batch_size
 
 
+def test_out_of_range_ids_are_reported_and_cannot_corrupt_the_tables():
+    """The reference only DCHECKs its ids; here a batch with ids outside the tables is clamped on the device behind
+    its upload and reported by the next synchronising call, on every upload path. The handle stays usable."""
+    c = dict(V=300, D=200, dw=32, dd=32, n=4, z=3, B=256, nonlinearity=nv.TANH, bn=False, num_batch_slots=2)
+    gm, om, rng = twin_models(**c)
+    f, fw, labels, w = make_batch(np.random.default_rng(2), c["B"], c["n"], c["V"], c["D"], c["z"])
+    W0, E0 = gm.get_tensor(nv.WORD_REPRS).copy(), gm.get_tensor(nv.ENTITY_REPRS).copy()
+    ids = gm.generate_labels(labels, rng)
+
+    bad_f = f.copy(); bad_f[17, 2] = c["V"]                       # one past the word table
+    res = gm.compute_cost(nv.Batch(c["B"], c["n"]).fill(bad_f, labels, fw, w), entity_ids=ids)
+    with pytest.raises(nv.NvsmError, match="word ids outside"):
+        res.get_cost()
+    bad_ids = ids.copy(); bad_ids[5] = -1                         # negative entity id
+    with pytest.raises(nv.NvsmError, match="entity ids outside"):
+        gm.stage_batch(1, nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w), bad_ids)
+    bad_labels = labels.copy(); bad_labels[3] = 10 ** 12          # device-sampler path: the positive label
+    gm.sampler_seed(nv.RNG(5))
+    gm.step_sampled(nv.Batch(c["B"], c["n"]).fill(f, bad_labels, fw, w), 0.01)
+    with pytest.raises(nv.NvsmError, match="entity ids outside"):
+        gm.last_cost()
+    gm.synchronize()                                              # reported once, then cleared
+    assert np.isfinite(gm.get_tensor(nv.WORD_REPRS)).all() and np.isfinite(gm.get_tensor(nv.ENTITY_REPRS)).all()
+
+    # a clean batch afterwards behaves like a fresh model would (parameters restored)
+    gm.set_tensor(nv.WORD_REPRS, W0); gm.set_tensor(nv.ENTITY_REPRS, E0)
+    gm.set_tensor(nv.TRANSFORM, om.get("T")); gm.set_tensor(nv.BIAS, om.get("b"))
+    cost = gm.compute_cost(nv.Batch(c["B"], c["n"]).fill(f, labels, fw, w), entity_ids=ids).get_cost()
+    ocost = om.compute_cost(f, fw, ids, w, c["n"])
+    assert abs(cost - ocost) <= RTOL * abs(ocost)
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json configs[1] at full size: size-independent properties.
 # ---------------------------------------------------------------------------------------------
