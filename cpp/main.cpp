@@ -36,7 +36,9 @@ struct Flags {
               {"synthetic_zipf", "0.0"}, {"device", "0"}, {"gemm", "3xtf32"}, {"host_sampler", "false"}, {"v", "0"},
               // pre-tokenised n-gram file (`<entity> <w_1> ... <w_n> [| weight]` per line) instead of the synthetic source,
               // prefetched by an AsyncSource with this many pinned batches (the reference uses 10, cpp/main.cu:212-219)
-              {"ngram_file", ""}, {"num_concurrent_batches", "10"}};
+              {"ngram_file", ""}, {"num_concurrent_batches", "10"},
+              // negatives ~ Zipf(s) over the entity ids instead of the reference's uniform draws (0 = uniform)
+              {"negative_sampling_zipf", "0.0"}};
   }
   void parse(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
@@ -194,6 +196,8 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   model.initialize(&rng);
   // negatives: the reference draws them on the host training thread (cpp/labels.cu:3-22, ~3.6 ms per
   // 51200-batch); by default the same stream is produced on the device, --host_sampler restores the loop.
+  if (flags.d("negative_sampling_zipf") > 0.0 && Ops::has_text)
+    model.set_label_generator(InverseCdfLabelGenerator<float, long>::zipf(D, flags.d("negative_sampling_zipf")));
   if (!flags.b("host_sampler") && Ops::has_text) model.use_device_sampler(&rng);
   if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
 

@@ -8,6 +8,6 @@ from .model import (ENTITY_ENTITY, TERM_TERM, TEXT_ENTITY, TEXT_ENTITY_ENTITY_EN
                     MultiForwardResult, SimilarityBatch, SimilarityForwardResult, ADAGRAD, ADAM, BIAS, DENSE_UPDATE, DENSE_UPDATE_DENSE_VARIANCE, ENTITY_REPRS, GEMM_3XTF32,
                     GEMM_FP32, GEMM_TF32, HARD_TANH, NONLINEARITIES, RNG, SGD, SPARSE, SPARSE_ALLGATHER, SPARSE_LOCAL, TANH, TRANSFORM,
                     UPDATE_METHODS, WORD_REPRS, Batch, ForwardResult, Gradients, Model, ModelDesc, NvsmError,
-                    TrainConfig, comm_unique_id)
+                    TrainConfig, comm_unique_id, zipf_cdf)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -19,7 +19,7 @@ SYMBOLS = [
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
     "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_comm_peer_export", "nvsm_comm_peer_import", "nvsm_comm_peer_status", "nvsm_comm_peer_disable", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
     "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_sampler_seed", "nvsm_sampler_state",
-    "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device",
+    "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device", "nvsm_generate_labels_cdf", "nvsm_sampler_set_cdf",
 ]
 
 
@@ -101,6 +101,9 @@ def load():
     f("nvsm_step_sampled", [vp, pl, pf, pl, pf, cl, cf, ci])
     f("nvsm_get_entity_ids", [vp, pl, cl])
     f("nvsm_generate_labels_device", [vp, pl, cl, cl, cl, pul, pl])
+    pd = ctypes.POINTER(ctypes.c_double)
+    f("nvsm_generate_labels_cdf", [pl, cl, cl, pd, cl, pul, pl])
+    f("nvsm_sampler_set_cdf", [vp, pd, cl])
     f("nvsm_comm_unique_id", [ctypes.c_char_p])
     f("nvsm_comm_init", [vp, ctypes.c_char_p, ci, ci])
     f("nvsm_comm_set_sparse_mode", [vp, ci])

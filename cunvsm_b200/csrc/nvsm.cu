@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -171,6 +172,7 @@ struct nvsm_model {
     int rng_cur = 0;
     bool rng_seeded = false;
     int *smp_counts = nullptr, *smp_offsets = nullptr, *smp_scan = nullptr, *smp_error = nullptr;
+    double* smp_cdf = nullptr;         // [D] cumulative distribution of the negatives (null: uniform, the reference's)
     long smp_capacity = 0;             // candidate chunks allocated
 
     // L2 Normalizer (cpp/cuda_utils.cu:3-141): per-n-gram norms of P; per-reference |E_d| and normalised score;
@@ -1384,6 +1386,13 @@ int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B,
         LAUNCH(m, sampler_copy_labels_kernel, (int)((B + 255) / 256), 256, 0, labels, B, ids);
         return 0;
     }
+    if (m->smp_cdf && D == m->D) {   // skewed negatives over the model's own entity table
+        const long draws = B * z;
+        LAUNCH(m, sampler_cdf_kernel, (int)((draws + 255) / 256), 256, 0, m->rng_dev + m->rng_cur,
+               m->rng_dev + (m->rng_cur ^ 1), labels, ids, draws, z, m->smp_cdf, D);
+        m->rng_cur ^= 1;
+        return 0;
+    }
     SamplerParams p;
     p.state_in = m->rng_dev + m->rng_cur;
     p.state_out = m->rng_dev + (m->rng_cur ^ 1);
@@ -1595,6 +1604,7 @@ void nvsm_destroy(nvsm_model* m) {
         if (p) cudaFree(p);
     if (m->pair_loss_host) cudaFreeHost(m->pair_loss_host);
     if (m->rng_dev) cudaFree(m->rng_dev);
+    if (m->smp_cdf) cudaFree(m->smp_cdf);
     int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
     for (int* p : sl)
         if (p) cudaFree(p);
@@ -1887,6 +1897,53 @@ int nvsm_generate_labels(const long* labels, long num_labels, long z, long num_o
         for (long k = 1; k <= z; ++k) out[i * R + k] = std::uniform_int_distribution<long>(0, num_objects - 1)(rng);
     }
     *rng_state = rng_state_of(rng);
+    return 0;
+}
+
+namespace {
+int check_cdf(const double* cdf, long n) {
+    if (!(cdf[0] >= 0.0)) return fail("cdf[0] must be >= 0");
+    for (long k = 1; k < n; ++k)
+        if (!(cdf[k] >= cdf[k - 1])) return fail("the cumulative distribution decreases at %ld", k);
+    if (cdf[n - 1] != 1.0) return fail("the cumulative distribution must end at exactly 1.0");
+    return 0;
+}
+}  // namespace
+
+int nvsm_generate_labels_cdf(const long* labels, long num_labels, long z, const double* cdf, long num_objects,
+                             unsigned long* rng_state, long* out) {
+    if (!labels || !rng_state || !out || !cdf) return fail("null argument");
+    if (num_labels < 0 || z < 0 || num_objects <= 0) return fail("invalid sampler arguments");
+    TRY(check_cdf(cdf, num_objects));
+    std::minstd_rand0 rng;
+    rng.seed(*rng_state);
+    const long R = z + 1;
+    for (long i = 0; i < num_labels; ++i) {
+        out[i * R] = labels[i];
+        for (long k = 1; k <= z; ++k) {
+            const double u = (double)(rng() - 1u) / 2147483646.0;
+            const long id = std::upper_bound(cdf, cdf + num_objects, u) - cdf;
+            out[i * R + k] = std::min(id, num_objects - 1);
+        }
+    }
+    *rng_state = rng_state_of(rng);
+    return 0;
+}
+
+int nvsm_sampler_set_cdf(nvsm_model* m, const double* cdf, long num_objects) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(m->copy_stream));
+    CU(cudaStreamSynchronize(m->stream));
+    if (!cdf) {                          // back to the reference's uniform negatives
+        if (m->smp_cdf) cudaFree(m->smp_cdf);
+        m->smp_cdf = nullptr;
+        return 0;
+    }
+    if (num_objects != m->D) return fail("the distribution has %ld entries, the entity table %ld", num_objects, m->D);
+    TRY(check_cdf(cdf, num_objects));
+    if (!m->smp_cdf) TRY(dev_alloc(&m->smp_cdf, (size_t)m->D, false));
+    CU(cudaMemcpy(m->smp_cdf, cdf, sizeof(double) * m->D, cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -93,6 +93,33 @@ __global__ void sampler_total_kernel(const int* __restrict__ counts, int* __rest
     offsets[nchunks] = offsets[nchunks - 1] + counts[nchunks - 1];
 }
 
+// Skewed negatives (BASELINE configs[4]: Zipf-skewed sampling; the reference ships only the uniform generator and
+// leaves LabelGenerator, include/cuNVSM/labels.h:7-18, as the plug point). Inverse-CDF sampling over a caller-supplied
+// cumulative distribution cdf[0..D-1] (non-decreasing, cdf[D-1] = 1): draw j = i * z + r consumes exactly one engine
+// output x_j = a^(j+1) x_0 mod m,  u = (x_j - 1) / (m - 1) in [0, 1),  id = min{k : cdf[k] > u}. No rejections, so the
+// jump-ahead makes every draw independent; the host loop (nvsm_generate_labels_cdf) is the same arithmetic in order.
+__global__ void __launch_bounds__(256) sampler_cdf_kernel(const unsigned int* __restrict__ state_in,
+                                                          unsigned int* __restrict__ state_out,
+                                                          const idx_t* __restrict__ labels, idx_t* __restrict__ ids,
+                                                          long num_draws, int z, const double* __restrict__ cdf,
+                                                          long num_objects) {
+    const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= num_draws) return;
+    const long i = j / z;
+    const int r = (int)(j - i * z);
+    const unsigned int x = lehmer_mulmod(lehmer_pow((unsigned long long)j + 1ull), *state_in);
+    const double u = (double)(x - 1u) / 2147483646.0;
+    long lo = 0, hi = num_objects;
+    while (lo < hi) {
+        const long mid = (lo + hi) >> 1;
+        if (__ldg(cdf + mid) <= u) lo = mid + 1; else hi = mid;
+    }
+    idx_t* const row = ids + i * (z + 1);
+    row[1 + r] = (idx_t)min(lo, num_objects - 1);
+    if (r == 0) row[0] = labels[i];
+    if (j == num_draws - 1) *state_out = x;
+}
+
 __global__ void sampler_copy_labels_kernel(const idx_t* __restrict__ labels, long B, idx_t* __restrict__ ids) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) ids[i] = labels[i];   // z == 0: R == 1

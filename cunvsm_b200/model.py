@@ -332,9 +332,27 @@ class Model:
         z = self.train_config.num_random_entities
         out = np.zeros(labels.size * (z + 1), dtype=np.int64)
         st = ctypes.c_ulong(rng.state)
-        check(self.L.nvsm_generate_labels(_pl(labels), labels.size, z, self.num_entities, ctypes.byref(st), _pl(out)))
+        cdf = getattr(self, "_cdf", None)
+        if cdf is not None:
+            check(self.L.nvsm_generate_labels_cdf(_pl(labels), labels.size, z, cdf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                  cdf.size, ctypes.byref(st), _pl(out)))
+        else:
+            check(self.L.nvsm_generate_labels(_pl(labels), labels.size, z, self.num_entities, ctypes.byref(st), _pl(out)))
         rng.state = st.value
         return out
+
+    def set_negative_distribution(self, cdf):
+        """Plug a skewed negative sampler in where the reference has LabelGenerator (include/cuNVSM/labels.h:7-18):
+        inverse-CDF draws over ``cdf`` [num_entities] (see zipf_cdf) on the same shared engine, one engine output per
+        negative — host (generate_labels) and device (step_sampled) draw identical ids. ``None`` restores the
+        reference's UniformLabelGenerator."""
+        if cdf is None:
+            self._cdf = None
+            check(self.L.nvsm_sampler_set_cdf(self.h, None, 0))
+            return
+        cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+        check(self.L.nvsm_sampler_set_cdf(self.h, cdf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), cdf.size))
+        self._cdf = cdf
 
     def compute_cost(self, batch, rng=None, entity_ids=None):
         """Model::compute_cost (cpp/objective.cu:30-313). Negatives are drawn from ``rng``
@@ -494,6 +512,16 @@ class Model:
         """SPARSE_LOCAL: per-rank local table updates; SPARSE_ALLGATHER: every replica applies the updates of
         the whole global batch (the single-GPU trajectory)."""
         check(self.L.nvsm_comm_set_sparse_mode(self.h, mode))
+
+
+def zipf_cdf(num_objects, exponent=1.0):
+    """Cumulative Zipf(s) distribution over ids 0..num_objects-1 (id k has weight (k+1)^-s), ending at exactly 1.0 —
+    the argument of Model.set_negative_distribution / nvsm_sampler_set_cdf."""
+    w = 1.0 / np.power(np.arange(1, num_objects + 1, dtype=np.float64), float(exponent))
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    cdf[-1] = 1.0
+    return cdf
 
 
 def comm_unique_id():

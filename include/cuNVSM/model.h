@@ -21,6 +21,7 @@
 #include "../nvsm_b200.h"
 #include "base.h"
 #include "data.h"
+#include "labels.h"
 #include "nvsm.pb.h"
 
 #define NVSM_ABORT_ON(rc) NVSM_CHECK((rc) == 0, nvsm_last_error())
@@ -267,8 +268,23 @@ class Model {
   // with the host loop). While enabled, compute_cost ignores its RNG* argument; sync_rng() writes the
   // device engine state back into the caller's RNG (synchronises).
   void use_device_sampler(RNG* const rng) {
+    NVSM_CHECK(label_generator_->on_device(), "the installed label generator only runs on the host");
     NVSM_ABORT_ON(nvsm_sampler_seed(handle_, nvsm_detail::rng_get_state(*rng)));
     device_sampler_ = true;
+  }
+  // The reference's Objective owns a LabelGenerator (UniformLabelGenerator, include/cuNVSM/objective.h / labels.h).
+  // Takes ownership. Generators with on_device() keep working under use_device_sampler (same ids); any other
+  // generator switches the model back to the host path.
+  void set_label_generator(LabelGenerator<FloatT, EntityIdxType>* const generator, RNG* const rng = nullptr) {
+    NVSM_CHECK(generator != nullptr, "null label generator");
+    if (device_sampler_ && !generator->on_device()) {
+      NVSM_CHECK(rng != nullptr, "switching to a host-only generator needs the RNG to hand the engine state back");
+      sync_rng(rng);
+      device_sampler_ = false;
+    }
+    label_generator_.reset(generator);
+    const std::vector<double>* const cdf = generator->on_device() ? generator->distribution() : nullptr;
+    NVSM_ABORT_ON(nvsm_sampler_set_cdf(handle_, cdf ? cdf->data() : nullptr, cdf ? static_cast<long>(cdf->size()) : 0));
   }
   void sync_rng(RNG* const rng) {
     if (!device_sampler_) return;
@@ -294,11 +310,9 @@ class Model {
       ++forward_counter_;
       return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
     }
-    entity_ids_.resize(B * R);
-    unsigned long st = nvsm_detail::rng_get_state(*rng);
-    NVSM_ABORT_ON(nvsm_generate_labels(batch.labels(), B, train_config_.num_random_entities(), num_entities_, &st,
-                                       entity_ids_.data()));
-    nvsm_detail::rng_set_state(rng, st);
+    // Objective::generate_labels, cpp/objective.cu:5-28
+    label_generator_->generate(batch.labels(), num_entities_, B, train_config_.num_random_entities(), &entity_ids_, rng);
+    NVSM_CHECK(entity_ids_.size() == B * R, "the label generator returned a wrong number of ids");
     NVSM_ABORT_ON(nvsm_compute_cost(handle_, batch.features(), batch.feature_weights(), entity_ids_.data(),
                                     batch.weights(), B));
     NVSM_ABORT_ON(nvsm_wait_upload(handle_));     // (entity_ids_ is reused by the next call as well)
@@ -387,6 +401,7 @@ class Model {
   nvsm_model* handle_ = nullptr;
   bool initialized_ = false;
   bool device_sampler_ = false;
+  std::unique_ptr<LabelGenerator<FloatT, EntityIdxType>> label_generator_{new UniformLabelGenerator<FloatT, EntityIdxType>()};
   mutable std::vector<long> entity_ids_;
   mutable long forward_counter_ = 0;
 };

@@ -169,6 +169,16 @@ NVSM_API int nvsm_generate_labels_device(nvsm_model* m, const long* labels, long
                                          long num_negative_labels, long num_objects,
                                          unsigned long* rng_state, long* out);
 
+/* Skewed negatives (BASELINE.json configs[4]: Zipf-skewed sampling). The reference ships only
+ * UniformLabelGenerator and leaves LabelGenerator (include/cuNVSM/labels.h:7-18) as the plug point; this is an
+ * inverse-CDF generator on the same shared minstd_rand0: every negative consumes ONE engine output x,
+ * u = (x - 1) / 2147483646 in [0, 1), id = min{k : cdf[k] > u}. cdf[0..num_objects-1] is non-decreasing and ends at
+ * exactly 1.0. nvsm_generate_labels_cdf is the host loop; nvsm_sampler_set_cdf installs the distribution for the
+ * device sampler (nvsm_step_sampled draws bit-identical ids); a NULL cdf restores the uniform generator. */
+NVSM_API int nvsm_generate_labels_cdf(const long* labels, long num_labels, long num_negative_labels,
+                                      const double* cdf, long num_objects, unsigned long* rng_state, long* out);
+NVSM_API int nvsm_sampler_set_cdf(nvsm_model* m, const double* cdf, long num_objects);
+
 /* Device-resident batches: copy a host batch into slot `slot` once, then run steps on it
  * without host traffic. */
 NVSM_API int nvsm_stage_batch(nvsm_model* m, int slot, const long* features, const float* feature_weights,

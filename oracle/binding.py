@@ -121,6 +121,24 @@ def generate_labels(labels, z, num_objects, state):
     return out, st.value
 
 
+def generate_labels_cdf(labels, z, cdf, state):
+    """Restatement of the inverse-CDF negative sampler (include/nvsm_b200.h: nvsm_generate_labels_cdf; the plug point is
+    the reference's LabelGenerator, include/cuNVSM/labels.h:7-18). Per negative, in order: x <- 16807 x mod (2^31-1)
+    (std::minstd_rand0), u = (x-1)/2147483646, id = #{k : cdf[k] <= u} clipped to D-1. Returns (ids[B*(z+1)], state)."""
+    labels = np.asarray(labels, dtype=np.int64)
+    cdf = np.asarray(cdf, dtype=np.float64)
+    n = labels.size * z
+    xs = np.empty(n, dtype=np.int64)
+    x = int(state)
+    for k in range(n):
+        x = (16807 * x) % 2147483647
+        xs[k] = x
+    u = (xs - 1).astype(np.float64) / 2147483646.0
+    neg = np.minimum(np.searchsorted(cdf, u, side="right"), cdf.size - 1).reshape(labels.size, z)
+    out = np.concatenate([labels.reshape(-1, 1), neg], axis=1).astype(np.int64).ravel()
+    return out, x
+
+
 def generate_random_indexes(maxv, num, state):
     out = np.zeros(num, dtype=np.int64)
     st = ctypes.c_ulong(state)

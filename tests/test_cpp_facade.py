@@ -183,3 +183,26 @@ def test_cli_ngram_file_source_async_prefetch(tmp_path):
         outs.append([float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)])
     assert len(outs[0]) == 2 and np.isfinite(outs[0]).all()
     np.testing.assert_allclose(outs[0], outs[1], rtol=1e-6)   # identical batches, identical negatives
+
+
+@pytest.mark.gpu
+def test_cli_zipf_negatives_host_and_device_samplers_agree():
+    """--negative_sampling_zipf installs InverseCdfLabelGenerator (the reference's LabelGenerator plug point,
+    include/cuNVSM/labels.h:7-18): the host loop and the device sampler draw the same skewed negatives, so the
+    two runs report the same costs; they differ from the uniform run."""
+    _build()
+    import re
+    costs = {}
+    for name, extra in (("host", ["--negative_sampling_zipf", "1.0", "--host_sampler"]),
+                        ("device", ["--negative_sampling_zipf", "1.0"]), ("uniform", [])):
+        res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "32",
+                              "--entity_repr_size", "16", "--batch_size", "1024", "--window_size", "4",
+                              "--num_random_entities", "5", "--seed", "9", "--update_method", "adagrad", "--nonlinearity", "tanh",
+                              "--gemm", "fp32", "--bias_negative_samples", "--synthetic_num_words", "800",
+                              "--synthetic_num_entities", "3000", "--synthetic_num_batches", "6"] + extra,
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        costs[name] = [float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)]
+        assert len(costs[name]) == 2 and np.isfinite(costs[name]).all()
+    np.testing.assert_allclose(costs["host"], costs["device"], rtol=1e-6)
+    assert abs(costs["host"][0] - costs["uniform"][0]) > 1e-4 * costs["uniform"][0]
