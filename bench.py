@@ -46,9 +46,9 @@ WORKLOADS = {
                V=200000, D=500000, dw=300, dd=256, n=10, z=16, B=51200, nonlinearity="hard_tanh", bn=True,
                update_method="adagrad", lr=1e-2, lam=1e-2, bias_neg=False),
     # configs[4] — LSE with bias_negative_samples, large document table (per-GPU batch 4096).
-    "C5": dict(name="LSE tanh bias_negative_samples B=4096 V=100k D=1M d=128 n=10 z=32 sgd",
+    "C5": dict(name="LSE tanh bias_negative_samples B=4096 V=100k D=1M d=128 n=10 z=32 sgd, Zipf(1.0) negatives",
                V=100000, D=1000000, dw=128, dd=128, n=10, z=32, B=4096, nonlinearity="tanh", bn=False,
-               update_method="sgd", lr=1e-2, lam=1e-2, bias_neg=True),
+               update_method="sgd", lr=1e-2, lam=1e-2, bias_neg=True, neg_zipf=1.0),
     # configs[0] — the reference's own small LSE case.
     "C1": dict(name="LSE tanh B=4096 V=2k D=200 d=64 n=10 z=4", V=2000, D=200, dw=64, dd=64, n=10, z=4, B=4096,
                nonlinearity="tanh", bn=False, update_method="sgd", lr=1e-2, lam=1e-2, bias_neg=False),
@@ -129,11 +129,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def zipf_ids(rng, cdf, size):
+    return np.minimum(np.searchsorted(cdf, rng.random(size), side="right"), cdf.size - 1).astype(np.int64)
+
+
 def make_batches(w, B, seed, num):
+    """Uniform word ids and positive document ids; word ids ~ Zipf(s) when the workload carries
+    word_zipf = s (the C3 gather/scatter sweep variant, --zipf_words)."""
     rng = np.random.default_rng(seed)
     out = []
+    word_cdf = None
+    if w.get("word_zipf", 0.0) > 0.0:
+        import cunvsm_b200 as nv
+        word_cdf = nv.zipf_cdf(w["V"], w["word_zipf"])
     for _ in range(num):
-        f = rng.integers(0, w["V"], size=(B, w["n"]), dtype=np.int64)
+        if word_cdf is not None:
+            f = zipf_ids(rng, word_cdf, (B, w["n"]))
+        else:
+            f = rng.integers(0, w["V"], size=(B, w["n"]), dtype=np.int64)
         labels = rng.integers(0, w["D"], size=B, dtype=np.int64)
         out.append((f, labels))
     return out
@@ -160,11 +173,18 @@ def cpu_port_run(w, steps, warmup, sample_B):
     fw = np.ones((sample_B, w["n"]), np.float32)
     iw = np.ones(sample_B, np.float32)
     cores = O.lib(native).oracle_num_threads()
+    neg_cdf = None
+    if w.get("neg_zipf", 0.0) > 0.0:
+        import cunvsm_b200 as nv
+        neg_cdf = nv.zipf_cdf(w["D"], w["neg_zipf"])
     times = []
     for it in range(warmup + steps):
         f, labels = batches[it % len(batches)]
         t0 = time.perf_counter()
-        ids, state = O.generate_labels(labels, w["z"], w["D"], state)   # serial host sampler, as the reference
+        if neg_cdf is not None:
+            ids, state = O.generate_labels_cdf(labels, w["z"], neg_cdf, state)
+        else:
+            ids, state = O.generate_labels(labels, w["z"], w["D"], state)   # serial host sampler, as the reference
         m.compute_cost(f, fw, ids, iw, w["n"])
         m.compute_gradients()
         m.update(w["lr"], m.scaled_lambda())
@@ -231,7 +251,9 @@ def run_reference(args, w, rank):
                     cpu_baseline={"value": r["value"], "unit": "n-grams/s", "cores": 1, "kind": "reference", "sample": sample},
                     e2e={"value": r["value"], "unit": "n-grams/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                     final_cost=r["final_cost"],
-                    note="single GPU only: the reference has no multi-GPU path; at N>1 this is still one GPU")
+                    note="single GPU only: the reference has no multi-GPU path; at N>1 this is still one GPU"
+                         + ("; negatives are uniform: UniformLabelGenerator is the reference's only generator"
+                            if w.get("neg_zipf", 0.0) > 0.0 else ""))
         print(json.dumps(line), flush=True)
         return
     sample_B = min(args.cpu_sample, w["B"])
@@ -277,6 +299,10 @@ def run_ours(args, w, rank, world, local_rank):
     sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0,
                              peer_exchange=not args.no_peer)
 
+    if w.get("neg_zipf", 0.0) > 0.0:
+        # skewed negatives (configs[4]): inverse-CDF generator at the reference's LabelGenerator plug point; the host
+        # loop (pre-sampled ids of `value`) and the device sampler (`e2e`) draw from the same distribution
+        model.set_negative_distribution(nv.zipf_cdf(w["D"], w["neg_zipf"]))
     # synthetic batches: every rank owns its own shard of n-gram rows
     raw = make_batches(w, B, 1234 + rank, NUM_BATCHES)
     batches, ids_list = [], []
@@ -413,8 +439,11 @@ def run_ours(args, w, rank, world, local_rank):
                              "%d distinct batches cycled" % NUM_BATCHES,
                        "sparse_tables": ("single GPU" if world == 1 else "replicated, per-rank local updates" if args.sparse_sync == "local"
                                          else "replicated, rows all-gathered: every replica applies the global update"),
-                       "negatives": "value: pre-sampled (bit-exact host sampler) and staged with the batch; e2e: drawn "
-                                    "inside the timed step by the bit-exact device sampler"},
+                       "negatives": ("value: pre-sampled (bit-exact host sampler) and staged with the batch; e2e: drawn "
+                                     "inside the timed step by the bit-exact device sampler"
+                                     + ("; Zipf(%g) over the entity ids (inverse-CDF generator)" % w["neg_zipf"]
+                                        if w.get("neg_zipf", 0.0) > 0.0 else "; uniform (the reference's generator)")),
+                       "word_ids": "Zipf(%g)" % w["word_zipf"] if w.get("word_zipf", 0.0) > 0.0 else "uniform"},
             "e2e": {"value": ngrams / (ms_e2e * 1e-3), "unit": "n-grams/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -447,10 +476,17 @@ def main():
                          "single-GPU trajectory (every replica applies all rows' updates)")
     ap.add_argument("--no_peer", action="store_true", help="N>1: small reductions through ncclAllReduce instead of the NVLink peer exchange")
     ap.add_argument("--no_alt", action="store_true", help="skip the extra single-pass TF32 measurement")
+    ap.add_argument("--zipf_words", type=float, default=0.0, help="word ids ~ Zipf(s) instead of uniform (C3 gather/scatter sweep)")
+    ap.add_argument("--zipf_negatives", type=float, default=None, help="negatives ~ Zipf(s) over the entity ids (C5 default 1.0; 0 = uniform)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.update_method:
         w["update_method"] = args.update_method
+    if args.zipf_words > 0.0:
+        w["word_zipf"] = args.zipf_words
+        w["name"] += ", Zipf(%g) word ids" % args.zipf_words
+    if args.zipf_negatives is not None:
+        w["neg_zipf"] = args.zipf_negatives
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference(args, w, rank)

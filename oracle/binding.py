@@ -128,11 +128,13 @@ def generate_labels_cdf(labels, z, cdf, state):
     labels = np.asarray(labels, dtype=np.int64)
     cdf = np.asarray(cdf, dtype=np.float64)
     n = labels.size * z
-    xs = np.empty(n, dtype=np.int64)
-    x = int(state)
-    for k in range(n):
-        x = (16807 * x) % 2147483647
-        xs[k] = x
+    M = np.uint64(2147483647)
+    # x_k = 16807^k x_0 mod M for k = 1..n; the powers by doubling (products stay below 2^62)
+    pw = np.array([16807], dtype=np.uint64)
+    while pw.size < n:
+        pw = np.concatenate([pw, (pw * pw[-1]) % M])
+    xs = ((pw[:n] * np.uint64(state)) % M).astype(np.int64)
+    x = int(xs[-1]) if n else int(state)
     u = (xs - 1).astype(np.float64) / 2147483646.0
     neg = np.minimum(np.searchsorted(cdf, u, side="right"), cdf.size - 1).reshape(labels.size, z)
     out = np.concatenate([labels.reshape(-1, 1), neg], axis=1).astype(np.int64).ravel()
