@@ -38,7 +38,10 @@ struct Flags {
               // prefetched by an AsyncSource with this many pinned batches (the reference uses 10, cpp/main.cu:212-219)
               {"ngram_file", ""}, {"num_concurrent_batches", "10"},
               // negatives ~ Zipf(s) over the entity ids instead of the reference's uniform draws (0 = uniform)
-              {"negative_sampling_zipf", "0.0"}};
+              {"negative_sampling_zipf", "0.0"},
+              // `<id_a> <id_b> <weight>` pairs for the similarity objectives (DataConfig.similarity_path of the reference);
+              // ids are the entity (or word) ids of the n-gram file / synthetic source
+              {"similarity_file", ""}};
   }
   void parse(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
@@ -84,15 +87,16 @@ void dump_model(const ModelT& model, const std::string& output, const std::strin
 }
 
 
-// Seeded synthetic similarity source (stands in for RepresentationSimilarity::DataSource over a similarity file,
-// cpp/data.cu:225-345): `num_batches` full batches of uniform random id pairs with unit weights per epoch.
-class SimilaritySource {
+// Seeded synthetic similarity source (used when no --similarity_file is given): `num_batches` full batches of uniform
+// random id pairs with unit weights per epoch.
+class SyntheticSimilaritySource : public DataSource<RepresentationSimilarity::Batch> {
  public:
-  SimilaritySource(size_t num_objects, size_t num_batches, unsigned long seed)
+  SyntheticSimilaritySource(size_t num_objects, size_t num_batches, unsigned long seed)
       : num_objects_(num_objects), num_batches_(num_batches), seed_(seed), emitted_(0), rng_(seed) {}
-  void reset() { emitted_ = 0; rng_.seed(seed_); }
-  bool has_next() const { return emitted_ < num_batches_; }
-  void next(RepresentationSimilarity::Batch* batch) {
+  virtual void reset() override { emitted_ = 0; rng_.seed(seed_); }
+  virtual bool has_next() const override { return emitted_ < num_batches_; }
+  virtual float32 progress() const override { return static_cast<float32>(emitted_) / num_batches_; }
+  virtual void next(RepresentationSimilarity::Batch* batch) override {
     std::uniform_int_distribution<long> pick(0, static_cast<long>(num_objects_) - 1);
     while (!batch->full()) batch->push_instance(std::make_tuple(pick(rng_), pick(rng_), 1.0f));
     ++emitted_;
@@ -106,7 +110,7 @@ class SimilaritySource {
 
 struct Sources {
   DataSource<TextEntity::Batch>* text;
-  SimilaritySource* pairs;
+  DataSource<RepresentationSimilarity::Batch>* pairs;
 };
 
 // BatchHandler of the reference (cpp/main.cu:159-228): uniform access to the batch type of every objective.
@@ -183,6 +187,30 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
     std::ofstream meta_file(flags.str("output") + "_meta", std::ios::binary);
     NVSM_CHECK(meta.SerializeToOstream(&meta_file), "cannot write the _meta file");
   }
+  // construct_data_source<EntityEntity / TermTerm>, cpp/main.cu:240-277: the similarity file resolved through the
+  // identifiers map of the text source (here: the decimal ids of the metadata), shuffled with the shared RNG and
+  // repeated for as long as the text epoch lasts; has_next of the pair = MultiSource semantics (BatchOps::has_next).
+  // Like the reference the sources are built (and first shuffled) BEFORE the model draws its initial parameters.
+  // Re-shuffles in the middle of an epoch use the host copy of the engine: with --host_sampler that is the reference's
+  // single stream, with the device sampler the negatives keep their own (device-resident) continuation of it.
+  std::unique_ptr<DataSource<RepresentationSimilarity::Batch>> similarity_source;
+  if (!flags.str("similarity_file").empty() && (!Ops::has_text || train_config.text_entity_weight() < 1.0f)) {
+    IdentifiersMapT identifiers_map;
+    if (Ops::pairs_over_entities) {
+      for (int j = 0; j < meta.object_size(); ++j) identifiers_map[std::to_string(meta.object(j).index_object_id())] = meta.object(j).model_object_id();
+    } else {
+      for (int i = 0; i < meta.term_size(); ++i) identifiers_map[std::to_string(meta.term(i).index_term_id())] = meta.term(i).model_term_id();
+    }
+    RepresentationSimilarity::DataSource* const pairs =
+        new RepresentationSimilarity::DataSource(flags.str("similarity_file"), identifiers_map, &rng);
+    std::printf("similarity file: %zu pairs\n", pairs->num_instances());
+    NVSM_CHECK(pairs->num_instances() >= static_cast<size_t>(train_config.batch_size()),
+               "the similarity file holds fewer pairs than one batch");
+    similarity_source.reset(new RepeatingSource<RepresentationSimilarity::Batch>(static_cast<size_t>(-1), pairs));
+  } else {
+    similarity_source.reset(new SyntheticSimilaritySource(Ops::pairs_over_entities ? D : V, flags.i("synthetic_num_batches"),
+                                                          flags.i("seed") + 17));
+  }
   const int gemm_mode = flags.str("gemm") == "fp32" ? NVSM_GEMM_FP32 : (flags.str("gemm") == "tf32" ? NVSM_GEMM_TF32 : NVSM_GEMM_3XTF32);
 
   std::printf("Model: word_repr_size=%d entity_repr_size=%d batch_normalization=%d nonlinearity=%s\n",
@@ -201,8 +229,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   if (!flags.b("host_sampler") && Ops::has_text) model.use_device_sampler(&rng);
   if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
 
-  SimilaritySource similarity_source(Ops::pairs_over_entities ? D : V, flags.i("synthetic_num_batches"), flags.i("seed") + 17);
-  Sources sources{&data_source, &similarity_source};
+  Sources sources{&data_source, similarity_source.get()};
   std::unique_ptr<typename Ops::BatchT> batch_ptr(Ops::make(train_config));
   typename Ops::BatchT& batch = *batch_ptr;
   const long max_threads_per_block = 1024;  // Runtime::props().maxThreadsPerBlock in the reference
@@ -248,7 +275,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   for (long epoch = 1; epoch <= train_config.num_epochs(); ++epoch) {
     // the file source shuffles with the shared engine (cpp/data_indri.cpp:386-397): bring its state back from the
     // device sampler first and hand it over again afterwards, so the stream matches the reference's single RNG
-    const bool device_rng = file_source && !flags.b("host_sampler") && Ops::has_text;
+    const bool device_rng = (file_source || !flags.str("similarity_file").empty()) && !flags.b("host_sampler") && Ops::has_text;
     if (device_rng) model.sync_rng(&rng);
     Ops::reset(sources);
     if (device_rng) model.use_device_sampler(&rng);

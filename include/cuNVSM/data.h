@@ -12,9 +12,12 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <limits>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -22,6 +25,7 @@
 #include <string>
 #include <thread>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../nvsm_b200.h"
@@ -31,6 +35,8 @@
 typedef int32 WordIdxType;
 typedef int32 ObjectIdxType;
 typedef FLOATING_POINT_TYPE WeightType;
+// external identifier (document name / term string) -> model id; reference: IdentifiersMapT, include/cuNVSM/data.h
+typedef std::map<std::string, ObjectIdxType> IdentifiersMapT;
 
 class BatchInterface {
  public:
@@ -445,9 +451,143 @@ class Batch : public BatchInterface {
   size_t num_instances_;
 };
 
+// reference: LoadSimilarities, cpp/data.cu:233-285 — one `<first> <second> <weight>` triple per line, identifiers
+// resolved through the map; pairs with an unknown identifier are skipped (with a warning).
+inline std::vector<InstanceT>* LoadSimilarities(std::istream& file, const IdentifiersMapT& identifiers_map) {
+  NVSM_CHECK(file.good(), "cannot read the similarity file");
+  NVSM_CHECK(!identifiers_map.empty(), "empty identifiers map");
+  std::vector<InstanceT>* const data = new std::vector<InstanceT>;
+  std::string line;
+  while (file.good() && std::getline(file, line)) {
+    std::istringstream iss(line);
+    std::string first, second;
+    WeightType weight = 0;
+    iss >> first >> second >> weight;
+    if (first.empty() && second.empty()) continue;
+    const auto a = identifiers_map.find(first), b = identifiers_map.find(second);
+    if (a == identifiers_map.end() || b == identifiers_map.end()) {
+      std::fprintf(stderr, "Entity '%s' not found; skipping pair.\n", (a == identifiers_map.end() ? first : second).c_str());
+      continue;
+    }
+    data->push_back(std::make_tuple(a->second, b->second, weight));
+  }
+  return data;
+}
+inline std::vector<InstanceT>* LoadSimilarities(const std::string& path, const IdentifiersMapT& identifiers_map) {
+  NVSM_CHECK(!path.empty(), "empty similarity path");
+  std::ifstream file(path);
+  return LoadSimilarities(file, identifiers_map);
+}
+
+// reference: RepresentationSimilarity::DataSource, include/cuNVSM/data.h:626-653 / cpp/data.cu:287-345 — the pairs in
+// an order shuffled with the SHARED RNG at construction and at every reset(); the last batch of a pass may be partial.
+class DataSource : public ::DataSource<Batch> {
+ public:
+  DataSource(const std::string& path, const IdentifiersMapT& identifiers_map, RNG* const rng)
+      : DataSource(LoadSimilarities(path, identifiers_map), rng) {}
+  // Takes ownership.
+  DataSource(const std::vector<InstanceT>* const data, RNG* const rng) : data_(data), rng_(rng) {
+    NVSM_CHECK(data_ != nullptr && rng_ != nullptr, "null similarity data or RNG");
+    reset();
+  }
+  virtual void reset() override {
+    instance_order_.resize(data_->size());
+    std::iota(instance_order_.begin(), instance_order_.end(), 0);
+    std::shuffle(instance_order_.begin(), instance_order_.end(), *rng_);
+  }
+  virtual void next(Batch* const batch) override {
+    NVSM_CHECK(batch->empty(), "RepresentationSimilarity::DataSource::next needs an empty batch");
+    while (!batch->full() && !instance_order_.empty()) {
+      batch->push_instance(data_->at(instance_order_.front()));
+      instance_order_.pop_front();
+    }
+  }
+  virtual bool has_next() const override { return !instance_order_.empty(); }
+  virtual float32 progress() const override {
+    return 1.0f - static_cast<float32>(instance_order_.size()) / static_cast<float32>(data_->size());
+  }
+  size_t num_instances() const { return data_->size(); }
+
+ private:
+  std::unique_ptr<const std::vector<InstanceT>> data_;
+  RNG* const rng_;
+  std::deque<size_t> instance_order_;
+};
+
 }  // namespace RepresentationSimilarity
 
-namespace EntityEntity { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; }
-namespace TermTerm { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; }
+// reference: RepeatingSource, include/cuNVSM/data.h:737-761 / cpp/data_repeating.cpp — replays the wrapped source
+// `num_repeats` times (size_t(-1): practically for ever, how the CLI pairs a short similarity file with a long text
+// epoch, cpp/main.cu:254-256). Takes ownership.
+template <typename BatchT>
+class RepeatingSource : public DataSource<BatchT> {
+ public:
+  typedef BatchT BatchType;
+  RepeatingSource(const size_t num_repeats, DataSource<BatchT>* const source)
+      : source_(source), num_repeats_(num_repeats), current_iteration_(0) {}
+  virtual void reset() override { current_iteration_ = 0; source_->reset(); }
+  virtual void next(BatchT* const batch) override {
+    if (!source_->has_next()) {
+      source_->reset();
+      ++current_iteration_;
+      NVSM_CHECK(current_iteration_ < num_repeats_, "RepeatingSource::next called without has_next");
+    }
+    source_->next(batch);
+  }
+  virtual bool has_next() const override {
+    if (current_iteration_ + 1 < num_repeats_) return true;
+    NVSM_CHECK(current_iteration_ + 1 == num_repeats_, "RepeatingSource ran past its last repeat");
+    return source_->has_next();
+  }
+  virtual float32 progress() const override {
+    return source_->progress() + static_cast<float32>(current_iteration_) / num_repeats_;
+  }
+  virtual void extract_metadata(lse::Metadata* const metadata) const override { source_->extract_metadata(metadata); }
+
+ private:
+  std::unique_ptr<DataSource<BatchT>> source_;
+  const size_t num_repeats_;
+  size_t current_iteration_;
+};
+
+// reference: MultiSource, include/cuNVSM/data.h:713-735 / cpp/data_multi.cpp — one source per element of a batch tuple:
+// next() advances all of them, has_next() needs all of them, progress() is the slowest one. Takes ownership.
+template <typename... BatchT>
+class MultiSource : public DataSource<std::tuple<BatchT...>> {
+ public:
+  typedef std::tuple<BatchT...> BatchType;
+  explicit MultiSource(const std::tuple<DataSource<BatchT>*...>& sources) { adopt(sources, std::index_sequence_for<BatchT...>()); }
+  virtual void reset() override { for_each([](auto& s) { s->reset(); }); }
+  virtual void next(BatchType* const batch) override { next_impl(batch, std::index_sequence_for<BatchT...>()); }
+  virtual bool has_next() const override {
+    bool value = true;
+    for_each([&](auto& s) { value = value && s->has_next(); });
+    return value;
+  }
+  virtual float32 progress() const override {
+    float32 value = 1.0f;
+    for_each([&](auto& s) { value = std::min(value, s->progress()); });
+    return value;
+  }
+  virtual void extract_metadata(lse::Metadata* const metadata) const override {
+    for_each([&](auto& s) { s->extract_metadata(metadata); });
+  }
+
+ private:
+  template <size_t... I>
+  void adopt(const std::tuple<DataSource<BatchT>*...>& sources, std::index_sequence<I...>) {
+    (void)std::initializer_list<int>{(std::get<I>(sources_).reset(std::get<I>(sources)), 0)...};
+  }
+  template <size_t... I>
+  void next_impl(BatchType* const batch, std::index_sequence<I...>) {
+    (void)std::initializer_list<int>{(std::get<I>(sources_)->next(&std::get<I>(*batch)), 0)...};
+  }
+  template <typename Fn>
+  void for_each(Fn fn) const { std::apply([&](auto&... s) { (void)std::initializer_list<int>{(fn(s), 0)...}; }, sources_); }
+  std::tuple<std::unique_ptr<DataSource<BatchT>>...> sources_;
+};
+
+namespace EntityEntity { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; using RepresentationSimilarity::DataSource; }
+namespace TermTerm { using RepresentationSimilarity::Batch; using RepresentationSimilarity::InstanceT; using RepresentationSimilarity::DataSource; }
 
 #endif  // CUNVSM_B200_DATA_H

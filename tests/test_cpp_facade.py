@@ -59,6 +59,22 @@ def test_cpp_host_code_builds_and_fails_loudly_without_gpu():
     assert res.returncode != 0 and "no CUDA device" in res.stderr
 
 
+def test_data_source_wrappers():
+    """MultiSource / RepeatingSource / LoadSimilarities against the reference's own test cases
+    (cpp/data_tests.cpp:828-908), on a plain batch type: no GPU needed."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "data_test")], capture_output=True, text=True)
+    assert res.returncode == 0 and "data tests ok" in res.stdout, res.stderr
+
+
+@pytest.mark.gpu
+def test_data_sources_on_pinned_batches():
+    """RepresentationSimilarity::DataSource (shared-RNG shuffle, partial last batch) and AsyncSource on page-locked batches."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "data_test"), "--pinned"], capture_output=True, text=True)
+    assert res.returncode == 0 and "pinned batches included" in res.stdout, res.stderr
+
+
 def test_cli_rejects_bad_flags():
     _build()
     cli = os.path.join(CPP, "cuNVSMTrainModel")
@@ -206,3 +222,35 @@ def test_cli_zipf_negatives_host_and_device_samplers_agree():
         assert len(costs[name]) == 2 and np.isfinite(costs[name]).all()
     np.testing.assert_allclose(costs["host"], costs["device"], rtol=1e-6)
     assert abs(costs["host"][0] - costs["uniform"][0]) > 1e-4 * costs["uniform"][0]
+
+
+@pytest.mark.gpu
+def test_cli_mixture_with_similarity_file(tmp_path):
+    """The TextEntityEntityEntity mixture fed like the reference feeds it (cpp/main.cu:279-305): n-gram source +
+    similarity file resolved through the identifiers map, shuffled with the shared RNG and repeated for the length of
+    the text epoch (RepeatingSource(-1)). Pairs naming an unknown entity are skipped."""
+    _build()
+    import re
+    rng = np.random.default_rng(1)
+    n, N, V, D = 4, 4096, 300, 90
+    words = rng.integers(0, V, size=(N, n))
+    docs = (words[:, 0] * 3 + words[:, 1]) % D
+    words[0, 0], docs[0] = V - 1, D - 1
+    ngrams = tmp_path / "ngrams.txt"
+    with open(ngrams, "w") as f:
+        for i in range(N):
+            f.write("%d %s\n" % (docs[i], " ".join(map(str, words[i]))))
+    pairs = tmp_path / "pairs.txt"
+    with open(pairs, "w") as f:
+        for i in range(1500):                      # fewer pairs than the text epoch needs: the source repeats
+            f.write("%d %d %.2f\n" % (rng.integers(0, D), rng.integers(0, D), 0.5 + (i % 3)))
+        f.write("%d 12 1.0\n" % (D + 5))           # unknown entity
+    res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--num_epochs", "2", "--word_repr_size", "32",
+                          "--entity_repr_size", "16", "--batch_size", "1024", "--window_size", str(n), "--num_random_entities", "3",
+                          "--seed", "4", "--update_method", "full_adam", "--nonlinearity", "tanh", "--gemm", "fp32",
+                          "--entity_similarity_weight", "0.3", "--ngram_file", str(ngrams), "--similarity_file", str(pairs),
+                          "--host_sampler"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "similarity file: 1500 pairs" in res.stdout and "not found; skipping pair" in res.stderr
+    costs = [float(x) for x in re.findall(r"mean cost ([0-9.eE+-]+)", res.stdout)]
+    assert len(costs) == 2 and np.isfinite(costs).all() and costs[1] < costs[0]
