@@ -2,8 +2,11 @@
 // MetaSourceTest.RepeatingSource :879-908, the similarity source tests). The wrappers are templates over the batch
 // type, so the CPU part runs them on a plain batch; `data_test --pinned` repeats the similarity / async part on the
 // real page-locked batches (needs the CUDA runtime, i.e. the GPU box).
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <sstream>
 
 #include "cuNVSM/data.h"
@@ -77,6 +80,39 @@ static int test_load_similarities() {
   return 0;
 }
 
+// NGramFileSource weighting strategies (cpp/data_indri.cpp:302-312,640-646; include/cuNVSM/data.h:464-487)
+static int test_ngram_file_weighting(const char* dir) {
+  const std::string path = std::string(dir) + "/weighting_ngrams.txt";
+  {
+    std::ofstream f(path);
+    f << "# entity w1 w2\n0 1 2\n0 2 3\n0 3 3\n1 0 1 | 2.0\n";   // document 0: 3 n-grams, document 1: 1 n-gram
+  }
+  long words[2], entity; float ww[2], weight;
+  {
+    TextEntity::NGramFileSource plain(path, 2, nullptr, true, TextEntity::UNIFORM, TextEntity::UNIFORM_TERM_WEIGHTING);
+    plain.instance(3, words, ww, &entity, &weight);
+    EXPECT(words[0] == 0 && words[1] == 1 && entity == 1 && ww[0] == 1.0f && ww[1] == 1.0f && weight == 2.0f);
+  }
+  {
+    // no_shuffle + AUTOMATIC -> INV_DOC_FREQUENCY: avg length = 4 n-grams / 2 documents = 2
+    TextEntity::NGramFileSource src(path, 2, nullptr, true, TextEntity::AUTOMATIC_WEIGHTING, TextEntity::SELF_INFORMATION_TERM_WEIGHTING);
+    src.instance(0, words, ww, &entity, &weight);
+    EXPECT(std::fabs(weight - 2.0f / 3.0f) < 1e-6f);
+    // 8 word occurrences: id 1 twice, id 2 twice, id 3 three times, id 0 once
+    EXPECT(std::fabs(ww[0] - (-std::log(2.0f / 8.0f))) < 1e-6f && std::fabs(ww[1] - (-std::log(2.0f / 8.0f))) < 1e-6f);
+    src.instance(2, words, ww, &entity, &weight);
+    EXPECT(std::fabs(ww[0] - (-std::log(3.0f / 8.0f))) < 1e-6f);
+    src.instance(3, words, ww, &entity, &weight);
+    EXPECT(std::fabs(weight - 2.0f * 2.0f) < 1e-5f && std::fabs(ww[0] - (-std::log(1.0f / 8.0f))) < 1e-6f);
+    RNG rng; rng.seed(3);
+    TextEntity::NGramFileSource shuffled(path, 2, &rng, false, TextEntity::AUTOMATIC_WEIGHTING);   // shuffling -> UNIFORM
+    shuffled.instance(0, words, ww, &entity, &weight);
+    EXPECT(weight == 1.0f);
+  }
+  std::remove(path.c_str());
+  return 0;
+}
+
 // page-locked batches: RepresentationSimilarity::DataSource fills pair batches in the order shuffled by the shared RNG,
 // last batch partial, reshuffled at reset(); RepeatingSource keeps it going; AsyncSource delivers the same batches.
 static int test_similarity_source_pinned() {
@@ -133,7 +169,8 @@ static int test_similarity_source_pinned() {
 }
 
 int main(int argc, char** argv) {
-  int failed = test_multi_source() + test_repeating_source() + test_load_similarities();
+  const char* tmp = std::getenv("TMPDIR");
+  int failed = test_multi_source() + test_repeating_source() + test_load_similarities() + test_ngram_file_weighting(tmp ? tmp : "/tmp");
   if (argc > 1 && std::strcmp(argv[1], "--pinned") == 0) failed += test_similarity_source_pinned();
   if (failed) return 1;
   std::printf("data tests ok%s\n", argc > 1 ? " (pinned batches included)" : "");

@@ -166,8 +166,13 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   const bool file_source = !flags.str("ngram_file").empty();
   if (file_source) {
     // construct_data_source + wrap_source_async of the reference (cpp/main.cu:212-240), on an n-gram file
+    const std::map<std::string, TextEntity::WeightingStrategy> WEIGHTING_STRATEGIES = {   // cpp/main.cu:136-146
+        {"auto", TextEntity::AUTOMATIC_WEIGHTING}, {"uniform", TextEntity::UNIFORM}, {"inv_doc_frequency", TextEntity::INV_DOC_FREQUENCY}};
+    const std::map<std::string, TextEntity::TermWeightingStrategy> FEATURE_WEIGHTING_STRATEGIES = {
+        {"uniform", TextEntity::UNIFORM_TERM_WEIGHTING}, {"self_information", TextEntity::SELF_INFORMATION_TERM_WEIGHTING}};
     TextEntity::NGramFileSource* const file = new TextEntity::NGramFileSource(
-        flags.str("ngram_file"), train_config.window_size(), &rng, train_config.no_shuffle());
+        flags.str("ngram_file"), train_config.window_size(), &rng, train_config.no_shuffle(),
+        WEIGHTING_STRATEGIES.at(flags.str("weighting")), FEATURE_WEIGHTING_STRATEGIES.at(flags.str("feature_weighting")));
     std::printf("n-gram file: %zu instances\n", file->num_instances());
     data_source_ptr.reset(new AsyncSource<TextEntity::Batch>(flags.i("num_concurrent_batches"), train_config.batch_size(),
                                                              train_config.window_size(), file));
@@ -311,6 +316,11 @@ int main(int argc, char** argv) {
   // cpp/main.cu:698-706
   NVSM_CHECK(flags.d("entity_similarity_weight") >= 0.0 && flags.d("entity_similarity_weight") <= 1.0, "--entity_similarity_weight must be in [0, 1]");
   NVSM_CHECK(flags.d("term_similarity_weight") >= 0.0 && flags.d("term_similarity_weight") <= 1.0, "--term_similarity_weight must be in [0, 1]");
+  // cpp/main.cu:634-638
+  NVSM_CHECK(flags.str("weighting") == "auto" || flags.str("weighting") == "uniform" || flags.str("weighting") == "inv_doc_frequency",
+             "Please specify a valid --weighting.");
+  NVSM_CHECK(flags.str("feature_weighting") == "uniform" || flags.str("feature_weighting") == "self_information",
+             "Please specify a valid --feature_weighting.");
   NVSM_CHECK(!flags.b("check_gradients"), "--check_gradients is provided by the test-suite (tests/), not the CLI");
 
   lse::ModelDesc model_desc;

@@ -219,9 +219,19 @@ class SyntheticSource : public DataSourceBase {
 // lines starting with '#' are comments. Like IndriSource::reset (cpp/data_indri.cpp:386-397) every epoch walks the
 // instances in an order shuffled with the SHARED RNG (unless no_shuffle), so the engine consumption order
 // init -> shuffle -> negatives of the reference is kept. Only full batches are emitted (the CLI skips others).
+// reference: include/cuNVSM/data.h:373-379
+enum WeightingStrategy { AUTOMATIC_WEIGHTING, UNIFORM, INV_DOC_FREQUENCY };
+enum TermWeightingStrategy { UNIFORM_TERM_WEIGHTING, SELF_INFORMATION_TERM_WEIGHTING };
+
 class NGramFileSource : public DataSourceBase {
  public:
-  NGramFileSource(const std::string& path, const size_t window_size, RNG* const rng, const bool no_shuffle = false)
+  // Instance weights (--weighting): INV_DOC_FREQUENCY = exp(log(avg_document_length) - log(document_length))
+  // (cpp/data_indri.cpp:302-312; a document's length is the number of its n-grams in the file), AUTOMATIC =
+  // UNIFORM when shuffling, INV_DOC_FREQUENCY otherwise (:640-646); an explicit `| weight` on a line multiplies it.
+  // Word weights (--feature_weighting): SELF_INFORMATION = -log(tf / total_terms) (include/cuNVSM/data.h:464-487).
+  NGramFileSource(const std::string& path, const size_t window_size, RNG* const rng, const bool no_shuffle = false,
+                  WeightingStrategy weighting_strategy = UNIFORM,
+                  const TermWeightingStrategy term_weighting_strategy = UNIFORM_TERM_WEIGHTING)
       : window_size_(window_size), rng_(rng), no_shuffle_(no_shuffle), position_(0), max_word_(-1), max_entity_(-1) {
     std::ifstream file(path);
     NVSM_CHECK(file.good(), ("cannot open n-gram file " + path).c_str());
@@ -249,6 +259,32 @@ class NGramFileSource : public DataSourceBase {
     NVSM_CHECK(!entities_.empty(), "empty n-gram file");
     order_.resize(entities_.size());
     std::iota(order_.begin(), order_.end(), 0);
+    if (weighting_strategy == AUTOMATIC_WEIGHTING) weighting_strategy = no_shuffle_ ? INV_DOC_FREQUENCY : UNIFORM;
+    if (weighting_strategy == INV_DOC_FREQUENCY) {
+      std::vector<long> length(corpus_size(), 0);
+      for (const long e : entities_) ++length[e];
+      size_t documents = 0;
+      for (const long l : length) documents += l > 0;
+      const WeightType avg_document_length = static_cast<WeightType>(entities_.size()) / documents;
+      for (size_t k = 0; k < entities_.size(); ++k)
+        weights_[k] *= std::exp(std::log(avg_document_length) - std::log(static_cast<WeightType>(length[entities_[k]])));
+    }
+    if (term_weighting_strategy == SELF_INFORMATION_TERM_WEIGHTING) {
+      std::vector<long> frequency(vocabulary_size(), 0);
+      for (const long w : words_) ++frequency[w];
+      word_weights_.resize(vocabulary_size());
+      for (size_t w = 0; w < word_weights_.size(); ++w)
+        word_weights_[w] = frequency[w] > 0 ? -std::log(static_cast<WeightType>(frequency[w]) / static_cast<WeightType>(words_.size())) : 0;
+    }
+  }
+  // Instance k of the file as next() delivers it: words[n], word weights[n], entity, instance weight.
+  void instance(const size_t k, long* const words, WeightType* const word_weights, long* const entity, WeightType* const weight) const {
+    for (size_t w = 0; w < window_size_; ++w) {
+      words[w] = words_[k * window_size_ + w];
+      word_weights[w] = word_weights_.empty() ? static_cast<WeightType>(1.0) : word_weights_[words[w]];
+    }
+    *entity = entities_[k];
+    *weight = weights_[k];
   }
   size_t num_instances() const { return entities_.size(); }
   size_t vocabulary_size() const { return static_cast<size_t>(max_word_ + 1); }
@@ -266,13 +302,9 @@ class NGramFileSource : public DataSourceBase {
     batch->clear();
     NVSM_CHECK(batch->window_size() == window_size_, "batch window does not match the n-gram file");
     const size_t B = std::min(batch->maximum_size(), order_.size() - position_);
-    for (size_t i = 0; i < B; ++i) {
-      const size_t k = order_[position_ + i];
-      std::copy(&words_[k * window_size_], &words_[(k + 1) * window_size_], &batch->features()[i * window_size_]);
-      std::fill(&batch->feature_weights()[i * window_size_], &batch->feature_weights()[(i + 1) * window_size_], 1.0f);
-      batch->labels()[i] = entities_[k];
-      batch->weights()[i] = weights_[k];
-    }
+    for (size_t i = 0; i < B; ++i)
+      instance(order_[position_ + i], &batch->features()[i * window_size_], &batch->feature_weights()[i * window_size_],
+               &batch->labels()[i], &batch->weights()[i]);
     batch->set_num_instances(B);
     position_ += B;
   }
@@ -293,6 +325,7 @@ class NGramFileSource : public DataSourceBase {
   long max_word_, max_entity_;
   std::vector<long> words_, entities_;
   std::vector<float> weights_;
+  std::vector<WeightType> word_weights_;   // per word id; empty = uniform term weighting
   std::vector<size_t> order_;
 };
 

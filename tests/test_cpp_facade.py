@@ -80,6 +80,9 @@ def test_cli_rejects_bad_flags():
     cli = os.path.join(CPP, "cuNVSMTrainModel")
     for args, msg in ((["--update_method", "bogus", "--nonlinearity", "tanh", "--seed", "1"], "valid --update_method"),
                       (["--update_method", "sgd", "--nonlinearity", "relu", "--seed", "1"], "valid --nonlinearity"),
+                      (["--update_method", "sgd", "--nonlinearity", "tanh", "--seed", "1", "--weighting", "bogus"], "valid --weighting"),
+                      (["--update_method", "sgd", "--nonlinearity", "tanh", "--seed", "1", "--feature_weighting", "tfidf"],
+                       "valid --feature_weighting"),
                       (["--update_method", "sgd", "--nonlinearity", "tanh"], "--seed")):
         res = subprocess.run([cli] + args, capture_output=True, text=True)
         assert res.returncode != 0 and msg in res.stderr, res.stderr
@@ -182,6 +185,7 @@ def test_cli_ngram_file_source_async_prefetch(tmp_path):
                               "--entity_repr_size", "16", "--batch_size", "1024", "--window_size", str(n),
                               "--num_random_entities", "3", "--seed", "11", "--update_method", "sgd", "--nonlinearity", "tanh",
                               "--gemm", "fp32", "--ngram_file", str(path), "--num_concurrent_batches", "3",
+                              "--feature_weighting", "self_information", "--weighting", "inv_doc_frequency",
                               "--output", str(tmp_path / "model")] + extra,
                              capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr
