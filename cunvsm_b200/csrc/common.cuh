@@ -45,6 +45,17 @@ __device__ __forceinline__ void load_vec_cs(const float* __restrict__ p, float (
     }
 }
 
+// L2-coherent load (bypasses L1): data another CTA of the running kernel has just published.
+template <int VEC>
+__device__ __forceinline__ void load_vec_cg(const float* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        v[0] = __ldcg(p);
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void store_vec_cs(float* __restrict__ p, const float (&v)[VEC]) {
     if constexpr (VEC == 4) {

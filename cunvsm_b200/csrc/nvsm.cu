@@ -142,6 +142,10 @@ struct nvsm_model {
     int *e_counts = nullptr, *e_offsets = nullptr, *e_refs = nullptr;
     int *w_counts = nullptr, *w_offsets = nullptr, *w_refs = nullptr;
     int* scan_tmp = nullptr;  // block totals of the two-level scan
+    // rows with more than kHeavyRefs references: work list + partial sums of pull_heavy_kernel, per table
+    // (the two table updates may run concurrently on different streams)
+    HeavyWork heavy_e{}, heavy_w{};
+    bool no_heavy = false;      // NVSM_NO_HEAVY=1: one warp per row whatever its reference count (A/B measurements)
     int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
                           // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
     bool use_tc = false;  // projection GEMMs on tcgen05 (gemm_mode != FP32 and shapes allow)
@@ -963,15 +967,61 @@ int build_buckets(nvsm_model* m, const idx_t* ids, long total, long num_rows, in
     return 0;
 }
 
+// Work list of pull_heavy_kernel for `references` bucketed references of rows `dim` wide (grown on demand: the
+// all-gather sparse mode buckets the global batch).
+int ensure_heavy(nvsm_model* m, HeavyWork* hw, long references, int dim) {
+    const int capacity = (int)(2 * references / kHeavyRefs + 1);
+    const int ld = ((dim + 3) / 4) * 4 + 4;
+    if (hw->items && hw->capacity >= capacity && hw->ld == ld) return 0;
+    CU(cudaDeviceSynchronize());
+    if (hw->items) cudaFree(hw->items);
+    if (hw->count) cudaFree(hw->count);
+    if (hw->part) cudaFree(hw->part);
+    if (hw->arrivals) cudaFree(hw->arrivals);
+    *hw = HeavyWork{};
+    TRY(dev_alloc(&hw->items, (size_t)capacity, false));
+    TRY(dev_alloc(&hw->count, 1));
+    TRY(dev_alloc(&hw->part, (size_t)capacity * ld, false));
+    TRY(dev_alloc(&hw->arrivals, (size_t)capacity));
+    hw->capacity = capacity;
+    hw->ld = ld;
+    return 0;
+}
+
+void free_heavy(HeavyWork* hw) {
+    if (hw->items) cudaFree(hw->items);
+    if (hw->count) cudaFree(hw->count);
+    if (hw->part) cudaFree(hw->part);
+    if (hw->arrivals) cudaFree(hw->arrivals);
+    *hw = HeavyWork{};
+}
+
+int heavy_grid(const nvsm_model* m, const HeavyWork& hw) {
+    return std::max(1, std::min(m->num_sms * 4, (hw.capacity + 7) / 8));
+}
+
 template <int VEC, int NCH>
 int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
-    if (entities)
+    HeavyWork* const hw = entities ? &m->heavy_e : &m->heavy_w;
+    TRY(ensure_heavy(m, hw, entities ? m->B * m->R : m->B * m->n, entities ? m->dd : m->dw));
+    CU(cudaMemsetAsync(hw->count, 0, sizeof(int), m->stream));
+    HeavyWork row_hw = *hw;
+    if (m->no_heavy) row_hw.items = nullptr;
+    if (entities) {
+        const float* const self_k = m->l2_entity ? (const float*)m->kself : (const float*)nullptr;
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, m->l2_entity ? (const float*)m->kself : (const float*)nullptr);
-    else
+               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, row_hw);
+        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
+               (const float*)m->mult, (const float*)m->Y, m->R, (const float*)nullptr, *hw,
+               AdamFullApply{m->E, m->optE.m, m->optE.v, k, self_k});
+    } else {
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr);
+               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, row_hw);
+        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
+               (const float*)m->cur->fweights, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
+               AdamFullApply{m->W, m->optW.m, m->optW.v, k, (const float*)nullptr});
+    }
     return 0;
 }
 
@@ -979,12 +1029,23 @@ template <int VEC, int NCH>
 int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool touch_all, float* acc, const float* ysq,
                     const float* word_coefs) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
-    if (entities)
+    HeavyWork* const hw = entities ? &m->heavy_e : &m->heavy_w;
+    TRY(ensure_heavy(m, hw, entities ? m->B * m->R : m->B * m->n, entities ? m->dd : m->dw));
+    CU(cudaMemsetAsync(hw->count, 0, sizeof(int), m->stream));
+    HeavyWork row_hw = *hw;
+    if (m->no_heavy) row_hw.items = nullptr;
+    if (entities) {
         LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f);
-    else
+               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, row_hw);
+        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
+               (const float*)m->mult, (const float*)m->Y, m->R, ysq, *hw, SgdApply{m->E, decay, lr, acc, 1e-6f});
+    } else {
         LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f);
+               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, row_hw);
+        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
+               word_coefs, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
+               SgdApply{m->W, decay, lr, (float*)nullptr, 1e-6f});
+    }
     return 0;
 }
 
@@ -1604,6 +1665,7 @@ void nvsm_destroy(nvsm_model* m) {
         if (p) cudaFree(p);
     if (m->pair_loss_host) cudaFreeHost(m->pair_loss_host);
     if (m->rng_dev) cudaFree(m->rng_dev);
+    free_heavy(&m->heavy_e); free_heavy(&m->heavy_w);
     if (m->smp_cdf) cudaFree(m->smp_cdf);
     int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
     for (int* p : sl)
@@ -1751,6 +1813,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         // table measured 12 -> 34 us through the pull path)
         const bool sgd_pull = (method == NVSM_SGD || method == NVSM_ADAGRAD) && cfg->objective == NVSM_OBJECTIVE_TEXT_ENTITY &&
                               !cfg->l2_normalize_entity_reprs && !getenv("NVSM_NO_PULL") && std::max(V, D) >= kPullMinRows;
+        m->no_heavy = getenv("NVSM_NO_HEAVY") != nullptr;
         m->pull = (full_adam_pull || sgd_pull) &&
                   V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
         if (m->pull) {

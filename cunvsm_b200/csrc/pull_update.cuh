@@ -76,6 +76,37 @@ struct AdamFullConsts {
     float s1, lr1, reg1, s2, lr2, lambda, lr, bc, eps;
 };
 
+// ---- skewed reference counts -------------------------------------------------------------------------------------
+// One warp per row is the right shape while rows have ~10 references (uniform ids). Real id streams are Zipfian (the
+// most frequent word of a 51200 x 10 batch over 50k words is referenced ~45 000 times; BASELINE configs[4] draws
+// Zipf-skewed negatives), and one warp walking thousands of references is a millisecond-long tail. Rows with more
+// than kHeavyRefs references are therefore not processed by the row kernel: it appends one work item per segment of
+// kHeavyRefs references to a list, and pull_heavy_kernel gives every segment its own warp, publishes the segment's
+// partial sum and lets the LAST segment to arrive (per-row arrival counter) add the partials in segment order and
+// apply the row's update. No float atomics; the summation order inside a row is fixed by the bucket order.
+constexpr int kHeavyRefs = 64;
+
+struct HeavyWork {
+    int2* items;      // (row, segment), appended by the row kernel; null = feature off
+    int* count;       // number of items; the host zeroes it before the row kernel
+    float* part;      // [capacity][ld] partial sums (+ the squared-gradient partial at [ld - 4])
+    int* arrivals;    // arrival counter of a row, at the index of its first item; reset by the last arrival
+    int capacity;     // items allocated: >= 2 * references / kHeavyRefs + 1 cannot overflow
+    int ld;           // floats per partial: dim rounded up to 4, + 4
+};
+
+// Called by the row kernels (whole warp): true when `row` was handed to the heavy list.
+__device__ __forceinline__ bool defer_heavy_row(const HeavyWork& hw, long row, int cnt, int lane) {
+    if (hw.items == nullptr || cnt <= kHeavyRefs) return false;
+    const int nseg = (cnt + kHeavyRefs - 1) / kHeavyRefs;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(hw.count, nseg);
+    pos = __shfl_sync(kFull, pos, 0);
+    for (int sgm = lane; sgm < nseg; sgm += kWarp)
+        if (pos + sgm < hw.capacity) hw.items[pos + sgm] = make_int2((int)row, sgm);
+    return true;
+}
+
 // One warp per table row. SRC rows (Y or gP) and the per-reference coefficient:
 //   ENTITY:  src row = ref / group, coef = (ref % group == 0 ? +1 : -1) * coefs[ref]   (group = R)
 //   WORD  :  src row = ref / group, coef = coefs[ref]                                  (group = n)
@@ -87,13 +118,14 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
                                                              const float* __restrict__ coefs,
                                                              const float* __restrict__ src, int group,
                                                              const AdamFullConsts k,
-                                                             const float* __restrict__ self_k) {
+                                                             const float* __restrict__ self_k, const HeavyWork hw) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim / VEC;
     for (long row = warp0; row < num_rows; row += nwarps) {
         const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        if (defer_heavy_row(hw, row, end - beg, lane)) continue;
         // entity normalisation: the gradient carries - self_k[row] * theta[row] (entity_norm_prep_kernel)
         const float ks = self_k ? __ldg(self_k + row) : 0.f;
         float agg[NCH][VEC];
@@ -167,7 +199,8 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
                                                        const int* __restrict__ offsets, const int* __restrict__ refs,
                                                        const float* __restrict__ coefs, const float* __restrict__ src,
                                                        int group, float decay, float lr, int touch_all,
-                                                       float* __restrict__ acc, const float* __restrict__ ysq, float eps) {
+                                                       float* __restrict__ acc, const float* __restrict__ ysq, float eps,
+                                                       const HeavyWork hw) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -175,6 +208,7 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
     for (long row = warp0; row < num_rows; row += nwarps) {
         const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
         if (beg == end && !touch_all) continue;
+        if (defer_heavy_row(hw, row, end - beg, lane)) continue;
         float agg[NCH][VEC];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
@@ -227,6 +261,173 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
                 store_vec_cs<VEC>(theta + o, th);
             }
         }
+    }
+}
+
+// Row updates of the two pull kernels as functors, for pull_heavy_kernel (same arithmetic, same order).
+struct AdamFullApply {
+    float *theta, *m, *v;
+    AdamFullConsts k;
+    const float* self_k;
+    template <int VEC, int NCH>
+    __device__ __forceinline__ void run(long row, int dim, int lane, int nvec, const float (&agg)[NCH][VEC], float) const {
+        const float ks = self_k ? __ldg(self_k + row) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            if (c < nvec) {
+                const long o = row * dim + c * VEC;
+                float th[VEC], mm[VEC], vv[VEC];
+                load_vec_cs<VEC>(theta + o, th);
+                load_vec_cs<VEC>(m + o, mm);
+                load_vec_cs<VEC>(v + o, vv);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const float ag = agg[j][q] - ks * th[q];
+                    const float g = ag + (-k.lambda * th[q]);
+                    mm[q] = (mm[q] * k.s1 + k.lr1 * ag) + (-k.reg1 * th[q]);
+                    vv[q] = vv[q] * k.s2 + (g * g) * k.lr2;
+                    th[q] = th[q] + (fast_div(mm[q], fast_sqrt(vv[q]) + k.eps) * k.bc) * k.lr;
+                }
+                store_vec_cs<VEC>(theta + o, th);
+                store_vec_cs<VEC>(m + o, mm);
+                store_vec_cs<VEC>(v + o, vv);
+            }
+        }
+    }
+};
+
+struct SgdApply {
+    float* theta;
+    float decay, lr;
+    float* acc;   // entity Adagrad accumulator or null
+    float eps;
+    template <int VEC, int NCH>
+    __device__ __forceinline__ void run(long row, int dim, int lane, int nvec, const float (&agg)[NCH][VEC], float sq) const {
+        float rs = 1.0f;
+        if (acc) {
+            const float a = acc[row] + sq;
+            __syncwarp();
+            if (lane == 0) acc[row] = a;
+            rs = 1.0f / sqrtf(a + eps);
+        }
+        const float step = lr * rs;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            if (c < nvec) {
+                const long o = row * dim + c * VEC;
+                float th[VEC];
+                load_vec_cs<VEC>(theta + o, th);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) th[q] = th[q] * decay + step * agg[j][q];
+                store_vec_cs<VEC>(theta + o, th);
+            }
+        }
+    }
+};
+
+// One warp per (row, segment) item of the heavy list; see HeavyWork. Four references are in flight per lane (the
+// FMAs still run in reference order), since here the walk is long enough for load latency to be the limit.
+template <int VEC, int NCH, bool ENTITY, typename Apply>
+__global__ void __launch_bounds__(256) pull_heavy_kernel(int dim, const int* __restrict__ offsets,
+                                                         const int* __restrict__ refs, const float* __restrict__ coefs,
+                                                         const float* __restrict__ src, int group,
+                                                         const float* __restrict__ ysq, const HeavyWork hw,
+                                                         const Apply apply) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim / VEC;
+    const int num_items = min(*hw.count, hw.capacity);
+    for (int item = warp0; item < num_items; item += nwarps) {
+        const int2 it = hw.items[item];
+        const long row = it.x;
+        const int base = item - it.y;   // the items of a row are contiguous, segment 0 first
+        const int rbeg = __ldg(offsets + row), rend = __ldg(offsets + row + 1);
+        const int nseg = (rend - rbeg + kHeavyRefs - 1) / kHeavyRefs;
+        const int beg = rbeg + it.y * kHeavyRefs, end = min(beg + kHeavyRefs, rend);
+        float agg[NCH][VEC];
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+        float sq = 0.f;
+        for (int b0 = beg; b0 < end; b0 += 32) {
+            const int cnt = min(32, end - b0);
+            int my_src = 0;
+            float my_coef = 0.f;
+            if (lane < cnt) {
+                const int ref = __ldg(refs + b0 + lane);
+                my_src = ref / group;
+                const float cf = __ldg(coefs + ref);
+                my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
+                if (ysq) sq += cf * cf * __ldg(ysq + my_src);
+            }
+            for (int t = 0; t < cnt; t += 4) {   // lanes >= cnt hold source row 0: loaded, never added
+                int srow[4];
+                float cf[4], x[4][NCH][VEC];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    srow[u] = __shfl_sync(kFull, my_src, (t + u) & 31);
+                    cf[u] = __shfl_sync(kFull, my_coef, (t + u) & 31);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const int c = lane + j * kWarp;
+                        if (c < nvec) load_vec_ro<VEC>(src + (long)srow[u] * dim + c * VEC, x[u][j]);
+                    }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        const int c = lane + j * kWarp;
+                        if (c < nvec && t + u < cnt) {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) agg[j][q] += cf[u] * x[u][j][q];
+                        }
+                    }
+            }
+        }
+        // publish this segment's partial, then count it in
+        float* const mine = hw.part + (long)item * hw.ld;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            const int c = lane + j * kWarp;
+            if (c < nvec) store_vec<VEC>(mine + c * VEC, agg[j]);
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) mine[hw.ld - 4] = sq;
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = atomicAdd(hw.arrivals + base, 1) == nseg - 1;
+        last = __shfl_sync(kFull, last, 0);
+        if (!last) continue;
+        __threadfence();
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+        sq = 0.f;
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+            const float* const p = hw.part + (long)(base + sgm) * hw.ld;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const int c = lane + j * kWarp;
+                if (c < nvec) {
+                    float x[VEC];
+                    load_vec_cg<VEC>(p + c * VEC, x);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) agg[j][q] += x[q];
+                }
+            }
+            sq += __ldcg(p + hw.ld - 4);
+        }
+        if (lane == 0) hw.arrivals[base] = 0;
+        apply.template run<VEC, NCH>(row, dim, lane, nvec, agg, sq);
     }
 }
 

@@ -176,6 +176,37 @@ def test_three_training_steps_match_oracle(opt, bn):
                 assert_close(gm.get_tensor(gname), om.get(oname), 1e-3, 1e-5, what="%s step %d" % (oname, step))
 
 
+@pytest.mark.parametrize("opt", [("sgd", nv.SGD, 0), ("adagrad", nv.ADAGRAD, 0), ("full_adam", nv.ADAM, nv.DENSE_UPDATE_DENSE_VARIANCE)],
+                         ids=["sgd", "adagrad", "full_adam"])
+def test_zipf_skewed_ids_take_the_heavy_row_path(opt):
+    """Zipf(1) word ids and Zipf(1) negatives: the most frequent word / document of a batch is referenced ~1000 times,
+    so the pull-style updates split those rows into 64-reference segments (pull_heavy_kernel: per-segment partial sums,
+    last arrival applies the row update). Three steps against the oracle, tables and optimiser state."""
+    _, method, mode = opt
+    V, D, dw, dd, n, z, B = 9000, 8500, 24, 20, 5, 4, 2048       # >= 8192 rows: SGD / Adagrad pull as well
+    lr = 0.01 if method != nv.ADAM else 0.001
+    gm, om, rng = twin_models(V, D, dw, dd, n=n, z=z, B=B, nonlinearity=nv.HARD_TANH, bn=True, method=method, adam_mode=mode, lam=0.01)
+    gm.set_negative_distribution(nv.zipf_cdf(D, 1.0))
+    wcdf = nv.zipf_cdf(V, 1.0)
+    nrng = np.random.default_rng(4)
+    for step in range(3):
+        f, fw, labels, w = make_batch(nrng, B, n, V, D, z)
+        f = np.minimum(np.searchsorted(wcdf, nrng.random((B, n)), side="right"), V - 1).astype(np.int64)
+        ids = gm.generate_labels(labels, rng)
+        assert np.bincount(f.ravel()).max() > 500 and np.bincount(ids).max() > 300     # the heavy path is really taken
+        batch = nv.Batch(B, n).fill(f, labels, fw, w)
+        res = gm.compute_cost(batch, entity_ids=ids)
+        cost, ocost = res.get_cost(), om.compute_cost(f, fw, ids, w, n)
+        assert abs(cost - ocost) <= 5e-4 * abs(ocost)
+        gm.compute_gradients(res); om.compute_gradients()
+        gm.update(None, lr, res.scaled_regularization_lambda()); om.update(lr, om.scaled_lambda())
+        for gname, oname in ((nv.WORD_REPRS, "W"), (nv.ENTITY_REPRS, "E"), (nv.TRANSFORM, "T"), (nv.BIAS, "b")):
+            assert_close(gm.get_tensor(gname), om.get(oname), 5e-4, 1e-5, what="%s step %d" % (oname, step))
+        for gname, oname in STATE_NAMES.items():
+            if gm.tensor_size(gname) > 0 and len(om.get(oname)) == gm.tensor_size(gname):
+                assert_close(gm.get_tensor(gname), om.get(oname), 1e-3, 1e-5, what="%s step %d" % (oname, step))
+
+
 def test_unweighted_rebalanced_lse_and_duplicates():
     """z > 1 without bias_negative_samples re-weights positives/negatives
     (cpp/objective.cu:268-290); tiny D forces id collisions (negatives == positive, duplicate rows
