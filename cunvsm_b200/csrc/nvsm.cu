@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -145,6 +146,7 @@ struct nvsm_model {
     // rows with more than kHeavyRefs references: work list + partial sums of pull_heavy_kernel, per table
     // (the two table updates may run concurrently on different streams)
     HeavyWork heavy_e{}, heavy_w{};
+    HeavyWork *heavy_e_dev = nullptr, *heavy_w_dev = nullptr;   // device copies of the descriptors (row kernels)
     bool no_heavy = false;      // NVSM_NO_HEAVY=1: one warp per row whatever its reference count (A/B measurements)
     int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
                           // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
@@ -230,7 +232,13 @@ namespace {
 template <typename T>
 int dev_alloc(T** p, size_t count, bool zero = true) {
     CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
-    if (zero) CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) {
+        // cudaMemset runs on the legacy default stream and is asynchronous; the model's streams are non-blocking, so
+        // without this wait a write enqueued on them right after the allocation (nvsm_sampler_seed -> rng_dev) can be
+        // overtaken by the zero fill.
+        CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+        CU(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     return 0;
 }
 
@@ -955,21 +963,9 @@ int scatter_word_meansq(nvsm_model* m, float* acc, float scale) {
 // ------------------------------------------------------------------------------------
 // pull-style full Adam (pull_update.cuh)
 // ------------------------------------------------------------------------------------
-int build_buckets(nvsm_model* m, const idx_t* ids, long total, long num_rows, int* counts, int* offsets, int* refs) {
-    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (num_rows + 1), m->stream));
-    const int g = (int)((total + 255) / 256);
-    LAUNCH(m, ref_count_kernel, g, 256, 0, ids, total, counts);
-    const int nb = (int)((num_rows + 1023) / 1024);
-    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, counts, num_rows, offsets, m->scan_tmp);
-    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->scan_tmp, (long)nb, m->scan_tmp + 1024, (int*)nullptr);
-    LAUNCH(m, scan_add_kernel, nb, 1024, 0, offsets, num_rows, m->scan_tmp + 1024, total);
-    LAUNCH(m, ref_fill_kernel, g, 256, 0, ids, total, offsets, counts, refs);
-    return 0;
-}
-
 // Work list of pull_heavy_kernel for `references` bucketed references of rows `dim` wide (grown on demand: the
 // all-gather sparse mode buckets the global batch).
-int ensure_heavy(nvsm_model* m, HeavyWork* hw, long references, int dim) {
+int ensure_heavy(nvsm_model* m, HeavyWork* hw, HeavyWork** hw_dev, long references, int dim) {
     const int capacity = (int)(2 * references / kHeavyRefs + 1);
     const int ld = ((dim + 3) / 4) * 4 + 4;
     if (hw->items && hw->capacity >= capacity && hw->ld == ld) return 0;
@@ -985,6 +981,8 @@ int ensure_heavy(nvsm_model* m, HeavyWork* hw, long references, int dim) {
     TRY(dev_alloc(&hw->arrivals, (size_t)capacity));
     hw->capacity = capacity;
     hw->ld = ld;
+    if (!*hw_dev) CU(cudaMalloc((void**)hw_dev, sizeof(HeavyWork)));
+    CU(cudaMemcpy(*hw_dev, hw, sizeof(HeavyWork), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1000,25 +998,50 @@ int heavy_grid(const nvsm_model* m, const HeavyWork& hw) {
     return std::max(1, std::min(m->num_sms * 4, (hw.capacity + 7) / 8));
 }
 
+// Both tables' reference buckets of a batch of B instances (local or gathered); the scan also resets the heavy-row
+// work lists of the pull kernels.
+int build_all_buckets(nvsm_model* m, const BatchSlot* s, long B);
+
+int build_buckets(nvsm_model* m, const idx_t* ids, long total, long num_rows, int* counts, int* offsets, int* refs,
+                  const HeavyWork* heavy, const HeavyWork* heavy_dev) {
+    CU(cudaMemsetAsync(counts, 0, sizeof(int) * (num_rows + 1), m->stream));
+    const int g = (int)((total + 255) / 256);
+    LAUNCH(m, ref_count_kernel, g, 256, 0, ids, total, counts);
+    const int nb = (int)((num_rows + 1023) / 1024);
+    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, counts, num_rows, offsets, m->scan_tmp, heavy_dev ? heavy->count : (int*)nullptr);
+    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->scan_tmp, (long)nb, m->scan_tmp + 1024, (int*)nullptr, (int*)nullptr);
+    LAUNCH(m, scan_add_kernel, nb, 1024, 0, offsets, num_rows, m->scan_tmp + 1024, total, (const int*)counts, heavy_dev);
+    LAUNCH(m, ref_fill_kernel, g, 256, 0, ids, total, offsets, counts, refs);
+    return 0;
+}
+
+int build_all_buckets(nvsm_model* m, const BatchSlot* s, long B) {
+    TRY(ensure_heavy(m, &m->heavy_e, &m->heavy_e_dev, B * m->R, m->dd));
+    TRY(ensure_heavy(m, &m->heavy_w, &m->heavy_w_dev, B * m->n, m->dw));
+    const bool on = !m->no_heavy;
+    TRY(build_buckets(m, s->ids, B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs, &m->heavy_e, on ? m->heavy_e_dev : nullptr));
+    return build_buckets(m, s->features, B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs, &m->heavy_w, on ? m->heavy_w_dev : nullptr);
+}
+
 template <int VEC, int NCH>
 int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
     HeavyWork* const hw = entities ? &m->heavy_e : &m->heavy_w;
-    TRY(ensure_heavy(m, hw, entities ? m->B * m->R : m->B * m->n, entities ? m->dd : m->dw));
-    CU(cudaMemsetAsync(hw->count, 0, sizeof(int), m->stream));
-    HeavyWork row_hw = *hw;
-    if (m->no_heavy) row_hw.items = nullptr;
+    if (!hw->items) return fail("pull update without a heavy-row work list (build_all_buckets)");
+    // rows above kHeavyRefs references are on the list the bucket build made: the row kernel skips them
+    const int row_hw = m->no_heavy ? 0 : 1;
+    const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
     if (entities) {
         const float* const self_k = m->l2_entity ? (const float*)m->kself : (const float*)nullptr;
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, row_hw);
-        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
+               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
+        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, (const float*)nullptr, *hw,
                AdamFullApply{m->E, m->optE.m, m->optE.v, k, self_k});
     } else {
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, row_hw);
-        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
+               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
+        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
                (const float*)m->cur->fweights, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
                AdamFullApply{m->W, m->optW.m, m->optW.v, k, (const float*)nullptr});
     }
@@ -1030,19 +1053,19 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
                     const float* word_coefs) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
     HeavyWork* const hw = entities ? &m->heavy_e : &m->heavy_w;
-    TRY(ensure_heavy(m, hw, entities ? m->B * m->R : m->B * m->n, entities ? m->dd : m->dw));
-    CU(cudaMemsetAsync(hw->count, 0, sizeof(int), m->stream));
-    HeavyWork row_hw = *hw;
-    if (m->no_heavy) row_hw.items = nullptr;
+    if (!hw->items) return fail("pull update without a heavy-row work list (build_all_buckets)");
+    // rows above kHeavyRefs references are on the list the bucket build made: the row kernel skips them
+    const int row_hw = m->no_heavy ? 0 : 1;
+    const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
     if (entities) {
         LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, row_hw);
-        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
+               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, ysq, *hw, SgdApply{m->E, decay, lr, acc, 1e-6f});
     } else {
         LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, row_hw);
-        LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
+               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
                word_coefs, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
                SgdApply{m->W, decay, lr, (float*)nullptr, 1e-6f});
     }
@@ -1096,8 +1119,7 @@ int start_bucket_build(nvsm_model* m, BatchSlot* s) {
     m->stream = m->aux_stream;   // LAUNCH targets m->stream
     const bool prof = m->profiling;
     m->profiling = false;
-    int rc = build_buckets(m, s->ids, s->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs);
-    if (rc == 0) rc = build_buckets(m, s->features, s->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs);
+    int rc = build_all_buckets(m, s, s->B);
     m->stream = main_stream;
     m->profiling = prof;
     if (rc) return rc;
@@ -1334,8 +1356,7 @@ int update(nvsm_model* m, float lr, float lambda) {
         if (int grc = gather_global_batch(m, &local)) { m->mult = mult_orig; return grc; }
         if (m->pull) {  // buckets over the gathered ids, on the main stream
             phase_begin(m, PH_UPD_ENTITIES);
-            int rc = build_buckets(m, m->cur->ids, m->B * m->R, m->D, m->e_counts, m->e_offsets, m->e_refs);
-            if (rc == 0) rc = build_buckets(m, m->cur->features, m->B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs);
+            int rc = build_all_buckets(m, m->cur, m->B);
             phase_end(m);
             if (rc) { restore_local_view(m, local); m->mult = mult_orig; return rc; }
             CU(cudaEventRecord(m->buckets_ready, m->stream));
@@ -1479,9 +1500,9 @@ int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B,
     const int grid = (int)((nchunks + 255) / 256);
     LAUNCH(m, sampler_count_kernel, grid, 256, 0, p);
     const int nb = (int)((nchunks + 1023) / 1024);
-    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, m->smp_counts, nchunks, m->smp_offsets, m->smp_scan);
-    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->smp_scan, (long)nb, m->smp_scan + 1024, (int*)nullptr);
-    LAUNCH(m, scan_add_kernel, nb, 1024, 0, m->smp_offsets, nchunks, m->smp_scan + 1024, 0L);
+    LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, m->smp_counts, nchunks, m->smp_offsets, m->smp_scan, (int*)nullptr);
+    LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->smp_scan, (long)nb, m->smp_scan + 1024, (int*)nullptr, (int*)nullptr);
+    LAUNCH(m, scan_add_kernel, nb, 1024, 0, m->smp_offsets, nchunks, m->smp_scan + 1024, 0L, (const int*)nullptr, (const HeavyWork*)nullptr);
     LAUNCH(m, sampler_total_kernel, 1, 1, 0, m->smp_counts, m->smp_offsets, nchunks);
     LAUNCH(m, sampler_fill_kernel, std::max(grid, (int)((B + 255) / 256)), 256, 0, p);
     m->rng_cur ^= 1;
@@ -1495,7 +1516,7 @@ int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B,
 int validate_ids(nvsm_model* m, cudaStream_t on, idx_t* words, long num_words, idx_t* entities, long num_entities) {
     cudaStream_t main_stream = m->stream;
     m->stream = on;
-    const int grid = grid_for(m, num_words + num_entities, 4 * 256, 2);
+    const int grid = grid_for(m, num_words + num_entities, 2 * 256, 8);
     int rc = [&]() -> int {
         LAUNCH(m, validate_ids_kernel, grid, 256, 0, words, num_words, m->V, entities, num_entities, m->D, m->id_flags);
         return 0;
@@ -1666,6 +1687,8 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->pair_loss_host) cudaFreeHost(m->pair_loss_host);
     if (m->rng_dev) cudaFree(m->rng_dev);
     free_heavy(&m->heavy_e); free_heavy(&m->heavy_w);
+    if (m->heavy_e_dev) cudaFree(m->heavy_e_dev);
+    if (m->heavy_w_dev) cudaFree(m->heavy_w_dev);
     if (m->smp_cdf) cudaFree(m->smp_cdf);
     int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
     for (int* p : sl)

@@ -23,11 +23,32 @@ __global__ void __launch_bounds__(256) ref_count_kernel(const idx_t* __restrict_
     if (c < total) atomicAdd(counts + __ldg(ids + c), 1);
 }
 
+// ---- skewed reference counts -------------------------------------------------------------------------------------
+// One warp per row is the right shape while rows have ~10 references (uniform ids). Real id streams are Zipfian (the
+// most frequent word of a 51200 x 10 batch over 50k words is referenced ~45 000 times; BASELINE configs[4] draws
+// Zipf-skewed negatives), and one warp walking thousands of references is a millisecond-long tail. Rows with more
+// than kHeavyRefs references are therefore skipped by the row kernel: the bucket build (scan_add_kernel, which runs on
+// the auxiliary stream under the forward pass) appends one work item per segment of kHeavyRefs references of such a
+// row to a list, and pull_heavy_kernel gives every segment its own warp, publishes the segment's
+// partial sum and lets the LAST segment to arrive (per-row arrival counter) add the partials in segment order and
+// apply the row's update. No float atomics; the summation order inside a row is fixed by the bucket order.
+constexpr int kHeavyRefs = 64;
+
+struct HeavyWork {
+    int2* items;      // (row, segment), appended by scan_add_kernel
+    int* count;       // number of items; reset by the first scan kernel of the bucket build
+    float* part;      // [capacity][ld] partial sums (+ the squared-gradient partial at [ld - 4])
+    int* arrivals;    // arrival counter of a row, at the index of its first item; reset by the last arrival
+    int capacity;     // items allocated: >= 2 * references / kHeavyRefs + 1 cannot overflow
+    int ld;           // floats per partial: dim rounded up to 4, + 4
+};
+
 // Exclusive scan, three small launches: per-block scan of 1024 counts + block totals,
 // scan of the (<= 1024 * 1024 / 1024) block totals, add back.
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict__ in, long n, int* __restrict__ out,
-                                                           int* __restrict__ block_sums) {
+                                                           int* __restrict__ block_sums, int* __restrict__ reset = nullptr) {
     __shared__ int warp_tot[32];
+    if (reset && blockIdx.x == 0 && threadIdx.x == 0) *reset = 0;   // HeavyWork::count, appended to by scan_add_kernel
     const long i = (long)blockIdx.x * 1024 + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int x = i < n ? in[i] : 0;
@@ -55,10 +76,20 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const int* __restrict
 }
 
 __global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, long n, const int* __restrict__ block_prefix,
-                                                        long total_refs) {
+                                                        long total_refs, const int* __restrict__ counts,
+                                                        const HeavyWork* __restrict__ heavy) {
     const long i = (long)blockIdx.x * 1024 + threadIdx.x;
     if (i < n) out[i] += block_prefix[blockIdx.x];
     if (i == 0) out[n] = (int)total_refs;  // sentinel: offsets[n] = number of references
+    if (heavy && i < n) {                  // rows the row kernel will skip: one work item per segment
+        const int cnt = counts[i];
+        if (cnt > kHeavyRefs) {
+            const HeavyWork hw = *heavy;
+            const int nseg = (cnt + kHeavyRefs - 1) / kHeavyRefs;
+            const int pos = atomicAdd(hw.count, nseg);
+            for (int sgm = 0; sgm < nseg && pos + sgm < hw.capacity; ++sgm) hw.items[pos + sgm] = make_int2((int)i, sgm);
+        }
+    }
 }
 
 // counts[] still holds the histogram; popping it hands out the slots of each bucket.
@@ -76,37 +107,6 @@ struct AdamFullConsts {
     float s1, lr1, reg1, s2, lr2, lambda, lr, bc, eps;
 };
 
-// ---- skewed reference counts -------------------------------------------------------------------------------------
-// One warp per row is the right shape while rows have ~10 references (uniform ids). Real id streams are Zipfian (the
-// most frequent word of a 51200 x 10 batch over 50k words is referenced ~45 000 times; BASELINE configs[4] draws
-// Zipf-skewed negatives), and one warp walking thousands of references is a millisecond-long tail. Rows with more
-// than kHeavyRefs references are therefore not processed by the row kernel: it appends one work item per segment of
-// kHeavyRefs references to a list, and pull_heavy_kernel gives every segment its own warp, publishes the segment's
-// partial sum and lets the LAST segment to arrive (per-row arrival counter) add the partials in segment order and
-// apply the row's update. No float atomics; the summation order inside a row is fixed by the bucket order.
-constexpr int kHeavyRefs = 64;
-
-struct HeavyWork {
-    int2* items;      // (row, segment), appended by the row kernel; null = feature off
-    int* count;       // number of items; the host zeroes it before the row kernel
-    float* part;      // [capacity][ld] partial sums (+ the squared-gradient partial at [ld - 4])
-    int* arrivals;    // arrival counter of a row, at the index of its first item; reset by the last arrival
-    int capacity;     // items allocated: >= 2 * references / kHeavyRefs + 1 cannot overflow
-    int ld;           // floats per partial: dim rounded up to 4, + 4
-};
-
-// Called by the row kernels (whole warp): true when `row` was handed to the heavy list.
-__device__ __forceinline__ bool defer_heavy_row(const HeavyWork& hw, long row, int cnt, int lane) {
-    if (hw.items == nullptr || cnt <= kHeavyRefs) return false;
-    const int nseg = (cnt + kHeavyRefs - 1) / kHeavyRefs;
-    int pos = 0;
-    if (lane == 0) pos = atomicAdd(hw.count, nseg);
-    pos = __shfl_sync(kFull, pos, 0);
-    for (int sgm = lane; sgm < nseg; sgm += kWarp)
-        if (pos + sgm < hw.capacity) hw.items[pos + sgm] = make_int2((int)row, sgm);
-    return true;
-}
-
 // One warp per table row. SRC rows (Y or gP) and the per-reference coefficient:
 //   ENTITY:  src row = ref / group, coef = (ref % group == 0 ? +1 : -1) * coefs[ref]   (group = R)
 //   WORD  :  src row = ref / group, coef = coefs[ref]                                  (group = n)
@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
                                                              const float* __restrict__ coefs,
                                                              const float* __restrict__ src, int group,
                                                              const AdamFullConsts k,
-                                                             const float* __restrict__ self_k, const HeavyWork hw) {
+                                                             const float* __restrict__ self_k, const int heavy_above) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim / VEC;
     for (long row = warp0; row < num_rows; row += nwarps) {
         const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
-        if (defer_heavy_row(hw, row, end - beg, lane)) continue;
+        if (end - beg > heavy_above) continue;   // pull_heavy_kernel owns this row
         // entity normalisation: the gradient carries - self_k[row] * theta[row] (entity_norm_prep_kernel)
         const float ks = self_k ? __ldg(self_k + row) : 0.f;
         float agg[NCH][VEC];
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
                                                        const float* __restrict__ coefs, const float* __restrict__ src,
                                                        int group, float decay, float lr, int touch_all,
                                                        float* __restrict__ acc, const float* __restrict__ ysq, float eps,
-                                                       const HeavyWork hw) {
+                                                       const int heavy_above) {
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
     for (long row = warp0; row < num_rows; row += nwarps) {
         const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
         if (beg == end && !touch_all) continue;
-        if (defer_heavy_row(hw, row, end - beg, lane)) continue;
+        if (end - beg > heavy_above) continue;   // pull_heavy_kernel owns this row
         float agg[NCH][VEC];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
