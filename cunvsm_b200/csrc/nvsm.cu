@@ -1005,13 +1005,13 @@ int build_all_buckets(nvsm_model* m, const BatchSlot* s, long B);
 int build_buckets(nvsm_model* m, const idx_t* ids, long total, long num_rows, int* counts, int* offsets, int* refs,
                   const HeavyWork* heavy, const HeavyWork* heavy_dev) {
     CU(cudaMemsetAsync(counts, 0, sizeof(int) * (num_rows + 1), m->stream));
-    const int g = (int)((total + 255) / 256);
-    LAUNCH(m, ref_count_kernel, g, 256, 0, ids, total, counts);
+    const int g = (int)((total + kAggThreads - 1) / kAggThreads);
+    LAUNCH(m, ref_count_kernel, g, kAggThreads, 0, ids, total, counts);
     const int nb = (int)((num_rows + 1023) / 1024);
     LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, counts, num_rows, offsets, m->scan_tmp, heavy_dev ? heavy->count : (int*)nullptr);
     LAUNCH(m, scan_blocks_kernel, 1, 1024, 0, m->scan_tmp, (long)nb, m->scan_tmp + 1024, (int*)nullptr, (int*)nullptr);
     LAUNCH(m, scan_add_kernel, nb, 1024, 0, offsets, num_rows, m->scan_tmp + 1024, total, (const int*)counts, heavy_dev);
-    LAUNCH(m, ref_fill_kernel, g, 256, 0, ids, total, offsets, counts, refs);
+    LAUNCH(m, ref_fill_kernel, g, kAggThreads, 0, ids, total, offsets, counts, refs);
     return 0;
 }
 

@@ -17,10 +17,32 @@
 
 namespace nvsm {
 
-__global__ void __launch_bounds__(256) ref_count_kernel(const idx_t* __restrict__ ids, long total,
-                                                        int* __restrict__ counts) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < total) atomicAdd(counts + __ldg(ids + c), 1);
+// Histogram of the batch's ids. Skewed id streams (Zipfian words, skewed negatives) would hammer one address with
+// tens of thousands of atomics — the L2 slice that owns it serialises them and stalls whatever else runs (measured: the
+// forward GEMM next to this kernel 54 -> 140 us under Zipf(1) word ids). Each block therefore first aggregates in a
+// small direct-mapped shared-memory table (slot claimed with a CAS on the id); ids that lose their slot to another id
+// go to global memory directly, as before. One global atomic per (block, hot id).
+constexpr int kAggSlots = 512;
+constexpr int kAggThreads = 1024;
+
+__device__ __forceinline__ int agg_slot(int id) { return (int)(((unsigned)id * 2654435761u) >> 23); }   // 9 bits
+
+__global__ void __launch_bounds__(kAggThreads) ref_count_kernel(const idx_t* __restrict__ ids, long total,
+                                                                int* __restrict__ counts) {
+    __shared__ int s_id[kAggSlots], s_cnt[kAggSlots];
+    for (int i = threadIdx.x; i < kAggSlots; i += kAggThreads) { s_id[i] = -1; s_cnt[i] = 0; }
+    __syncthreads();
+    const long c = (long)blockIdx.x * kAggThreads + threadIdx.x;
+    if (c < total) {
+        const int id = (int)__ldg(ids + c);
+        const int slot = agg_slot(id);
+        const int prev = atomicCAS(&s_id[slot], -1, id);
+        if (prev == -1 || prev == id) atomicAdd(&s_cnt[slot], 1);
+        else atomicAdd(counts + id, 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAggSlots; i += kAggThreads)
+        if (s_cnt[i] > 0) atomicAdd(counts + s_id[i], s_cnt[i]);
 }
 
 // ---- skewed reference counts -------------------------------------------------------------------------------------
@@ -92,15 +114,31 @@ __global__ void __launch_bounds__(1024) scan_add_kernel(int* __restrict__ out, l
     }
 }
 
-// counts[] still holds the histogram; popping it hands out the slots of each bucket.
-__global__ void __launch_bounds__(256) ref_fill_kernel(const idx_t* __restrict__ ids, long total,
-                                                       const int* __restrict__ offsets, int* __restrict__ counts,
-                                                       int* __restrict__ refs) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total) return;
-    const idx_t id = __ldg(ids + c);
-    const int pos = atomicSub(counts + id, 1) - 1;
-    refs[offsets[id] + pos] = (int)c;
+// counts[] still holds the histogram; popping it hands out the slots of each bucket. Same block-level aggregation as
+// ref_count_kernel: a block reserves a range of a hot bucket with ONE atomicSub and its threads take consecutive slots.
+__global__ void __launch_bounds__(kAggThreads) ref_fill_kernel(const idx_t* __restrict__ ids, long total,
+                                                               const int* __restrict__ offsets, int* __restrict__ counts,
+                                                               int* __restrict__ refs) {
+    __shared__ int s_id[kAggSlots], s_cnt[kAggSlots], s_base[kAggSlots];
+    for (int i = threadIdx.x; i < kAggSlots; i += kAggThreads) { s_id[i] = -1; s_cnt[i] = 0; }
+    __syncthreads();
+    const long c = (long)blockIdx.x * kAggThreads + threadIdx.x;
+    int id = -1, slot = -1, rank = 0;
+    if (c < total) {
+        id = (int)__ldg(ids + c);
+        slot = agg_slot(id);
+        const int prev = atomicCAS(&s_id[slot], -1, id);
+        if (prev == -1 || prev == id) rank = atomicAdd(&s_cnt[slot], 1);
+        else slot = -1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAggSlots; i += kAggThreads)
+        if (s_cnt[i] > 0) s_base[i] = atomicSub(counts + s_id[i], s_cnt[i]);
+    __syncthreads();
+    if (c < total) {
+        const int pos = slot >= 0 ? s_base[slot] - 1 - rank : atomicSub(counts + id, 1) - 1;
+        refs[offsets[id] + pos] = (int)c;
+    }
 }
 
 struct AdamFullConsts {
@@ -327,10 +365,82 @@ struct SgdApply {
     }
 };
 
-// One warp per (row, segment) item of the heavy list; see HeavyWork. Four references are in flight per lane (the
+constexpr int kHeavyGroup = 16;   // segments per first-level reduction group of pull_heavy_kernel
+
+// Rows a lane keeps in flight in pull_heavy_kernel (register budget: 128 at two blocks per SM).
+template <int VEC, int NCH>
+__host__ __device__ constexpr int heavy_in_flight() { return VEC * NCH >= 32 ? 1 : (VEC * NCH >= 12 ? 2 : 4); }
+
+// partial sum of a warp -> part[0 .. dim) (+ the scalar at [ld - 4]); made visible device-wide before returning
+template <int VEC, int NCH>
+__device__ __forceinline__ void store_partial(float* p, int ld, int lane, int nvec, const float (&agg)[NCH][VEC], float sq) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = lane + j * kWarp;
+        if (c < nvec) store_vec<VEC>(p + c * VEC, agg[j]);
+    }
+    __syncwarp();   // (every lane has read the scalar of a slot that is being overwritten)
+    if (lane == 0) p[ld - 4] = sq;
+    __threadfence();
+    __syncwarp();
+}
+
+// Count this warp in at `counter`; true for the warp that completes `expected` arrivals (it also re-arms the counter
+// for the next step). The fences pair the partial stores of the others with the loads of the last one.
+__device__ __forceinline__ bool arrive_last(int* counter, int expected, int lane) {
+    int last = 0;
+    if (lane == 0) {
+        last = atomicAdd(counter, 1) == expected - 1;
+        if (last) *counter = 0;
+    }
+    last = __shfl_sync(kFull, last, 0);
+    if (last) __threadfence();
+    return last != 0;
+}
+
+// agg = p[0] + p[stride] + ... (count partials of width ld, in that order; heavy_in_flight rows in flight per lane)
+template <int VEC, int NCH>
+__device__ __forceinline__ void sum_partials(const float* p, long stride, int ld, int count, int lane, int nvec,
+                                             float (&agg)[NCH][VEC], float& sq) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+    sq = 0.f;
+    constexpr int U = heavy_in_flight<VEC, NCH>();
+    for (int k0 = 0; k0 < count; k0 += U) {
+        float x[U][NCH][VEC], s4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float* const pu = p + (long)min(k0 + u, count - 1) * stride;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const int c = lane + j * kWarp;
+                if (c < nvec) load_vec_cg<VEC>(pu + c * VEC, x[u][j]);
+            }
+            s4[u] = __ldcg(pu + ld - 4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (k0 + u < count) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+                    if (c < nvec) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) agg[j][q] += x[u][j][q];
+                    }
+                }
+                sq += s4[u];
+            }
+        }
+    }
+}
+
+// One warp per (row, segment) item of the heavy list; see HeavyWork. Several references are in flight per lane (the
 // FMAs still run in reference order), since here the walk is long enough for load latency to be the limit.
 template <int VEC, int NCH, bool ENTITY, typename Apply>
-__global__ void __launch_bounds__(256) pull_heavy_kernel(int dim, const int* __restrict__ offsets,
+__global__ void __launch_bounds__(256, 2) pull_heavy_kernel(int dim, const int* __restrict__ offsets,
                                                          const int* __restrict__ refs, const float* __restrict__ coefs,
                                                          const float* __restrict__ src, int group,
                                                          const float* __restrict__ ysq, const HeavyWork hw,
@@ -364,23 +474,24 @@ __global__ void __launch_bounds__(256) pull_heavy_kernel(int dim, const int* __r
                 my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
                 if (ysq) sq += cf * cf * __ldg(ysq + my_src);
             }
-            for (int t = 0; t < cnt; t += 4) {   // lanes >= cnt hold source row 0: loaded, never added
-                int srow[4];
-                float cf[4], x[4][NCH][VEC];
+            constexpr int U = heavy_in_flight<VEC, NCH>();
+            for (int t = 0; t < cnt; t += U) {   // lanes >= cnt hold source row 0: loaded, never added
+                int srow[U];
+                float cf[U], x[U][NCH][VEC];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     srow[u] = __shfl_sync(kFull, my_src, (t + u) & 31);
                     cf[u] = __shfl_sync(kFull, my_coef, (t + u) & 31);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int j = 0; j < NCH; ++j) {
                         const int c = lane + j * kWarp;
                         if (c < nvec) load_vec_ro<VEC>(src + (long)srow[u] * dim + c * VEC, x[u][j]);
                     }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
                     for (int j = 0; j < NCH; ++j) {
                         const int c = lane + j * kWarp;
@@ -391,42 +502,32 @@ __global__ void __launch_bounds__(256) pull_heavy_kernel(int dim, const int* __r
                     }
             }
         }
-        // publish this segment's partial, then count it in
-        float* const mine = hw.part + (long)item * hw.ld;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            const int c = lane + j * kWarp;
-            if (c < nvec) store_vec<VEC>(mine + c * VEC, agg[j]);
-        }
+        // Publish this segment's partial and count it in. The partials of a row are added up in two levels so that
+        // no warp walks hundreds of them: the last segment to arrive in a group of kHeavyGroup consecutive segments
+        // adds the group's partials (in segment order) and publishes the group sum in the group's first slot; the
+        // last GROUP to arrive adds the group sums (in group order) and applies the row update.
+        const int grp = it.y / kHeavyGroup;
+        const int gfirst = base + grp * kHeavyGroup;                    // item index of the group's first segment
+        const int gsize = min(kHeavyGroup, nseg - grp * kHeavyGroup);
+        const int ngrp = (nseg + kHeavyGroup - 1) / kHeavyGroup;
         sq = warp_sum(sq);
-        if (lane == 0) mine[hw.ld - 4] = sq;
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) last = atomicAdd(hw.arrivals + base, 1) == nseg - 1;
-        last = __shfl_sync(kFull, last, 0);
-        if (!last) continue;
-        __threadfence();
-#pragma unroll
-        for (int j = 0; j < NCH; ++j)
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
-        sq = 0.f;
-        for (int sgm = 0; sgm < nseg; ++sgm) {
-            const float* const p = hw.part + (long)(base + sgm) * hw.ld;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                const int c = lane + j * kWarp;
-                if (c < nvec) {
-                    float x[VEC];
-                    load_vec_cg<VEC>(p + c * VEC, x);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) agg[j][q] += x[q];
-                }
-            }
-            sq += __ldcg(p + hw.ld - 4);
+        // level 0: my partial -> my slot, group counter; level 1: the group sum -> the group's first slot, row counter
+        long slot = item, first = gfirst, stride = hw.ld;
+        int* counter = hw.arrivals + gfirst;
+        int expected = gsize;
+        bool mine_to_apply = false;
+        for (int level = 0; level < 2; ++level) {
+            store_partial<VEC, NCH>(hw.part + slot * hw.ld, hw.ld, lane, nvec, agg, sq);
+            if (!arrive_last(counter, expected, lane)) break;
+            sum_partials<VEC, NCH>(hw.part + first * hw.ld, stride, hw.ld, expected, lane, nvec, agg, sq);
+            if (level == 1 || ngrp == 1) { mine_to_apply = true; break; }
+            // (row counter: the slot after the row's first item — a heavy row has at least two segments, and group
+            // counters sit at multiples of kHeavyGroup >= 2)
+            slot = gfirst; first = base; stride = (long)hw.ld * kHeavyGroup;
+            counter = hw.arrivals + base + 1;
+            expected = ngrp;
         }
-        if (lane == 0) hw.arrivals[base] = 0;
+        if (!mine_to_apply) continue;
         apply.template run<VEC, NCH>(row, dim, lane, nvec, agg, sq);
     }
 }
