@@ -111,6 +111,12 @@ __device__ __forceinline__ float fast_div(float a, float b) {
     return r;
 }
 
+// Block-level aggregation of per-id atomics (bucket build, per-object scalar accumulators): ids hash into a small
+// direct-mapped shared-memory table; see ref_count_kernel.
+constexpr int kAggSlots = 512;
+constexpr int kAggThreads = 1024;
+__device__ __forceinline__ int agg_slot(int id) { return (int)(((unsigned)id * 2654435761u) >> 23); }   // 9 bits
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

@@ -848,16 +848,38 @@ __global__ void __launch_bounds__(256) row_meansq_kernel(const float* __restrict
 
 // With entity normalisation the column is (mult / |e|) * (y - s e / |e|), s = e.y / |e| (mult already holds
 // mult / |e|): mean_k of its square = mult^2 * (mean_k y^2 - s^2 / dd).
+// acc[id] += v for every thread of the block (id < 0: nothing), with the block's contributions to one id combined
+// in shared memory first: a Zipfian id stream otherwise lands tens of thousands of atomics on one address.
+// Call with all threads of a kAggThreads block.
+__device__ __forceinline__ void block_aggregated_add(float* __restrict__ acc, int id, float v) {
+    __shared__ int s_id[kAggSlots];
+    __shared__ float s_sum[kAggSlots];
+    for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) { s_id[i] = -1; s_sum[i] = 0.f; }
+    __syncthreads();
+    if (id >= 0) {
+        const int slot = agg_slot(id);
+        const int prev = atomicCAS(&s_id[slot], -1, id);
+        if (prev == -1 || prev == id) atomicAdd(&s_sum[slot], v);
+        else atomicAdd(acc + id, v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x)
+        if (s_id[i] >= 0) atomicAdd(acc + s_id[i], s_sum[i]);
+}
+
 __global__ void entity_scalar_scatter_kernel(const idx_t* __restrict__ ids, const float* __restrict__ mult,
                                              const float* __restrict__ ysq, long total, int R, float scale,
                                              float* __restrict__ acc, const float* __restrict__ escore,
                                              float inv_dim) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total) return;
-    const float m = mult[c];
-    float q = ysq[c / R];
-    if (escore) { const float sc = escore[c]; q = fmaxf(q - sc * sc * inv_dim, 0.f); }
-    atomicAdd(acc + ids[c], scale * (m * m * q));
+    float v = 0.f;
+    if (c < total) {
+        const float m = mult[c];
+        float q = ysq[c / R];
+        if (escore) { const float sc = escore[c]; q = fmaxf(q - sc * sc * inv_dim, 0.f); }
+        v = scale * (m * m * q);
+    }
+    block_aggregated_add(acc, c < total ? (int)ids[c] : -1, v);
 }
 
 // =====================================================================================
@@ -956,8 +978,7 @@ __global__ void word_scalar_scatter_kernel(const idx_t* __restrict__ ids, const 
                                            const float* __restrict__ msq, long total, int n, float scale,
                                            float* __restrict__ acc) {
     const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= total) return;
-    atomicAdd(acc + ids[c], scale * fw[c] * msq[c / n]);
+    block_aggregated_add(acc, c < total ? (int)ids[c] : -1, c < total ? scale * fw[c] * msq[c / n] : 0.f);
 }
 
 // =====================================================================================

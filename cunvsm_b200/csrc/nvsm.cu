@@ -99,7 +99,7 @@ struct nvsm_model {
     cudaEvent_t buckets_ready = nullptr, buckets_consumed = nullptr;
     // fused steps: the entity-table update only needs the forward pass, so it runs on the auxiliary stream under
     // batch-norm backward and the two backward GEMMs of the main stream (start_entity_update)
-    cudaEvent_t score_done = nullptr, entity_done = nullptr;
+    cudaEvent_t score_done = nullptr, entity_done = nullptr, word_rows_done = nullptr;
     bool entity_async = false, entity_async_running = false;
     float* rowtmp_e = nullptr;   // entity-side row scratch (the word side may run concurrently)
     bool buckets_in_flight = false, buckets_ever_consumed = false;
@@ -945,7 +945,7 @@ int scatter_entity_meansq(nvsm_model* m, float* acc, float scale) {
     LAUNCH(m, row_meansq_act_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->Z,
            act_params(m, m->cfg.batch_normalization != 0), m->B, m->dd, inv_dim, tmp);
     const long total = m->B * m->R;
-    LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->ids, m->mult, tmp,
+    LAUNCH(m, entity_scalar_scatter_kernel, (int)((total + kAggThreads - 1) / kAggThreads), kAggThreads, 0, m->cur->ids, m->mult, tmp,
            total, m->R, scale, acc, m->l2_entity ? (const float*)m->escore : (const float*)nullptr, inv_dim);
     return 0;
 }
@@ -954,7 +954,7 @@ int scatter_word_meansq(nvsm_model* m, float* acc, float scale) {
     const float inv_dim = (float)std::exp(-std::log((double)m->dw));
     LAUNCH(m, row_meansq_kernel, grid_for(m, m->B, 8, 8), 256, 0, m->gP, m->B, m->dw, inv_dim, m->rowtmp);
     const long total = m->B * m->n;
-    LAUNCH(m, word_scalar_scatter_kernel, (int)((total + 255) / 256), 256, 0, m->cur->features, m->cur->fweights,
+    LAUNCH(m, word_scalar_scatter_kernel, (int)((total + kAggThreads - 1) / kAggThreads), kAggThreads, 0, m->cur->features, m->cur->fweights,
            m->rowtmp, total, m->n, scale, acc);
     return 0;
 }
@@ -1023,6 +1023,36 @@ int build_all_buckets(nvsm_model* m, const BatchSlot* s, long B) {
     return build_buckets(m, s->features, B * m->n, m->V, m->w_counts, m->w_offsets, m->w_refs, &m->heavy_w, on ? m->heavy_w_dev : nullptr);
 }
 
+// In a fused step the entity table is updated on the auxiliary stream (start_entity_update). The heavy-row kernel of
+// the WORD table goes there as well, behind it: the projection update on the main stream then does not wait for it —
+// with uniform ids it is an empty launch, with skewed ids tens of microseconds of work that now overlap — and
+// update()'s join (entity_done, re-recorded here) orders everything after the step behind it.
+struct HeavyStream {
+    nvsm_model* m;
+    cudaStream_t saved;
+    bool cross;
+};
+
+int heavy_stream_begin(nvsm_model* m, bool entities, HeavyStream* hs) {
+    hs->m = m;
+    hs->saved = m->stream;
+    hs->cross = !entities && m->entity_async && !m->entity_async_running && m->stream != m->aux_stream;
+    if (hs->cross) {
+        CU(cudaEventRecord(m->word_rows_done, m->stream));
+        CU(cudaStreamWaitEvent(m->aux_stream, m->word_rows_done, 0));
+        m->stream = m->aux_stream;
+    }
+    return 0;
+}
+
+int heavy_stream_end(HeavyStream* hs, int rc) {
+    if (!hs->cross) return rc;
+    hs->m->stream = hs->saved;
+    if (rc) return rc;
+    CU(cudaEventRecord(hs->m->entity_done, hs->m->aux_stream));
+    return 0;
+}
+
 template <int VEC, int NCH>
 int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int grid = grid_for(m, entities ? m->D : m->V, 8, 8);
@@ -1041,9 +1071,17 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     } else {
         LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
                m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
-        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
-               (const float*)m->cur->fweights, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
-               AdamFullApply{m->W, m->optW.m, m->optW.v, k, (const float*)nullptr});
+        if (row_hw) {
+            HeavyStream hs;
+            TRY(heavy_stream_begin(m, entities, &hs));
+            const int rc = [&]() -> int {
+                LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets,
+                       m->w_refs, (const float*)m->cur->fweights, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
+                       AdamFullApply{m->W, m->optW.m, m->optW.v, k, (const float*)nullptr});
+                return 0;
+            }();
+            TRY(heavy_stream_end(&hs, rc));
+        }
     }
     return 0;
 }
@@ -1065,9 +1103,17 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
     } else {
         LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
                (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
-        if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets, m->w_refs,
-               word_coefs, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
-               SgdApply{m->W, decay, lr, (float*)nullptr, 1e-6f});
+        if (row_hw) {
+            HeavyStream hs;
+            TRY(heavy_stream_begin(m, entities, &hs));
+            const int rc = [&]() -> int {
+                LAUNCH(m, (pull_heavy_kernel<VEC, NCH, false, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dw, m->w_offsets,
+                       m->w_refs, word_coefs, (const float*)m->gP, m->n, (const float*)nullptr, *hw,
+                       SgdApply{m->W, decay, lr, (float*)nullptr, 1e-6f});
+                return 0;
+            }();
+            TRY(heavy_stream_end(&hs, rc));
+        }
     }
     return 0;
 }
@@ -1712,6 +1758,7 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
     if (m->score_done) cudaEventDestroy(m->score_done);
     if (m->entity_done) cudaEventDestroy(m->entity_done);
+    if (m->word_rows_done) cudaEventDestroy(m->word_rows_done);
     if (m->rowtmp_e) cudaFree(m->rowtmp_e);
     if (m->buckets_ready) cudaEventDestroy(m->buckets_ready);
     if (m->buckets_consumed) cudaEventDestroy(m->buckets_consumed);
@@ -1759,6 +1806,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         CU(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&m->score_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->entity_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->word_rows_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buckets_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->buckets_consumed, cudaEventDisableTiming));
         const long V = m->V, D = m->D, maxB = m->maxB;

@@ -22,10 +22,6 @@ namespace nvsm {
 // forward GEMM next to this kernel 54 -> 140 us under Zipf(1) word ids). Each block therefore first aggregates in a
 // small direct-mapped shared-memory table (slot claimed with a CAS on the id); ids that lose their slot to another id
 // go to global memory directly, as before. One global atomic per (block, hot id).
-constexpr int kAggSlots = 512;
-constexpr int kAggThreads = 1024;
-
-__device__ __forceinline__ int agg_slot(int id) { return (int)(((unsigned)id * 2654435761u) >> 23); }   // 9 bits
 
 __global__ void __launch_bounds__(kAggThreads) ref_count_kernel(const idx_t* __restrict__ ids, long total,
                                                                 int* __restrict__ counts) {
