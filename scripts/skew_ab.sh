@@ -22,5 +22,3 @@ for n in sorted(glob.glob("gpurun_out/ab_${T}_*.json")):
     except Exception as e:
         print(n, "ERR", e)
 PY
-timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_${T}_zipf.csv \
-    python bench.py --steps 2 --warmup 3 --no_cpu_baseline --no_alt --zipf_words 1.0 > gpurun_out/launches_${T}_zipf.log 2>&1; stamp "ncu zipf launch list rc=$?"
