@@ -22,11 +22,9 @@ class LabelGenerator {
  public:
   virtual ~LabelGenerator() {}
 
-  virtual void generate(const EntityIdxType* const labels,
-                        const size_t num_objects,
-                        const size_t num_labels,
-                        const size_t num_negative_labels,
-                        std::vector<EntityIdxType>* const instance_entities,
+  // instance_entities[i * (z + 1)] = labels[i], then z negatives out of [0, num_objects); consumes *rng in draw order
+  virtual void generate(const EntityIdxType* const labels, const size_t num_objects, const size_t num_labels,
+                        const size_t num_negative_labels, std::vector<EntityIdxType>* const instance_entities,
                         RNG* const rng) const = 0;
 
   // Device sampler support: true when nvsm_step_sampled reproduces generate() bit for bit, with the cumulative
