@@ -93,3 +93,46 @@ def test_parser_rejects_truncated_file(tmp_path):
     path.write_bytes(data[:-2])
     r = subprocess.run([tool(), "print", str(path)], capture_output=True, text=True)
     assert r.returncode != 0 and "not an lse.Metadata message" in (r.stderr + r.stdout)
+
+
+def test_python_loader_reads_meta_and_dump(tmp_path):
+    """cunvsm_b200/io.py: the `_meta` parser agrees with the protobuf runtime, and DumpedModel reproduces the
+    reference's query-side arithmetic (py/nvsm/base.py: query_representation / infer) and the oracle's Model::infer."""
+    from cunvsm_b200 import io
+    from oracle import binding as O
+    meta_cls = metadata_class()
+    meta = meta_cls()
+    V, D, dw, dd = 40, 12, 8, 6
+    for k in range(V):
+        meta.term.add(index_term_id=1000 + 3 * k, model_term_id=k, term_frequency=5 + k)
+    for j in range(D):
+        meta.object.add(index_object_id=70000 - j, model_object_id=j)
+    meta.total_terms = sum(5 + k for k in range(V))
+    out = str(tmp_path / "model")
+    with open(out + "_meta", "wb") as f:
+        f.write(meta.SerializeToString())
+    parsed = io.load_meta(out)
+    assert parsed["total_terms"] == meta.total_terms
+    assert parsed["term"] == [(t.index_term_id, t.model_term_id, t.term_frequency) for t in meta.term]
+    assert parsed["object"] == [(o.index_object_id, o.model_object_id) for o in meta.object]
+    # negative ids and unknown fields survive
+    assert io.parse_metadata(b"\x0a\x0b\x08\xfd\xff\xff\xff\xff\xff\xff\xff\xff\x01\x20\x07")["term"] == [(-3, 0, 0)]
+
+    om = O.Model(V, D, dw, dd, nonlinearity=O.TANH, batch_normalization=False, dtype=np.float32)
+    om.initialize(3)
+    rng = np.random.default_rng(0)
+    om.set("b", rng.normal(size=dd).astype(np.float32))
+    names = dict(zip(io.DATASETS, ("W", "E", "T", "b")))
+    for name, short in names.items():
+        a = np.asarray(om.get(short), dtype=np.float32)
+        shape = {"W": (V, dw), "E": (D, dd), "T": (dw, dd), "b": (1, dd)}[short]
+        np.save("%s_%d.%s.npy" % (out, 2, name), a.reshape(shape))
+    model = io.load_model(parsed, out, 2)
+    assert (model.num_terms, model.term_repr_size, model.num_objects, model.object_repr_size) == (V, dw, D, dd)
+    query = [1000 + 3 * 4, 1000 + 3 * 9, 999999, 1000 + 3 * 17]          # one out-of-vocabulary term
+    projected = model.infer(model.query_representation(query))
+    expect = om.infer(np.array([[4, 9, 17]]), 3)[0]                          # gather-mean -> T p + b -> tanh
+    np.testing.assert_allclose(projected, expect, rtol=2e-5, atol=1e-6)
+    ranked = model.rank(query, 3)
+    assert len(ranked) == 3 and ranked[0][0] >= ranked[1][0] >= ranked[2][0] and all(70000 - D < d <= 70000 for _, d in ranked)
+    assert io.load_model(parsed, out, 2, strict=True).query_representation(query) is None
