@@ -71,6 +71,7 @@ def lib(native=False):
         f("bn_destroy", [vp])
         f("bn_forward", [vp, pf, pf, cl, cl, pf])
         f("bn_backward", [vp, pf, pf, cl, pf, pf])
+        f("normalizer", [pf, pf, cl, cl, pf, pf])
         f("repr_updater_create", [ci, ci, cl, cl, ct, ct, ct], vp)
         f("repr_updater_destroy", [vp])
         f("repr_updater_update", [vp, pf, ci, ppf, ppl, pl, pl, ppf, ct, ct])
@@ -180,6 +181,19 @@ def update_dense(param, grad, lr, lam, square=False):
     grad = np.ascontiguousarray(grad, dtype=param.dtype)
     getattr(lib(), "oracle_update_dense_" + suf)(_p(param, ct), param.size, _p(grad, ct), lr, lam, int(square))
     return param
+
+
+def normalizer(x, grad_output=None, dtype=np.float64):
+    """Normalizer::forward (+ backward) of cpp/cuda_utils.cu:3-141 on instances x[N][dim]: (y, dx or None)."""
+    suf, ct = _dt(dtype)
+    x = np.ascontiguousarray(x, dtype=dtype)
+    N, dim = x.shape
+    y = np.zeros_like(x)
+    dx = np.zeros_like(x) if grad_output is not None else None
+    dy = np.ascontiguousarray(grad_output, dtype=dtype) if grad_output is not None else None
+    getattr(lib(), "oracle_normalizer_" + suf)(_p(x, ct), _p(dy, ct) if dy is not None else None, N, dim, _p(y, ct),
+                                               _p(dx, ct) if dx is not None else None)
+    return y, dx
 
 
 class BatchNorm:

@@ -178,6 +178,39 @@ void transform_storage_update(F* T, size_t nT, F* b, size_t nb, const F* gT,
 // training mode, gamma == 1, beta = transform bias; formulas pinned by
 // cpp/cudnn_utils_tests.cu:143-176).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// L2 Normalizer (cpp/cuda_utils.cu:3-141; golden vectors cpp/cuda_utils_tests.cu:51-92).
+// Instances are the columns of the reference's matrices = rows here: x[N][dim].
+//   forward  (:12-45):  norms[i] = sqrt(sum_k x[i][k]^2);  y[i] = x[i] / norms[i]
+//   backward (:69-128): dx[i] = (dy[i] * norms[i]^2 - x[i] * (x[i] . dy[i])) / norms[i]^3   (x = the cached INPUT)
+// ---------------------------------------------------------------------------
+template <typename F>
+struct Normalizer {
+    std::vector<F> norms, input_cache;
+    size_t dim = 0;
+
+    // y may alias x (the reference's own test normalises in place).
+    void forward(const F* x, size_t N, size_t dim_, F* y) {
+        dim = dim_;
+        input_cache.assign(x, x + N * dim);
+        norms.assign(N, F(0));
+        for (size_t i = 0; i < N; ++i) {
+            F s = 0;
+            for (size_t k = 0; k < dim; ++k) s += input_cache[i * dim + k] * input_cache[i * dim + k];
+            norms[i] = std::sqrt(s);
+            for (size_t k = 0; k < dim; ++k) y[i * dim + k] = input_cache[i * dim + k] / norms[i];
+        }
+    }
+    void backward(const F* dy, size_t N, F* dx) const {
+        for (size_t i = 0; i < N; ++i) {
+            F cross = 0;
+            for (size_t k = 0; k < dim; ++k) cross += input_cache[i * dim + k] * dy[i * dim + k];
+            const F n2 = norms[i] * norms[i], n3 = std::pow(norms[i], F(3.0));
+            for (size_t k = 0; k < dim; ++k) dx[i * dim + k] = (dy[i * dim + k] * n2 + F(-1.0) * (input_cache[i * dim + k] * cross)) / n3;
+        }
+    }
+};
+
 template <typename F>
 struct BatchNorm {
     size_t C = 0;

@@ -138,6 +138,12 @@ static Config to_config(const oracle_config* c) {
     void oracle_bn_backward_##SUF(void* p, const F* dy, const F* x, long N, F* dx, F* dbias) {  \
         ((BatchNorm<F>*)p)->backward(dy, x, N, dx, dbias);                                      \
     }                                                                                           \
+    /* L2 Normalizer: forward into y (may alias x) + backward of dy against the cached input */ \
+    void oracle_normalizer_##SUF(const F* x, const F* dy, long N, long dim, F* y, F* dx) {      \
+        Normalizer<F> nz;                                                                       \
+        nz.forward(x, N, dim, y);                                                               \
+        if (dy && dx) nz.backward(dy, N, dx);                                                   \
+    }                                                                                           \
     /* Optimisers as free-standing objects (updates_tests.cu style). */                         \
     void* oracle_repr_updater_create_##SUF(int method, int adam_mode, long num_objects,         \
                                            long dim, F b1, F b2, F eps) {                       \

@@ -59,6 +59,16 @@ def main():
         "m_bias_t2": literals(ut, 415, 417),
         "v_bias_t2": literals(ut, 421, 423),
     }
+    cu = "cpp/cuda_utils_tests.cu"
+    with open(os.path.join(REF, cu)) as f:
+        block = "".join(f.readlines()[81:92])          # the ElementsAre(...) of grad_input, :82-92
+    out["normalizer"] = {
+        "source": cu + ":51-92",
+        "input": [[1, 2, 3, 4, 5], [6, 7, 8, 9, 10]],
+        "grad_output": [[10000, 10001, 10002, 10003, 10004], [10005, 10006, 10007, 10008, 10009]],
+        "grad_input": [float(x) for x in re.findall(r"(-?[0-9]+\.[0-9]+)", block)],
+    }
+    assert len(out["normalizer"]["grad_input"]) == 10, out["normalizer"]["grad_input"]
     assert len(out["transform_backward"]["grad_transform"]) == 6
     assert len(out["transform_backward"]["grad_bias"]) == 3
     assert len(out["transform_backward"]["grad_phrase"]) == 64

@@ -326,3 +326,16 @@ def test_glorot_range_and_stream():
     for _ in range(21):
         x = (x * 16807) % 2147483647
     assert st == x
+
+
+def test_normalizer_golden():  # cpp/cuda_utils_tests.cu:51-92
+    """L2 Normalizer forward (closed form) and backward (the reference's ten literals), float64 like the reference's
+    test build."""
+    g = GOLD["normalizer"]
+    x = np.array(g["input"], dtype=np.float64)
+    y, dx = O.normalizer(x, np.array(g["grad_output"], dtype=np.float64))
+    np.testing.assert_allclose(y, x / np.sqrt((x * x).sum(axis=1, keepdims=True)), rtol=1e-15)
+    np.testing.assert_allclose(dx.ravel(), g["grad_input"], rtol=1e-12)
+    # in place, like the reference's own call (normalizer.forward(input, &input))
+    y32, dx32 = O.normalizer(x, np.array(g["grad_output"]), dtype=np.float32)
+    np.testing.assert_allclose(dx32.ravel(), g["grad_input"], rtol=2e-3)     # float32: |dy| ~ 1e4 cancels to ~1e2
