@@ -19,7 +19,27 @@
 
 #include "cuNVSM/model.h"
 
+// NVTX ranges with the reference's names (Epoch / Batch / FetchData / ComputeCost / ComputeGradients /
+// UpdateParameters, cpp/main.cu:386-431,463,582,619). nvtx3 is header-only and a no-op without a profiler attached.
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define NVSM_HAVE_NVTX 1
+#endif
+#endif
+
 namespace {
+
+struct NvtxRange {
+#ifdef NVSM_HAVE_NVTX
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+#else
+  explicit NvtxRange(const char*) {}
+#endif
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Flags {
   std::map<std::string, std::string> values;
@@ -245,15 +265,24 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
     const auto t0 = std::chrono::steady_clock::now();
     std::unique_ptr<typename ObjectiveT::ForwardResultType> previous;
     while (Ops::has_next(sources)) {
-      Ops::clear(&batch);
-      Ops::next(sources, &batch);
+      NvtxRange batch_range("Batch");
+      {
+        NvtxRange fetch_range("FetchData");
+        Ops::clear(&batch);
+        Ops::next(sources, &batch);
+      }
       if (Ops::num_instances(batch) % max_threads_per_block != 0) {
         std::fprintf(stderr, "Skipping Batch #%zu as it is not a multiple of %ld (%zu instances).\n", *num_batches,
                      max_threads_per_block, Ops::num_instances(batch));
       } else {
-        std::unique_ptr<typename ObjectiveT::ForwardResultType> result(model.compute_cost(batch, &rng));
-        std::unique_ptr<TextEntity::Gradients> gradients(model.compute_gradients(*result));
-        if (backpropagate) model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
+        std::unique_ptr<typename ObjectiveT::ForwardResultType> result;
+        std::unique_ptr<TextEntity::Gradients> gradients;
+        { NvtxRange r("ComputeCost"); result.reset(model.compute_cost(batch, &rng)); }
+        { NvtxRange r("ComputeGradients"); gradients.reset(model.compute_gradients(*result)); }
+        if (backpropagate) {
+          NvtxRange r("UpdateParameters");
+          model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
+        }
         // read the previous batch's loss while this one runs (the reference synchronises every batch)
         if (previous) {
           const float c = previous->get_cost();
@@ -284,6 +313,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
     if (device_rng) model.sync_rng(&rng);
     Ops::reset(sources);
     if (device_rng) model.use_device_sampler(&rng);
+    NvtxRange epoch_range("Epoch");
     iterate(true, &nb, &cost, &secs);
     total_batches += nb; total_secs += secs;
     std::printf("Epoch #%ld: mean cost %g; %.2f batches/second, %.0f n-grams/second\n", epoch, cost / nb,
