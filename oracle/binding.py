@@ -72,6 +72,7 @@ def lib(native=False):
         f("bn_forward", [vp, pf, pf, cl, cl, pf])
         f("bn_backward", [vp, pf, pf, cl, pf, pf])
         f("normalizer", [pf, pf, cl, cl, pf, pf])
+        f("similarity_step", [pf, cl, pl, pf, cl, ci, pf, pf], ct)
         f("repr_updater_create", [ci, ci, cl, cl, ct, ct, ct], vp)
         f("repr_updater_destroy", [vp])
         f("repr_updater_update", [vp, pf, ci, ppf, ppl, pl, pl, ppf, ct, ct])
@@ -181,6 +182,22 @@ def update_dense(param, grad, lr, lam, square=False):
     grad = np.ascontiguousarray(grad, dtype=param.dtype)
     getattr(lib(), "oracle_update_dense_" + suf)(_p(param, ct), param.size, _p(grad, ct), lr, lam, int(square))
     return param
+
+
+def similarity_step(table, pair_ids, weights, clip_sigmoid=True, dtype=np.float64):
+    """RepresentationSimilarity::Objective compute_cost + compute_gradients (cpp/objective.cu:485-672) over
+    table[rows][dim]: returns (cost, probs[N], grad[2N][dim]) — grad rows belong to pair_ids.ravel(), window 1."""
+    suf, ct = _dt(dtype)
+    table = np.ascontiguousarray(table, dtype=dtype)
+    ids = np.ascontiguousarray(pair_ids, dtype=np.int64).ravel()
+    w = np.ascontiguousarray(weights, dtype=dtype)
+    N = w.size
+    assert ids.size == 2 * N
+    probs = np.zeros(N, dtype=dtype)
+    grad = np.zeros((2 * N, table.shape[1]), dtype=dtype)
+    cost = getattr(lib(), "oracle_similarity_step_" + suf)(_p(table, ct), table.shape[1], _pl(ids), _p(w, ct), N,
+                                                           int(clip_sigmoid), _p(probs, ct), _p(grad, ct))
+    return float(cost), probs, grad
 
 
 def normalizer(x, grad_output=None, dtype=np.float64):

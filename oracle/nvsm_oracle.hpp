@@ -179,6 +179,40 @@ void transform_storage_update(F* T, size_t nT, F* b, size_t nb, const F* gT,
 // cpp/cudnn_utils_tests.cu:143-176).
 // ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
+// RepresentationSimilarity objective (EntityEntity / TermTerm; cpp/objective.cu:485-672) on one table[rows][dim]:
+// pairs (ids[2i], ids[2i+1]) with weight w[i].
+//   compute_cost (:487-573): s_i = <table[a_i], table[b_i]>, p_i = truncated_sigmoid(s_i, clip ? 1e-7 : 0),
+//                            mass_i = w_i log p_i;  cost = -(1/N) sum_i mass_i (intermediate_results.cu:80-124)
+//   compute_gradients (:575-672): mult_i = w_i * sigmoid_to_log_sigmoid_deriv(p_i, clip ? 1e-6 : 0) * exp(-log N);
+//                            the gradient column of a pair member is mult_i times its PARTNER's row
+//                            (flip_adjacent_columns), ascent direction; applied like any window-1 sparse gradient.
+// ---------------------------------------------------------------------------
+template <typename F>
+F similarity_step(const F* table, size_t dim, const long* ids, const F* weights, size_t N, bool clip_sigmoid,
+                  F* probs, F* grad /* [2N][dim] or null */) {
+    const F eps_fwd = clip_sigmoid ? F(1e-7) : F(0), eps_bwd = clip_sigmoid ? F(1e-6) : F(0);
+    const F bsn = std::exp(-std::log(F(N)));
+    F total = 0;
+    for (size_t i = 0; i < N; ++i) {
+        const F* a = table + ids[2 * i] * dim;
+        const F* b = table + ids[2 * i + 1] * dim;
+        F sc = 0;
+        for (size_t k = 0; k < dim; ++k) sc += a[k] * b[k];
+        const F p = truncated_sigmoid<F>(sc, eps_fwd);
+        if (probs) probs[i] = p;
+        total += weights[i] * std::log(p);
+        if (grad) {
+            const F mult = weights[i] * (sigmoid_to_log_sigmoid_deriv<F>(p, eps_bwd) * bsn);
+            for (size_t k = 0; k < dim; ++k) {
+                grad[(2 * i) * dim + k] = mult * b[k];
+                grad[(2 * i + 1) * dim + k] = mult * a[k];
+            }
+        }
+    }
+    return -total / F(N);
+}
+
+// ---------------------------------------------------------------------------
 // L2 Normalizer (cpp/cuda_utils.cu:3-141; golden vectors cpp/cuda_utils_tests.cu:51-92).
 // Instances are the columns of the reference's matrices = rows here: x[N][dim].
 //   forward  (:12-45):  norms[i] = sqrt(sum_k x[i][k]^2);  y[i] = x[i] / norms[i]

@@ -138,6 +138,10 @@ static Config to_config(const oracle_config* c) {
     void oracle_bn_backward_##SUF(void* p, const F* dy, const F* x, long N, F* dx, F* dbias) {  \
         ((BatchNorm<F>*)p)->backward(dy, x, N, dx, dbias);                                      \
     }                                                                                           \
+    F oracle_similarity_step_##SUF(const F* table, long dim, const long* ids, const F* weights, \
+                                   long N, int clip, F* probs, F* grad) {                       \
+        return similarity_step<F>(table, dim, ids, weights, N, clip != 0, probs, grad);         \
+    }                                                                                           \
     /* L2 Normalizer: forward into y (may alias x) + backward of dy against the cached input */ \
     void oracle_normalizer_##SUF(const F* x, const F* dy, long N, long dim, F* y, F* dx) {      \
         Normalizer<F> nz;                                                                       \

@@ -282,6 +282,8 @@ def test_similarity_objective_matches_reference(objective, method):
     for step in range(3):
         pairs = nrng.integers(0, limit, size=(N, 2), dtype=np.int64)
         w = nrng.uniform(0.0, 2.0, size=N).astype(np.float32)
+        table_name = nv.ENTITY_REPRS if objective == nv.ENTITY_ENTITY else nv.WORD_REPRS
+        table = gm.get_tensor(table_name).reshape(limit, -1).copy()      # before the update: the oracle's input
         rm.fill_pairs(pairs, w); rm.forward()
         res = gm.similarity_compute_cost(nv.SimilarityBatch(N).fill(pairs, w))
         rcost = rm.get_cost()
@@ -289,6 +291,10 @@ def test_similarity_objective_matches_reference(objective, method):
         assert abs(res.scaled_regularization_lambda() - rm.scaled_lambda()) <= 1e-9
         rm.compute_gradients(); gm.compute_gradients(res)
         assert_close(gm.get_tensor("grad_similarity"), rm.get(gname), 2e-4, 1e-5, "pair gradient step %d" % step)
+        # third witness: the CPU restatement (oracle/nvsm_oracle.hpp: similarity_step)
+        ocost, _, ograd = O.similarity_step(table, pairs, w, clip_sigmoid=c["clip"], dtype=np.float32)
+        assert abs(res.get_cost() - ocost) <= 2e-4 * abs(ocost) + 1e-7
+        assert_close(gm.get_tensor("grad_similarity"), ograd, 2e-4, 1e-5, "pair gradient vs oracle, step %d" % step)
         rm.update(lr, rm.scaled_lambda()); gm.update(None, lr, res.scaled_regularization_lambda())
         _check_params(gm, rm, method, lr, "after step %d" % step)
 

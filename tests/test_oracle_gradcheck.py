@@ -55,3 +55,42 @@ def test_oracle_gradients_match_central_differences(nonlin, bn, bias_neg):
             m.set(name, theta)
             numeric = -(cp - cm) / (2 * eps)        # ascent direction
             assert abs(numeric - grad[i]) <= 1e-5 * max(1.0, abs(grad[i])) + 2e-7, (name, i, numeric, grad[i])
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_similarity_objective_gradients_match_central_differences(clip):
+    """RepresentationSimilarity objective (EntityEntity / TermTerm, cpp/objective.cu:485-672): closed form of the cost,
+    and the analytic gradient (ascent direction, a member's gradient is its partner's row) against central differences."""
+    rng = np.random.default_rng(7)
+    rows, dim, N = 9, 5, 40
+    table = rng.normal(scale=0.6, size=(rows, dim))
+    ids = rng.integers(0, rows, size=(N, 2))
+    ids[3] = (4, 4)                                  # a pair of an object with itself: both halves land on one row
+    w = rng.uniform(0.5, 2.0, size=N)
+    cost, probs, grad = O.similarity_step(table, ids, w, clip_sigmoid=clip)
+    s = (table[ids[:, 0]] * table[ids[:, 1]]).sum(axis=1)
+    p = 1.0 / (1.0 + np.exp(-s))
+    np.testing.assert_allclose(probs, p, rtol=1e-12)
+    np.testing.assert_allclose(cost, -(w * np.log(p)).sum() / N, rtol=1e-12)
+    dense = dense_table_grad(grad.ravel(), ids.ravel(), 1, None, rows, dim)
+    eps = 1e-6
+    for r in range(rows):
+        for k in range(dim):
+            t = table.copy(); t[r, k] += eps
+            up = O.similarity_step(t, ids, w, clip_sigmoid=clip)[0]
+            t[r, k] -= 2 * eps
+            down = O.similarity_step(t, ids, w, clip_sigmoid=clip)[0]
+            numeric = (up - down) / (2 * eps)
+            assert abs(-dense[r, k] - numeric) <= 1e-6 * max(1.0, abs(numeric)), (r, k, dense[r, k], numeric)
+
+
+def test_similarity_objective_saturation_band():
+    """clip_sigmoid: probabilities clamp at 1e-7 / 1 - 1e-7 and the multiplier vanishes outside (1e-6, 1 - 1e-6)
+    (cpp/objective.cu:545-549, 612-616), exactly like the TextEntity objective."""
+    table = np.array([[30.0, 0.0], [1.0, 0.0], [-1.0, 0.0], [0.1, 0.2]])
+    ids = np.array([[0, 1], [0, 2], [3, 3]])
+    cost, probs, grad = O.similarity_step(table, ids, np.ones(3), clip_sigmoid=True)
+    assert probs[0] == 1.0 - 1e-7 and probs[1] == 1e-7
+    assert (grad[0:4] == 0).all() and (grad[4:6] != 0).any()
+    _, probs_open, grad_open = O.similarity_step(table, ids, np.ones(3), clip_sigmoid=False)
+    assert probs_open[1] < 1e-12 and (grad_open[2:4] != 0).any()
