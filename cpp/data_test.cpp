@@ -141,6 +141,21 @@ static int test_similarity_source_pinned() {
   source.reset();
   EXPECT(source.has_next() && nvsm_detail::rng_get_state(rng) != nvsm_detail::rng_get_state(expect_rng));
 
+  // instance overflow (cpp/data_tests.cpp:130-190): a full batch refuses further instances and keeps its contents
+  {
+    RepresentationSimilarity::Batch small(2);
+    EXPECT(small.push_instance(std::make_tuple(1L, 2L, 1.0f)) && small.push_instance(std::make_tuple(3L, 4L, 2.0f)));
+    EXPECT(small.full() && !small.push_instance(std::make_tuple(5L, 6L, 3.0f)));
+    EXPECT(small.num_instances() == 2 && small.features()[2] == 3 && small.features()[3] == 4 && small.weights()[1] == 2.0f);
+    TextEntity::Batch text(2, 3);
+    EXPECT(text.push_instance({1, 2, 3}, {}, 7, 1.0f) && text.push_instance({4, 5, 6}, {0.5f, 1.5f, 2.5f}, 8, 0.25f));
+    EXPECT(text.full() && !text.push_instance({7, 8, 9}, {}, 9, 1.0f));
+    EXPECT(text.features()[3] == 4 && text.feature_weights()[0] == 1.0f && text.feature_weights()[4] == 1.5f &&
+           text.labels()[1] == 8 && text.weights()[1] == 0.25f);
+    text.clear();
+    EXPECT(text.empty() && text.push_instance({9, 9, 9}, {}, 1, 1.0f));
+  }
+
   // TextEntity n-gram batches through AsyncSource == the same source read directly
   struct Seq : public DataSource<TextEntity::Batch> {
     size_t i = 0;
