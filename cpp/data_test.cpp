@@ -80,6 +80,47 @@ static int test_load_similarities() {
   return 0;
 }
 
+// AsyncSource (cpp/data_async.cpp) on a heap batch: the prefetch / swap / reset protocol without page-locked memory,
+// so that it also runs on the CPU (and under -fsanitize=thread).
+struct HeapBatch {
+  HeapBatch(size_t batch_size, size_t /*window_size*/) : capacity(batch_size) {}
+  void clear() { values.clear(); }
+  bool empty() const { return values.empty(); }
+  void swap(HeapBatch* const other) { values.swap(other->values); std::swap(capacity, other->capacity); }
+  size_t capacity;
+  std::vector<long> values;
+};
+
+class HeapCountingSource : public DataSource<HeapBatch> {   // epoch e emits batches filled with e * 100 + i, i < n
+ public:
+  explicit HeapCountingSource(size_t n) : n_(n), i_(0), epoch_(0) {}
+  virtual void reset() override { i_ = 0; ++epoch_; }
+  virtual void next(HeapBatch* const batch) override { batch->values.assign(batch->capacity, static_cast<long>(epoch_ * 100 + i_)); ++i_; }
+  virtual bool has_next() const override { return i_ < n_; }
+  virtual float32 progress() const override { return static_cast<float32>(i_) / n_; }
+ private:
+  const size_t n_;
+  size_t i_, epoch_;
+};
+
+static int test_async_source_protocol() {
+  AsyncSource<HeapBatch> async(3, 16, 1, new HeapCountingSource(7));
+  HeapBatch batch(16, 1);
+  for (long epoch = 0; epoch < 4; ++epoch) {
+    long seen = 0;
+    while (async.has_next()) {
+      batch.clear();
+      async.next(&batch);
+      EXPECT(batch.values.size() == 16 && batch.values[0] == epoch * 100 + seen && batch.values[15] == epoch * 100 + seen);
+      ++seen;
+      if (epoch == 2 && seen == 3) break;   // abandon an epoch half way: reset() must drop what was prefetched
+    }
+    EXPECT(seen == (epoch == 2 ? 3 : 7));
+    async.reset();
+  }
+  return 0;
+}
+
 // NGramFileSource weighting strategies (cpp/data_indri.cpp:302-312,640-646; include/cuNVSM/data.h:464-487)
 static int test_ngram_file_weighting(const char* dir) {
   const std::string path = std::string(dir) + "/weighting_ngrams.txt";
@@ -185,7 +226,8 @@ static int test_similarity_source_pinned() {
 
 int main(int argc, char** argv) {
   const char* tmp = std::getenv("TMPDIR");
-  int failed = test_multi_source() + test_repeating_source() + test_load_similarities() + test_ngram_file_weighting(tmp ? tmp : "/tmp");
+  int failed = test_multi_source() + test_repeating_source() + test_load_similarities() + test_async_source_protocol() +
+               test_ngram_file_weighting(tmp ? tmp : "/tmp");
   if (argc > 1 && std::strcmp(argv[1], "--pinned") == 0) failed += test_similarity_source_pinned();
   if (failed) return 1;
   std::printf("data tests ok%s\n", argc > 1 ? " (pinned batches included)" : "");
