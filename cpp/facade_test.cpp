@@ -62,6 +62,27 @@ int main() {
     double mcs = 0;
     for (const auto& kv : mix.get_data()) for (float x : kv.second.data) mcs += x;
     std::printf("mixchecksum %.9g\n", mcs);
+    // The CLI reads the loss of batch k-1 after batch k has been enqueued (cpp/main.cpp, iterate): a deferred read
+    // must report the costs of ITS batch for both constituents (the pair loss is cached when the result is made).
+    {
+      RNG a; a.seed(9); RNG b; b.seed(9);
+      Model<TextEntityEntityEntity::Objective> eager(100, 60, desc, mtc, 0, NVSM_GEMM_FP32), lazy(100, 60, desc, mtc, 0, NVSM_GEMM_FP32);
+      eager.initialize(&a); lazy.initialize(&b);
+      std::unique_ptr<MultiForwardResult> previous;
+      int deferred_ok = 1;
+      float eager_cost[3];
+      for (int step = 0; step < 3; ++step) {
+        std::unique_ptr<MultiForwardResult> r(eager.compute_cost(both, &a));
+        eager_cost[step] = r->get_cost();
+        eager.backprop(*r, 0.01f);
+        std::unique_ptr<MultiForwardResult> q(lazy.compute_cost(both, &b));
+        lazy.backprop(*q, 0.01f);
+        if (previous && previous->get_cost() != eager_cost[step - 1]) deferred_ok = 0;
+        previous = std::move(q);
+      }
+      if (previous->get_cost() != eager_cost[2]) deferred_ok = 0;
+      std::printf("deferred_mixture_cost_ok %d\n", deferred_ok);
+    }
   }
   return 0;
 }

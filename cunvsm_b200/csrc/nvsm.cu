@@ -371,6 +371,24 @@ int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer,
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), with headroom.
 constexpr uint32_t kTcMaxDynSmem = 232448u - 2048u;
 
+// Dynamic shared memory above 48 KB is an opt-in per function AND per device: called by nvsm_create for the device of
+// every model (a process-wide "done once" flag would leave a second device without it).
+int set_kernel_attributes() {
+    const int mx = (int)kTcMaxDynSmem;
+    CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+#define NVSM_TC_ATTR(A_, B_, S_, K_) CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<A_, B_, S_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+    NVSM_TC_ATTR(false, false, false, 32); NVSM_TC_ATTR(false, false, true, 32); NVSM_TC_ATTR(true, true, false, 32); NVSM_TC_ATTR(true, true, true, 32);
+    NVSM_TC_ATTR(false, false, false, 16); NVSM_TC_ATTR(false, false, true, 16); NVSM_TC_ATTR(true, true, false, 16); NVSM_TC_ATTR(true, true, true, 16);
+#undef NVSM_TC_ATTR
+#define NVSM_RING_ATTR(N_) \
+    CU(cudaFuncSetAttribute(score_ring_kernel<N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    CU(cudaFuncSetAttribute(score_ring_kernel<N_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    NVSM_RING_ATTR(1); NVSM_RING_ATTR(2); NVSM_RING_ATTR(3); NVSM_RING_ATTR(4); NVSM_RING_ATTR(8);
+#undef NVSM_RING_ATTR
+    return 0;
+}
+
 bool tc_shapes_ok(int dw, int dd) {
     // TMA needs 16-byte row strides; grad_transform's MN-major B tile needs dd % 32 == 0.
     return dw % 4 == 0 && dd % 32 == 0 && dd <= 512 && dw <= 512;
@@ -414,13 +432,6 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
             const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
             const int num_tiles = p.m_tiles * p.n_tiles;
             const int grid = 2 * std::min(num_tiles, m->num_sms / 2);
-            static bool attr2 = false;
-            if (!attr2) {
-                const int mx = (int)kTcMaxDynSmem;
-                CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-                CU(cudaFuncSetAttribute(tc::gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-                attr2 = true;
-            }
             if (split3) LAUNCH(m, (tc::gemm_tc2_kernel<true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
             else LAUNCH(m, (tc::gemm_tc2_kernel<false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
             if (splits_out) *splits_out = 1;
@@ -465,15 +476,6 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(num_tiles, m->num_sms);
-    static bool attr = false;
-    if (!attr) {
-        const int mx = (int)kTcMaxDynSmem;
-#define NVSM_TC_ATTR(A_, B_, S_, K_) CU(cudaFuncSetAttribute(tc::gemm_tc_kernel<A_, B_, S_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
-        NVSM_TC_ATTR(false, false, false, 32); NVSM_TC_ATTR(false, false, true, 32); NVSM_TC_ATTR(true, true, false, 32); NVSM_TC_ATTR(true, true, true, 32);
-        NVSM_TC_ATTR(false, false, false, 16); NVSM_TC_ATTR(false, false, true, 16); NVSM_TC_ATTR(true, true, false, 16); NVSM_TC_ATTR(true, true, true, 16);
-#undef NVSM_TC_ATTR
-        attr = true;
-    }
 #define NVSM_TC_LAUNCH(A_, B_, S_, K_) LAUNCH(m, (tc::gemm_tc_kernel<A_, B_, S_, K_>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p)
     if (kb == 32) {
         if (!mn_major && !split3) NVSM_TC_LAUNCH(false, false, false, 32);
@@ -555,12 +557,6 @@ int launch_score(nvsm_model* m, const ScoreParams& sp) {
 
 template <int NCH>
 int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t smem) {
-    static bool attr = false;
-    if (!attr) {
-        CU(cudaFuncSetAttribute(score_ring_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(score_ring_kernel<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
     if (q.s.dd == NCH * 128) LAUNCH(m, (score_ring_kernel<NCH, true>), grid, q.warps * 32, smem, q);
     else LAUNCH(m, (score_ring_kernel<NCH, false>), grid, q.warps * 32, smem, q);
     return 0;
@@ -1584,6 +1580,14 @@ int check_id_flags(nvsm_model* m) {
                 bad_words ? m->V : m->D);
 }
 
+// compute_cost without update (cuNVSMTrainModel --compute_initial_cost): the bucket build of that forward pass reads the
+// slot's ids on the auxiliary stream and nothing has joined it into the main stream, so a `consumed` event recorded on
+// the main stream alone would let the copy stream overwrite the ids between ref_count_kernel and ref_fill_kernel.
+int join_unconsumed_buckets(nvsm_model* m) {
+    if (m->buckets_in_flight) CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
+    return 0;
+}
+
 int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float* fw, const long* ids,
                  const float* w, long B, bool use_copy_stream) {
     if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
@@ -1591,6 +1595,7 @@ int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float*
     cudaStream_t cs = use_copy_stream ? m->copy_stream : m->stream;
     if (cs != m->stream) {
         if (s->in_use) {  // forward without update: order after everything enqueued so far
+            TRY(join_unconsumed_buckets(m));
             CU(cudaEventRecord(s->consumed, m->stream));
             s->ever_consumed = true;
         }
@@ -1800,6 +1805,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
     m->num_sms = prop.multiProcessorCount;
 
     auto build = [&]() -> int {
+        TRY(set_kernel_attributes());
         CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         m->own_stream = true;
         CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -2242,7 +2248,7 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     TRY(ensure_sampler(m));
     BatchSlot* s = next_live_slot(m);
     cudaStream_t cs = m->copy_stream;
-    if (s->in_use) { CU(cudaEventRecord(s->consumed, m->stream)); s->ever_consumed = true; }
+    if (s->in_use) { TRY(join_unconsumed_buckets(m)); CU(cudaEventRecord(s->consumed, m->stream)); s->ever_consumed = true; }
     if (s->ever_consumed) CU(cudaStreamWaitEvent(cs, s->consumed, 0));
     s->in_use = false;
     CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));

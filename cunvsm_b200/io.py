@@ -85,9 +85,14 @@ def load_meta(path):
 
 
 class DumpedModel:
-    """The reference's `NVSM` model object (py/nvsm/base.py:165-330) over a .npy dump."""
+    """The reference's `NVSM` model object (py/nvsm/base.py:165-330) over a .npy dump.
 
-    def __init__(self, meta, tensors, bias_coefficient=1.0, nonlinearity=np.tanh, self_information=False, strict=False):
+    ``bias_coefficient`` defaults to 0.0 like the reference (py/nvsm/base.py:171), where the projection bias then
+    contributes nothing to the query projection (its `if not bias_coefficient != 0.0` keeps a zero vector for 0.0 and
+    drops the bias otherwise). Here a non-zero coefficient scales and ADDS the trained bias, which is what
+    Model::infer (cpp/model.cu:105-133) computes with coefficient 1.0."""
+
+    def __init__(self, meta, tensors, bias_coefficient=0.0, nonlinearity=np.tanh, self_information=False, strict=False):
         self.total_terms = meta["total_terms"]
         self.self_information, self.nonlinearity, self.strict = self_information, nonlinearity, strict
         self.word_representations = tensors[DATASETS[0]]

@@ -124,25 +124,28 @@ namespace RepresentationSimilarity {
 class ForwardResult {
  public:
   typedef Typedefs::FloatT FloatT;
-  FloatT get_cost() const {
-    if (!have_cost_) { NVSM_ABORT_ON(nvsm_similarity_get_cost(model_, &cost_)); have_cost_ = true; }
-    return cost_;
-  }
+  // The library keeps ONE pair loss (the latest nvsm_similarity_compute_cost), so the cost is read when the result is
+  // made (Model::pair_forward synchronises anyway): a result read after a later compute_cost -- the CLI reads the
+  // loss of batch k-1 under batch k -- still reports its own batch.
+  FloatT get_cost() const { return cost_; }
   FloatT scaled_regularization_lambda() const { return lambda_; }
   std::vector<FloatT> get_similarity_probs() const {
+    NVSM_CHECK(age() == 0, "forward state has been overwritten by a later compute_cost");
     const long n = nvsm_tensor_size(model_, "similarity_pair_probs");
     std::vector<FloatT> out(n);
     NVSM_ABORT_ON(nvsm_get_tensor(model_, "similarity_pair_probs", out.data(), n));
     return out;
   }
-  long age() const { return 0; }
+  long age() const { return *counter_ - serial_; }
 
  private:
-  ForwardResult(nvsm_model* m, FloatT lambda) : model_(m), lambda_(lambda) {}
+  ForwardResult(nvsm_model* m, FloatT lambda, FloatT cost, const long* counter)
+      : model_(m), lambda_(lambda), cost_(cost), counter_(counter), serial_(*counter) {}
   nvsm_model* model_;
   FloatT lambda_;
-  mutable FloatT cost_ = 0;
-  mutable bool have_cost_ = false;
+  FloatT cost_;
+  const long* counter_;
+  long serial_;
   template <typename O> friend class ::Model;
 };
 
@@ -177,7 +180,7 @@ class MultiForwardResult {
   FloatT scaled_regularization_lambda() const {
     return (text_->scaled_regularization_lambda() + pair_->scaled_regularization_lambda()) / 2;
   }
-  long age() const { return text_->age(); }
+  long age() const { return text_->age() > pair_->age() ? text_->age() : pair_->age(); }
   const TextEntity::ForwardResult& text() const { return *text_; }
   const RepresentationSimilarity::ForwardResult& similarity() const { return *pair_; }
 
@@ -324,7 +327,11 @@ class Model {
   RepresentationSimilarity::ForwardResult* pair_forward(const RepresentationSimilarity::Batch& batch) const {
     NVSM_ABORT_ON(nvsm_similarity_compute_cost(handle_, batch.features(), batch.weights(), batch.num_instances()));
     NVSM_ABORT_ON(nvsm_synchronize(handle_));     // pair batches are copied on the compute stream: cheap, and recyclable after
-    return new RepresentationSimilarity::ForwardResult(handle_, nvsm_similarity_scaled_regularization_lambda(handle_));
+    FloatT cost = 0;
+    NVSM_ABORT_ON(nvsm_similarity_get_cost(handle_, &cost));   // (already on the host: the forward ends in its D2H copy)
+    ++pair_counter_;
+    return new RepresentationSimilarity::ForwardResult(handle_, nvsm_similarity_scaled_regularization_lambda(handle_), cost,
+                                                       &pair_counter_);
   }
 
   // TextEntity{EntityEntity,TermTerm}::Objective::compute_cost, cpp/objective.cu:713-724,762-773
@@ -404,6 +411,7 @@ class Model {
   std::unique_ptr<LabelGenerator<FloatT, EntityIdxType>> label_generator_{new UniformLabelGenerator<FloatT, EntityIdxType>()};
   mutable std::vector<long> entity_ids_;
   mutable long forward_counter_ = 0;
+  mutable long pair_counter_ = 0;
 };
 
 typedef Model<TextEntity::Objective> DefaultModel;

@@ -129,6 +129,8 @@ def test_cpp_facade_matches_python_driver():
         assert abs(r.get_cost() - float(lines["mixcost %d" % step])) <= 2e-6 * abs(r.get_cost())
     mcs = sum(float(v.astype(np.float64).sum()) for v in mm.get_data().values())
     assert abs(mcs - float(lines["mixchecksum"])) <= 1e-4 * abs(mcs) + 1e-3
+    # a mixture result read one step late (the CLI's deferred loss read) reports its own batch's cost
+    assert lines["deferred_mixture_cost_ok"] == "1"
 
 
 @pytest.mark.gpu

@@ -127,7 +127,8 @@ def test_python_loader_reads_meta_and_dump(tmp_path):
         a = np.asarray(om.get(short), dtype=np.float32)
         shape = {"W": (V, dw), "E": (D, dd), "T": (dw, dd), "b": (1, dd)}[short]
         np.save("%s_%d.%s.npy" % (out, 2, name), a.reshape(shape))
-    model = io.load_model(parsed, out, 2)
+    assert io.load_model(parsed, out, 2).transform_bias is None      # reference default: the bias plays no part
+    model = io.load_model(parsed, out, 2, bias_coefficient=1.0)        # Model::infer adds it
     assert (model.num_terms, model.term_repr_size, model.num_objects, model.object_repr_size) == (V, dw, D, dd)
     query = [1000 + 3 * 4, 1000 + 3 * 9, 999999, 1000 + 3 * 17]          # one out-of-vocabulary term
     projected = model.infer(model.query_representation(query))
