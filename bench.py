@@ -57,8 +57,10 @@ NUM_BATCHES = 10
 
 
 def algorithmic_bytes_per_ngram(w):
-    """gather W and E rows once, read-modify-write the same rows once, ids as
-    delivered (8 B), weights (4 B). Dense optimiser passes are amortised separately."""
+    """SURVEY.md §8d, per REFERENCE: gather W and E rows once, read-modify-write the same rows once, ids as
+    delivered (8 B), weights (4 B). Every table row is referenced ~10x per batch and the tables fit the 126 MB L2, so
+    these are bytes L2 serves: they are reported against the measured L2 gather peak (roofline.l2), never against
+    the HBM peak."""
     n, R, dw, dd = w["n"], w["z"] + 1, w["dw"], w["dd"]
     per_phase = {
         "gather_mean": 4 * n * dw + 8 * n + 4 * n,
@@ -72,6 +74,46 @@ def algorithmic_bytes_per_ngram(w):
     return per_phase
 
 
+def expected_unique(num_rows, references):
+    """Expected number of distinct rows hit by `references` uniform draws over `num_rows`."""
+    return num_rows * (1.0 - np.exp(-float(references) / num_rows))
+
+
+def compulsory_bytes_per_launch(w, B, gemm_mode, unique_words=None, unique_entities=None):
+    """Bytes that MUST cross HBM per launch of each gather-type kernel of the design that is built:
+    every distinct table row once (re-references are L2 hits by construction), the per-step tensors the kernel
+    streams, its index / weight arrays, and -- for the pull updates -- one read-modify-write of every state row the
+    optimiser touches. This is the numerator of roofline.frac (against the measured HBM copy peak)."""
+    n, R, dw, dd, V, D = w["n"], w["z"] + 1, w["dw"], w["dd"], w["V"], w["D"]
+    uw = expected_unique(V, B * n) if unique_words is None else unique_words
+    ue = expected_unique(D, B * R) if unique_entities is None else unique_entities
+    tc = gemm_mode != 0 and dw % 4 == 0 and dd % 32 == 0
+    ldp = (dw + 31) // 32 * 32 if tc else dw
+    lo = 2 if (tc and gemm_mode == 2) else 1
+    method = w["update_method"]
+    lam = w["lam"] > 0
+    pull = method == "full_adam" or (method in ("sgd", "adagrad") and max(V, D) >= 8192)
+    out = {
+        # W rows once, ids + weights, P (+ P_lo) written
+        "gather_mean": 4 * uw * dw + 12 * B * n + 4 * B * ldp * lo,
+        # Z read, E rows once, ids, instance weights; Gp, (Y), probs, mult written
+        "score_loss_bwd": 4 * B * dd + 4 * ue * dd + 8 * B * R + 4 * B + 4 * B * dd + (4 * B * dd if pull else 0) + 8 * B * R,
+    }
+    def table(rows, dim, touched, refs, src_bytes):
+        if method == "full_adam":
+            state = 24 * rows * dim                      # theta, m, v: read + write, every row (decay)
+        elif method in ("sgd", "adagrad"):
+            state = 8 * (rows if lam else touched) * dim  # dense decay when lambda > 0 (cpp/storage.cu:65-67)
+            if method == "adagrad":
+                state += 8 * touched
+        else:                                            # sparse / dense-update Adam: m dense, theta dense or touched
+            state = 16 * rows * dim + 8 * rows
+        return state + src_bytes + 4 * refs + 4 * rows   # + reference list + bucket offsets
+    out["update_entities"] = table(D, dd, ue, B * R, 4 * B * dd + 4 * B * R)       # Y rows + multipliers
+    out["update_words"] = table(V, dw, uw, B * n, 4 * B * dw + 4 * B * n)          # grad_phrase rows + word weights
+    return out
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -80,53 +122,86 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons of one GPU, polled from a thread through NVML (nvidia_ml_py) every ~2 ms from before
+    the warm-up until after the last timed loop; `window()` brackets the timed regions so that the summary is
+    computed over samples taken DURING them (a 20-step timed region lasts ~13 ms, far below nvidia-smi's own polling
+    period, which is why round 1 reported "no samples"). nvidia-smi -lms is the fallback when NVML cannot be loaded."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.samples, self.windows, self._stop = gpu_index, [], [], False
+        self.thread, self.how, self.smi = None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.how = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.smi = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                         "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def pump():
+                for line in self.smi.stdout:
+                    parts = [x.strip() for x in line.split(",")]
+                    try:
+                        mask = sum(bit for (_, bit), val in zip(self.REASONS, parts[2:6]) if val.lower().startswith("active"))
+                        self.max_mhz = float(parts[1])
+                        self.samples.append((time.perf_counter(), float(parts[0]), mask))
+                    except Exception:
+                        continue
+            self.how = "nvidia-smi -lms 20"
+            self.thread = threading.Thread(target=pump, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.smi = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop = True
+        if self.smi:
+            self.smi.terminate()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.how:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler (NVML and nvidia-smi unavailable)"]}
+        timed = [x for x in self.samples if any(a <= x[0] <= b for a, b in self.windows)]
+        # a timed region shorter than the polling period: fall back to the samples between the first warm-up step
+        # and the end of the last timed loop (the GPU runs the same steps back to back there)
+        scope = "timed regions"
+        if len(timed) < 3 and self.windows:
+            lo = min(a for a, _ in self.windows) - getattr(self, "lead_s", 0.0)
+            timed = [x for x in self.samples if lo <= x[0] <= max(b for _, b in self.windows)]
+            scope = "warm-up + timed regions"
+        if not timed:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": ["no samples"], "how": self.how}
+        mask = 0
+        for x in timed:
+            mask |= x[2]
+        return {"sm_mhz": float(np.median([x[1] for x in timed])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(nm for nm, bit in self.REASONS if mask & bit), "samples": len(timed),
+                "samples_total": len(self.samples), "scope": scope, "how": self.how}
 
 
 def zipf_ids(rng, cdf, size):
@@ -256,7 +331,7 @@ def run_reference(args, w, rank):
                             if w.get("neg_zipf", 0.0) > 0.0 else ""))
         print(json.dumps(line), flush=True)
         return
-    sample_B = min(args.cpu_sample, w["B"])
+    sample_B = min(args.cpu_sample, w["B"]) if args.cpu_sample > 0 else min(5120, w["B"])
     r = cpu_port_run(w, args.steps, max(args.warmup, 1), sample_B)
     sample = ("%d n-grams/step (1/%d of the %d batch), full-size tables, float32, sampler+forward+backward+update; "
               "%s build" % (sample_B, max(1, w["B"] // sample_B), w["B"], "-march=native" if r["native"] else "portable"))
@@ -272,125 +347,273 @@ def run_reference(args, w, rank):
 # -------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------
+def pin_rank_to_cores(local_rank, world):
+    """N processes on one node: give every rank its own slice of the host cores (launch thread, NCCL proxy and clock
+    sampler stay off each other's cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if world > 1 and per >= 1:
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            return per
+    except Exception:
+        pass
+    return None
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
+    """N > 1, outside every timed region: ONE step of the workload's global batch (w["B"] rows) sharded over the
+    `world` ranks, compared on rank 0 with (a) the same library on one GPU over the whole batch and (b) the
+    reference itself (oracle/_ref: the unmodified cpp/*.cu, float32) -- loss, grad_transform, grad_bias, the
+    batch-norm statistics, and T / b after the update. Same seed, same bit-exact negatives everywhere."""
+    Bg = w["B"]
+    if Bg % world:
+        return {"ok": None, "skipped": "global batch %d does not split over %d ranks" % (Bg, world)}
+    method, mode = nv.UPDATE_METHODS[w["update_method"]]
+    desc = nv.ModelDesc(word_repr_size=w["dw"], entity_repr_size=w["dd"], batch_normalization=w["bn"],
+                        nonlinearity=nv.NONLINEARITIES[w["nonlinearity"]], clip_sigmoid=True, bias_negative_samples=w["bias_neg"])
+    mk = lambda bs: nv.TrainConfig(batch_size=bs, window_size=w["n"], num_random_entities=w["z"], regularization_lambda=w["lam"],
+                                   learning_rate=w["lr"], update_method=method, adam_mode=mode)
+    f, labels = make_batches(w, Bg, 4321, 1)[0]          # identical on every rank
+    fw, iw = np.ones((Bg, w["n"]), np.float32), np.ones(Bg, np.float32)
+    pm = nv.Model(w["V"], w["D"], desc, mk(Bg // world), device=local_rank, gemm_mode=args.gemm_mode)
+    prng = nv.RNG(1)
+    pm.initialize(prng)
+    sampler_state = prng.state
+    ids = pm.generate_labels(labels, nv.RNG(sampler_state))      # uniform negatives: the reference's own generator
+    sharding.init_model_comm(pm, dist, rank, world, peer_exchange=not args.no_peer)
+    sf, sfw, sl, sw, sids = sharding.shard_batch(f, fw, labels, iw, ids, rank, world)
+    names = ["grad_transform", "grad_bias"] + (["bn_mean", "bn_invstd"] if w["bn"] else [])
+
+    def one_step(model, batch, entity_ids):
+        res = model.compute_cost(batch, entity_ids=entity_ids)
+        out = {"loss": res.get_cost()}
+        model.compute_gradients(res)
+        for nm in names:
+            out[nm] = model.get_tensor(nm)
+        model.update(None, w["lr"], res.scaled_regularization_lambda())
+        out["T"], out["b"] = model.get_tensor(nv.TRANSFORM), model.get_tensor(nv.BIAS)
+        return out
+
+    got = one_step(pm, nv.Batch(Bg // world, w["n"]).fill(sf, sl, sfw, sw), sids)
+    peer_err = pm.comm_peer_status()[1]
+    pm.close()
+    report = None
+    if rank == 0:
+        tol = 2e-4 if args.gemm_mode != 1 else 2e-2
+        um = nv.Model(w["V"], w["D"], desc, mk(Bg), device=local_rank, gemm_mode=args.gemm_mode)
+        um.initialize(nv.RNG(1))
+        want = one_step(um, nv.Batch(Bg, w["n"]).fill(f, labels, fw, iw), ids)
+        um.close()
+        vs_un = {k: (abs(got[k] - want[k]) / abs(want[k]) if k == "loss" else rel_err(got[k], want[k])) for k in got}
+        report = {"global_batch": Bg, "ranks": world, "tolerance": tol, "vs_unsharded": vs_un,
+                  "what": "one sharded step vs one GPU on the concatenated batch and vs oracle/_ref (reference, float32): "
+                          "loss relative; tensors max|a-b| / max|b|; T and b after the update"}
+        worst = max(vs_un.values())
+        try:
+            from oracle import ref_binding as R
+            if R.available(np.float32) and not args.no_ref_check:
+                um_ = {"sgd": (R.SGD, 0), "adagrad": (R.ADAGRAD, 0), "sparse_adam": (R.ADAM, R.SPARSE),
+                       "dense_adam": (R.ADAM, R.DENSE_UPDATE), "full_adam": (R.ADAM, R.DENSE_UPDATE_DENSE_VARIANCE)}[w["update_method"]]
+                rm = R.Model(w["V"], w["D"], w["dw"], w["dd"], batch_size=Bg, window_size=w["n"], num_random_entities=w["z"],
+                             nonlinearity=R.HARD_TANH if w["nonlinearity"] == "hard_tanh" else R.TANH, batch_normalization=w["bn"],
+                             clip_sigmoid=True, bias_negative_samples=w["bias_neg"], update_method=um_[0], adam_mode=um_[1],
+                             regularization_lambda=w["lam"], seed=1, dtype=np.float32)
+                assert rm.rng_state == sampler_state, "reference and library consumed the engine differently in initialize"
+                rm.forward(rm.new_batch().fill(f, labels, fw, iw))
+                ids_equal = bool((rm.entity_ids() == ids).all())
+                ref = {"loss": rm.get_cost()}
+                rm.compute_gradients()
+                ref["grad_transform"], ref["grad_bias"] = rm.get("grad_transform"), rm.get("grad_bias")
+                rm.update(w["lr"], rm.scaled_lambda())
+                ref["T"], ref["b"] = rm.get("transform"), rm.get("bias")
+                vs_ref = {k: (abs(got[k] - ref[k]) / abs(ref[k]) if k == "loss" else rel_err(got[k], ref[k])) for k in ref}
+                vs_ref["sampled_ids_bit_exact"] = ids_equal
+                report["vs_reference"] = vs_ref
+                worst = max(worst, max(v for k, v in vs_ref.items() if k != "sampled_ids_bit_exact"))
+                if not ids_equal:
+                    worst = float("inf")
+                del rm
+            else:
+                report["vs_reference"] = "oracle/_ref not built" if not R.available(np.float32) else "skipped (--no_ref_check)"
+        except Exception as e:   # the checker must not take the bench line down
+            report["vs_reference"] = "failed: %r" % (e,)
+            worst = float("inf")
+        report["max_rel_err"] = worst
+        report["peer_exchange_error"] = peer_err
+        report["ok"] = bool(worst <= tol and peer_err == 0)
+    return report
+
+
 def run_ours(args, w, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
     import cunvsm_b200 as nv
+    from cunvsm_b200 import sharding
 
+    cores_per_rank = pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
-    B = w["B"]  # per GPU (weak scaling)
+    B = w["B"]  # per GPU in the headline numbers (weak scaling); the strong block below shards w["B"] itself
     method, mode = nv.UPDATE_METHODS[w["update_method"]]
     desc = nv.ModelDesc(word_repr_size=w["dw"], entity_repr_size=w["dd"], batch_normalization=w["bn"],
                         nonlinearity=nv.NONLINEARITIES[w["nonlinearity"]], clip_sigmoid=True,
                         bias_negative_samples=w["bias_neg"])
     tc = nv.TrainConfig(batch_size=B, window_size=w["n"], num_random_entities=w["z"],
                         regularization_lambda=w["lam"], learning_rate=w["lr"], update_method=method, adam_mode=mode)
-    model = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=args.gemm_mode,
-                     num_batch_slots=NUM_BATCHES)
     stream = torch.cuda.Stream(device=local_rank)
-    model.set_stream(stream.cuda_stream)
-    rng = nv.RNG(1)
-    model.initialize(rng)   # identical on every rank: same seed, same engine
-    from cunvsm_b200 import sharding
-    sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0,
-                             peer_exchange=not args.no_peer)
+    sparse_mode = 1 if args.sparse_sync == "allgather" else 0
 
-    if w.get("neg_zipf", 0.0) > 0.0:
-        # skewed negatives (configs[4]): inverse-CDF generator at the reference's LabelGenerator plug point; the host
-        # loop (pre-sampled ids of `value`) and the device sampler (`e2e`) draw from the same distribution
-        model.set_negative_distribution(nv.zipf_cdf(w["D"], w["neg_zipf"]))
-    # synthetic batches: every rank owns its own shard of n-gram rows
-    raw = make_batches(w, B, 1234 + rank, NUM_BATCHES)
-    batches, ids_list = [], []
+    def make_model(gemm_mode):
+        m = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=gemm_mode, num_batch_slots=NUM_BATCHES)
+        m.set_stream(stream.cuda_stream)
+        r = nv.RNG(1)
+        m.initialize(r)   # identical on every rank: same seed, same engine
+        sharding.init_model_comm(m, dist, rank, world, sparse_mode=sparse_mode, peer_exchange=not args.no_peer)
+        if w.get("neg_zipf", 0.0) > 0.0:
+            # skewed negatives (configs[4]): inverse-CDF generator at the reference's LabelGenerator plug point; the
+            # host loop (pre-sampled ids of `value`) and the device sampler (`e2e`) draw from the same distribution
+            m.set_negative_distribution(nv.zipf_cdf(w["D"], w["neg_zipf"]))
+        return m, r
+
+    model, rng = make_model(args.gemm_mode)
     srng = nv.RNG(rng.state + rank)
-    for f, labels in raw:
-        b = nv.Batch(B, w["n"]).fill(f, labels)
-        ids = model.generate_labels(labels, srng)
-        pinned_ids = torch.from_numpy(ids).pin_memory()
-        batches.append(b); ids_list.append(pinned_ids)
-    ids_np = [t.numpy() for t in ids_list]
-    for s in range(NUM_BATCHES):
-        model.stage_batch(s, batches[s], ids_np[s])
+
+    def make_staged(m, rows, seed):
+        """Synthetic batches of `rows` n-grams for this rank, staged in the model's device slots."""
+        raw = make_batches(w, rows, seed + rank, NUM_BATCHES)
+        bs, ids_keep = [], []
+        for k, (f, labels) in enumerate(raw):
+            b = nv.Batch(rows, w["n"]).fill(f, labels)
+            ids = m.generate_labels(labels, srng)
+            m.stage_batch(k, b, ids)
+            bs.append(b); ids_keep.append(ids)
+        return bs, raw, ids_keep
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    sampler = ClockSampler(local_rank)
+
+    def timed(m, fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = model.kernel_launches()
+        l0 = m.kernel_launches()
+        t0 = time.perf_counter()
         e0.record(stream)
         for it in range(steps):
             fn(it)
         e1.record(stream)
         e1.synchronize()
+        sampler.window(t0, time.perf_counter())
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
             ms = sharding.max_over_ranks(dist, ms, device="cuda")
-        return ms, model.kernel_launches() - l0
+        return ms, m.kernel_launches() - l0
 
     lr = w["lr"]
-    staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
 
-    def host_fed(it):
-        # the reference-facing call on HOST buffers: features / weights / positive labels go up every step,
-        # the z negatives per instance are drawn on the device (bit-exact with the reference's host sampler)
-        k = it % NUM_BATCHES
-        model.step_sampled(batches[k], lr)
-        if it > 0:
-            model.last_cost(1)  # loss of the previous step: D2H read every step, one step lagged
+    def measure(m, batches, steps, warmup):
+        """(device-resident ms, launches, host-fed ms) of `steps` steps on the batches staged in / fed to `m`."""
+        staged = lambda it: m.train_step_staged(it % NUM_BATCHES, lr)
 
-    for it in range(args.warmup):
-        staged(it)
-    sampler = ClockSampler(local_rank)
+        def host_fed(it):
+            # the reference-facing call on HOST buffers: features / weights / positive labels go up every step,
+            # the z negatives per instance are drawn on the device (bit-exact with the reference's host sampler)
+            m.step_sampled(batches[it % NUM_BATCHES], lr)
+            if it > 0:
+                m.last_cost(1)  # loss of the previous step: D2H read every step, one step lagged
+        for it in range(warmup):
+            staged(it)
+        ms, launches = timed(m, staged, steps)
+        cost = m.last_cost()
+        m.sampler_seed(srng)
+        for it in range(max(3, min(warmup, 5))):
+            host_fed(it)
+        ms_e2e, _ = timed(m, host_fed, steps)
+        m.last_cost()
+        return ms, launches, ms_e2e, cost
+
+    batches, raw, ids_keep = make_staged(model, B, 1234)
     if rank == 0:
+        sampler.lead_s = 0.0
         sampler.start()
-    ms, launches = timed(staged, args.steps)
+        time.sleep(0.05)
+    t_warm = time.perf_counter()
+    ms, launches, ms_e2e, final_cost = measure(model, batches, args.steps, args.warmup)
+    sampler.lead_s = (min(a for a, _ in sampler.windows) - t_warm) if sampler.windows else 0.0
     clocks = sampler.stop() if rank == 0 else None
-    final_cost = model.last_cost()
-
-    model.sampler_seed(srng)
-    for it in range(max(3, min(args.warmup, 5))):
-        host_fed(it)
-    ms_e2e, _ = timed(host_fed, args.steps)
-    model.last_cost()
 
     # per-phase device time (CUDA events around every phase on the model's stream)
     model.set_profiling(True)
     model.reset_phase_ms()
     prof_steps = min(args.steps, 20)
     for it in range(prof_steps):
-        staged(it)
+        model.train_step_staged(it % NUM_BATCHES, lr)
     phases = {k: v / prof_steps for k, v in model.phase_ms().items()}
     model.set_profiling(False)
+
+    # strong scaling (BASELINE configs[3] as written): the SAME global batch w["B"] sharded over the ranks
+    strong = None
+    if world > 1 and args.scaling in ("both", "strong") and w["B"] % world == 0:
+        Bs = w["B"] // world
+        sbatches, _, _ = make_staged(model, Bs, 5678)
+        s_ms, _, s_ms_e2e, _ = measure(model, sbatches, args.steps, max(3, args.warmup))
+        strong = {"global_batch": w["B"], "per_gpu_batch": Bs, "value": w["B"] * args.steps / (s_ms * 1e-3),
+                  "ms_per_step": s_ms / args.steps,
+                  "e2e": {"value": w["B"] * args.steps / (s_ms_e2e * 1e-3), "ms_per_step": s_ms_e2e / args.steps},
+                  "unit": "n-grams/s",
+                  "note": "speed-up = value / the N=1 line's value (the driver computes it); what does not shrink with "
+                          "N on replicated tables: the dense optimiser pass over every table row and the bucket build "
+                          "over all table rows (see DESIGN.md section 5)"}
+        model.set_profiling(True)
+        model.reset_phase_ms()
+        for it in range(prof_steps):
+            model.train_step_staged(it % NUM_BATCHES, lr)
+        strong["phase_ms"] = {k: round(v / prof_steps, 4) for k, v in model.phase_ms().items()}
+        model.set_profiling(False)
+
+    # roofline denominators measured in place (rank 0): L2-resident gather and streaming copy
+    probes = None
+    if rank == 0 and not args.no_probes:
+        table_bytes = 4 * w["V"] * w["dw"]
+        probes = {"l2_gather_gbs": model.bench_memory(0, min(table_bytes, 64 << 20), row_floats=(w["dw"] + 3) // 4 * 4,
+                                                      rows_per_item=w["n"], items=B, iters=20),
+                  "l2_gather_probe": "warp-per-item gather of n=%d rows x %d floats from a %d MB table, 2 rows in flight" % (
+                      w["n"], (w["dw"] + 3) // 4 * 4, min(table_bytes, 64 << 20) >> 20),
+                  "stream_copy_gbs": model.bench_memory(1, 1 << 30, iters=10)}
+
+    peer_ok = world > 1 and model.comm_peer_status()[0]
+    if world > 1 and model.comm_peer_status()[1]:
+        raise RuntimeError("NVLink peer exchange timed out waiting for a peer")
 
     alt = None
     if args.gemm_mode == 2 and not args.no_alt:
         # the same timed loop with single-pass TF32 GEMMs (looser parity, see tests/test_gpu_loss_curve.py)
         model.close()
-        model = nv.Model(w["V"], w["D"], desc, tc, device=local_rank, gemm_mode=1, num_batch_slots=NUM_BATCHES)
-        model.set_stream(stream.cuda_stream)
-        model.initialize(nv.RNG(1))
-        sharding.init_model_comm(model, dist, rank, world, sparse_mode=1 if args.sparse_sync == "allgather" else 0,
-                             peer_exchange=not args.no_peer)
-        for s_ in range(NUM_BATCHES):
-            model.stage_batch(s_, batches[s_], ids_np[s_])
-        staged = lambda it: model.train_step_staged(it % NUM_BATCHES, lr)
+        model, _ = make_model(1)
+        make_staged(model, B, 1234)
         for it in range(args.warmup):
-            staged(it)
-        ms_alt, _ = timed(staged, args.steps)
+            model.train_step_staged(it % NUM_BATCHES, lr)
+        ms_alt, _ = timed(model, lambda it: model.train_step_staged(it % NUM_BATCHES, lr), args.steps)
         alt = {"gemm": "tf32_tcgen05", "value": B * world * args.steps / (ms_alt * 1e-3), "ms_per_step": ms_alt / args.steps}
+    model.close()
 
-    peer_ok = world > 1 and model.comm_peer_status()[0]
-    if world > 1 and model.comm_peer_status()[1]:
-        raise RuntimeError("NVLink peer exchange timed out waiting for a peer")
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = parity_check(args, w, nv, sharding, dist, rank, world, local_rank)
+
     if rank == 0:
         peaks = {}
         try:
@@ -399,36 +622,62 @@ def run_ours(args, w, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        f0, l0 = raw[0]
+        uniq_w, uniq_e = int(np.unique(f0).size), int(np.unique(ids_keep[0]).size)
+        comp = compulsory_bytes_per_launch(w, B, args.gemm_mode, unique_words=uniq_w, unique_entities=uniq_e)
         alg = algorithmic_bytes_per_ngram(w)
-        cand = {k: phases.get(k, 0.0) for k in alg}
+        cand = {k: phases.get(k, 0.0) for k in comp}
         dom = max(cand, key=cand.get)
         dom_ms = cand[dom]
-        achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        total_alg = sum(alg.values()) * B
+        achieved = comp[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(args.workload, {}).get(dom)
         except Exception:
             pass
+        l2_peak = probes["l2_gather_gbs"] if probes else None
+        per_kernel = {}
+        for k in comp:
+            t = phases.get(k, 0.0) * 1e-3
+            if t <= 0:
+                continue
+            per_kernel[k] = {"ms": round(phases[k], 4), "hbm_compulsory_gbs": round(comp[k] / t / 1e9, 1),
+                             "hbm_frac": round(comp[k] / t / 1e9 / peak, 3),
+                             "l2_reference_gbs": round(alg[k] * B / t / 1e9, 1),
+                             "l2_frac": round(alg[k] * B / t / 1e9 / l2_peak, 3) if l2_peak else None}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    # achieved counts ALGORITHMIC bytes (every referenced row gathered once and read-modify-written
-                    # once); rows are referenced ~10x per step and the tables fit the 126 MB L2, so most of that is
-                    # served by L2 and frac can exceed 1. dram_gbs is the ncu-measured DRAM traffic over the same time.
+                    # achieved = COMPULSORY HBM bytes of the kernel as built (distinct table rows once, streamed per-step
+                    # tensors, one read-modify-write of every optimiser-state row; compulsory_bytes_per_launch) / its
+                    # CUDA-event time. traffic = ncu dram bytes of the same launch (profiles/traffic.json).
+                    "compulsory_bytes_per_launch": comp[dom], "kernel_ms": dom_ms,
                     "dram_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if (traffic and dom_ms > 0) else None,
                     "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if (traffic and dom_ms > 0) else None,
-                    "algorithmic_bytes_per_launch": alg[dom] * B, "kernel_ms": dom_ms,
-                    "step_algorithmic_gbs": total_alg / (ms / args.steps * 1e-3) / 1e9,
+                    "excess_traffic": (traffic / comp[dom]) if traffic else None,
+                    # second ceiling: the gather-type kernels re-read every table row ~10x per batch out of L2; bytes per
+                    # REFERENCE against the L2-resident gather rate measured on this GPU just now
+                    "l2": {"achieved": alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None, "peak": l2_peak,
+                           "unit": "GB/s", "frac": (alg[dom] * B / (dom_ms * 1e-3) / 1e9 / l2_peak) if (l2_peak and dom_ms > 0) else None,
+                           "bytes_per_launch": alg[dom] * B, "peak_source": probes["l2_gather_probe"] if probes else None},
+                    "stream_copy_gbs_here": probes["stream_copy_gbs"] if probes else None,
+                    "per_kernel": per_kernel,
+                    "step_compulsory_hbm_gbs": sum(comp.values()) / (ms / args.steps * 1e-3) / 1e9,
                     "phase_ms": {k: round(v, 4) for k, v in phases.items()}}
         h2d = int(B * w["n"] * 8 + B * w["n"] * 4 + B * 8 + B * 4)
         ngrams = B * world * args.steps
         cpu = None
-        if not args.no_cpu_baseline:
-            r = cpu_port_run(w, 2, 1, min(args.cpu_sample, w["B"]))
+        if not args.no_cpu_baseline and world == 1:
+            # bounded sample: whole batches of the same workload for ~args.cpu_seconds of host time (probe step first)
+            sample_B = min(args.cpu_sample, w["B"]) if args.cpu_sample > 0 else w["B"]
+            probe = cpu_port_run(w, 1, 1, sample_B)
+            cpu_steps = int(min(40, max(2, round(args.cpu_seconds / max(probe["ms_per_step"] * 1e-3, 1e-6)))))
+            r = cpu_port_run(w, cpu_steps, 0, sample_B)
             cpu = {"value": r["value"], "unit": "n-grams/s", "cores": r["cores"], "kind": "port",
-                   "sample": "%d n-grams/step x 2 steps of the same workload (full-size tables), float32 oracle, "
-                             "sampler+forward+backward+update, %s build" % (args.cpu_sample, "-march=native" if r["native"] else "portable")}
+                   "sample": "%d n-grams/step x %d steps (%.1f s) of the same workload (full-size tables), float32 oracle "
+                             "port, host sampler + forward + backward + update, OpenMP over %d threads, %s build" % (
+                                 sample_B, cpu_steps, r["ms_per_step"] * cpu_steps * 1e-3, r["cores"],
+                                 "-march=native" if r["native"] else "portable")}
         line = {
             "metric": "n-grams/sec", "value": ngrams / (ms * 1e-3), "unit": "n-grams/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -443,7 +692,8 @@ def run_ours(args, w, rank, world, local_rank):
                                      "inside the timed step by the bit-exact device sampler"
                                      + ("; Zipf(%g) over the entity ids (inverse-CDF generator)" % w["neg_zipf"]
                                         if w.get("neg_zipf", 0.0) > 0.0 else "; uniform (the reference's generator)")),
-                       "word_ids": "Zipf(%g)" % w["word_zipf"] if w.get("word_zipf", 0.0) > 0.0 else "uniform"},
+                       "word_ids": "Zipf(%g)" % w["word_zipf"] if w.get("word_zipf", 0.0) > 0.0 else "uniform",
+                       "host_cores_per_rank": cores_per_rank},
             "e2e": {"value": ngrams / (ms_e2e * 1e-3), "unit": "n-grams/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -452,6 +702,9 @@ def run_ours(args, w, rank, world, local_rank):
                             {"small_reductions": "nvlink peer exchange (peer_allreduce.cuh)" if peer_ok else "ncclAllReduce",
                              "grad_transform": "ncclAllReduce on a side stream under grad_phrase + word update"}),
         }
+        if world > 1:
+            line["strong"] = strong
+            line["parity_check"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -467,7 +720,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--update_method", default=None)
     ap.add_argument("--gemm_mode", type=int, default=2, help="0 fp32 SIMT, 1 tf32 tcgen05, 2 3xtf32 tcgen05 (default: fp32-level parity)")
-    ap.add_argument("--cpu_sample", type=int, default=5120)
+    ap.add_argument("--cpu_sample", type=int, default=0, help="n-grams per step of the CPU sample (0 = the workload's whole batch)")
+    ap.add_argument("--cpu_seconds", type=float, default=10.0, help="host time budget of the cpu_baseline sample")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--reference_kind", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: auto = the reference's own CUDA step (oracle/_ref) when built, else the CPU port")
@@ -476,6 +730,13 @@ def main():
                          "single-GPU trajectory (every replica applies all rows' updates)")
     ap.add_argument("--no_peer", action="store_true", help="N>1: small reductions through ncclAllReduce instead of the NVLink peer exchange")
     ap.add_argument("--no_alt", action="store_true", help="skip the extra single-pass TF32 measurement")
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
+                    help="N>1: `value` is always the weak-scaling number (per-GPU batch fixed); both / strong add a "
+                         "`strong` block with the workload's batch itself sharded over the ranks (BASELINE configs[3])")
+    ap.add_argument("--no_parity_check", action="store_true", help="N>1: skip the sharded-vs-unsharded-vs-reference step check")
+    ap.add_argument("--no_ref_check", action="store_true", help="N>1 parity check without the oracle/_ref leg")
+    ap.add_argument("--no_probes", action="store_true", help="skip the L2-gather / stream-copy roofline probes")
+
     ap.add_argument("--zipf_words", type=float, default=0.0, help="word ids ~ Zipf(s) instead of uniform (C3 gather/scatter sweep)")
     ap.add_argument("--zipf_negatives", type=float, default=None, help="negatives ~ Zipf(s) over the entity ids (C5 default 1.0; 0 = uniform)")
     args = ap.parse_args()

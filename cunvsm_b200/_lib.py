@@ -18,7 +18,7 @@ SYMBOLS = [
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
     "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_comm_peer_export", "nvsm_comm_peer_import", "nvsm_comm_peer_status", "nvsm_comm_peer_disable", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
-    "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_sampler_seed", "nvsm_sampler_state",
+    "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_bench_memory", "nvsm_sampler_seed", "nvsm_sampler_state",
     "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device", "nvsm_generate_labels_cdf", "nvsm_sampler_set_cdf",
 ]
 
@@ -96,6 +96,7 @@ def load():
     f("nvsm_kernel_launches", [vp], cl)
     f("nvsm_test_gemm_tc", [vp, ci, ci, ci, ci, pf, pf, pf, cf, pf, ci])
     f("nvsm_bench_gemm_tc", [vp, ci, ci, ci, ci, ci, ci, ci, pf])
+    f("nvsm_bench_memory", [vp, ci, cl, ci, ci, cl, ci, pf])
     f("nvsm_sampler_seed", [vp, ctypes.c_ulong])
     f("nvsm_sampler_state", [vp, pul])
     f("nvsm_step_sampled", [vp, pl, pf, pl, pf, cl, cf, ci])

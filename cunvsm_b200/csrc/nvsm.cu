@@ -23,6 +23,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include "kernels.cuh"
+#include "microbench.cuh"
 #include "nccl_dyn.h"
 #include "peer_allreduce.cuh"
 #include "pull_update.cuh"
@@ -2466,6 +2467,60 @@ int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int spli
     };
     const int rc = run();
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+// Roofline denominators measured in place (microbench.cuh). kind 0: gather of `rows_per_item` pseudo-random rows of
+// `row_floats` floats per item out of a table of `table_bytes` (L2-resident when it fits the 126 MB L2), GB/s of
+// gathered bytes; kind 1: streaming copy of `table_bytes` (read + write bytes), GB/s.
+int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats, int rows_per_item, long items, int iters,
+                      float* gbs_out) {
+    if (!m || !gbs_out) return fail("null argument");
+    if (iters <= 0 || table_bytes <= 0) return fail("invalid probe arguments");
+    CU(cudaSetDevice(m->device));
+    float4 *table = nullptr, *out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto run = [&]() -> int {
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        float ms = 0.f;
+        if (kind == 1) {
+            const long n = table_bytes / 16;
+            CU(cudaMalloc((void**)&table, n * 16)); CU(cudaMalloc((void**)&out, n * 16));
+            CU(cudaMemsetAsync(table, 0, n * 16, m->stream));
+            const int grid = m->num_sms * 8;
+            for (int it = 0; it < iters + 2; ++it) {
+                if (it == 2) CU(cudaEventRecord(e0, m->stream));
+                LAUNCH(m, stream_copy_probe_kernel, grid, 256, 0, (const float4*)table, out, n);
+            }
+            CU(cudaEventRecord(e1, m->stream)); CU(cudaEventSynchronize(e1));
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            *gbs_out = (float)(2.0 * n * 16 * iters / (ms * 1e-3) / 1e9);
+            return 0;
+        }
+        if (row_floats <= 0 || row_floats % 4 != 0 || row_floats > 512 || rows_per_item <= 0 || items <= 0)
+            return fail("gather probe: row_floats must be a multiple of 4 up to 512");
+        const int row_vec4 = row_floats / 4;
+        const long num_rows = std::max<long>(1, table_bytes / (16L * row_vec4));
+        CU(cudaMalloc((void**)&table, num_rows * row_vec4 * 16)); CU(cudaMalloc((void**)&out, items * row_vec4 * 16));
+        CU(cudaMemsetAsync(table, 0, num_rows * row_vec4 * 16, m->stream));
+        const int grid = grid_for(m, items, 8, 8);
+        const int K = (row_vec4 + 31) / 32;
+        for (int it = 0; it < iters + 2; ++it) {
+            if (it == 2) CU(cudaEventRecord(e0, m->stream));
+            const unsigned seed = 0x1234567u + (unsigned)it * 7919u;
+#define NVSM_PROBE(K_) LAUNCH(m, (l2_gather_probe_kernel<K_, 2>), grid, 256, 0, (const float4*)table, num_rows, row_vec4, rows_per_item, items, out, seed)
+            if (K <= 1) NVSM_PROBE(1); else if (K == 2) NVSM_PROBE(2); else if (K == 3) NVSM_PROBE(3); else NVSM_PROBE(4);
+#undef NVSM_PROBE
+        }
+        CU(cudaEventRecord(e1, m->stream)); CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        *gbs_out = (float)((double)items * rows_per_item * row_floats * 4.0 * iters / (ms * 1e-3) / 1e9);
+        return 0;
+    };
+    const int rc = run();
+    cudaFree(table); cudaFree(out);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;

@@ -484,6 +484,13 @@ class Model:
         check(self.L.nvsm_get_phase_ms(self.h, out, n))
         return {self.L.nvsm_phase_name(i).decode(): out[i] for i in range(n)}
 
+    def bench_memory(self, kind, table_bytes, row_floats=256, rows_per_item=10, items=51200, iters=20):
+        """Roofline denominators measured in place (nvsm_bench_memory): kind 0 = GB/s of a plain row gather out of a
+        `table_bytes` table (L2-resident when it fits), kind 1 = GB/s of a streaming copy."""
+        out = ctypes.c_float()
+        check(self.L.nvsm_bench_memory(self.h, kind, int(table_bytes), row_floats, rows_per_item, int(items), iters, ctypes.byref(out)))
+        return out.value
+
     def kernel_launches(self):
         return self.L.nvsm_kernel_launches(self.h)
 

@@ -212,6 +212,15 @@ NVSM_API int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, 
 NVSM_API int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int splits, int with_stats,
                                 int iters, float* ms_out);
 
+/* Micro-benchmark hook for the roofline denominators bench.py reports (csrc/microbench.cuh), measured on the device
+ * the model lives on. kind 0: GB/s of a plain warp-per-item gather of `rows_per_item` pseudo-random rows of
+ * `row_floats` floats out of a `table_bytes` table (L2-resident when it fits) -- the ceiling of the step's gather-type
+ * kernels, which re-read every embedding row ~10x per batch (reference access pattern: average_repr_kernel,
+ * cpp/params.cu:75-95, and update_repr_kernel, cpp/storage.cu:37-49); kind 1: GB/s (read + write) of a streaming copy
+ * of `table_bytes`. */
+NVSM_API int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats, int rows_per_item, long items,
+                               int iters, float* gbs_out);
+
 /* RepresentationSimilarity::Objective::compute_cost + compute_gradients — cpp/objective.cu:487-672 — on a
  * RepresentationSimilarity::Batch (include/cuNVSM/data.h:560-614): pair_ids [2*num_pairs] HOST (adjacent ids form a
  * pair, rows of the entity table for *_ENTITY_ENTITY objectives, of the word table for *_TERM_TERM), weights
