@@ -587,11 +587,16 @@ def run_ours(args, w, rank, world, local_rank):
     # roofline denominators measured in place (rank 0): L2-resident gather and streaming copy
     probes = None
     if rank == 0 and not args.no_probes:
-        table_bytes = 4 * w["V"] * w["dw"]
-        probes = {"l2_gather_gbs": model.bench_memory(0, min(table_bytes, 64 << 20), row_floats=(w["dw"] + 3) // 4 * 4,
-                                                      rows_per_item=w["n"], items=B, iters=20),
-                  "l2_gather_probe": "warp-per-item gather of n=%d rows x %d floats from a %d MB table, 2 rows in flight" % (
-                      w["n"], (w["dw"] + 3) // 4 * 4, min(table_bytes, 64 << 20) >> 20),
+        table_bytes = min(4 * w["V"] * w["dw"], 64 << 20)
+        rowf = (w["dw"] + 3) // 4 * 4
+        gathers = {u: model.bench_memory(kind, table_bytes, row_floats=rowf, rows_per_item=w["n"], items=B, iters=20)
+                   for kind, u in ((4, 1), (0, 2), (3, 4))}
+        best_u = max(gathers, key=gathers.get)
+        probes = {"l2_gather_gbs": gathers[best_u],
+                  "l2_gather_probe": "warp-per-item gather of n=%d rows x %d floats from a %d MB (L2-resident) table, %d rows in "
+                                     "flight per warp (best of 1 / 2 / 4: %s GB/s)" % (
+                                         w["n"], rowf, table_bytes >> 20, best_u, " / ".join("%.0f" % gathers[u] for u in (1, 2, 4))),
+                  "l2_read_gbs": model.bench_memory(2, 32 << 20, items=32, iters=5),
                   "stream_copy_gbs": model.bench_memory(1, 1 << 30, iters=10)}
 
     peer_ok = world > 1 and model.comm_peer_status()[0]
@@ -630,22 +635,26 @@ def run_ours(args, w, rank, world, local_rank):
         dom = max(cand, key=cand.get)
         dom_ms = cand[dom]
         achieved = comp[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        traffic = None
+        traffic, tr = None, {}
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(args.workload, {}).get(dom)
         except Exception:
             pass
-        l2_peak = probes["l2_gather_gbs"] if probes else None
+        l2_peak = max(probes["l2_gather_gbs"], probes["l2_read_gbs"]) if probes else None
+        l2_bytes = tr.get(args.workload + "_l2", {})   # SM <-> L2 bytes per launch (ncu lts__t_sectors_srcunit_tex x 32 B)
         per_kernel = {}
         for k in comp:
             t = phases.get(k, 0.0) * 1e-3
             if t <= 0:
                 continue
+            l2b = l2_bytes.get(k)
             per_kernel[k] = {"ms": round(phases[k], 4), "hbm_compulsory_gbs": round(comp[k] / t / 1e9, 1),
                              "hbm_frac": round(comp[k] / t / 1e9 / peak, 3),
-                             "l2_reference_gbs": round(alg[k] * B / t / 1e9, 1),
-                             "l2_frac": round(alg[k] * B / t / 1e9 / l2_peak, 3) if l2_peak else None}
+                             "l2_gbs": round(l2b / t / 1e9, 1) if l2b else None,
+                             "l2_frac": round(l2b / t / 1e9 / l2_peak, 3) if (l2b and l2_peak) else None,
+                             "per_reference_gbs": round(alg[k] * B / t / 1e9, 1)}
+        dom_l2 = l2_bytes.get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     # achieved = COMPULSORY HBM bytes of the kernel as built (distinct table rows once, streamed per-step
@@ -655,11 +664,14 @@ def run_ours(args, w, rank, world, local_rank):
                     "dram_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if (traffic and dom_ms > 0) else None,
                     "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if (traffic and dom_ms > 0) else None,
                     "excess_traffic": (traffic / comp[dom]) if traffic else None,
-                    # second ceiling: the gather-type kernels re-read every table row ~10x per batch out of L2; bytes per
-                    # REFERENCE against the L2-resident gather rate measured on this GPU just now
-                    "l2": {"achieved": alg[dom] * B / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None, "peak": l2_peak,
-                           "unit": "GB/s", "frac": (alg[dom] * B / (dom_ms * 1e-3) / 1e9 / l2_peak) if (l2_peak and dom_ms > 0) else None,
-                           "bytes_per_launch": alg[dom] * B, "peak_source": probes["l2_gather_probe"] if probes else None},
+                    # second ceiling: the gather-type kernels re-read every table row ~10x per batch out of L2. achieved =
+                    # SM <-> L2 bytes of the launch (ncu lts__t_sectors_srcunit_tex, profiles/traffic.json) / CUDA-event time;
+                    # peak = the best of an L2-resident row gather and an L2-resident streaming read measured on this GPU now
+                    "l2": {"achieved": (dom_l2 / (dom_ms * 1e-3) / 1e9) if (dom_l2 and dom_ms > 0) else None, "peak": l2_peak,
+                           "unit": "GB/s", "frac": (dom_l2 / (dom_ms * 1e-3) / 1e9 / l2_peak) if (dom_l2 and l2_peak and dom_ms > 0) else None,
+                           "bytes_per_launch": dom_l2, "gather_probe_gbs": probes["l2_gather_gbs"] if probes else None,
+                           "read_probe_gbs": probes["l2_read_gbs"] if probes else None,
+                           "peak_source": (probes["l2_gather_probe"] + "; L2-resident streaming read of a 32 MB buffer") if probes else None},
                     "stream_copy_gbs_here": probes["stream_copy_gbs"] if probes else None,
                     "per_kernel": per_kernel,
                     "step_compulsory_hbm_gbs": sum(comp.values()) / (ms / args.steps * 1e-3) / 1e9,

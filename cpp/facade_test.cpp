@@ -1,6 +1,7 @@
 // Exercises the C++ façade the way the reference's own callers do (compute_cost ->
 // compute_gradients -> update -> get_cost, get_data, infer) and prints values the Python test
 // compares with the same sequence driven through ctypes.
+#include <cmath>
 #include <cstdio>
 #include <memory>
 #include <tuple>
@@ -64,6 +65,8 @@ int main() {
     std::printf("mixchecksum %.9g\n", mcs);
     // The CLI reads the loss of batch k-1 after batch k has been enqueued (cpp/main.cpp, iterate): a deferred read
     // must report the costs of ITS batch for both constituents (the pair loss is cached when the result is made).
+    // Two model instances: the mixture's scatter-added gradients sum in a run-dependent order, so the twins agree to
+    // float round-off (1e-5), while successive batches' costs differ in the second digit.
     {
       RNG a; a.seed(9); RNG b; b.seed(9);
       Model<TextEntityEntityEntity::Objective> eager(100, 60, desc, mtc, 0, NVSM_GEMM_FP32), lazy(100, 60, desc, mtc, 0, NVSM_GEMM_FP32);
@@ -77,10 +80,12 @@ int main() {
         eager.backprop(*r, 0.01f);
         std::unique_ptr<MultiForwardResult> q(lazy.compute_cost(both, &b));
         lazy.backprop(*q, 0.01f);
-        if (previous && previous->get_cost() != eager_cost[step - 1]) deferred_ok = 0;
+        if (previous && std::fabs(previous->get_cost() - eager_cost[step - 1]) > 1e-5f * std::fabs(eager_cost[step - 1])) deferred_ok = 0;
         previous = std::move(q);
       }
-      if (previous->get_cost() != eager_cost[2]) deferred_ok = 0;
+      if (std::fabs(previous->get_cost() - eager_cost[2]) > 1e-5f * std::fabs(eager_cost[2])) deferred_ok = 0;
+      if (!(std::fabs(eager_cost[0] - eager_cost[1]) > 1e-3f * std::fabs(eager_cost[0]))) deferred_ok = 0;   // the check can tell batches apart
+      std::printf("deferred costs %.9g %.9g %.9g\n", eager_cost[0], eager_cost[1], eager_cost[2]);
       std::printf("deferred_mixture_cost_ok %d\n", deferred_ok);
     }
   }

@@ -53,6 +53,35 @@ __global__ void __launch_bounds__(256) l2_gather_probe_kernel(const float4* __re
     }
 }
 
+// (volatile: the sweeps re-read the same addresses and must not be merged by the compiler)
+__device__ __forceinline__ float4 ld_cg_volatile(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// L2-resident streaming read: every thread walks the whole `n`-float4 buffer `reps` times with 8 independent 128-bit
+// loads in flight (the buffer is sized to stay in L2, so after the first sweep every load is an L2 hit). GB/s of this
+// is the SM <-> L2 ceiling every gather-type kernel of the step sits under.
+__global__ void __launch_bounds__(256) l2_read_probe_kernel(const float4* __restrict__ in, long n, int reps,
+                                                            float4* __restrict__ out) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long t0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < reps; ++r) {
+        long i = t0;
+        for (; i + 7 * stride < n; i += 8 * stride) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ld_cg_volatile(in + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; i < n; i += stride) { const float4 v = ld_cg_volatile(in + i); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    if (acc.x == 123.456f) out[t0] = acc;   // never true for a zero-filled buffer: keeps the loads alive
+}
+
 // Streaming read + write of `n` float4 (HBM copy peak cross-check against MEASURED_PEAKS.json).
 __global__ void __launch_bounds__(256) stream_copy_probe_kernel(const float4* __restrict__ in, float4* __restrict__ out, long n) {
     const long stride = (long)gridDim.x * blockDim.x;

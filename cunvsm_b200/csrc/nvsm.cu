@@ -2472,9 +2472,10 @@ int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int spli
     return rc;
 }
 
-// Roofline denominators measured in place (microbench.cuh). kind 0: gather of `rows_per_item` pseudo-random rows of
-// `row_floats` floats per item out of a table of `table_bytes` (L2-resident when it fits the 126 MB L2), GB/s of
-// gathered bytes; kind 1: streaming copy of `table_bytes` (read + write bytes), GB/s.
+// Roofline denominators measured in place (microbench.cuh). kind 0 / 3 / 4: gather of `rows_per_item` pseudo-random
+// rows of `row_floats` floats per item out of a table of `table_bytes` (L2-resident when it fits the 126 MB L2) with
+// 2 / 4 / 1 rows in flight per warp, GB/s of gathered bytes; kind 1: streaming copy of `table_bytes` (read + write
+// bytes), GB/s; kind 2: L2-resident streaming read (`items` sweeps over a `table_bytes` buffer per launch), GB/s.
 int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats, int rows_per_item, long items, int iters,
                       float* gbs_out) {
     if (!m || !gbs_out) return fail("null argument");
@@ -2499,6 +2500,21 @@ int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats,
             *gbs_out = (float)(2.0 * n * 16 * iters / (ms * 1e-3) / 1e9);
             return 0;
         }
+        if (kind == 2) {   // L2-resident streaming read: `items` = sweeps over the buffer per launch
+            const long n = table_bytes / 16;
+            const int reps = (int)std::max<long>(1, items);
+            CU(cudaMalloc((void**)&table, n * 16)); CU(cudaMalloc((void**)&out, (size_t)m->num_sms * 8 * 256 * 16));
+            CU(cudaMemsetAsync(table, 0, n * 16, m->stream));
+            for (int it = 0; it < iters + 2; ++it) {
+                if (it == 2) CU(cudaEventRecord(e0, m->stream));
+                LAUNCH(m, l2_read_probe_kernel, m->num_sms * 8, 256, 0, (const float4*)table, n, reps, out);
+            }
+            CU(cudaEventRecord(e1, m->stream)); CU(cudaEventSynchronize(e1));
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            *gbs_out = (float)((double)n * 16 * reps * iters / (ms * 1e-3) / 1e9);
+            return 0;
+        }
+        if (kind != 0 && kind != 3 && kind != 4) return fail("unknown probe kind %d", kind);
         if (row_floats <= 0 || row_floats % 4 != 0 || row_floats > 512 || rows_per_item <= 0 || items <= 0)
             return fail("gather probe: row_floats must be a multiple of 4 up to 512");
         const int row_vec4 = row_floats / 4;
@@ -2510,8 +2526,10 @@ int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats,
         for (int it = 0; it < iters + 2; ++it) {
             if (it == 2) CU(cudaEventRecord(e0, m->stream));
             const unsigned seed = 0x1234567u + (unsigned)it * 7919u;
-#define NVSM_PROBE(K_) LAUNCH(m, (l2_gather_probe_kernel<K_, 2>), grid, 256, 0, (const float4*)table, num_rows, row_vec4, rows_per_item, items, out, seed)
-            if (K <= 1) NVSM_PROBE(1); else if (K == 2) NVSM_PROBE(2); else if (K == 3) NVSM_PROBE(3); else NVSM_PROBE(4);
+#define NVSM_PROBE(K_, U_) LAUNCH(m, (l2_gather_probe_kernel<K_, U_>), grid, 256, 0, (const float4*)table, num_rows, row_vec4, rows_per_item, items, out, seed)
+#define NVSM_PROBE_K(U_) do { if (K <= 1) NVSM_PROBE(1, U_); else if (K == 2) NVSM_PROBE(2, U_); else if (K == 3) NVSM_PROBE(3, U_); else NVSM_PROBE(4, U_); } while (0)
+            if (kind == 0) NVSM_PROBE_K(2); else if (kind == 3) NVSM_PROBE_K(4); else NVSM_PROBE_K(1);   // rows in flight per warp
+#undef NVSM_PROBE_K
 #undef NVSM_PROBE
         }
         CU(cudaEventRecord(e1, m->stream)); CU(cudaEventSynchronize(e1));

@@ -213,11 +213,12 @@ NVSM_API int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K,
                                 int iters, float* ms_out);
 
 /* Micro-benchmark hook for the roofline denominators bench.py reports (csrc/microbench.cuh), measured on the device
- * the model lives on. kind 0: GB/s of a plain warp-per-item gather of `rows_per_item` pseudo-random rows of
- * `row_floats` floats out of a `table_bytes` table (L2-resident when it fits) -- the ceiling of the step's gather-type
- * kernels, which re-read every embedding row ~10x per batch (reference access pattern: average_repr_kernel,
- * cpp/params.cu:75-95, and update_repr_kernel, cpp/storage.cu:37-49); kind 1: GB/s (read + write) of a streaming copy
- * of `table_bytes`. */
+ * the model lives on. kind 0 / 3 / 4: GB/s of a plain warp-per-item gather of `rows_per_item` pseudo-random rows of
+ * `row_floats` floats out of a `table_bytes` table (L2-resident when it fits), 2 / 4 / 1 rows in flight per warp -- the
+ * access pattern of the step's gather-type kernels, which re-read every embedding row ~10x per batch (reference:
+ * average_repr_kernel, cpp/params.cu:75-95, and update_repr_kernel, cpp/storage.cu:37-49); kind 1: GB/s (read + write)
+ * of a streaming copy of `table_bytes`; kind 2: GB/s of an L2-resident streaming read (`items` sweeps over a
+ * `table_bytes` buffer per launch): the SM <-> L2 ceiling. */
 NVSM_API int nvsm_bench_memory(nvsm_model* m, int kind, long table_bytes, int row_floats, int rows_per_item, long items,
                                int iters, float* gbs_out);
 

@@ -99,9 +99,10 @@ def adam_check(rname, step, got, ref, before, lr):
     frob = np.linalg.norm(d_got - d_ref) / max(np.linalg.norm(d_ref), 1e-30)
     worst = np.abs(got - ref).max() / lr
     outside = float((np.abs(got - ref) > 5e-4 * np.abs(ref) + 2e-3 * lr).mean())
-    assert frob <= 2e-3, (rname, step, "relative Frobenius error of the update", frob)
-    assert worst <= 0.25, (rname, step, "largest deviation / lr", worst)
-    assert outside <= 1e-4, (rname, step, "fraction of elements outside 5e-4 rel + 2e-3 lr", outside)
+    # measured on B200 (round 2): Frobenius 2e-6 .. 9e-6, no element outside the band
+    assert frob <= 2e-4, (rname, step, "relative Frobenius error of the update", frob)
+    assert worst <= 0.05, (rname, step, "largest deviation / lr", worst)
+    assert outside <= 1e-5, (rname, step, "fraction of elements outside 5e-4 rel + 2e-3 lr", outside)
     return rname, step, frob, worst, outside
 
 
