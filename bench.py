@@ -523,6 +523,7 @@ def run_ours(args, w, rank, world, local_rank):
         return ms, m.kernel_launches() - l0
 
     lr = w["lr"]
+    breakdown = []
 
     def measure(m, batches, steps, warmup):
         """(device-resident ms, launches, host-fed ms) of `steps` steps on the batches staged in / fed to `m`."""
@@ -543,6 +544,30 @@ def run_ours(args, w, rank, world, local_rank):
             host_fed(it)
         ms_e2e, _ = timed(m, host_fed, steps)
         m.last_cost()
+        if args.e2e_breakdown:
+            # where the host-fed step differs from the device-resident one: host time inside the call (enqueue cost),
+            # the per-step loss read, and the H2D + sampling work itself
+            host_s = [0.0]
+
+            def host_fed_timed(it):
+                t0 = time.perf_counter()
+                m.step_sampled(batches[it % NUM_BATCHES], lr)
+                host_s[0] += time.perf_counter() - t0
+                if it > 0:
+                    m.last_cost(1)
+            ms_a, _ = timed(m, host_fed_timed, steps)
+            ms_b, _ = timed(m, lambda it: m.step_sampled(batches[it % NUM_BATCHES], lr), steps)   # no per-step loss read
+            m.last_cost()
+            stage_s = [0.0]
+
+            def staged_timed(it):
+                t0 = time.perf_counter()
+                m.train_step_staged(it % NUM_BATCHES, lr)
+                stage_s[0] += time.perf_counter() - t0
+            ms_c, _ = timed(m, staged_timed, steps)
+            breakdown.append({"rows": batches[0].num_instances_, "e2e_ms": ms_a / steps, "e2e_no_loss_read_ms": ms_b / steps,
+                              "staged_ms": ms_c / steps, "host_us_in_step_sampled": 1e6 * host_s[0] / steps,
+                              "host_us_in_train_step_staged": 1e6 * stage_s[0] / steps})
         return ms, launches, ms_e2e, cost
 
     batches, raw, ids_keep = make_staged(model, B, 1234)
@@ -717,6 +742,8 @@ def run_ours(args, w, rank, world, local_rank):
         if world > 1:
             line["strong"] = strong
             line["parity_check"] = parity
+        if breakdown:
+            line["e2e_breakdown"] = breakdown
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -747,6 +774,7 @@ def main():
                          "`strong` block with the workload's batch itself sharded over the ranks (BASELINE configs[3])")
     ap.add_argument("--no_parity_check", action="store_true", help="N>1: skip the sharded-vs-unsharded-vs-reference step check")
     ap.add_argument("--no_ref_check", action="store_true", help="N>1 parity check without the oracle/_ref leg")
+    ap.add_argument("--e2e_breakdown", action="store_true", help="extra timed loops that split the host-fed step's overhead (rank 0's view)")
     ap.add_argument("--no_probes", action="store_true", help="skip the L2-gather / stream-copy roofline probes")
 
     ap.add_argument("--zipf_words", type=float, default=0.0, help="word ids ~ Zipf(s) instead of uniform (C3 gather/scatter sweep)")
