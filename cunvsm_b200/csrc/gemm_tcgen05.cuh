@@ -53,7 +53,14 @@ struct Params {
     long split_stride;     // elements between split-K partial outputs
     float alpha;
     const float* bias;     // nullable, per output column
+    // Optional fused column statistics of C (batch-norm forward, cpp/cudnn_utils.cu:107-124): every epilogue warp
+    // adds the column sums and sums of squares of the rows it drains and writes one fp32 partial row
+    // stat_part[(blockIdx.x * 4 + warp) * 2 * N + {0, N} + column] when the kernel ends (n_tiles == 1, splits == 1,
+    // N % 16 == 0, no bias: C = alpha * A.B). Replaces a separate pass over C (col_stats4_kernel).
+    float* stat_part;
 };
+
+constexpr int kStatCols = 256;   // widest tile the fused statistics cover
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -157,6 +164,37 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Transposing butterfly: every lane brings 32 partials x[0..31]; afterwards lane l holds the warp total of partial l.
+// 31 shuffles instead of 160.
+__device__ __forceinline__ float warp_reduce32_transposed(float (&x)[32], int lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool up = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float keep = up ? x[i + step] : x[i];
+            const float send = up ? x[i] : x[i + step];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return x[0];
+}
+
+// Column statistics of one drained chunk: v = this lane's row, 16 consecutive columns of the tile (chunk `ch`).
+// Lane l < 16 accumulates the sum of column 16 ch + l, lane l >= 16 the sum of squares of column 16 ch + l - 16, in
+// the warp's own 512-float strip of shared memory (slot 32 ch + l: no other thread touches it).
+__device__ __forceinline__ void stat_accumulate(float* warp_strip, int ch, int lane, const float (&v)[16]) {
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { x[i] = v[i]; x[16 + i] = v[i] * v[i]; }
+    const float r = warp_reduce32_transposed(x, lane);
+    warp_strip[32 * ch + lane] += r;
+}
+__device__ __forceinline__ void stat_flush(const float* warp_strip, float* part_row, int n, int lane) {
+    for (int ch = 0; ch * 16 < n; ++ch)
+        part_row[(lane >> 4) * n + 16 * ch + (lane & 15)] = warp_strip[32 * ch + lane];
+}
+
 // Persistent, warp-specialised GEMM: grid = min(#tiles, #SMs); every CTA walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ... The TMA producer runs ahead across tile boundaries
 // (the smem ring never drains), the MMA warp alternates between two TMEM accumulator buffers,
@@ -179,6 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float stat_strip[4][2 * kStatCols];   // fused column statistics (Params::stat_part)
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -322,6 +361,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* __restrict__ bias = p.bias;
         const int Nv = p.N;
         const bool vec_ok = (p.ldc & 3) == 0;
+        float* const strip = stat_strip[q];
+        if (p.stat_part)
+            for (int t = lane; t < 2 * kStatCols; t += 32) strip[t] = 0.f;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
             int m0, n0, kb0, nkb, split;
@@ -375,6 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (c0 + i < Nv) crow[c0 + i] = v[i];
                     }
                 }
+                if (p.stat_part) stat_accumulate(strip, ch, lane, v);   // (rows past M are zero: zero-filled A, no bias)
                 if (nkb > 0 && ch + 1 < nchunks) {
                     tmem_ld_wait();
 #pragma unroll
@@ -385,6 +428,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        }
+        if (p.stat_part) {
+            __syncwarp();
+            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane);
         }
     }
     tc_fence_before();

@@ -79,6 +79,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float stat_strip[4][2 * kStatCols];   // fused column statistics (Params::stat_part)
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,6 +195,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const float* __restrict__ bias = p.bias;
         const int Nv = p.N;
         const bool vec_ok = (p.ldc & 3) == 0;
+        float* const strip = stat_strip[q];
+        if (p.stat_part)
+            for (int t = lane; t < 2 * kStatCols; t += 32) strip[t] = 0.f;
         uint32_t lt = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
             int m0, n0;
@@ -237,6 +241,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             if (c0 + i < Nv) crow[c0 + i] = v[i];
                     }
                 }
+                if (p.stat_part) stat_accumulate(strip, ch, lane, v);   // (rows past M are zero: zero-filled A, no bias)
                 if (ch + 1 < nchunks) {
                     tmem_ld_wait();
 #pragma unroll
@@ -250,6 +255,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (leader) mbar_arrive(bar_local);
                 else mbar_arrive_cluster(map_to_cta(bar_local, 0));
             }
+        }
+        if (p.stat_part) {
+            __syncwarp();
+            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane);
         }
     }
     tc_fence_before();

@@ -284,30 +284,35 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int dd, doub
     shift[c] = bias[c] - mf * isf;
 }
 
-// Single-GPU: the partial reduction (col_stats_reduce_kernel) and the finalisation in one launch. One CTA owns 32
-// columns: 8 slices of the partial rows per column, sums and sums of squares together, double accumulation.
+// Single-GPU: the partial reduction (col_stats_reduce_kernel) and the finalisation in one launch. One CTA owns 8
+// columns x 128 slices of the partial rows (ncu r1i: the former 32-column x 32-slice shape ran 8 CTAs for 14.7 us, a
+// serial chain of ~19 dependent L2 round trips per thread; this one runs dd / 8 CTAs with <= 5 per thread). Sums and
+// sums of squares together, double accumulation, fixed summation order.
 __global__ void __launch_bounds__(1024) col_stats_reduce_finalize_kernel(const float* __restrict__ partials, int nblocks, int dd,
                                                                          double batch, double eps, double* __restrict__ sums,
                                                                          float* __restrict__ mean, float* __restrict__ invstd,
                                                                          const float* __restrict__ bias,
                                                                          float* __restrict__ scale, float* __restrict__ shift) {
-    constexpr int S = 32;   // slices of the partial rows per column (blockDim = 32 columns x S)
-    __shared__ double sm[2][S][32];
-    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int slice = threadIdx.x >> 5;
+    constexpr int C = 8, S = 128;   // blockDim = C columns x S slices
+    __shared__ double sm[2][32][C];
+    const int cl = threadIdx.x & (C - 1), slice = threadIdx.x / C;
+    const int col = blockIdx.x * C + cl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a = 0.0, q = 0.0;
     if (col < dd)
         for (int b = slice; b < nblocks; b += S) {
             a += (double)__ldg(partials + (long)b * 2 * dd + col);
             q += (double)__ldg(partials + (long)b * 2 * dd + dd + col);
         }
-    sm[0][slice][threadIdx.x & 31] = a;
-    sm[1][slice][threadIdx.x & 31] = q;
+    // lanes l, l ^ 8, l ^ 16, l ^ 24 hold the same column
+    a += __shfl_xor_sync(kFull, a, 8);  q += __shfl_xor_sync(kFull, q, 8);
+    a += __shfl_xor_sync(kFull, a, 16); q += __shfl_xor_sync(kFull, q, 16);
+    if (lane < C) { sm[0][warp][lane] = a; sm[1][warp][lane] = q; }
     __syncthreads();
-    if (slice == 0 && col < dd) {
+    if (threadIdx.x < C && col < dd) {
         double s = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int g = 0; g < S; ++g) { s += sm[0][g][threadIdx.x]; s2 += sm[1][g][threadIdx.x]; }
+#pragma unroll 8
+        for (int g = 0; g < 32; ++g) { s += sm[0][g][threadIdx.x]; s2 += sm[1][g][threadIdx.x]; }
         sums[col] = s;
         sums[dd + col] = s2;
         const double mu = s / batch;

@@ -148,6 +148,7 @@ struct nvsm_model {
     // (the two table updates may run concurrently on different streams)
     HeavyWork heavy_e{}, heavy_w{};
     HeavyWork *heavy_e_dev = nullptr, *heavy_w_dev = nullptr;   // device copies of the descriptors (row kernels)
+    bool adam_pipe = false;     // NVSM_ADAM_PIPE=1: software-pipelined row loop in adam_full_pull_kernel (A/B measurements)
     bool no_heavy = false;      // NVSM_NO_HEAVY=1: one warp per row whatever its reference count (A/B measurements)
     int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
                           // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
@@ -370,7 +371,7 @@ int make_tensor_map(CUtensorMap* map, const float* base, long inner, long outer,
 }
 
 // 227 KB opt-in limit minus the kernel's static shared memory (barriers), with headroom.
-constexpr uint32_t kTcMaxDynSmem = 232448u - 2048u;
+constexpr uint32_t kTcMaxDynSmem = 232448u - 2048u - 8192u;   // (8 KB static: the fused column-statistics strips)
 
 // Dynamic shared memory above 48 KB is an opt-in per function AND per device: called by nvsm_create for the device of
 // every model (a process-wide "done once" flag would leave a second device without it).
@@ -401,8 +402,12 @@ bool tc_shapes_ok(int dw, int dd) {
 // splits > 1 writes `splits` partial products to C + z * split_stride.
 int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
                 float* C, int ldc, int splits, long split_stride, float alpha, const float* bias,
-                int* splits_out = nullptr, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+                int* splits_out = nullptr, const float* A_lo = nullptr, const float* B_lo = nullptr,
+                float* stat_part = nullptr, int* stat_rows_out = nullptr) {
+    // stat_part: fused column statistics of C (tc::Params::stat_part); *stat_rows_out = partial rows written, 0 when
+    // this launch could not fuse them (the caller then runs col_stats4_kernel)
     const bool split3 = A_lo != nullptr && B_lo != nullptr;
+    if (stat_rows_out) *stat_rows_out = 0;
     {
         // Two-SM (cta_group::2) kernel for the K-major, un-split GEMMs (forward, grad_phrase); see gemm_tcgen05_2cta.cuh.
         // Default: on when one 256-wide tile covers N (the forward projection: B traffic per SM halves, measured
@@ -425,6 +430,8 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
             if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
             p.tmem_cols = 512;   // whole TMEM: both CTAs of the pair must get base 0
             p.C = C; p.ldc = ldc; p.split_stride = 0; p.alpha = alpha; p.bias = bias;
+            const bool fuse_stats = stat_part && p.n_tiles == 1 && !bias && N % 16 == 0 && N <= tc::kStatCols;
+            p.stat_part = fuse_stats ? stat_part : nullptr;
             CUtensorMap tmA, tmB, tmAlo, tmBlo;
             TRY(make_tensor_map(&tmA, A, K, M, lda, tc::kBlockK, tc::kBlockM));
             TRY(make_tensor_map(&tmB, Bm, K, N, ldb, tc::kBlockK, p.bn / 2));
@@ -436,6 +443,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
             if (split3) LAUNCH(m, (tc::gemm_tc2_kernel<true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
             else LAUNCH(m, (tc::gemm_tc2_kernel<false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
             if (splits_out) *splits_out = 1;
+            if (stat_rows_out && fuse_stats) *stat_rows_out = grid * 4;
             return 0;
         }
     }
@@ -462,6 +470,8 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
     p.C = C; p.ldc = ldc; p.split_stride = split_stride; p.alpha = alpha; p.bias = bias;
+    const bool fuse_stats = stat_part && p.n_tiles == 1 && p.splits == 1 && !bias && N % 16 == 0 && N <= tc::kStatCols;
+    p.stat_part = fuse_stats ? stat_part : nullptr;
     CUtensorMap tmA, tmB, tmAlo, tmBlo;
     if (!mn_major) {
         TRY(make_tensor_map(&tmA, A, K, M, lda, kb, tc::kBlockM));
@@ -491,6 +501,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     }
 #undef NVSM_TC_LAUNCH
     if (splits_out) *splits_out = p.splits;
+    if (stat_rows_out && fuse_stats) *stat_rows_out = grid * 4;
     return 0;
 }
 
@@ -579,12 +590,16 @@ int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
     const char* ew = getenv("NVSM_SCORE_W"); const char* es = getenv("NVSM_SCORE_S");
     if (ew) W = std::max(1, std::min(8, atoi(ew)));
     if (!ew && !es) {
-        // single stage: blocks of W warps, as many blocks per SM as fit
-        for (W = 8; W >= 2; W /= 2) {
-            const size_t blocks = budget / (W * stage_bytes + fixed + 1024);
-            if (blocks * W >= 8) { S = 1; break; }
+        // single stage: blocks of W warps, as many blocks per SM as fit; the block size that keeps the most warps
+        // resident wins (C3, R = 17: 18 KB per stage -> one 8-warp block per SM = 12.5 % occupancy in ncu r2a, three
+        // 4-warp blocks = 12 warps), ties go to the larger block
+        int best_w = 0, best_warps = 0;
+        for (int cand = 8; cand >= 2; cand /= 2) {
+            const size_t blocks = std::min<size_t>(budget / (cand * stage_bytes + fixed + 1024), 2048 / (cand * 32));
+            const int warps = (int)blocks * cand;
+            if (warps >= 8 && warps > best_warps) { best_warps = warps; best_w = cand; }
         }
-        if (S == 0) W = 8;
+        if (best_w) { W = best_w; S = 1; } else W = 8;
     }
     if (S == 0) {
         for (; W >= 2; W /= 2) {
@@ -683,14 +698,17 @@ int forward(nvsm_model* m, BatchSlot* s) {
     phase_end(m);
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
+    int stat_rows = 0;   // > 0: the GEMM epilogue wrote that many partial rows of column statistics into stat_part
     phase_begin(m, PH_GEMM_FWD);
     if (m->use_tc) {
         if (m->t_copies_stale) {   // after initialize / set_tensor; update() keeps the copies current otherwise
             LAUNCH(m, transpose_kernel, dim3((dd + 31) / 32, (dw + 31) / 32), dim3(32, 8), 0, m->T, dw, dd, m->Tt, m->ldP, m->Tr, m->Tt_lo, m->Tr_lo);
             m->t_copies_stale = false;
         }
+        // batch-norm: the column sums / sums of squares of Z come out of the GEMM's epilogue (no second pass over Z)
+        float* const fuse = (bn && !getenv("NVSM_NO_FUSED_STATS")) ? m->stat_part : (float*)nullptr;
         TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b, nullptr,
-                        m->P_lo, m->Tt_lo));
+                        m->P_lo, m->Tt_lo, fuse, &stat_rows));
     } else {
         TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, m->ldP, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
     }
@@ -705,10 +723,13 @@ int forward(nvsm_model* m, BatchSlot* s) {
             const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
             int bps = 4;   // blocks per SM (NVSM_STATS_BPS: experiment knob)
             { const char* e = getenv("NVSM_STATS_BPS"); if (e) bps = std::max(1, std::min(8, atoi(e))); }
-            const int nblk = grid_for(m, B, 16, bps);
-            LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
+            int nblk = stat_rows;
+            if (nblk == 0) {
+                nblk = grid_for(m, B, 16, bps);
+                LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
+            }
             if (m->nranks <= 1) {
-                LAUNCH(m, col_stats_reduce_finalize_kernel, (dd + 31) / 32, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                LAUNCH(m, col_stats_reduce_finalize_kernel, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
                        1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift);
             } else {
                 LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
@@ -1060,14 +1081,22 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
     if (entities) {
         const float* const self_k = m->l2_entity ? (const float*)m->kself : (const float*)nullptr;
-        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
+        if (m->adam_pipe)
+            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
+                   m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
+        else
+            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true, false>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
+                   m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
         if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, (const float*)nullptr, *hw,
                AdamFullApply{m->E, m->optE.m, m->optE.v, k, self_k});
     } else {
-        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
+        if (m->adam_pipe)
+            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false, true>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
+                   m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
+        else
+            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
+                   m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
         if (row_hw) {
             HeavyStream hs;
             TRY(heavy_stream_begin(m, entities, &hs));
@@ -1092,14 +1121,26 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
     // rows above kHeavyRefs references are on the list the bucket build made: the row kernel skips them
     const int row_hw = m->no_heavy ? 0 : 1;
     const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
+    // software-pipelined row loop when rows carry references (latency-bound chain per row); the plain loop when the
+    // pass is mostly an unreferenced streaming decay. NVSM_SGD_PIPE=0 / 1 forces it.
+    bool pipe = (double)(entities ? m->B * m->R : m->B * m->n) >= 0.5 * (double)(entities ? m->D : m->V);
+    { const char* e = getenv("NVSM_SGD_PIPE"); if (e) pipe = atoi(e) != 0; }
     if (entities) {
-        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        if (pipe)
+            LAUNCH(m, (sgd_pull_pipe_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        else
+            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
         if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, ysq, *hw, SgdApply{m->E, decay, lr, acc, 1e-6f});
     } else {
-        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        if (pipe)
+            LAUNCH(m, (sgd_pull_pipe_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+                   (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        else
+            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+                   (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
         if (row_hw) {
             HeavyStream hs;
             TRY(heavy_stream_begin(m, entities, &hs));
@@ -1892,6 +1933,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const bool sgd_pull = (method == NVSM_SGD || method == NVSM_ADAGRAD) && cfg->objective == NVSM_OBJECTIVE_TEXT_ENTITY &&
                               !cfg->l2_normalize_entity_reprs && !getenv("NVSM_NO_PULL") && std::max(V, D) >= kPullMinRows;
         m->no_heavy = getenv("NVSM_NO_HEAVY") != nullptr;
+        { const char* e = getenv("NVSM_ADAM_PIPE"); m->adam_pipe = e && atoi(e) != 0; }
         m->pull = (full_adam_pull || sgd_pull) &&
                   V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
         if (m->pull) {
