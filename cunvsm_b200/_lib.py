@@ -19,6 +19,11 @@ SYMBOLS = [
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
     "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_comm_peer_export", "nvsm_comm_peer_import", "nvsm_comm_peer_status", "nvsm_comm_peer_disable", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
     "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_bench_memory", "nvsm_sampler_seed", "nvsm_sampler_state",
+    "nvsm_ops_create", "nvsm_ops_destroy", "nvsm_ops_synchronize", "nvsm_ops_kernel_launches", "nvsm_dev_malloc", "nvsm_dev_free",
+    "nvsm_dev_upload", "nvsm_dev_download", "nvsm_dev_copy", "nvsm_dev_fill", "nvsm_op_average_representations", "nvsm_op_project",
+    "nvsm_op_activation", "nvsm_op_batchnorm_forward", "nvsm_op_batchnorm_backward", "nvsm_op_update_dense",
+    "nvsm_op_representations_update", "nvsm_op_transform_update", "nvsm_updater_create", "nvsm_updater_destroy",
+    "nvsm_updater_update_representations", "nvsm_updater_update_transform", "nvsm_updater_state",
     "nvsm_step_sampled", "nvsm_get_entity_ids", "nvsm_generate_labels_device", "nvsm_generate_labels_cdf", "nvsm_sampler_set_cdf",
 ]
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnvsm_b200.so")
 SOURCES = ["nvsm.cu"]
-DEPS = ["nvsm.cu", "kernels.cuh", "common.cuh", "gemm_simt.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "similarity.cuh", "peer_allreduce.cuh", "pull_update.cuh", "score_ring.cuh", "sampler.cuh", "nccl_dyn.h",
+DEPS = ["nvsm.cu", "kernels.cuh", "common.cuh", "gemm_simt.cuh", "gemm_tcgen05.cuh", "gemm_tcgen05_2cta.cuh", "similarity.cuh", "peer_allreduce.cuh", "pull_update.cuh", "score_ring.cuh", "sampler.cuh", "nccl_dyn.h", "microbench.cuh", "ops.cuh", "ops_host.inc",
         os.path.join("..", "..", "include", "nvsm_b200.h")]
 
 

@@ -24,6 +24,7 @@
 #include "gemm_tcgen05_2cta.cuh"
 #include "kernels.cuh"
 #include "microbench.cuh"
+#include "ops.cuh"
 #include "nccl_dyn.h"
 #include "peer_allreduce.cuh"
 #include "pull_update.cuh"
@@ -148,7 +149,6 @@ struct nvsm_model {
     // (the two table updates may run concurrently on different streams)
     HeavyWork heavy_e{}, heavy_w{};
     HeavyWork *heavy_e_dev = nullptr, *heavy_w_dev = nullptr;   // device copies of the descriptors (row kernels)
-    bool adam_pipe = false;     // NVSM_ADAM_PIPE=1: software-pipelined row loop in adam_full_pull_kernel (A/B measurements)
     bool no_heavy = false;      // NVSM_NO_HEAVY=1: one warp per row whatever its reference count (A/B measurements)
     int ldP = 0;          // row stride of P (and Tt): d_w rounded up to 32 floats on the tensor-core path so
                           // that every 128-byte TMA box row is 128-byte aligned (d_w = 300 -> 320)
@@ -1081,22 +1081,14 @@ int launch_pull(nvsm_model* m, bool entities, const AdamFullConsts& k) {
     const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
     if (entities) {
         const float* const self_k = m->l2_entity ? (const float*)m->kself : (const float*)nullptr;
-        if (m->adam_pipe)
-            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-                   m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
-        else
-            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true, false>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
-                   m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
+        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->optE.m, m->optE.v, m->D, m->dd,
+               m->e_offsets, m->e_refs, m->mult, m->Y, m->R, k, self_k, heavy_above);
         if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, AdamFullApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, (const float*)nullptr, *hw,
                AdamFullApply{m->E, m->optE.m, m->optE.v, k, self_k});
     } else {
-        if (m->adam_pipe)
-            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false, true>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-                   m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
-        else
-            LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
-                   m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
+        LAUNCH(m, (adam_full_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->optW.m, m->optW.v, m->V, m->dw,
+               m->w_offsets, m->w_refs, m->cur->fweights, m->gP, m->n, k, (const float*)nullptr, heavy_above);
         if (row_hw) {
             HeavyStream hs;
             TRY(heavy_stream_begin(m, entities, &hs));
@@ -1121,26 +1113,14 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
     // rows above kHeavyRefs references are on the list the bucket build made: the row kernel skips them
     const int row_hw = m->no_heavy ? 0 : 1;
     const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
-    // software-pipelined row loop when rows carry references (latency-bound chain per row); the plain loop when the
-    // pass is mostly an unreferenced streaming decay. NVSM_SGD_PIPE=0 / 1 forces it.
-    bool pipe = (double)(entities ? m->B * m->R : m->B * m->n) >= 0.5 * (double)(entities ? m->D : m->V);
-    { const char* e = getenv("NVSM_SGD_PIPE"); if (e) pipe = atoi(e) != 0; }
     if (entities) {
-        if (pipe)
-            LAUNCH(m, (sgd_pull_pipe_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
-        else
-            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
         if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, ysq, *hw, SgdApply{m->E, decay, lr, acc, 1e-6f});
     } else {
-        if (pipe)
-            LAUNCH(m, (sgd_pull_pipe_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-                   (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
-        else
-            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-                   (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
         if (row_hw) {
             HeavyStream hs;
             TRY(heavy_stream_begin(m, entities, &hs));
@@ -1933,7 +1913,6 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         const bool sgd_pull = (method == NVSM_SGD || method == NVSM_ADAGRAD) && cfg->objective == NVSM_OBJECTIVE_TEXT_ENTITY &&
                               !cfg->l2_normalize_entity_reprs && !getenv("NVSM_NO_PULL") && std::max(V, D) >= kPullMinRows;
         m->no_heavy = getenv("NVSM_NO_HEAVY") != nullptr;
-        { const char* e = getenv("NVSM_ADAM_PIPE"); m->adam_pipe = e && atoi(e) != 0; }
         m->pull = (full_adam_pull || sgd_pull) &&
                   V < (1L << 30) && D < (1L << 30) && maxB * std::max<long>(m->R, m->n) < (1L << 31);
         if (m->pull) {
@@ -2487,19 +2466,31 @@ int nvsm_test_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, const flo
 // Device-resident timing of the tensor-core GEMM alone (scripts/bench_gemm.py).
 int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int splits, int with_stats, int iters,
                        float* ms_out) {
+    // with_stats: bit 0 = fused column statistics in the epilogue, bit 1 = 3xTF32 (hi / lo operand pairs)
     if (!m || !ms_out) return fail("null argument");
     CU(cudaSetDevice(m->device));
-    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
-    double* dS = nullptr;
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dAlo = nullptr, *dBlo = nullptr, *dS = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool stats = (with_stats & 1) != 0, split3 = (with_stats & 2) != 0;
+    // K-major operands keep the step's 128-byte-aligned row stride (d_w = 300 -> 320 floats)
+    const int ldk = (K + 31) / 32 * 32;
+    const size_t na = variant ? (size_t)K * M : (size_t)M * ldk, nb = variant ? (size_t)K * N : (size_t)N * ldk;
     auto run = [&]() -> int {
-        CU(cudaMalloc((void**)&dA, (size_t)M * K * 4)); CU(cudaMalloc((void**)&dB, (size_t)N * K * 4));
-        CU(cudaMalloc((void**)&dC, (size_t)M * N * 4 * std::max(1, splits))); CU(cudaMalloc((void**)&dS, (size_t)N * 16));
-        CU(cudaMemset(dA, 0, (size_t)M * K * 4)); CU(cudaMemset(dB, 0, (size_t)N * K * 4)); CU(cudaMemset(dS, 0, (size_t)N * 16));
+        CU(cudaMalloc((void**)&dA, na * 4)); CU(cudaMalloc((void**)&dB, nb * 4));
+        CU(cudaMalloc((void**)&dC, (size_t)M * N * 4 * std::max(1, splits)));
+        CU(cudaMemset(dA, 0, na * 4)); CU(cudaMemset(dB, 0, nb * 4));
+        if (split3) {
+            CU(cudaMalloc((void**)&dAlo, na * 4)); CU(cudaMalloc((void**)&dBlo, nb * 4));
+            CU(cudaMemset(dAlo, 0, na * 4)); CU(cudaMemset(dBlo, 0, nb * 4));
+        }
+        if (stats) CU(cudaMalloc((void**)&dS, (size_t)8 * m->num_sms * 2 * N * 4));
         CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
         for (int it = 0; it < iters + 3; ++it) {
             if (it == 3) CU(cudaEventRecord(e0, m->stream));
-            TRY(run_gemm_tc(m, variant != 0, M, N, K, dA, variant ? M : K, dB, variant ? N : K, dC, N, splits, (long)M * N, 1.0f, nullptr, nullptr));
+            int rows = 0;
+            TRY(run_gemm_tc(m, variant != 0, M, N, K, dA, variant ? M : ldk, dB, variant ? N : ldk, dC, N, splits, (long)M * N, 1.0f,
+                            nullptr, nullptr, dAlo, dBlo, dS, &rows));
+            if (stats && rows == 0) return fail("this GEMM shape cannot fuse the column statistics");
         }
         CU(cudaEventRecord(e1, m->stream));
         CU(cudaEventSynchronize(e1));
@@ -2508,7 +2499,7 @@ int nvsm_bench_gemm_tc(nvsm_model* m, int variant, int M, int N, int K, int spli
         return 0;
     };
     const int rc = run();
-    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS); cudaFree(dAlo); cudaFree(dBlo);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;
@@ -2700,5 +2691,7 @@ int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode) {
     m->sparse_mode = mode;
     return 0;
 }
+
+#include "ops_host.inc"
 
 }  // extern "C"

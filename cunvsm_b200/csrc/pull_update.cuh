@@ -144,38 +144,7 @@ struct AdamFullConsts {
 // One warp per table row. SRC rows (Y or gP) and the per-reference coefficient:
 //   ENTITY:  src row = ref / group, coef = (ref % group == 0 ? +1 : -1) * coefs[ref]   (group = R)
 //   WORD  :  src row = ref / group, coef = coefs[ref]                                  (group = n)
-// Metadata of one table row, fetched one row AHEAD of its use (software pipeline of the pull kernels): bucket bounds,
-// and -- lane l -- the l-th reference of the row resolved to (source row, signed coefficient, squared-gradient term).
-// The offsets -> refs -> coefs chain of dependent loads then overlaps the gather and the update of the previous row.
-struct RowMeta {
-    int beg, end, src;
-    float cf, sq;
-};
-
-template <bool ENTITY>
-__device__ __forceinline__ RowMeta fetch_row_meta(long row, long num_rows, int lane, const int* __restrict__ offsets,
-                                                  const int* __restrict__ refs, const float* __restrict__ coefs, int group,
-                                                  const float* __restrict__ ysq, int heavy_above) {
-    RowMeta r{0, 0, 0, 0.f, 0.f};
-    if (row < num_rows) {
-        r.beg = __ldg(offsets + row);
-        r.end = __ldg(offsets + row + 1);
-        const int cnt = r.end - r.beg;
-        if (cnt <= heavy_above && lane < min(cnt, 32)) {
-            const int ref = __ldg(refs + r.beg + lane);
-            r.src = ref / group;
-            const float c = __ldg(coefs + ref);
-            r.cf = (ENTITY && (ref - r.src * group) != 0) ? -c : c;
-            if (ysq) r.sq = c * c * __ldg(ysq + r.src);
-        }
-    }
-    return r;
-}
-
-// PIPE: the software-pipelined row loop of sgd_pull_kernel (next row's metadata in flight, theta / m / v requested
-// before the gather). Costs 3 x NCH x VEC registers; selected at run time (NVSM_ADAM_PIPE) -- on C2 the kernel is bound
-// by SM <-> L2 throughput (ncu r2a: 9 - 10 TB/s), not by the load chain.
-template <int VEC, int NCH, bool ENTITY, bool PIPE>
+template <int VEC, int NCH, bool ENTITY>
 __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__ theta, float* __restrict__ m,
                                                              float* __restrict__ v, long num_rows, int dim,
                                                              const int* __restrict__ offsets,
@@ -188,51 +157,26 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim / VEC;
-    RowMeta cur{0, 0, 0, 0.f, 0.f};
-    if constexpr (PIPE) cur = fetch_row_meta<ENTITY>(warp0, num_rows, lane, offsets, refs, coefs, group, nullptr, heavy_above);
     for (long row = warp0; row < num_rows; row += nwarps) {
-        RowMeta nxt{0, 0, 0, 0.f, 0.f};
-        int beg, end;
-        if constexpr (PIPE) {
-            nxt = fetch_row_meta<ENTITY>(row + nwarps, num_rows, lane, offsets, refs, coefs, group, nullptr, heavy_above);
-            beg = cur.beg; end = cur.end;
-        } else {
-            beg = __ldg(offsets + row); end = __ldg(offsets + row + 1);
-        }
-        if (end - beg > heavy_above) { cur = nxt; continue; }   // pull_heavy_kernel owns this row
+        const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        if (end - beg > heavy_above) continue;   // pull_heavy_kernel owns this row
         // entity normalisation: the gradient carries - self_k[row] * theta[row] (entity_norm_prep_kernel)
         const float ks = self_k ? __ldg(self_k + row) : 0.f;
-        float th[NCH][VEC], mm[NCH][VEC], vv[NCH][VEC];
-        if constexpr (PIPE) {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                const int c = lane + j * kWarp;
-                if (c < nvec) {
-                    const long o = row * dim + c * VEC;
-                    load_vec_cs<VEC>(theta + o, th[j]);
-                    load_vec_cs<VEC>(m + o, mm[j]);
-                    load_vec_cs<VEC>(v + o, vv[j]);
-                }
-            }
-        }
         float agg[NCH][VEC];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
 #pragma unroll
             for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
-        int my_src = cur.src;
-        float my_coef = cur.cf;
         for (int base = beg; base < end; base += 32) {
             // lanes fetch up to 32 references of this row at once, then walk them together
             const int cnt = min(32, end - base);
-            if (!PIPE || base != beg) {
-                my_src = 0; my_coef = 0.f;
-                if (lane < cnt) {
-                    const int ref = __ldg(refs + base + lane);
-                    my_src = ref / group;
-                    const float cf = __ldg(coefs + ref);
-                    my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
-                }
+            int my_src = 0;
+            float my_coef = 0.f;
+            if (lane < cnt) {
+                const int ref = __ldg(refs + base + lane);
+                my_src = ref / group;
+                const float cf = __ldg(coefs + ref);
+                my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
             }
             for (int t = 0; t < cnt; ++t) {
                 const int srow = __shfl_sync(kFull, my_src, t);
@@ -254,27 +198,25 @@ __global__ void __launch_bounds__(256) adam_full_pull_kernel(float* __restrict__
             const int c = lane + j * kWarp;
             if (c < nvec) {
                 const long o = row * dim + c * VEC;
-                if constexpr (!PIPE) {
-                    // theta / m / v stream through once per step: evict-first, so the gathered source rows (Y, grad_phrase:
-                    // 52 / 61 MB, each row referenced ~10 times) stay L2-resident (ncu before: 2.7 - 3x DRAM re-reads of them)
-                    load_vec_cs<VEC>(theta + o, th[j]);
-                    load_vec_cs<VEC>(m + o, mm[j]);
-                    load_vec_cs<VEC>(v + o, vv[j]);
-                }
+                float th[VEC], mm[VEC], vv[VEC];
+                // theta / m / v stream through once per step: evict-first, so the gathered source rows (Y, grad_phrase:
+                // 52 / 61 MB, each row referenced ~10 times) stay L2-resident (ncu before: 2.7 - 3x DRAM re-reads of them)
+                load_vec_cs<VEC>(theta + o, th);
+                load_vec_cs<VEC>(m + o, mm);
+                load_vec_cs<VEC>(v + o, vv);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    const float ag = agg[j][q] - ks * th[j][q];
-                    const float g = ag + (-k.lambda * th[j][q]);
-                    mm[j][q] = (mm[j][q] * k.s1 + k.lr1 * ag) + (-k.reg1 * th[j][q]);
-                    vv[j][q] = vv[j][q] * k.s2 + (g * g) * k.lr2;
-                    th[j][q] = th[j][q] + (fast_div(mm[j][q], fast_sqrt(vv[j][q]) + k.eps) * k.bc) * k.lr;
+                    const float ag = agg[j][q] - ks * th[q];
+                    const float g = ag + (-k.lambda * th[q]);
+                    mm[q] = (mm[q] * k.s1 + k.lr1 * ag) + (-k.reg1 * th[q]);
+                    vv[q] = vv[q] * k.s2 + (g * g) * k.lr2;
+                    th[q] = th[q] + (fast_div(mm[q], fast_sqrt(vv[q]) + k.eps) * k.bc) * k.lr;
                 }
-                store_vec_cs<VEC>(theta + o, th[j]);
-                store_vec_cs<VEC>(m + o, mm[j]);
-                store_vec_cs<VEC>(v + o, vv[j]);
+                store_vec_cs<VEC>(theta + o, th);
+                store_vec_cs<VEC>(m + o, mm);
+                store_vec_cs<VEC>(v + o, vv);
             }
         }
-        cur = nxt;
     }
 }
 
@@ -353,106 +295,6 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
                 store_vec_cs<VEC>(theta + o, th);
             }
         }
-    }
-}
-
-// PIPE: two-deep software pipeline of the row loop (C3: 500k entity rows x 1.7 references -- per row the kernel is a
-// chain of dependent loads: offsets -> refs -> coefs -> source rows -> theta; ncu r2a: 57 % of the HBM peak at 59 %
-// occupancy). The next row's metadata is fetched while this row gathers, and theta / acc are requested before the
-// gather starts. Costs registers (occupancy), so tables whose rows are mostly unreferenced (C5: 0.13 references per
-// row, a pure streaming decay at 85 % of the HBM peak) keep the plain loop; the host picks by references per row.
-template <int VEC, int NCH, bool ENTITY>
-__global__ void __launch_bounds__(256, 4) sgd_pull_pipe_kernel(float* __restrict__ theta, long num_rows, int dim,
-                                                       const int* __restrict__ offsets, const int* __restrict__ refs,
-                                                       const float* __restrict__ coefs, const float* __restrict__ src,
-                                                       int group, float decay, float lr, int touch_all,
-                                                       float* __restrict__ acc, const float* __restrict__ ysq, float eps,
-                                                       const int heavy_above) {
-    constexpr bool PIPE = true;
-    const int lane = threadIdx.x & 31;
-    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-    const int nvec = dim / VEC;
-    const float* const ysq_used = acc ? ysq : nullptr;
-    RowMeta cur{0, 0, 0, 0.f, 0.f};
-    if constexpr (PIPE) cur = fetch_row_meta<ENTITY>(warp0, num_rows, lane, offsets, refs, coefs, group, ysq_used, heavy_above);
-    for (long row = warp0; row < num_rows; row += nwarps) {
-        RowMeta nxt{0, 0, 0, 0.f, 0.f};
-        int beg, end;
-        if constexpr (PIPE) {
-            nxt = fetch_row_meta<ENTITY>(row + nwarps, num_rows, lane, offsets, refs, coefs, group, ysq_used, heavy_above);
-            beg = cur.beg; end = cur.end;
-        } else {
-            beg = __ldg(offsets + row); end = __ldg(offsets + row + 1);
-        }
-        const bool skip = (beg == end && !touch_all) || (end - beg > heavy_above);   // (heavy: pull_heavy_kernel owns the row)
-        if (!skip) {
-            float th[NCH][VEC];
-            float acc_old = 0.f;
-            if constexpr (PIPE) {
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    const int c = lane + j * kWarp;
-                    if (c < nvec) load_vec_cs<VEC>(theta + row * dim + c * VEC, th[j]);
-                }
-                if (acc) acc_old = acc[row];
-            }
-            float agg[NCH][VEC];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j)
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
-            float sq = cur.sq;
-            int my_src = cur.src;
-            float my_coef = cur.cf;
-            for (int base = beg; base < end; base += 32) {
-                const int cnt = min(32, end - base);
-                if (!PIPE || base != beg) {   // (PIPE: the first 32 references came with the row's metadata)
-                    my_src = 0; my_coef = 0.f;
-                    if (lane < cnt) {
-                        const int ref = __ldg(refs + base + lane);
-                        my_src = ref / group;
-                        const float cf = __ldg(coefs + ref);
-                        my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
-                        if (acc) sq += cf * cf * __ldg(ysq + my_src);
-                    }
-                }
-                for (int t = 0; t < cnt; ++t) {
-                    const int srow = __shfl_sync(kFull, my_src, t);
-                    const float cf = __shfl_sync(kFull, my_coef, t);
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j) {
-                        const int c = lane + j * kWarp;
-                        if (c < nvec) {
-                            float x[VEC];
-                            load_vec_ro<VEC>(src + (long)srow * dim + c * VEC, x);
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q) agg[j][q] += cf * x[q];
-                        }
-                    }
-                }
-            }
-            float rs = 1.0f;
-            if (acc) {
-                sq = warp_sum(sq);
-                if constexpr (!PIPE) acc_old = acc[row];
-                const float a = acc_old + sq;
-                if (lane == 0 && beg != end) acc[row] = a;
-                rs = 1.0f / sqrtf(a + eps);
-            }
-            const float step = lr * rs;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-                const int c = lane + j * kWarp;
-                if (c < nvec) {
-                    if constexpr (!PIPE) load_vec_cs<VEC>(theta + row * dim + c * VEC, th[j]);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) th[j][q] = th[j][q] * decay + step * agg[j][q];
-                    store_vec_cs<VEC>(theta + row * dim + c * VEC, th[j]);
-                }
-            }
-        }
-        cur = nxt;
     }
 }
 

@@ -262,6 +262,84 @@ NVSM_API int nvsm_comm_peer_status(nvsm_model* m, int* ready, int* error);
  * Model::update (cpp/model.cu:187-220) on the global batch. Call after nvsm_comm_init. */
 NVSM_API int nvsm_comm_set_sparse_mode(nvsm_model* m, int mode);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stand-alone operators: the reference's Params / Storage / Updates / BatchNormalization classes, one operation per
+ * call, on caller-owned DEVICE tensors (row-major [objects, dim]; ids are `long`). The header-only classes in
+ * include/cuNVSM/{device_matrix,storage,updates,params,cudnn_utils}.h (this repo) bind exactly these symbols; the fused
+ * training step above does not pass through them.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nvsm_ops nvsm_ops;         /* launch context of the operators: one device, one stream */
+typedef struct nvsm_updater nvsm_updater; /* optimiser state of one parameter group (GradientUpdater::storages_) */
+
+/* RepresentationsStorage::SingleGradientType (include/cuNVSM/storage.h:64-69): grad [count, dim] (may be overwritten:
+ * sparse Adam turns it into the step, like the reference), ids [count * window], weights [count * window] or NULL. */
+typedef struct nvsm_grad_desc {
+    float* grad;
+    const long* ids;
+    long count;
+    int window;
+    const float* weights;
+} nvsm_grad_desc;
+
+NVSM_API int nvsm_ops_create(int device, nvsm_ops** out);   /* Streams / DefaultStream (include/cuNVSM/cuda_utils.h) */
+NVSM_API void nvsm_ops_destroy(nvsm_ops* ops);
+NVSM_API int nvsm_ops_synchronize(nvsm_ops* ops);
+NVSM_API long nvsm_ops_kernel_launches(nvsm_ops* ops);
+/* device_matrix storage (the un-vendored device_matrix library's constructor / fillwith / copy / to_host, as used by
+ * cpp/storage.cu:6-10, cpp/updates_tests.cu:34-60): zero-initialised allocation, host <-> device copies, fill. */
+NVSM_API int nvsm_dev_malloc(nvsm_ops* ops, void** ptr, unsigned long bytes);
+NVSM_API int nvsm_dev_free(nvsm_ops* ops, void* ptr);
+NVSM_API int nvsm_dev_upload(nvsm_ops* ops, void* dst_dev, const void* src_host, unsigned long bytes);
+NVSM_API int nvsm_dev_download(nvsm_ops* ops, void* dst_host, const void* src_dev, unsigned long bytes);
+NVSM_API int nvsm_dev_copy(nvsm_ops* ops, void* dst_dev, const void* src_dev, unsigned long bytes);
+NVSM_API int nvsm_dev_fill(nvsm_ops* ops, float* ptr, long n, float value);
+
+/* Representations::get_average_representations (cpp/params.cu:138-172; average_repr_kernel :75-95): out[o, :] =
+ * (1 / window) sum_w weights[o, w] * table[ids[o, w], :]; weights may be NULL. window 1 without weights =
+ * Representations::get_representations (cpp/params.cu:97-117). */
+NVSM_API int nvsm_op_average_representations(nvsm_ops* ops, const float* table, long num_objects, int dim, const long* ids,
+                                             const float* weights, long num_out, int window, float* out);
+/* The projection inside Transform::transform (cpp/params.cu:396-421): out[B, d_d] = P[B, d_w] . T[d_w, d_d] (+ bias when
+ * not NULL: the reference pre-broadcasts it into the destination and runs the GEMM with beta = 1). Exact fp32. */
+NVSM_API int nvsm_op_project(nvsm_ops* ops, const float* T, int word_repr_size, int entity_repr_size, const float* P,
+                             long num_instances, const float* bias, float* out);
+/* tanh / hard_tanh of Transform::transform (cpp/params.cu:425-446; func::clip, include/cuNVSM/cuda_utils.h:86-111). */
+NVSM_API int nvsm_op_activation(nvsm_ops* ops, const float* x, long n, int nonlinearity, float* y);
+/* BatchNormalization::forward / backward (cpp/cudnn_utils.cu:82-129, 143-183; include/cuNVSM/cudnn_utils.h:84-127):
+ * per-activation statistics over the rows, biased variance, epsilon inside the sqrt, gamma == 1, beta = bias; mean and
+ * invstd are the caches the backward pass consumes. y may alias x, dx may alias dy. */
+NVSM_API int nvsm_op_batchnorm_forward(nvsm_ops* ops, const float* x, const float* bias, long rows, int num_features,
+                                       float epsilon, float* y, float* mean, float* invstd);
+NVSM_API int nvsm_op_batchnorm_backward(nvsm_ops* ops, const float* dy, const float* x, const float* mean, const float* invstd,
+                                        long rows, int num_features, float* dx, float* dbias);
+/* update_dense (include/cuNVSM/storage_inl.h:4-32): param = param (1 - lambda lr) + op(grad) lr, op = identity | square. */
+NVSM_API int nvsm_op_update_dense(nvsm_ops* ops, float* param, const float* grad, long n, float lr, float lambda, int square);
+/* RepresentationsStorage::update (cpp/storage.cu:51-102; update_repr_kernel :37-49): dense decay when lambda > 0, then
+ * table[ids[x, y], :] += lr * weights[x, y] * grad[x, :] for every descriptor. */
+NVSM_API int nvsm_op_representations_update(nvsm_ops* ops, float* table, long num_objects, int dim, const nvsm_grad_desc* descs,
+                                            int num_descs, float lr, float lambda);
+/* TransformStorage::update (cpp/storage.cu:198-228): T with decay, the bias without. */
+NVSM_API int nvsm_op_transform_update(nvsm_ops* ops, float* T, float* b, const float* gT, const float* gb, long num_transform,
+                                      int num_bias, float lr, float lambda);
+
+/* GradientUpdater construction (include/cuNVSM/updates.h:87-203): kind 0 = *RepresentationsGradientUpdater over a
+ * [num_objects, dim] table, kind 1 = *TransformGradientUpdater over T [dim, target_dim] + b [target_dim]. */
+NVSM_API int nvsm_updater_create(nvsm_ops* ops, int kind, int update_method, int adam_mode, long num_objects, int dim,
+                                 int target_dim, float beta1, float beta2, float epsilon, nvsm_updater** out);
+NVSM_API void nvsm_updater_destroy(nvsm_updater* updater);
+/* {SGD,Adagrad,Adam}RepresentationsGradientUpdater::update (cpp/updates.cu:37-48, cpp/updates_adagrad.cu:99-179,
+ * cpp/updates_adam.cu:153-385). Adagrad and sparse Adam take a single descriptor (the reference aborts otherwise) and,
+ * like the reference, rewrite its gradient in place (g / sqrt(mean acc + eps); the window-averaged Adam step). */
+NVSM_API int nvsm_updater_update_representations(nvsm_updater* updater, float* table, const nvsm_grad_desc* descs, int num_descs,
+                                                 float lr, float lambda);
+/* {SGD,Adagrad,Adam}TransformGradientUpdater::update (cpp/updates.cu:24-35, cpp/updates_adagrad.cu:33-70,
+ * cpp/updates_adam.cu:46-105). Adagrad and Adam leave the applied step direction in gT / gb, like the reference. */
+NVSM_API int nvsm_updater_update_transform(nvsm_updater* updater, float* T, float* b, float* gT, float* gb, float lr,
+                                           float lambda);
+/* GradientUpdater::storages_ as the reference's tests read them (cpp/updates_tests.cu:299-425): "acc", "m", "v" and, for a
+ * transform, "acc_bias" / "m_bias" / "v_bias". Borrowed device pointer + element count. */
+NVSM_API int nvsm_updater_state(nvsm_updater* updater, const char* name, float** dev_ptr, long* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,22 @@ def test_cpp_host_code_builds_and_fails_loudly_without_gpu():
         pytest.skip("GPU present: covered by the gpu tests")
     res = subprocess.run([os.path.join(CPP, "facade_test")], capture_output=True, text=True)
     assert res.returncode != 0 and "no CUDA device" in res.stderr
+    # the Params / Storage / Updates / BatchNormalization class surface: same rule, no silent CPU path
+    assert os.path.exists(os.path.join(CPP, "classes_test"))
+    res = subprocess.run([os.path.join(CPP, "classes_test")], capture_output=True, text=True)
+    assert res.returncode != 0 and "no CUDA device" in res.stderr
+
+
+@pytest.mark.gpu
+def test_reference_class_surface_closed_form_cases():
+    """cpp/classes_test.cpp: Representations / Transform / *Storage / the nine *GradientUpdater classes / BatchNormalization
+    (include/cuNVSM/{params,storage,updates,cudnn_utils}.h over nvsm_op_* / nvsm_updater_*) on the inputs and closed forms of
+    the reference's own unit tests (cpp/updates_tests.cu:34-775, cpp/model_tests.cu:52-339,468-521,
+    cpp/cudnn_utils_tests.cu:19-177), all four (lambda, learning rate) parameterisations."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "classes_test")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "CLASSES_TEST_OK" in res.stdout, res.stdout[-4000:] + res.stderr[-2000:]
+    assert res.stdout.count("\nok  ") + res.stdout.startswith("ok  ") >= 40, res.stdout[-2000:]
 
 
 def test_data_source_wrappers():
