@@ -7,7 +7,8 @@
 //                                 update_dense, Transform::transform;  :468-521 transform + batch-norm + tanh golden values
 //   cpp/cudnn_utils_tests.cu:19-177  BatchNormalization forward (closed form), backward (golden grad_bias), in-place == out-of-place
 // Expected values are recomputed here in double from the definitions (sums per object, window means, bias correction);
-// literals are only used where the reference pins a literal. float32 library vs double expectation: 1e-5 relative.
+// literals are only used where the reference pins a literal. float32 library vs double expectation: 3e-5 relative
+// (beta2 = 0.999 is 0.99900001 in float32, so every (1 - beta2) factor carries 1.3e-5, like the reference's float build).
 // Prints one line per case and "CLASSES_TEST_OK" when everything held; exit status = number of failed cases.
 #include <cmath>
 #include <cstdio>
@@ -25,7 +26,7 @@ typedef std::vector<double> Vec;
 
 static int g_failed = 0, g_cases = 0;
 
-static bool near(const std::vector<FloatT>& got, const Vec& want, const char* what, double rel = 1e-5, double abs_tol = 1e-6) {
+static bool near(const std::vector<FloatT>& got, const Vec& want, const char* what, double rel = 3e-5, double abs_tol = 1e-6) {
   if (got.size() != want.size()) { std::printf("  %s: size %zu vs %zu\n", what, got.size(), want.size()); return false; }
   for (size_t i = 0; i < got.size(); ++i)
     if (!(std::fabs(got[i] - want[i]) <= abs_tol + rel * std::fabs(want[i]))) {
