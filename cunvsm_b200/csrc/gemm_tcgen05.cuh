@@ -3,9 +3,7 @@
 // read back with tcgen05.ld for the epilogue. One warp-specialised CTA per output tile:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     MMA issuer   (one elected lane)
-//   warps 2-9  epilogue     (warp w reads the 32 TMEM lanes of quarter w % 4; the two warps of a quarter split the
-//              tile's 16-column chunks: with one warp per scheduler the epilogue is latency-bound, measured
-//              r2d: 47 us forward GEMM of which ~12 us per tile were the drain)
+//   warps 2-5  epilogue     (each owns the 32 TMEM lanes of its warp_id % 4 quarter)
 // connected by a ring of `stages` full/empty mbarriers and one accumulator-ready mbarrier.
 //
 // The three contractions of the step (replacing cuBLAS SGEMM behind device_matrix's
@@ -36,8 +34,7 @@ namespace tc {
 constexpr int kBlockM = 128;        // UMMA M (cta_group::1)
 constexpr int kBlockK = 32;         // fp32 elements per 128-byte swizzled row (KB = 32); KB = 16 uses 64-byte rows
 constexpr int kUmmaK = 8;           // tf32 K per instruction
-constexpr int kThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
-constexpr int kEpiWarps = 8;
+constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr uint32_t kGroupBytes = kBlockK * 32 * 4;       // one 32(MN) x 32(k) box: 4 KB
 
@@ -193,9 +190,8 @@ __device__ __forceinline__ void stat_accumulate(float* warp_strip, int ch, int l
     const float r = warp_reduce32_transposed(x, lane);
     warp_strip[32 * ch + lane] += r;
 }
-// `half`: the two epilogue warps of a TMEM lane quarter share a strip and own chunks [0, 8) and [8, 16) of it.
-__device__ __forceinline__ void stat_flush(const float* warp_strip, float* part_row, int n, int lane, int half) {
-    for (int ch = 8 * half; ch < 8 * half + 8 && ch * 16 < n; ++ch)
+__device__ __forceinline__ void stat_flush(const float* warp_strip, float* part_row, int n, int lane) {
+    for (int ch = 0; ch * 16 < n; ++ch)
         part_row[(lane >> 4) * n + 16 * ch + (lane & 15)] = warp_strip[32 * ch + lane];
 }
 
@@ -241,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full_bar[b]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[b]), kEpiWarps);   // one arrival per epilogue warp
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 4);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -365,10 +361,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float* __restrict__ bias = p.bias;
         const int Nv = p.N;
         const bool vec_ok = (p.ldc & 3) == 0;
-        const int half = (warp - 2) >> 2;       // which half of the tile's chunks this warp of the quarter drains
         float* const strip = stat_strip[q];
         if (p.stat_part)
-            for (int t = lane; t < kStatCols; t += 32) strip[half * kStatCols + t] = 0.f;   // (chunk slots 8 half .. 8 half + 7)
+            for (int t = lane; t < 2 * kStatCols; t += 32) strip[t] = 0.f;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
             int m0, n0, kb0, nkb, split;
@@ -383,13 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
             }
             const int ncols = min(p.bn, Nv - n0);                 // valid columns of this tile
-            const int nchunks_all = (min(p.bn, max(ncols, 0)) + 15) / 16;
-            // this warp's chunks: [ch_begin, nchunks); slot 8 * half + k of the statistics strip belongs to chunk 8 * half + k
-            const int ch_begin = half * 8;
-            const int nchunks = half == 0 ? min(nchunks_all, 8) : nchunks_all;
+            const int nchunks = (min(p.bn, max(ncols, 0)) + 15) / 16;
             uint32_t rcur[16], rnext[16];
-            if (nkb > 0 && nchunks > ch_begin) { tmem_ld16_nowait(tacc + (uint32_t)ch_begin * 16u, rcur); tmem_ld_wait(); }
-            for (int ch = ch_begin; ch < nchunks; ++ch) {
+            if (nkb > 0 && nchunks > 0) { tmem_ld16_nowait(tacc, rcur); tmem_ld_wait(); }
+            for (int ch = 0; ch < nchunks; ++ch) {
                 const int c0 = n0 + ch * 16;
                 if (nkb > 0 && ch + 1 < nchunks) tmem_ld16_nowait(tacc + (uint32_t)(ch + 1) * 16u, rnext);   // in flight during the stores
                 float v[16];
@@ -439,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.stat_part) {
             __syncwarp();
-            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane, half);
+            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane);
         }
     }
     tc_fence_before();

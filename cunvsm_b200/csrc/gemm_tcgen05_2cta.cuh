@@ -5,12 +5,12 @@
 // (gemm_tcgen05.cuh) is bound exactly there: tf32 operands are 4 bytes, 3xTF32 issues three MMAs per k-step, and
 // TMA fill + MMA operand reads exceed the 128 B/cycle shared-memory port (ncu: tensor pipe ~52 % busy, L2 ~50 %).
 //
-// Protocol (per CTA: warp 0 TMA producer, warp 1 MMA issuer -- leader CTA only --, warps 2-9 epilogue):
+// Protocol (per CTA: warp 0 TMA producer, warp 1 MMA issuer -- leader CTA only --, warps 2-5 epilogue):
 //   full_bar[s]       leader's copy only: armed by the leader's producer with the bytes of BOTH CTAs; every TMA of the
 //                     pair signals it (the peer addresses it through mapa).
 //   empty_bar[s]      one per CTA, released by the leader's tcgen05.commit multicast to both CTAs.
 //   tmem_full_bar[b]  one per CTA, same multicast commit after the last k-block of a tile.
-//   tmem_empty_bar[b] leader's copy only, 16 arrivals (8 epilogue warps x 2 CTAs; the peer's arrive remotely).
+//   tmem_empty_bar[b] leader's copy only, 8 arrivals (4 epilogue warps x 2 CTAs; the peer's arrive remotely).
 // Each CTA drains its own 128 accumulator rows from its own TMEM.
 #pragma once
 
@@ -100,7 +100,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full_bar[b]), 1);
-            mbar_init(smem_u32(&tmem_empty_bar[b]), 2 * kEpiWarps);   // the epilogue warps of both CTAs of the pair
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 8);   // 4 epilogue warps of each CTA of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -195,10 +195,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const float* __restrict__ bias = p.bias;
         const int Nv = p.N;
         const bool vec_ok = (p.ldc & 3) == 0;
-        const int half = (warp - 2) >> 2;       // the two warps of a TMEM lane quarter split the tile's chunks
         float* const strip = stat_strip[q];
         if (p.stat_part)
-            for (int t = lane; t < kStatCols; t += 32) strip[half * kStatCols + t] = 0.f;
+            for (int t = lane; t < 2 * kStatCols; t += 32) strip[t] = 0.f;
         uint32_t lt = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
             int m0, n0;
@@ -211,12 +210,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(smem_u32(&tmem_full_bar[buf]), (lt >> 1) & 1u);
             tc_fence_after();
             const int ncols = min(p.bn, Nv - n0);
-            const int nchunks_all = (min(p.bn, max(ncols, 0)) + 15) / 16;
-            const int ch_begin = half * 8;
-            const int nchunks = half == 0 ? min(nchunks_all, 8) : nchunks_all;
+            const int nchunks = (min(p.bn, max(ncols, 0)) + 15) / 16;
             uint32_t rcur[16], rnext[16];
-            if (nchunks > ch_begin) { tmem_ld16_nowait(tacc + (uint32_t)ch_begin * 16u, rcur); tmem_ld_wait(); }
-            for (int ch = ch_begin; ch < nchunks; ++ch) {
+            if (nchunks > 0) { tmem_ld16_nowait(tacc, rcur); tmem_ld_wait(); }
+            for (int ch = 0; ch < nchunks; ++ch) {
                 const int c0 = n0 + ch * 16;
                 if (ch + 1 < nchunks) tmem_ld16_nowait(tacc + (uint32_t)(ch + 1) * 16u, rnext);
                 float v[16];
@@ -261,7 +258,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.stat_part) {
             __syncwarp();
-            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane, half);
+            stat_flush(strip, p.stat_part + ((size_t)blockIdx.x * 4 + q) * 2 * Nv, Nv, lane);
         }
     }
     tc_fence_before();
