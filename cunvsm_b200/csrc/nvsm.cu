@@ -80,6 +80,7 @@ struct BatchSlot {
     cudaEvent_t consumed = nullptr;  // last step reading it has been enqueued and finished
     bool ever_consumed = false;
     bool in_use = false;  // a forward result reads it and no `consumed` event covers that yet
+    long fw_ones = 0, w_ones = 0;   // leading elements of fweights / weights known to hold 1.0f (uniform weights: no H2D)
 };
 
 struct TableOpt {  // optimiser state of one embedding table
@@ -1142,7 +1143,10 @@ int pull_sgd(nvsm_model* m, bool entities, float lr, float lambda) {
     CU(cudaStreamWaitEvent(m->stream, m->buckets_ready, 0));
     const bool adagrad = m->cfg.update_method == NVSM_ADAGRAD;
     const float decay = lambda > 0.0f ? (float)(1.0 - (double)(lambda * lr)) : 1.0f;
-    const bool touch_all = lambda > 0.0f;
+    // The reference's dense whole-table decay (cpp/storage.cu:65-67) multiplies by the FLOAT 1 - lambda_s * lr. For the
+    // large-batch configurations that factor rounds to exactly 1.0f (C3: lambda_s lr = 2e-9, C5: 2.4e-8, both below half
+    // an ulp of 1), so the pass is a bit-exact no-op: rows without references are then not touched at all.
+    const bool touch_all = decay != 1.0f;
     float* acc = nullptr;
     const float* ysq = nullptr;
     const float* word_coefs = m->cur->fweights;
@@ -1257,7 +1261,7 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
         if (self)
             LAUNCH(m, scale_rows_self_kernel, grid_for(m, count, 256 * 4, 8), 256, 0, theta, N, dim, decay, lr,
                    (const float*)m->kself, acc, eps);
-        else if (lambda > 0.0f) TRY(scale_table(m, theta, count, decay));
+        else if (decay != 1.0f) TRY(scale_table(m, theta, count, decay));   // (x * 1.0f == x: skipping is bit-exact)
         return scatter(theta, lr, acc, eps);
     };
     const int method = m->cfg.update_method;
@@ -1305,7 +1309,7 @@ int update_table(nvsm_model* m, bool entities, float lr, float lambda) {
         return 0;
     }
     // SPARSE: window-averaged step, applied through the SGD scatter with dense decay.
-    if (lambda > 0.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
+    if (lambda > 0.0f && (float)(1.0 - (double)(lambda * lr)) != 1.0f) TRY(scale_table(m, theta, count, (float)(1.0 - (double)(lambda * lr))));
     if (pair) {   // single descriptor, window 1: same per-reference step as the entity side
         const int grid = grid_for(m, pairM, 8, 8);
         if (vec4_ok(dim))
@@ -1610,10 +1614,33 @@ int join_unconsumed_buckets(nvsm_model* m) {
     return 0;
 }
 
+// Word weights / instance weights of a batch: H2D copy, or -- NULL = uniform weighting, the reference's default
+// (feature_weights_ and weights_ are 1.0 unless self-information / idf weighting is selected, include/cuNVSM/data.h:465-467)
+// -- a device-side fill with 1.0f that is skipped while the slot still holds ones from an earlier batch. At 8 GPUs the
+// host-fed step is bound by the node's aggregate H2D bandwidth (measured r2f: 8 x 6.8 MB per 0.80 ms = 67 GB/s while the
+// device-resident step takes 0.67 ms); the two weight arrays are a third of those bytes.
+int upload_weights(nvsm_model* m, cudaStream_t cs, float* dst, const float* src, long count, long* ones) {
+    if (src) {
+        CU(cudaMemcpyAsync(dst, src, sizeof(float) * count, cudaMemcpyHostToDevice, cs));
+        *ones = 0;
+        return 0;
+    }
+    if (*ones >= count) return 0;
+    cudaStream_t main_stream = m->stream;
+    m->stream = cs;
+    const int rc = [&]() -> int {
+        LAUNCH(m, op_fill_kernel, grid_for(m, count, 1024, 8), 256, 0, dst, count, 1.0f);
+        return 0;
+    }();
+    m->stream = main_stream;
+    if (rc == 0) *ones = count;
+    return rc;
+}
+
 int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float* fw, const long* ids,
                  const float* w, long B, bool use_copy_stream) {
     if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
-    if (!features || !fw || !ids || !w) return fail("null batch pointer");
+    if (!features || !ids) return fail("null batch pointer");
     cudaStream_t cs = use_copy_stream ? m->copy_stream : m->stream;
     if (cs != m->stream) {
         if (s->in_use) {  // forward without update: order after everything enqueued so far
@@ -1626,9 +1653,9 @@ int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float*
     s->in_use = false;
     if (cs == m->stream) phase_begin(m, PH_H2D);
     CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
+    TRY(upload_weights(m, cs, s->fweights, fw, B * m->n, &s->fw_ones));
     CU(cudaMemcpyAsync(s->ids, ids, sizeof(long) * B * m->R, cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
+    TRY(upload_weights(m, cs, s->weights, w, B, &s->w_ones));
     TRY(validate_ids(m, cs, s->features, B * m->n, s->ids, B * m->R));
     if (cs == m->stream) phase_end(m);
     CU(cudaEventRecord(s->ready, cs));
@@ -2264,7 +2291,7 @@ int nvsm_sampler_state(nvsm_model* m, unsigned long* state) {
 int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, const long* labels, const float* w,
                       long B, float lr, int train) {
     if (!m) return fail("null model");
-    if (!features || !fw || !labels || !w) return fail("null batch pointer");
+    if (!features || !labels) return fail("null batch pointer");
     if (B <= 0 || B > m->maxB) return fail("num_instances %ld outside (0, max_batch_size=%ld]", B, m->maxB);
     CU(cudaSetDevice(m->device));
     TRY(ensure_sampler(m));
@@ -2274,9 +2301,9 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     if (s->ever_consumed) CU(cudaStreamWaitEvent(cs, s->consumed, 0));
     s->in_use = false;
     CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(s->fweights, fw, sizeof(float) * B * m->n, cudaMemcpyHostToDevice, cs));
+    TRY(upload_weights(m, cs, s->fweights, fw, B * m->n, &s->fw_ones));
     CU(cudaMemcpyAsync(s->labels, labels, sizeof(long) * B, cudaMemcpyHostToDevice, cs));
-    CU(cudaMemcpyAsync(s->weights, w, sizeof(float) * B, cudaMemcpyHostToDevice, cs));
+    TRY(upload_weights(m, cs, s->weights, w, B, &s->w_ones));
     s->B = B;
     TRY(validate_ids(m, cs, s->features, B * m->n, s->labels, B));   // the sampled negatives are in range by construction
     {

@@ -76,6 +76,12 @@ def _pf(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 
+def _fw(batch):
+    """feature_weights / weights of a Batch for the C ABI: NULL when the batch was filled with uniform weights."""
+    return (None if getattr(batch, "uniform_feature_weights_", False) else _pf(batch.feature_weights_),
+            None if getattr(batch, "uniform_weights_", False) else _pf(batch.weights_))
+
+
 def _pinned(shape, dtype):
     """Page-locked host array (falls back to pageable memory when torch/CUDA is absent)."""
     try:
@@ -109,6 +115,7 @@ class Batch:
         self.labels_ = alloc(self.batch_size_, np.int64)
         self.weights_ = alloc(self.batch_size_, np.float32)
         self.num_instances_ = 0
+        self.uniform_feature_weights_ = self.uniform_weights_ = False
 
     def window_size(self):
         return self.window_size_
@@ -137,6 +144,7 @@ class Batch:
         self.labels_[i] = object_id
         self.weights_[i] = weight
         self.num_instances_ += 1
+        self.uniform_feature_weights_ = self.uniform_weights_ = False
 
     def fill(self, features, labels, feature_weights=None, weights=None):
         features = np.asarray(features, dtype=np.int64).reshape(-1, self.window_size_)
@@ -147,6 +155,8 @@ class Batch:
         self.labels_[:B] = labels
         self.weights_[:B] = 1.0 if weights is None else weights
         self.num_instances_ = B
+        # uniform weighting (the reference's default): the arrays hold 1.0 and need not cross PCIe (NULL over the C ABI)
+        self.uniform_feature_weights_, self.uniform_weights_ = feature_weights is None, weights is None
         return self
 
 
@@ -364,8 +374,8 @@ class Model:
         entity_ids = np.ascontiguousarray(entity_ids, dtype=np.int64)
         assert entity_ids.size == B * (self.train_config.num_random_entities + 1)
         self._keepalive = (batch, entity_ids)
-        check(self.L.nvsm_compute_cost(self.h, _pl(batch.features_), _pf(batch.feature_weights_), _pl(entity_ids),
-                                       _pf(batch.weights_), B))
+        fw, w = _fw(batch)
+        check(self.L.nvsm_compute_cost(self.h, _pl(batch.features_), fw, _pl(entity_ids), w, B))
         return ForwardResult(self, B)
 
     def compute_gradients(self, result=None):
@@ -404,8 +414,8 @@ class Model:
         """compute_cost + compute_gradients + update on host buffers, no synchronisation."""
         B = batch.num_instances_
         self._keepalive = (batch, entity_ids)
-        check(self.L.nvsm_train_step(self.h, _pl(batch.features_), _pf(batch.feature_weights_), _pl(entity_ids),
-                                     _pf(batch.weights_), B, learning_rate))
+        fw, w = _fw(batch)
+        check(self.L.nvsm_train_step(self.h, _pl(batch.features_), fw, _pl(entity_ids), w, B, learning_rate))
 
     # --- device sampler ---------------------------------------------------------------------
     def sampler_seed(self, rng):
@@ -421,8 +431,9 @@ class Model:
         """Upload the batch, draw the negatives on the device (bit-exact with the host sampler) and run
         compute_cost (+ compute_gradients + update when train). No synchronisation."""
         self._keepalive = (batch,)
-        check(self.L.nvsm_step_sampled(self.h, _pl(batch.features_), _pf(batch.feature_weights_), _pl(batch.labels_),
-                                       _pf(batch.weights_), batch.num_instances_, learning_rate, int(train)))
+        fw, w = _fw(batch)
+        check(self.L.nvsm_step_sampled(self.h, _pl(batch.features_), fw, _pl(batch.labels_), w, batch.num_instances_,
+                                       learning_rate, int(train)))
 
     def generate_labels_device(self, labels, rng, z=None, num_objects=None):
         """nvsm_generate_labels on the device (bit-exact): returns ids [B*(z+1)], advances rng."""
@@ -443,8 +454,8 @@ class Model:
 
     def stage_batch(self, slot, batch, entity_ids):
         entity_ids = np.ascontiguousarray(entity_ids, dtype=np.int64)
-        check(self.L.nvsm_stage_batch(self.h, slot, _pl(batch.features_), _pf(batch.feature_weights_),
-                                      _pl(entity_ids), _pf(batch.weights_), batch.num_instances_))
+        fw, w = _fw(batch)
+        check(self.L.nvsm_stage_batch(self.h, slot, _pl(batch.features_), fw, _pl(entity_ids), w, batch.num_instances_))
 
     def compute_cost_staged(self, slot):
         check(self.L.nvsm_compute_cost_staged(self.h, slot))

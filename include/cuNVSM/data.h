@@ -104,7 +104,7 @@ class Batch : public BatchInterface {
   Batch(const Batch&) = delete;
   Batch& operator=(const Batch&) = delete;
 
-  virtual void clear() override { num_instances_ = 0; }
+  virtual void clear() override { num_instances_ = 0; uniform_feature_weights_ = uniform_weights_ = false; }
   virtual bool full() const override { return num_instances_ == batch_size_; }
   virtual bool empty() const override { return num_instances_ == 0; }
   virtual size_t num_instances() const override { return num_instances_; }
@@ -140,6 +140,14 @@ class Batch : public BatchInterface {
   const ObjectIdxType* labels() const { return labels_; }
   const WeightType* weights() const { return weights_; }
   void set_num_instances(size_t n) { NVSM_CHECK(n <= batch_size_, "too many instances"); num_instances_ = n; }
+  // A source whose weighting is uniform (the reference's default: every feature weight / instance weight is 1.0,
+  // include/cuNVSM/data.h:465-467) says so after filling the batch; Model::compute_cost then passes NULL for that array
+  // and the library fills ones on the device instead of copying them over PCIe. Reset by clear().
+  void set_uniform_weights(const bool feature_weights, const bool instance_weights) {
+    uniform_feature_weights_ = feature_weights; uniform_weights_ = instance_weights;
+  }
+  bool uniform_feature_weights() const { return uniform_feature_weights_; }
+  bool uniform_weights() const { return uniform_weights_; }
 
   // reference: TextEntity::Batch::swap, cpp/data.cu:76-92 — exchanges the pinned arrays, no copy
   virtual void swap(BatchInterface* const other) override {
@@ -149,6 +157,7 @@ class Batch : public BatchInterface {
     std::swap(features_, o->features_); std::swap(feature_weights_, o->feature_weights_);
     std::swap(labels_, o->labels_); std::swap(weights_, o->weights_);
     std::swap(num_instances_, o->num_instances_);
+    std::swap(uniform_feature_weights_, o->uniform_feature_weights_); std::swap(uniform_weights_, o->uniform_weights_);
   }
 
  private:
@@ -164,6 +173,7 @@ class Batch : public BatchInterface {
   ObjectIdxType* labels_ = nullptr;
   WeightType* weights_ = nullptr;
   size_t num_instances_;
+  bool uniform_feature_weights_ = false, uniform_weights_ = false;
   friend class TextEntity::Objective;
 };
 
@@ -187,6 +197,7 @@ class SyntheticSource : public DataSourceBase {
     for (size_t i = 0; i < B * n; ++i) { batch->features()[i] = draw(num_words_, word_cdf_); batch->feature_weights()[i] = 1.0f; }
     for (size_t i = 0; i < B; ++i) { batch->labels()[i] = draw(num_entities_, entity_cdf_); batch->weights()[i] = 1.0f; }
     batch->set_num_instances(B);
+    batch->set_uniform_weights(true, true);
     ++emitted_;
   }
   // identity id mapping; synthetic ids carry no corpus statistics
@@ -269,6 +280,8 @@ class NGramFileSource : public DataSourceBase {
       for (size_t k = 0; k < entities_.size(); ++k)
         weights_[k] *= std::exp(std::log(avg_document_length) - std::log(static_cast<WeightType>(length[entities_[k]])));
     }
+    instance_weights_uniform_ = true;
+    for (const float w : weights_) instance_weights_uniform_ = instance_weights_uniform_ && w == 1.0f;
     if (term_weighting_strategy == SELF_INFORMATION_TERM_WEIGHTING) {
       std::vector<long> frequency(vocabulary_size(), 0);
       for (const long w : words_) ++frequency[w];
@@ -306,6 +319,7 @@ class NGramFileSource : public DataSourceBase {
       instance(order_[position_ + i], &batch->features()[i * window_size_], &batch->feature_weights()[i * window_size_],
                &batch->labels()[i], &batch->weights()[i]);
     batch->set_num_instances(B);
+    batch->set_uniform_weights(word_weights_.empty(), instance_weights_uniform_);
     position_ += B;
   }
   // reference: IndriSource::extract_metadata, cpp/data_indri.cpp:534-555. The file is pre-tokenised, so index ids ==
@@ -326,6 +340,7 @@ class NGramFileSource : public DataSourceBase {
   std::vector<long> words_, entities_;
   std::vector<float> weights_;
   std::vector<WeightType> word_weights_;   // per word id; empty = uniform term weighting
+  bool instance_weights_uniform_ = false;  // every instance weight is exactly 1.0 (uniform weighting, unweighted file)
   std::vector<size_t> order_;
 };
 

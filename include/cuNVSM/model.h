@@ -307,7 +307,7 @@ class Model {
     const size_t B = batch.num_instances(), R = train_config_.num_random_entities() + 1;
     NVSM_CHECK(batch.window_size() == static_cast<size_t>(train_config_.window_size()), "window size mismatch");
     if (device_sampler_) {
-      NVSM_ABORT_ON(nvsm_step_sampled(handle_, batch.features(), batch.feature_weights(), batch.labels(), batch.weights(),
+      NVSM_ABORT_ON(nvsm_step_sampled(handle_, batch.features(), fw_or_null(batch), batch.labels(), w_or_null(batch),
                                       B, 0.0f, /*train=*/0));
       NVSM_ABORT_ON(nvsm_wait_upload(handle_));   // the caller may recycle the batch (AsyncSource) once we return
       ++forward_counter_;
@@ -316,8 +316,7 @@ class Model {
     // Objective::generate_labels, cpp/objective.cu:5-28
     label_generator_->generate(batch.labels(), num_entities_, B, train_config_.num_random_entities(), &entity_ids_, rng);
     NVSM_CHECK(entity_ids_.size() == B * R, "the label generator returned a wrong number of ids");
-    NVSM_ABORT_ON(nvsm_compute_cost(handle_, batch.features(), batch.feature_weights(), entity_ids_.data(),
-                                    batch.weights(), B));
+    NVSM_ABORT_ON(nvsm_compute_cost(handle_, batch.features(), fw_or_null(batch), entity_ids_.data(), w_or_null(batch), B));
     NVSM_ABORT_ON(nvsm_wait_upload(handle_));     // (entity_ids_ is reused by the next call as well)
     ++forward_counter_;
     return new TextEntity::ForwardResult(handle_, B, nvsm_scaled_regularization_lambda(handle_), &forward_counter_);
@@ -394,6 +393,10 @@ class Model {
 
   nvsm_model* handle() const { return handle_; }
   const lse::ModelDesc& desc() const { return desc_; }
+
+  // uniform weighting declared by the data source (Batch::set_uniform_weights): NULL over the C ABI, no H2D copy
+  static const float* fw_or_null(const TextEntity::Batch& b) { return b.uniform_feature_weights() ? nullptr : b.feature_weights(); }
+  static const float* w_or_null(const TextEntity::Batch& b) { return b.uniform_weights() ? nullptr : b.weights(); }
 
  private:
   void fetch(DataType* data, const char* name, size_t rows, size_t cols) const {

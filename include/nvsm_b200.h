@@ -123,7 +123,11 @@ NVSM_API int nvsm_generate_labels(const long* labels, long num_labels, long num_
  * sampled entity ids passed in (so the sampler stays swappable). All four arrays are HOST
  * buffers laid out as TextEntity::Batch (include/cuNVSM/data.h:114-177): features
  * [B*n], feature_weights [B*n], entity_ids [B*(z+1)] positive first, weights [B]. Copies
- * them to the device and enqueues the forward pass; does not synchronise. */
+ * them to the device and enqueues the forward pass; does not synchronise.
+ * feature_weights and / or weights may be NULL (here and in nvsm_train_step / nvsm_step_sampled / nvsm_stage_batch):
+ * uniform weighting, i.e. all 1.0 -- what the reference's data sources write unless self-information / idf weighting is
+ * selected (include/cuNVSM/data.h:465-467, cpp/data_indri.cpp). Nothing is transferred for a NULL array: the device copy
+ * is filled with ones (once per batch slot). */
 NVSM_API int nvsm_compute_cost(nvsm_model* m, const long* features, const float* feature_weights,
                       const long* entity_ids, const float* weights, long num_instances);
 

@@ -255,6 +255,38 @@ def test_staged_batch_equals_host_batch():
     assert abs(a - b) <= 1e-6 * abs(a)
 
 
+def test_null_weights_mean_uniform_weights_bit_exact():
+    """feature_weights / weights == NULL over the C ABI (Batch.fill without weights) is the reference's uniform weighting:
+    the device copy is filled with ones instead of being transferred. Same results as passing arrays of 1.0 through
+    every upload path, also when the batch slot held other weights before (two model instances: float atomics and the
+    bucket order make later steps agree to round-off, not bitwise)."""
+    c = dict(V=600, D=400, dw=300, dd=256, n=10, z=10, B=512, nonlinearity=nv.HARD_TANH, bn=True,
+             method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE)
+    a, _, rng_a = twin_models(**c, num_batch_slots=2)
+    b, _, rng_b = twin_models(**c, num_batch_slots=2)
+    nrng = np.random.default_rng(21)
+    ones_fw, ones_w = np.ones((512, 10), np.float32), np.ones(512, np.float32)
+    for step in range(4):
+        f, fw, labels, w = make_batch(nrng, 512, 10, 600, 400, 10)
+        ids = a.generate_labels(labels, rng_a)
+        assert (b.generate_labels(labels, rng_b) == ids).all()
+        if step == 1:   # a weighted batch in between: the slots' "holds ones" state must be invalidated
+            explicit, implicit = nv.Batch(512, 10).fill(f, labels, fw, w), nv.Batch(512, 10).fill(f, labels, fw, w)
+        else:
+            explicit, implicit = nv.Batch(512, 10).fill(f, labels, ones_fw, ones_w), nv.Batch(512, 10).fill(f, labels)
+            assert implicit.uniform_feature_weights_ and implicit.uniform_weights_ and not explicit.uniform_weights_
+        ra, rb = a.compute_cost(explicit, entity_ids=ids), b.compute_cost(implicit, entity_ids=ids)
+        ca, cb = ra.get_cost(), rb.get_cost()
+        assert (ca == cb) if step == 0 else abs(ca - cb) <= 2e-6 * abs(ca), (step, ca, cb)
+        a.backprop(ra, 0.01); b.backprop(rb, 0.01)
+        a.train_step(explicit, ids, 0.01); b.train_step(implicit, ids, 0.01)        # copy-stream upload path
+        a.stage_batch(1, explicit, ids); b.stage_batch(1, implicit, ids)            # staged path
+        a.train_step_staged(1, 0.01); b.train_step_staged(1, 0.01)
+        assert abs(a.last_cost() - b.last_cost()) <= 2e-6 * abs(a.last_cost()), step
+    for name in (nv.WORD_REPRS, nv.ENTITY_REPRS, nv.TRANSFORM, nv.BIAS):
+        assert_close(a.get_tensor(name), b.get_tensor(name), 2e-4, 2e-4, name)
+
+
 def test_errors_are_reported_not_swallowed():
     with pytest.raises(nv.NvsmError):   # a mixture objective with a zero weight (CHECK_NE in cpp/objective.cu:709-710)
         nv.Model(10, 10, nv.ModelDesc(), nv.TrainConfig(text_entity_weight=1.0, entity_entity_weight=0.0),
