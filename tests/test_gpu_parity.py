@@ -260,7 +260,7 @@ def test_null_weights_mean_uniform_weights_bit_exact():
     the device copy is filled with ones instead of being transferred. Same results as passing arrays of 1.0 through
     every upload path, also when the batch slot held other weights before (two model instances: float atomics and the
     bucket order make later steps agree to round-off, not bitwise)."""
-    c = dict(V=600, D=400, dw=300, dd=256, n=10, z=10, B=512, nonlinearity=nv.HARD_TANH, bn=True,
+    c = dict(V=600, D=400, dw=300, dd=256, n=10, z=10, B=512, nonlinearity=nv.TANH, bn=True,   # (tanh: no clip-boundary flips)
              method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE)
     a, _, rng_a = twin_models(**c, num_batch_slots=2)
     b, _, rng_b = twin_models(**c, num_batch_slots=2)
