@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "cuNVSM/gradient_check.h"
 #include "cuNVSM/model.h"
 
 // NVTX ranges with the reference's names (Epoch / Batch / FetchData / ComputeCost / ComputeGradients /
@@ -49,7 +50,7 @@ struct Flags {
               {"learning_rate", "0.0"}, {"update_method", ""}, {"weighting", "auto"}, {"feature_weighting", "uniform"},
               {"bias_negative_samples", "false"}, {"nonlinearity", ""}, {"l2_phrase_normalization", "false"},
               {"l2_entity_normalization", "false"}, {"batch_normalization", "false"}, {"compute_initial_cost", "false"},
-              {"check_gradients", "false"}, {"no_shuffle", "false"}, {"dump_initial_model", "false"}, {"dump_every", "0"},
+              {"check_gradients", "false"}, {"gradient_check_epsilon", "1e-2"}, {"no_shuffle", "false"}, {"dump_initial_model", "false"}, {"dump_every", "0"},
               {"entity_similarity_weight", "0.0"}, {"term_similarity_weight", "0.0"}, {"output", ""},
               // replacements for the Indri positional argument
               {"synthetic_num_words", "50000"}, {"synthetic_num_entities", "50000"}, {"synthetic_num_batches", "100"},
@@ -147,6 +148,18 @@ struct BatchOps<TextEntity::Objective> {
   static bool has_next(Sources& s) { return s.text->has_next(); }
   static void reset(Sources& s) { s.text->reset(); }
   static size_t num_instances(const BatchT& b) { return b.num_instances(); }
+  // --check_gradients (cpp/main.cu:414-420): every parameter, central differences, abort on failure
+  template <typename ModelT, typename ResultT>
+  static void check_gradients(ModelT* model, const BatchT& batch, const ResultT& result, const TextEntity::Gradients& gradients,
+                              const double epsilon, const std::stringstream& rng_state, RNG* rng, const bool verbose) {
+    GradientCheckFn<ModelT> check;
+    const bool ok = check(model, batch, result, gradients, static_cast<float>(epsilon), 1e-1f /* relative_error_threshold */,
+                          rng_state, rng, 1e-7, verbose ? 1 : 0);
+    const auto& r = check.report();
+    std::printf("Gradient check: %zu parameters checked, %zu below the noise floor, worst relative error %.3g (%s)\n", r.checked,
+                r.skipped, r.worst_relative_error, r.worst.c_str());
+    NVSM_CHECK(ok, "Gradient check failed.");
+  }
 };
 
 template <int K>
@@ -159,6 +172,10 @@ struct BatchOps<RepresentationSimilarity::ObjectiveT<K>> {
   static bool has_next(Sources& s) { return s.pairs->has_next(); }
   static void reset(Sources& s) { s.pairs->reset(); }
   static size_t num_instances(const BatchT& b) { return b.num_instances(); }
+  template <typename ModelT, typename ResultT>
+  static void check_gradients(ModelT*, const BatchT&, const ResultT&, const TextEntity::Gradients&, double, const std::stringstream&, RNG*, bool) {
+    NVSM_CHECK(false, "--check_gradients covers the TextEntity objective (no similarity weights)");
+  }
 };
 
 template <int K>
@@ -171,6 +188,10 @@ struct BatchOps<MixtureObjectiveT<K>> {
   static bool has_next(Sources& s) { return s.text->has_next() && s.pairs->has_next(); }   // MultiSource semantics
   static void reset(Sources& s) { s.text->reset(); s.pairs->reset(); }
   static size_t num_instances(const BatchT& b) { return std::get<0>(b).num_instances(); }
+  template <typename ModelT, typename ResultT>
+  static void check_gradients(ModelT*, const BatchT&, const ResultT&, const TextEntity::Gradients&, double, const std::stringstream&, RNG*, bool) {
+    NVSM_CHECK(false, "--check_gradients covers the TextEntity objective (no similarity weights)");
+  }
 };
 
 // train<ObjectiveT> of the reference (cpp/main.cu:471-621)
@@ -251,7 +272,8 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   // 51200-batch); by default the same stream is produced on the device, --host_sampler restores the loop.
   if (flags.d("negative_sampling_zipf") > 0.0 && Ops::has_text)
     model.set_label_generator(InverseCdfLabelGenerator<float, long>::zipf(D, flags.d("negative_sampling_zipf")));
-  if (!flags.b("host_sampler") && Ops::has_text) model.use_device_sampler(&rng);
+  // (--check_gradients replays every batch's negatives from the saved host RNG state: host sampler)
+  if (!flags.b("host_sampler") && !flags.b("check_gradients") && Ops::has_text) model.use_device_sampler(&rng);
   if (flags.b("dump_initial_model")) dump_model(model, flags.str("output"), "initial");
 
   Sources sources{&data_source, similarity_source.get()};
@@ -259,6 +281,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
   typename Ops::BatchT& batch = *batch_ptr;
   const long max_threads_per_block = 1024;  // Runtime::props().maxThreadsPerBlock in the reference
   const bool verbose = flags.i("v") > 0;
+  const bool check_gradients = flags.b("check_gradients");
 
   auto iterate = [&](const bool backpropagate, size_t* num_batches, double* agg_cost, double* seconds) {
     *num_batches = 0; *agg_cost = 0.0;
@@ -277,8 +300,17 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
       } else {
         std::unique_ptr<typename ObjectiveT::ForwardResultType> result;
         std::unique_ptr<TextEntity::Gradients> gradients;
+        std::stringstream rng_state;   // (reference: cpp/main.cu:400-402 -- saved for the gradient check)
+        if (check_gradients) rng_state << rng;
         { NvtxRange r("ComputeCost"); result.reset(model.compute_cost(batch, &rng)); }
         { NvtxRange r("ComputeGradients"); gradients.reset(model.compute_gradients(*result)); }
+        if (check_gradients) {
+          Ops::check_gradients(&model, batch, *result, *gradients, flags.d("gradient_check_epsilon"), rng_state, &rng, verbose);
+          // the probes ran in the model's workspace: replay the step's own forward / backward (same negatives)
+          std::stringstream copy; copy << rng_state.str(); copy >> rng;
+          result.reset(model.compute_cost(batch, &rng));
+          gradients.reset(model.compute_gradients(*result));
+        }
         if (backpropagate) {
           NvtxRange r("UpdateParameters");
           model.update(*gradients, train_config.learning_rate(), result->scaled_regularization_lambda());
@@ -351,7 +383,6 @@ int main(int argc, char** argv) {
              "Please specify a valid --weighting.");
   NVSM_CHECK(flags.str("feature_weighting") == "uniform" || flags.str("feature_weighting") == "self_information",
              "Please specify a valid --feature_weighting.");
-  NVSM_CHECK(!flags.b("check_gradients"), "--check_gradients is provided by the test-suite (tests/), not the CLI");
 
   lse::ModelDesc model_desc;
   model_desc.set_word_repr_size(flags.i("word_repr_size"));

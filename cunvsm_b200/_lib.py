@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("NVSM_LIB_PATH") or os.path.join(HERE, "libnvsm_b200.s
 SYMBOLS = [
     "nvsm_last_error", "nvsm_version", "nvsm_host_alloc", "nvsm_host_free", "nvsm_create", "nvsm_destroy", "nvsm_set_stream", "nvsm_synchronize",
     "nvsm_initialize", "nvsm_tensor_size", "nvsm_get_tensor", "nvsm_set_tensor", "nvsm_generate_labels",
-    "nvsm_compute_cost", "nvsm_wait_upload", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost",
+    "nvsm_compute_cost", "nvsm_wait_upload", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost", "nvsm_read_cost_f64",
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
     "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
@@ -101,6 +101,7 @@ def load():
     f("nvsm_kernel_launches", [vp], cl)
     f("nvsm_test_gemm_tc", [vp, ci, ci, ci, ci, pf, pf, pf, cf, pf, ci])
     f("nvsm_bench_gemm_tc", [vp, ci, ci, ci, ci, ci, ci, ci, pf])
+    f("nvsm_read_cost_f64", [vp, ci, ctypes.POINTER(ctypes.c_double)])
     f("nvsm_bench_memory", [vp, ci, cl, ci, ci, cl, ci, pf])
     f("nvsm_sampler_seed", [vp, ctypes.c_ulong])
     f("nvsm_sampler_state", [vp, pul])

@@ -865,7 +865,9 @@ int backward(nvsm_model* m) {
         int nparts = nz;
         if (m->use_tc) {
             const int mtiles = (dw + tc::kBlockM - 1) / tc::kBlockM;
-            const int want = std::max(1, std::min(m->gt_splits, m->num_sms / mtiles));
+            // split-K over the batch: one CTA per (M tile, split), but at least 8 k-blocks of 32 rows per split -- a small
+            // batch otherwise becomes 128 one-k-block CTAs whose partials the projection update then has to sum (C5: 22 us)
+            const int want = std::max(1, std::min(std::min(m->gt_splits, m->num_sms / mtiles), (int)(B / 256)));
             TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts,
                             m->P_lo, m->Gp_lo));
         } else {
@@ -2240,6 +2242,20 @@ int nvsm_read_cost(nvsm_model* m, int steps_back, float* cost) {
 }
 
 int nvsm_get_cost(nvsm_model* m, float* cost) { return nvsm_read_cost(m, 0, cost); }
+
+// The same cost without the final float rounding: the loss is accumulated in double on the device, and a central
+// difference over a float32 forward pass (gradient checking, cpp/gradient_check.cu:3-133) needs every digit of it.
+int nvsm_read_cost_f64(nvsm_model* m, int steps_back, double* cost) {
+    if (!m || !cost) return fail("null argument");
+    if (steps_back < 0 || steps_back >= nvsm_model::kCostRing - 1) return fail("steps_back %d out of range", steps_back);
+    if (m->forward_count - steps_back <= 0) return fail("get_cost called without a forward result");
+    CU(cudaSetDevice(m->device));
+    const int slot = (int)((m->forward_count - 1 - steps_back) % nvsm_model::kCostRing);
+    CU(cudaEventSynchronize(m->loss_ev[slot]));
+    TRY(check_id_flags(m));
+    *cost = -m->loss_host[slot] / (double)m->loss_B[slot];
+    return 0;
+}
 
 float nvsm_scaled_regularization_lambda(nvsm_model* m) {
     if (!m || m->Bglobal <= 0) return 0.f;

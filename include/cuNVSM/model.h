@@ -289,6 +289,7 @@ class Model {
     const std::vector<double>* const cdf = generator->on_device() ? generator->distribution() : nullptr;
     NVSM_ABORT_ON(nvsm_sampler_set_cdf(handle_, cdf ? cdf->data() : nullptr, cdf ? static_cast<long>(cdf->size()) : 0));
   }
+  bool uses_device_sampler() const { return device_sampler_; }
   void sync_rng(RNG* const rng) {
     if (!device_sampler_) return;
     unsigned long st = 0;

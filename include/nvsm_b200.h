@@ -148,6 +148,9 @@ NVSM_API int nvsm_get_cost(nvsm_model* m, float* cost);
 /* Same, for the forward pass `steps_back` calls ago (0 = latest, < 15): waits only for that
  * step's loss read-back, so a training loop can read step k-1 while step k runs. */
 NVSM_API int nvsm_read_cost(nvsm_model* m, int steps_back, float* cost);
+/* The same value before the final rounding to float (the device accumulates the loss in double): what the central
+ * differences of GradientCheckFn (cpp/gradient_check.cu:3-133, --check_gradients) are taken over. */
+NVSM_API int nvsm_read_cost_f64(nvsm_model* m, int steps_back, double* cost);
 NVSM_API float nvsm_scaled_regularization_lambda(nvsm_model* m);
 
 /* One whole training step on host buffers = compute_cost + compute_gradients + update

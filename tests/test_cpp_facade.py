@@ -166,6 +166,28 @@ def test_cli_trains_on_synthetic_source(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("extra", [["--nonlinearity", "tanh"], ["--nonlinearity", "tanh", "--batch_normalization"],
+                                   ["--nonlinearity", "tanh", "--bias_negative_samples"]], ids=["lse", "bn", "biased"])
+def test_cli_check_gradients(extra):
+    """cuNVSMTrainModel --check_gradients (cpp/main.cu:63,414-420; GradientCheckFn, cpp/gradient_check.cu:3-133): every
+    parameter of a tiny model against central differences of the cost on every batch, negatives replayed from the saved
+    RNG state; the CLI aborts when a gradient points the wrong way or is off by more than 10 %."""
+    _build()
+    res = subprocess.run([os.path.join(CPP, "cuNVSMTrainModel"), "--check_gradients", "--num_epochs", "1", "--word_repr_size", "8",
+                          "--entity_repr_size", "6", "--batch_size", "1024", "--window_size", "3", "--num_random_entities", "2",
+                          "--seed", "5", "--update_method", "sgd", "--learning_rate", "0.05", "--synthetic_num_words", "30",
+                          "--synthetic_num_entities", "20", "--synthetic_num_batches", "2", "--gemm", "fp32"] + extra,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("Gradient check:")]
+    assert len(lines) == 2, res.stdout
+    for l in lines:
+        checked = int(l.split()[2])
+        assert checked >= 200, l          # 30*8 + 20*6 + 8*6 + 6 = 414 parameters, most above the noise floor
+    assert "Epoch #1" in res.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("flag", ["--entity_similarity_weight", "--term_similarity_weight"])
 def test_cli_trains_mixture_objective(tmp_path, flag):
     """cuNVSMTrainModel with a mixture weight selects TextEntityEntityEntity / TextEntityTermTerm (cpp/main.cu:729-757)."""
