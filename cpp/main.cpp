@@ -154,7 +154,7 @@ struct BatchOps<TextEntity::Objective> {
                               const double epsilon, const std::stringstream& rng_state, RNG* rng, const bool verbose) {
     GradientCheckFn<ModelT> check;
     const bool ok = check(model, batch, result, gradients, static_cast<float>(epsilon), 1e-1f /* relative_error_threshold */,
-                          rng_state, rng, 1e-7, verbose ? 1 : 0);
+                          rng_state, rng, 2e-6, verbose ? 1 : 0);
     const auto& r = check.report();
     std::printf("Gradient check: %zu parameters checked, %zu below the noise floor, worst relative error %.3g (%s)\n", r.checked,
                 r.skipped, r.worst_relative_error, r.worst.c_str());

@@ -241,21 +241,23 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
     const int nvec = dim / VEC;
     // Without a dense decay (touch_all == 0: lambda == 0, or the float factor 1 - lambda_s lr rounds to exactly 1.0f) rows
     // without references are skipped, and then the scan itself is the cost when most rows are empty (C5: 1 M entity rows,
-    // 135 k references -- one offsets round trip per row and warp was 70 us). The lanes of a warp look at 32 consecutive
-    // rows at once (coalesced offsets) and the warp only walks the ones that have work.
+    // 135 k references -- one offsets round trip per row and warp was 70 us). The lanes of a warp look at the warp's next
+    // 32 rows at once and the warp only walks the ones that have work.
+    // (Rows stay dealt round-robin -- warp w owns rows w, w + nwarps, ... --: skewed id streams put the referenced rows
+    // next to each other, and a warp that owned 32 CONSECUTIVE rows of the hot region ran 4x longer than the rest.)
     const long row_step = touch_all ? 1 : 32;
-    for (long row0 = warp0 * row_step; row0 < num_rows; row0 += nwarps * row_step) {
+    for (long row0 = warp0; row0 < num_rows; row0 += nwarps * row_step) {
       unsigned todo = 1u;
       int lane_beg = 0, lane_end = 0;
       if (!touch_all) {
-          const long r = row0 + lane;
+          const long r = row0 + (long)lane * nwarps;
           if (r < num_rows) { lane_beg = __ldg(offsets + r); lane_end = __ldg(offsets + r + 1); }
           todo = __ballot_sync(kFull, lane_end > lane_beg && lane_end - lane_beg <= heavy_above);
       }
       while (todo) {
         const int sub = __ffs(todo) - 1;
         todo &= todo - 1;
-        const long row = row0 + sub;
+        const long row = row0 + (long)sub * nwarps;
         int beg, end;
         if (touch_all) {
             beg = __ldg(offsets + row); end = __ldg(offsets + row + 1);
