@@ -1116,14 +1116,26 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
     // rows above kHeavyRefs references are on the list the bucket build made: the row kernel skips them
     const int row_hw = m->no_heavy ? 0 : 1;
     const int heavy_above = row_hw ? kHeavyRefs : INT_MAX;
+    // sgd_pull_sparse_kernel: no dense decay and at most ~2 references per row on average (C3 entities 1.7, C5 0.13): the
+    // scan and the per-row load chain are the cost. Denser tables keep the plain row loop (more warps, fewer registers).
+    bool sparse = !touch_all && (double)(entities ? m->B * m->R : m->B * m->n) <= 2.0 * (double)(entities ? m->D : m->V);
+    { const char* e = getenv("NVSM_SGD_SPARSE"); if (e) sparse = !touch_all && atoi(e) != 0; }
     if (entities) {
-        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
-               (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        if (!sparse)
+            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, touch_all ? 1 : 0, acc, ysq, 1e-6f, heavy_above);
+        else
+            LAUNCH(m, (sgd_pull_sparse_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
+                   (const float*)m->mult, (const float*)m->Y, m->R, decay, lr, acc, ysq, 1e-6f, heavy_above);
         if (row_hw) LAUNCH(m, (pull_heavy_kernel<VEC, NCH, true, SgdApply>), heavy_grid(m, *hw), 256, 0, m->dd, m->e_offsets, m->e_refs,
                (const float*)m->mult, (const float*)m->Y, m->R, ysq, *hw, SgdApply{m->E, decay, lr, acc, 1e-6f});
     } else {
-        LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
-               (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        if (!sparse)
+            LAUNCH(m, (sgd_pull_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+                   (const float*)m->gP, m->n, decay, lr, touch_all ? 1 : 0, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
+        else
+            LAUNCH(m, (sgd_pull_sparse_kernel<VEC, NCH, false>), grid, 256, 0, m->W, m->V, m->dw, m->w_offsets, m->w_refs, word_coefs,
+                   (const float*)m->gP, m->n, decay, lr, (float*)nullptr, (const float*)nullptr, 1e-6f, heavy_above);
         if (row_hw) {
             HeavyStream hs;
             TRY(heavy_stream_begin(m, entities, &hs));

@@ -239,32 +239,10 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     const int nvec = dim / VEC;
-    // Without a dense decay (touch_all == 0: lambda == 0, or the float factor 1 - lambda_s lr rounds to exactly 1.0f) rows
-    // without references are skipped, and then the scan itself is the cost when most rows are empty (C5: 1 M entity rows,
-    // 135 k references -- one offsets round trip per row and warp was 70 us). The lanes of a warp look at the warp's next
-    // 32 rows at once and the warp only walks the ones that have work.
-    // (Rows stay dealt round-robin -- warp w owns rows w, w + nwarps, ... --: skewed id streams put the referenced rows
-    // next to each other, and a warp that owned 32 CONSECUTIVE rows of the hot region ran 4x longer than the rest.)
-    const long row_step = touch_all ? 1 : 32;
-    for (long row0 = warp0; row0 < num_rows; row0 += nwarps * row_step) {
-      unsigned todo = 1u;
-      int lane_beg = 0, lane_end = 0;
-      if (!touch_all) {
-          const long r = row0 + (long)lane * nwarps;
-          if (r < num_rows) { lane_beg = __ldg(offsets + r); lane_end = __ldg(offsets + r + 1); }
-          todo = __ballot_sync(kFull, lane_end > lane_beg && lane_end - lane_beg <= heavy_above);
-      }
-      while (todo) {
-        const int sub = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const long row = row0 + (long)sub * nwarps;
-        int beg, end;
-        if (touch_all) {
-            beg = __ldg(offsets + row); end = __ldg(offsets + row + 1);
-            if (end - beg > heavy_above) continue;   // pull_heavy_kernel owns this row
-        } else {
-            beg = __shfl_sync(kFull, lane_beg, sub); end = __shfl_sync(kFull, lane_end, sub);
-        }
+    for (long row = warp0; row < num_rows; row += nwarps) {
+        const int beg = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+        if (beg == end && !touch_all) continue;
+        if (end - beg > heavy_above) continue;   // pull_heavy_kernel owns this row
         float agg[NCH][VEC];
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
@@ -317,7 +295,146 @@ __global__ void __launch_bounds__(256) sgd_pull_kernel(float* __restrict__ theta
                 store_vec_cs<VEC>(theta + o, th);
             }
         }
-      }
+    }
+}
+
+// The same update when NO row is touched unless it is referenced (touch_all == 0: lambda == 0, or the float decay factor
+// 1 - lambda_s lr rounds to exactly 1.0f -- a bit-exact no-op, C3 / C5). Then (i) the scan over the rows is the cost when
+// most rows are empty (C5: 1 M entity rows, 135 k references: one offsets round trip per row and warp was 70 us of a
+// 0.18 ms step), and (ii) a referenced row is a chain of dependent loads -- offsets -> refs -> coefs -> source rows ->
+// theta -- with ~1.7 references per row (C3: 57 % of the HBM peak, ncu r2a). Here the 32 lanes of a warp fetch the
+// bucket bounds AND the first two references (source row, signed coefficient, squared-gradient term) of the warp's next
+// 32 rows at once; the warp then walks only the rows that have work, with everything but the source rows and theta
+// already in registers, and theta is requested before the gather. Rows stay dealt round-robin (warp w owns rows w,
+// w + nwarps, ...): skewed id streams put the referenced rows next to each other, and a warp owning 32 CONSECUTIVE
+// rows of the hot region ran 4x longer than the rest. Same arithmetic and summation order as sgd_pull_kernel.
+template <int VEC, int NCH, bool ENTITY>
+__global__ void __launch_bounds__(256) sgd_pull_sparse_kernel(float* __restrict__ theta, long num_rows, int dim,
+                                                              const int* __restrict__ offsets, const int* __restrict__ refs,
+                                                              const float* __restrict__ coefs, const float* __restrict__ src,
+                                                              int group, float decay, float lr, float* __restrict__ acc,
+                                                              const float* __restrict__ ysq, float eps, const int heavy_above) {
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = dim / VEC;
+    for (long row0 = warp0; row0 < num_rows; row0 += nwarps * 32) {
+        // ---- lane l: metadata of row row0 + l * nwarps ----
+        const long lrow = row0 + (long)lane * nwarps;
+        int lbeg = 0, lend = 0;
+        if (lrow < num_rows) { lbeg = __ldg(offsets + lrow); lend = __ldg(offsets + lrow + 1); }
+        const int lcnt = lend - lbeg;
+        const bool lwork = lcnt > 0 && lcnt <= heavy_above;     // (rows above heavy_above: pull_heavy_kernel)
+        int src0 = 0, src1 = 0;
+        float cf0 = 0.f, cf1 = 0.f, sq0 = 0.f, sq1 = 0.f;
+        if (lwork) {
+            const int ref = __ldg(refs + lbeg);
+            src0 = ref / group;
+            const float c = __ldg(coefs + ref);
+            cf0 = (ENTITY && (ref - src0 * group) != 0) ? -c : c;
+            if (acc) sq0 = c * c * __ldg(ysq + src0);
+            if (lcnt > 1) {
+                const int ref1 = __ldg(refs + lbeg + 1);
+                src1 = ref1 / group;
+                const float c1 = __ldg(coefs + ref1);
+                cf1 = (ENTITY && (ref1 - src1 * group) != 0) ? -c1 : c1;
+                if (acc) sq1 = c1 * c1 * __ldg(ysq + src1);
+            }
+        }
+        unsigned todo = __ballot_sync(kFull, lwork);
+        while (todo) {
+            const int sub = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long row = row0 + (long)sub * nwarps;
+            const int beg = __shfl_sync(kFull, lbeg, sub), end = __shfl_sync(kFull, lend, sub);
+            float th[NCH][VEC];
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const int c = lane + j * kWarp;
+                if (c < nvec) load_vec_cs<VEC>(theta + row * dim + c * VEC, th[j]);
+            }
+            float acc_old = 0.f;
+            if (acc) acc_old = acc[row];
+            float agg[NCH][VEC];
+#pragma unroll
+            for (int j = 0; j < NCH; ++j)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) agg[j][q] = 0.f;
+            float sq;
+            if (end - beg <= 2) {
+                // both references came with the metadata; sq: lanes 0 and 1 of sgd_pull_kernel hold one term each and
+                // warp_sum adds them -- the same two-term sum
+                const int s0 = __shfl_sync(kFull, src0, sub), s1 = __shfl_sync(kFull, src1, sub);
+                const float c0 = __shfl_sync(kFull, cf0, sub), c1 = __shfl_sync(kFull, cf1, sub);
+                sq = __shfl_sync(kFull, sq0, sub) + __shfl_sync(kFull, sq1, sub);
+                float x0[NCH][VEC], x1[NCH][VEC];
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+                    if (c < nvec) {
+                        load_vec_ro<VEC>(src + (long)s0 * dim + c * VEC, x0[j]);
+                        load_vec_ro<VEC>(src + (long)s1 * dim + c * VEC, x1[j]);     // (one reference: row s1 = 0, coefficient 0)
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    const int c = lane + j * kWarp;
+                    if (c < nvec) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) agg[j][q] += c0 * x0[j][q];
+                        if (end - beg == 2) {
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) agg[j][q] += c1 * x1[j][q];
+                        }
+                    }
+                }
+            } else {
+                sq = 0.f;
+                for (int base = beg; base < end; base += 32) {
+                    const int cnt = min(32, end - base);
+                    int my_src = 0;
+                    float my_coef = 0.f;
+                    if (lane < cnt) {
+                        const int ref = __ldg(refs + base + lane);
+                        my_src = ref / group;
+                        const float cf = __ldg(coefs + ref);
+                        my_coef = (ENTITY && (ref - my_src * group) != 0) ? -cf : cf;
+                        if (acc) sq += cf * cf * __ldg(ysq + my_src);
+                    }
+                    for (int t = 0; t < cnt; ++t) {
+                        const int srow = __shfl_sync(kFull, my_src, t);
+                        const float cf = __shfl_sync(kFull, my_coef, t);
+#pragma unroll
+                        for (int j = 0; j < NCH; ++j) {
+                            const int c = lane + j * kWarp;
+                            if (c < nvec) {
+                                float x[VEC];
+                                load_vec_ro<VEC>(src + (long)srow * dim + c * VEC, x);
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) agg[j][q] += cf * x[q];
+                            }
+                        }
+                    }
+                }
+                if (acc) sq = warp_sum(sq);
+            }
+            float rs = 1.0f;
+            if (acc) {
+                const float a = acc_old + sq;
+                if (lane == 0) acc[row] = a;
+                rs = 1.0f / sqrtf(a + eps);
+            }
+            const float step = lr * rs;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+                const int c = lane + j * kWarp;
+                if (c < nvec) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) th[j][q] = th[j][q] * decay + step * agg[j][q];
+                    store_vec_cs<VEC>(theta + row * dim + c * VEC, th[j]);
+                }
+            }
+        }
     }
 }
 
