@@ -310,6 +310,7 @@ int train(const Flags& flags, const lse::ModelDesc& model_desc, const lse::Train
           std::stringstream copy; copy << rng_state.str(); copy >> rng;
           result.reset(model.compute_cost(batch, &rng));
           gradients.reset(model.compute_gradients(*result));
+          (void)result->get_cost();   // read now (cached): the next batch's probes would push it out of the loss ring
         }
         if (backpropagate) {
           NvtxRange r("UpdateParameters");

@@ -15,9 +15,11 @@ PHASES = (("gather_mean", ("gather_mean",)), ("gemm_fwd", ("gemm_tc2_kernel", "g
           ("bn_backward", ("bn_backward",)), ("gemm_grad_transform", ("gemm_tc_kernel<1, 1",)),
           ("gemm_grad_phrase", ("gemm_tc_kernel<0, 0",)),
           ("update_entities", ("adam_full_pull_kernel<4, 2, 1>", "adam_full_pull_kernel<4, 1, 1>", "sgd_pull_kernel<4, 2, 1>",
-                               "sgd_pull_kernel<4, 1, 1>", "row_meansq_act_kernel")),
+                               "sgd_pull_kernel<4, 1, 1>", "sgd_pull_sparse_kernel<4, 2, 1>", "sgd_pull_sparse_kernel<4, 1, 1>",
+                               "row_meansq_act_kernel")),
           ("update_words", ("adam_full_pull_kernel<4, 3, 0>", "adam_full_pull_kernel<4, 1, 0>", "sgd_pull_kernel<4, 3, 0>",
-                            "sgd_pull_kernel<4, 1, 0>", "row_meansq_kernel", "word_scalar_scatter", "word_adagrad_coef")))
+                            "sgd_pull_kernel<4, 1, 0>", "sgd_pull_sparse_kernel<4, 3, 0>", "sgd_pull_sparse_kernel<4, 1, 0>",
+                            "row_meansq_kernel", "word_scalar_scatter", "word_adagrad_coef")))
 
 
 def to_bytes(value, unit):
