@@ -592,6 +592,21 @@ def run_ours(args, w, rank, world, local_rank):
     phases = {k: v / prof_steps for k, v in model.phase_ms().items()}
     model.set_profiling(False)
 
+    if args.timeline and rank == 0:
+        # overlapped timeline of fused steps: every phase's (start, end) on whatever stream it ran (nvsm_set_profiling 2)
+        for it in range(3):
+            model.train_step_staged(it % NUM_BATCHES, lr)
+        model.synchronize()
+        model.set_profiling(2)
+        for it in range(3):
+            model.train_step_staged(it % NUM_BATCHES, lr)
+        tl = model.timeline()
+        model.set_profiling(False)
+        with open(args.timeline, "w") as f:
+            f.write("# timeline of 3 fused steps (ms since the first launch; streams overlap)\n\n| phase | start | end | us |\n|---|---|---|---|\n")
+            for name, a, b in sorted(tl, key=lambda x: x[1]):
+                f.write("| %s | %.4f | %.4f | %.1f |\n" % (name, a, b, 1e3 * (b - a)))
+
     # strong scaling (BASELINE configs[3] as written): the SAME global batch w["B"] sharded over the ranks
     strong = None
     if world > 1 and args.scaling in ("both", "strong") and w["B"] % world == 0:
@@ -782,6 +797,7 @@ def main():
     ap.add_argument("--no_parity_check", action="store_true", help="N>1: skip the sharded-vs-unsharded-vs-reference step check")
     ap.add_argument("--no_ref_check", action="store_true", help="N>1 parity check without the oracle/_ref leg")
     ap.add_argument("--e2e_breakdown", action="store_true", help="extra timed loops that split the host-fed step's overhead (rank 0's view)")
+    ap.add_argument("--timeline", default=None, help="write the overlapped per-phase timeline of three fused steps to this markdown file")
     ap.add_argument("--no_probes", action="store_true", help="skip the L2-gather / stream-copy roofline probes")
 
     ap.add_argument("--zipf_words", type=float, default=0.0, help="word ids ~ Zipf(s) instead of uniform (C3 gather/scatter sweep)")

@@ -16,7 +16,7 @@ SYMBOLS = [
     "nvsm_compute_cost", "nvsm_wait_upload", "nvsm_compute_gradients", "nvsm_update", "nvsm_get_cost", "nvsm_read_cost", "nvsm_read_cost_f64",
     "nvsm_scaled_regularization_lambda", "nvsm_train_step", "nvsm_stage_batch", "nvsm_compute_cost_staged",
     "nvsm_train_step_staged", "nvsm_infer", "nvsm_increment_parameter", "nvsm_set_profiling", "nvsm_num_phases",
-    "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
+    "nvsm_phase_name", "nvsm_get_phase_ms", "nvsm_get_timeline", "nvsm_reset_phase_ms", "nvsm_kernel_launches", "nvsm_comm_unique_id",
     "nvsm_comm_init", "nvsm_comm_set_sparse_mode", "nvsm_comm_peer_export", "nvsm_comm_peer_import", "nvsm_comm_peer_status", "nvsm_comm_peer_disable", "nvsm_similarity_compute_cost", "nvsm_similarity_get_cost",
     "nvsm_similarity_scaled_regularization_lambda", "nvsm_test_gemm_tc", "nvsm_bench_gemm_tc", "nvsm_bench_memory", "nvsm_sampler_seed", "nvsm_sampler_state",
     "nvsm_ops_create", "nvsm_ops_destroy", "nvsm_ops_synchronize", "nvsm_ops_kernel_launches", "nvsm_dev_malloc", "nvsm_dev_free",
@@ -98,6 +98,7 @@ def load():
     f("nvsm_phase_name", [ci], cs)
     f("nvsm_get_phase_ms", [vp, pf, ci])
     f("nvsm_reset_phase_ms", [vp])
+    f("nvsm_get_timeline", [vp, ctypes.POINTER(ci), pf, pf, ci])
     f("nvsm_kernel_launches", [vp], cl)
     f("nvsm_test_gemm_tc", [vp, ci, ci, ci, ci, pf, pf, pf, cf, pf, ci])
     f("nvsm_bench_gemm_tc", [vp, ci, ci, ci, ci, ci, ci, ci, pf])

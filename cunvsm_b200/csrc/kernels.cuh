@@ -10,6 +10,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "peer_allreduce.cuh"
 
 namespace nvsm {
 
@@ -288,11 +289,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int dd, doub
 // columns x 128 slices of the partial rows (ncu r1i: the former 32-column x 32-slice shape ran 8 CTAs for 14.7 us, a
 // serial chain of ~19 dependent L2 round trips per thread; this one runs dd / 8 CTAs with <= 5 per thread). Sums and
 // sums of squares together, double accumulation, fixed summation order.
+// XCHG (N > 1, NVLink peer exchange): between the reduction and the finalisation every block pushes the sums of ITS eight
+// columns to every peer and waits for the peers' (per-block flags), i.e. partial rows -> local sums -> global sums ->
+// mean / invstd in one launch instead of reduce, one-block all-reduce and finalize kernels.
+template <bool XCHG>
 __global__ void __launch_bounds__(1024) col_stats_reduce_finalize_kernel(const float* __restrict__ partials, int nblocks, int dd,
                                                                          double batch, double eps, double* __restrict__ sums,
                                                                          float* __restrict__ mean, float* __restrict__ invstd,
                                                                          const float* __restrict__ bias,
-                                                                         float* __restrict__ scale, float* __restrict__ shift) {
+                                                                         float* __restrict__ scale, float* __restrict__ shift,
+                                                                         const PeerXchg* __restrict__ xp, unsigned long long epoch,
+                                                                         int* __restrict__ xchg_error) {
     constexpr int C = 8, S = 128;   // blockDim = C columns x S slices
     __shared__ double sm[2][32][C];
     const int cl = threadIdx.x & (C - 1), slice = threadIdx.x / C;
@@ -309,10 +316,36 @@ __global__ void __launch_bounds__(1024) col_stats_reduce_finalize_kernel(const f
     a += __shfl_xor_sync(kFull, a, 16); q += __shfl_xor_sync(kFull, q, 16);
     if (lane < C) { sm[0][warp][lane] = a; sm[1][warp][lane] = q; }
     __syncthreads();
-    if (threadIdx.x < C && col < dd) {
-        double s = 0.0, s2 = 0.0;
+    if (warp != 0) return;
+    const bool own = threadIdx.x < C && col < dd;
+    double s = 0.0, s2 = 0.0;
+    if (own) {
 #pragma unroll 8
         for (int g = 0; g < 32; ++g) { s += sm[0][g][threadIdx.x]; s2 += sm[1][g][threadIdx.x]; }
+    }
+    if (XCHG) {
+        const PeerXchg& x = *xp;
+        const int parity = (int)(epoch & 1ull);
+        if (own)
+            for (int p = 0; p < x.nranks; ++p) {
+                double* dst = x.inbox[p] + peer_slot_index(x, 0, parity, x.rank);
+                dst[col] = s;
+                dst[dd + col] = s2;
+            }
+        __threadfence_system();
+        __syncwarp();
+        peer_publish(x, 0, parity, blockIdx.x, epoch, lane);
+        peer_wait(x, 0, parity, blockIdx.x, epoch, lane, xchg_error);
+        __syncwarp();
+        if (own) {
+            s = 0.0; s2 = 0.0;
+            for (int p = 0; p < x.nranks; ++p) {   // rank order: bit-identical on every rank
+                s += peer_inbox_value(x, 0, parity, p, col);
+                s2 += peer_inbox_value(x, 0, parity, p, dd + col);
+            }
+        }
+    }
+    if (own) {
         sums[col] = s;
         sums[dd + col] = s2;
         const double mu = s / batch;
@@ -398,6 +431,12 @@ struct ScoreParams {
     // normalised dot product e.y / |e| are kept for the backward pass (cpp/cuda_utils.cu:69-127).
     float* enorm;          // [B*R] nullable
     float* escore;         // [B*R] nullable
+    // N > 1 with the NVLink peer exchange: the last block to finish all-reduces col_sums + loss_acc (contiguous,
+    // [2*dd + 1]) across the ranks inside this kernel (peer_sums_tail). Null: single GPU, or the caller reduces.
+    const PeerXchg* xchg;
+    unsigned long long xchg_epoch;
+    unsigned int* xchg_counter;
+    int* xchg_error;
 };
 
 // Reduce four per-lane partial sums across the warp with 6 shuffles (instead of 20): after the
@@ -571,6 +610,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)smem[t]);
     if (threadIdx.x == 0) atomicAdd(p.loss_acc, (double)smem[2 * dd]);
+    if (p.xchg) peer_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error);
 }
 
 // =====================================================================================

@@ -63,11 +63,11 @@ int fail(const char* fmt, ...) {
 
 enum Phase {
     PH_H2D = 0, PH_GATHER, PH_GEMM_FWD, PH_BN_STATS, PH_SCORE, PH_BN_BWD, PH_GEMM_GT, PH_GEMM_GP,
-    PH_UPD_ENTITIES, PH_UPD_WORDS, PH_UPD_TRANSFORM, PH_ALLREDUCE, PH_COUNT
+    PH_UPD_ENTITIES, PH_UPD_WORDS, PH_UPD_TRANSFORM, PH_ALLREDUCE, PH_BUCKETS, PH_COUNT
 };
 const char* kPhaseNames[PH_COUNT] = {
     "h2d", "gather_mean", "gemm_fwd", "bn_stats", "score_loss_bwd", "bn_backward", "gemm_grad_transform",
-    "gemm_grad_phrase", "update_entities", "update_words", "update_transform", "allreduce"};
+    "gemm_grad_phrase", "update_entities", "update_words", "update_transform", "allreduce", "bucket_build"};
 
 struct BatchSlot {
     idx_t* features = nullptr;   // [maxB*n]
@@ -168,7 +168,11 @@ struct nvsm_model {
 
     // instrumentation
     long launches = 0;
-    bool profiling = false;
+    bool profiling = false;   // serial phase timing: the stream overlaps are switched off so that phases add up
+    bool timeline = false;    // overlaps kept: every phase reports (start, end) against one origin event, whatever its stream
+    cudaEvent_t tl_origin = nullptr;
+    struct Interval { int phase; float start_ms, end_ms; };
+    std::vector<Interval> intervals;
     struct Ev { int phase; cudaEvent_t a, b; };
     std::vector<Ev> pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -206,12 +210,18 @@ struct nvsm_model {
     // small reductions over NVLink peer memory (peer_allreduce.cuh); NCCL is the fallback and carries grad_transform
     bool peer_ready = false;
     PeerXchg peer{};
+    PeerXchg* peer_dev = nullptr;                // device copy (kernels that take it by pointer)
+    unsigned int* xchg_counter = nullptr;        // arrival counter of the score kernels' last-block exchange
+    bool no_fused_xchg = false;
     double* peer_inbox = nullptr;                // this rank's inbox (exported with CUDA IPC)
     unsigned long long* peer_flags = nullptr;
     void* peer_mapped[2 * kPeerMaxRanks] = {nullptr};   // IPC mappings to close
     unsigned long long peer_epoch[kPeerKinds] = {0, 0, 0, 0};
     int* peer_error = nullptr;
     cudaStream_t comm_stream = nullptr;          // grad_transform all-reduce, under grad_phrase and the word update
+    cudaStream_t gt_stream = nullptr;            // fused steps: grad_transform GEMM (+ all-reduce) under the word update
+    cudaEvent_t dx_ready = nullptr;
+    bool gt_side = false, in_fused_step = false, no_fused_reduce = false;
     cudaEvent_t gt_ready = nullptr, gt_reduced_ev = nullptr;
     bool gt_allreduce_pending = false;
     // NVSM_SPARSE_ALLGATHER: every rank applies the table updates of ALL rows (exact single-GPU trajectory).
@@ -257,14 +267,14 @@ cudaEvent_t get_event(nvsm_model* m) {
 }
 
 void phase_begin(nvsm_model* m, int phase) {
-    if (!m->profiling) return;
+    if (!m->profiling && !m->timeline) return;
     m->open_phase = phase;
     m->open_ev = get_event(m);
     cudaEventRecord(m->open_ev, m->stream);
 }
 
 void phase_end(nvsm_model* m) {
-    if (!m->profiling || m->open_phase < 0) return;
+    if ((!m->profiling && !m->timeline) || m->open_phase < 0) return;
     cudaEvent_t e = get_event(m);
     cudaEventRecord(e, m->stream);
     m->pending.push_back({m->open_phase, m->open_ev, e});
@@ -274,10 +284,17 @@ void phase_end(nvsm_model* m) {
 int collect_phases(nvsm_model* m) {
     if (m->pending.empty()) return 0;
     CU(cudaStreamSynchronize(m->stream));
+    if (m->aux_stream) CU(cudaStreamSynchronize(m->aux_stream));
+    if (m->gt_stream) CU(cudaStreamSynchronize(m->gt_stream));
     for (auto& ev : m->pending) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev.a, ev.b);
         m->phase_ms[ev.phase] += ms;
+        if (m->timeline && m->tl_origin) {
+            float t0 = 0.f;
+            if (cudaEventElapsedTime(&t0, m->tl_origin, ev.a) == cudaSuccess) m->intervals.push_back({ev.phase, t0, t0 + ms});
+            else (void)cudaGetLastError();
+        }
         m->ev_pool.push_back(ev.a);
         m->ev_pool.push_back(ev.b);
     }
@@ -555,6 +572,14 @@ int allgather_bytes(nvsm_model* m, const void* src, void* dst, size_t bytes_per_
     return 0;
 }
 
+// The two per-step reductions on the critical path run INSIDE compute kernels when the NVLink peer exchange is up
+// (peer_allreduce.cuh: col_stats_reduce_finalize_kernel<true>, peer_sums_tail); NVSM_NO_FUSED_XCHG=1 restores the
+// stand-alone one-block all-reduce launches (A/B measurements), and without peer memory they are ncclAllReduce calls.
+bool fused_xchg(const nvsm_model* m) {
+    return m->nranks > 1 && m->peer_ready && m->peer_dev && !m->no_fused_xchg && 2 * m->dd + 1 <= m->peer.slot_doubles &&
+           (m->dd + 7) / 8 <= kPeerFlagStride;
+}
+
 bool exact_sparse(const nvsm_model* m) { return m->nranks > 1 && m->sparse_mode == NVSM_SPARSE_ALLGATHER; }
 
 // ------------------------------------------------------------------------------------
@@ -730,14 +755,21 @@ int forward(nvsm_model* m, BatchSlot* s) {
                 LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
             }
             if (m->nranks <= 1) {
-                LAUNCH(m, col_stats_reduce_finalize_kernel, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
-                       1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift);
+                LAUNCH(m, col_stats_reduce_finalize_kernel<false>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                       1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift,
+                       (const PeerXchg*)nullptr, 0ull, (int*)nullptr);
+            } else if (fused_xchg(m)) {
+                // partial rows -> local sums -> NVLink exchange -> global mean / invstd in ONE launch (per-block flags)
+                const unsigned long long epoch = ++m->peer_epoch[0];
+                LAUNCH(m, col_stats_reduce_finalize_kernel<true>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                       1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift,
+                       (const PeerXchg*)m->peer_dev, epoch, m->peer_error);
             } else {
                 LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
             }
         }
         phase_end(m);
-        if (m->nranks > 1) {
+        if (m->nranks > 1 && !fused_xchg(m)) {
             TRY(allreduce(m, m->fwd_sums(), 2 * (size_t)dd, true, 0));
             phase_begin(m, PH_BN_STATS);
             LAUNCH(m, bn_finalize_kernel, (dd + 127) / 128, 128, 0, m->fwd_sums(), dd, (double)m->Bglobal,
@@ -788,11 +820,17 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.loss_acc = m->loss_acc(); sp.col_sums = m->bwd_sums();
         sp.enorm = m->l2_entity ? m->enorm : nullptr;
         sp.escore = m->l2_entity ? m->escore : nullptr;
+        // N > 1: the backward column sums + loss are all-reduced by the score kernel's last block (peer_sums_tail)
+        sp.xchg = nullptr; sp.xchg_epoch = 0; sp.xchg_counter = nullptr; sp.xchg_error = nullptr;
+        if (fused_xchg(m)) {
+            sp.xchg = m->peer_dev; sp.xchg_epoch = ++m->peer_epoch[3];
+            sp.xchg_counter = m->xchg_counter; sp.xchg_error = m->peer_error;
+        }
         m->entity_prep_done = false;
         TRY(dispatch_score(m, sp));
     }
     phase_end(m);
-    TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true, 3));
+    if (!fused_xchg(m)) TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true, 3));
     {
         const int slot = (int)(m->forward_count % nvsm_model::kCostRing);
         CU(cudaMemcpyAsync(m->loss_host + slot, m->loss_acc(), sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -853,8 +891,8 @@ int backward(nvsm_model* m) {
     phase_end(m);
 
     // grad_transform[dw, dd] = P^T . dX  (K = B: split-K partials + deterministic reduce)
-    phase_begin(m, PH_GEMM_GT);
-    {
+    auto run_gt = [&]() -> int {
+        phase_begin(m, PH_GEMM_GT);
         const int tiles = ((dw + GEMM_BM - 1) / GEMM_BM) * ((dd + GEMM_BN - 1) / GEMM_BN);
         int splits = std::max(1, std::min(m->gt_splits, (2 * m->num_sms + tiles - 1) / tiles));
         splits = (int)std::min<long>(splits, std::max<long>(1, B / 64));
@@ -875,37 +913,63 @@ int backward(nvsm_model* m) {
         }
         m->gt_nparts = nparts;
         m->gt_reduced = false;
-        if (m->nranks > 1 || getenv("NVSM_NO_FUSED_REDUCE")) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
-    }
-    phase_end(m);
-    if (m->nranks > 1) {
-        // grad_transform is only consumed by the projection update at the very end of the step: its all-reduce runs on
-        // the communication stream under the grad_phrase GEMM and the word update (joined in update_transform).
-        if (m->comm_stream && !m->profiling) {
-            CU(cudaEventRecord(m->gt_ready, m->stream));
-            CU(cudaStreamWaitEvent(m->comm_stream, m->gt_ready, 0));
-            const int arc = nccl_api().AllReduce(m->gT, m->gT, (size_t)dw * dd, kNcclFloat32, kNcclSum, m->comm, (void*)m->comm_stream);
-            if (arc != 0) return fail("ncclAllReduce: %s", nccl_api().GetErrorString(arc));
-            CU(cudaEventRecord(m->gt_reduced_ev, m->comm_stream));
-            m->gt_allreduce_pending = true;
-        } else {
-            TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
-        }
-    }
-
+        if (m->nranks > 1 || m->no_fused_reduce) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
+        phase_end(m);
+        return 0;
+    };
     // grad_phrase[B, dw] = dX . T^T, scaled by 1/n (cpp/objective.cu:453-476)
-    phase_begin(m, PH_GEMM_GP);
-    {
+    auto run_gp = [&]() -> int {
+        phase_begin(m, PH_GEMM_GP);
         const float inv_n = (float)std::exp(-std::log((double)m->n));
         if (m->use_tc)
             TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->Tr, dd, m->gP, dw, 1, 0, inv_n, nullptr, nullptr, m->Gp_lo, m->Tr_lo));
         else
             TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
+        if (m->l2_phrase)   // Normalizer::backward on grad_phrase (cpp/objective.cu:461-468); linear, so 1/n commutes
+            LAUNCH(m, row_l2_normalize_backward_kernel, grid_for(m, B, 8, 8), 256, 0, m->gP, dw, m->P, m->P_lo, m->ldP,
+                   m->p_norms, B, dw);
+        phase_end(m);
+        return 0;
+    };
+    auto nccl_gt = [&](cudaStream_t on) -> int {
+        const int arc = nccl_api().AllReduce(m->gT, m->gT, (size_t)dw * dd, kNcclFloat32, kNcclSum, m->comm, (void*)on);
+        if (arc != 0) return fail("ncclAllReduce: %s", nccl_api().GetErrorString(arc));
+        return 0;
+    };
+
+    if (m->gt_side && m->in_fused_step && !m->profiling) {
+        // Fused steps: grad_transform is only consumed by the projection update at the very end of the step, while
+        // grad_phrase feeds the word update. The grad_phrase GEMM is issued first (critical path); the grad_transform
+        // GEMM (+ its all-reduce at N > 1) goes to a side stream and shares the SMs with the L2-bound word update
+        // instead of delaying it. Joined in update_transform.
+        CU(cudaEventRecord(m->dx_ready, m->stream));
+        TRY(run_gp());
+        CU(cudaStreamWaitEvent(m->gt_stream, m->dx_ready, 0));
+        cudaStream_t main_stream = m->stream;
+        m->stream = m->gt_stream;
+        int rc = run_gt();
+        if (rc == 0 && m->nranks > 1) rc = nccl_gt(m->gt_stream);
+        m->stream = main_stream;
+        if (rc) return rc;
+        CU(cudaEventRecord(m->gt_reduced_ev, m->gt_stream));
+        m->gt_allreduce_pending = true;
+    } else {
+        TRY(run_gt());
+        if (m->nranks > 1) {
+            // grad_transform is only consumed by the projection update at the very end of the step: its all-reduce runs on
+            // the communication stream under the grad_phrase GEMM and the word update (joined in update_transform).
+            if (m->comm_stream && !m->profiling) {
+                CU(cudaEventRecord(m->gt_ready, m->stream));
+                CU(cudaStreamWaitEvent(m->comm_stream, m->gt_ready, 0));
+                TRY(nccl_gt(m->comm_stream));
+                CU(cudaEventRecord(m->gt_reduced_ev, m->comm_stream));
+                m->gt_allreduce_pending = true;
+            } else {
+                TRY(allreduce(m, m->gT, (size_t)dw * dd, false));
+            }
+        }
+        TRY(run_gp());
     }
-    if (m->l2_phrase)   // Normalizer::backward on grad_phrase (cpp/objective.cu:461-468); linear, so 1/n commutes
-        LAUNCH(m, row_l2_normalize_backward_kernel, grid_for(m, B, 8, 8), 256, 0, m->gP, dw, m->P, m->P_lo, m->ldP,
-               m->p_norms, B, dw);
-    phase_end(m);
     m->have_gradients = true;
     return 0;
 }
@@ -1201,7 +1265,9 @@ int start_bucket_build(nvsm_model* m, BatchSlot* s) {
     m->stream = m->aux_stream;   // LAUNCH targets m->stream
     const bool prof = m->profiling;
     m->profiling = false;
+    phase_begin(m, PH_BUCKETS);   // (timeline mode only)
     int rc = build_all_buckets(m, s, s->B);
+    phase_end(m);
     m->stream = main_stream;
     m->profiling = prof;
     if (rc) return rc;
@@ -1494,7 +1560,9 @@ int start_entity_update(nvsm_model* m, float lr, float lambda) {
     cudaStream_t main_stream = m->stream;
     m->stream = m->aux_stream;
     m->entity_async_running = true;
+    phase_begin(m, PH_UPD_ENTITIES);   // (timeline mode only: serial profiling never gets here)
     const int rc = update_table(m, true, lr, lambda);
+    phase_end(m);
     m->entity_async_running = false;
     m->stream = main_stream;
     if (rc) return rc;
@@ -1507,7 +1575,10 @@ int fused_step(nvsm_model* m, BatchSlot* s, float lr) {
     TRY(forward(m, s));
     const float lambda = m->cfg.regularization_lambda / (float)m->Bglobal;
     TRY(start_entity_update(m, lr, lambda));
-    TRY(backward(m));
+    m->in_fused_step = true;
+    const int brc = backward(m);
+    m->in_fused_step = false;
+    if (brc) return brc;
     return update(m, lr, lambda);
 }
 
@@ -1776,7 +1847,11 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->peer_inbox) cudaFree(m->peer_inbox);
     if (m->peer_flags) cudaFree(m->peer_flags);
     if (m->peer_error) cudaFree(m->peer_error);
+    if (m->peer_dev) cudaFree(m->peer_dev);
+    if (m->xchg_counter) cudaFree(m->xchg_counter);
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+    if (m->gt_stream) cudaStreamDestroy(m->gt_stream);
+    if (m->dx_ready) cudaEventDestroy(m->dx_ready);
     if (m->gt_ready) cudaEventDestroy(m->gt_ready);
     if (m->gt_reduced_ev) cudaEventDestroy(m->gt_reduced_ev);
     float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->Tr, m->P_lo, m->Gp_lo, m->Tt_lo, m->Tr_lo, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
@@ -1818,6 +1893,7 @@ void nvsm_destroy(nvsm_model* m) {
     }
     for (auto& ev : m->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto e : m->ev_pool) cudaEventDestroy(e);
+    if (m->tl_origin) cudaEventDestroy(m->tl_origin);
     if (m->loss_host) cudaFreeHost(m->loss_host);
     if (m->id_flags) cudaFreeHost(m->id_flags);
     for (auto e : m->loss_ev)
@@ -1873,6 +1949,12 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         m->own_stream = true;
         CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&m->gt_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->dx_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->gt_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
+        { const char* e = getenv("NVSM_GT_SIDE"); m->gt_side = e ? atoi(e) != 0 : false; }
+        m->no_fused_reduce = getenv("NVSM_NO_FUSED_REDUCE") != nullptr;
         CU(cudaEventCreateWithFlags(&m->score_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->entity_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->word_rows_done, cudaEventDisableTiming));
@@ -2458,8 +2540,28 @@ int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx, float ep
 int nvsm_set_profiling(nvsm_model* m, int enabled) {
     if (!m) return fail("null model");
     TRY(collect_phases(m));
-    m->profiling = enabled != 0;
+    m->profiling = enabled == 1;
+    m->timeline = enabled == 2;
+    if (m->timeline) {
+        CU(cudaSetDevice(m->device));
+        if (!m->tl_origin) CU(cudaEventCreate(&m->tl_origin));
+        m->intervals.clear();
+        CU(cudaEventRecord(m->tl_origin, m->stream));
+    }
     return 0;
+}
+
+int nvsm_get_timeline(nvsm_model* m, int* phases, float* start_ms, float* end_ms, int capacity) {
+    if (!m) return fail("null model");
+    CU(cudaSetDevice(m->device));
+    TRY(collect_phases(m));
+    const int n = (int)m->intervals.size();
+    for (int i = 0; i < n && i < capacity; ++i) {
+        if (phases) phases[i] = m->intervals[i].phase;
+        if (start_ms) start_ms[i] = m->intervals[i].start_ms;
+        if (end_ms) end_ms[i] = m->intervals[i].end_ms;
+    }
+    return n;
 }
 
 int nvsm_get_phase_ms(nvsm_model* m, float* ms_out, int capacity) {
@@ -2656,11 +2758,7 @@ int nvsm_comm_init(nvsm_model* m, const char* id_128, int num_ranks, int rank) {
     if (rc != 0) return fail("ncclCommInitRank: %s", nccl_api().GetErrorString(rc));
     m->nranks = num_ranks;
     m->rank = rank;
-    if (!m->comm_stream) {
-        CU(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&m->gt_ready, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
-    }
+    if (!m->comm_stream) CU(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
     return 0;
 }
 
@@ -2676,8 +2774,11 @@ int nvsm_comm_peer_export(nvsm_model* m, char* handles_out_128) {
         m->peer.slot_doubles = 2 * m->dd + 8;
         const size_t nslots = (size_t)kPeerKinds * 2 * m->nranks;
         TRY(dev_alloc(&m->peer_inbox, nslots * m->peer.slot_doubles));
-        TRY(dev_alloc(&m->peer_flags, nslots));
+        TRY(dev_alloc(&m->peer_flags, nslots * kPeerFlagStride));
         TRY(dev_alloc(&m->peer_error, 1));
+        TRY(dev_alloc(&m->peer_dev, 1));
+        TRY(dev_alloc(&m->xchg_counter, 1));
+        m->no_fused_xchg = getenv("NVSM_NO_FUSED_XCHG") != nullptr;
         CU(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h[2];
@@ -2707,6 +2808,7 @@ int nvsm_comm_peer_import(nvsm_model* m, const char* all_handles) {
         m->peer.inbox[p] = (double*)inbox;
         m->peer.flags[p] = (unsigned long long*)flags;
     }
+    CU(cudaMemcpy(m->peer_dev, &m->peer, sizeof(PeerXchg), cudaMemcpyHostToDevice));
     m->peer_ready = true;
     return 0;
 }

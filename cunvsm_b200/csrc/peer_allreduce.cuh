@@ -15,6 +15,8 @@ namespace nvsm {
 
 constexpr int kPeerMaxRanks = 16;
 constexpr int kPeerKinds = 4;   // independent reduction sites per step, each with its own epoch counter
+constexpr int kPeerFlagStride = 128;   // flags per (kind, parity, source rank): one per block of a fused exchange (block 0 =
+                                       // the stand-alone one-block kernel and the score kernels' last-block tail)
 
 struct PeerXchg {
     int nranks, rank;
@@ -23,12 +25,74 @@ struct PeerXchg {
     unsigned long long* flags[kPeerMaxRanks];
 };
 
-// inbox layout: [kind][parity][src_rank][slot_doubles]; flags: [kind][parity][src_rank]
+// inbox layout: [kind][parity][src_rank][slot_doubles]; flags: [kind][parity][src_rank][kPeerFlagStride]
 __device__ __forceinline__ size_t peer_slot_index(const PeerXchg& x, int kind, int parity, int src) {
     return ((size_t)(kind * 2 + parity) * x.nranks + src) * x.slot_doubles;
 }
-__device__ __forceinline__ size_t peer_flag_index(const PeerXchg& x, int kind, int parity, int src) {
-    return (size_t)(kind * 2 + parity) * x.nranks + src;
+__device__ __forceinline__ size_t peer_flag_index(const PeerXchg& x, int kind, int parity, int src, int blk = 0) {
+    return ((size_t)(kind * 2 + parity) * x.nranks + src) * kPeerFlagStride + blk;
+}
+
+// Building blocks of the exchanges that are FUSED into compute kernels (the producer's last stage pushes its partial
+// result over NVLink, the same kernel -- or block -- waits for the peers' and goes on with the reduced values):
+//   col_stats_reduce_finalize_kernel<true>  batch-norm forward sums: partial-row reduction -> exchange -> mean / invstd
+//   peer_sums_tail (score kernels)          backward column sums + loss: the last block to finish exchanges them
+// Call with threads `t` = 0 .. nranks-1 of one warp / block, after every pushing thread's __threadfence_system() and a
+// barrier among them.
+__device__ __forceinline__ void peer_publish(const PeerXchg& x, int kind, int parity, int blk, unsigned long long epoch, int t) {
+    if (t < x.nranks) {
+        unsigned long long* f = x.flags[t] + peer_flag_index(x, kind, parity, x.rank, blk);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    }
+}
+// (bounded: a lost peer sets the error flag instead of hanging the GPU)
+__device__ __forceinline__ void peer_wait(const PeerXchg& x, int kind, int parity, int blk, unsigned long long epoch, int t,
+                                          int* error_flag) {
+    if (t < x.nranks) {
+        const unsigned long long* f = x.flags[x.rank] + peer_flag_index(x, kind, parity, t, blk);
+        unsigned long long v = 0;
+        long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (++spins > (1L << 28)) { atomicExch(error_flag, 1); break; }
+        } while (v < epoch);
+    }
+}
+// value i of source rank p in MY inbox (written by the peer over NVLink: read past L1)
+__device__ __forceinline__ double peer_inbox_value(const PeerXchg& x, int kind, int parity, int p, int i) {
+    return __ldcg(x.inbox[x.rank] + peer_slot_index(x, kind, parity, p) + i);
+}
+
+// Tail of the score kernels at N > 1: every block has added its column sums / loss to `buf` [n] with double atomics; the
+// last block to arrive (done_counter) pushes the GPU's totals to every peer, waits for theirs and leaves the global sums
+// in `buf` -- in rank order, so bit-identical on every rank. Replaces a separate one-block all-reduce launch between the
+// score kernel and batch-norm backward. All threads of the block must call it.
+__device__ __forceinline__ void peer_sums_tail(const PeerXchg* __restrict__ xp, double* __restrict__ buf, int n,
+                                               unsigned long long epoch, int kind, unsigned int* __restrict__ done_counter,
+                                               int* __restrict__ error_flag) {
+    __threadfence();      // this thread's atomics on buf are performed before the counter moves
+    __syncthreads();
+    int mine = 0;
+    if (threadIdx.x == 0) mine = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    if (!__syncthreads_or(mine)) return;   // (no static shared memory: score_ring_kernel opts into all 227 KB as dynamic)
+    __threadfence();
+    const PeerXchg& x = *xp;
+    const int parity = (int)(epoch & 1ull);
+    for (int p = 0; p < x.nranks; ++p) {
+        double* dst = x.inbox[p] + peer_slot_index(x, kind, parity, x.rank);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(buf + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    peer_publish(x, kind, parity, 0, epoch, threadIdx.x);
+    peer_wait(x, kind, parity, 0, epoch, threadIdx.x, error_flag);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < x.nranks; ++p) s += peer_inbox_value(x, kind, parity, p, i);
+        buf[i] = s;
+    }
+    if (threadIdx.x == 0) *done_counter = 0u;   // next launch
 }
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(const PeerXchg x, double* __restrict__ buf, int n, int kind,

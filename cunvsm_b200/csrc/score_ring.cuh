@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)sums[t]);
     if (threadIdx.x == 0) atomicAdd(p.loss_acc, (double)sums[2 * dd]);
+    if (p.xchg) peer_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error);
     (void)nvec;
 }
 

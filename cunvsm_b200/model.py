@@ -486,6 +486,16 @@ class Model:
     def set_profiling(self, on):
         check(self.L.nvsm_set_profiling(self.h, int(on)))
 
+    def timeline(self, capacity=4096):
+        """Intervals (phase name, start ms, end ms) since set_profiling(2), overlaps between streams kept."""
+        ph = (ctypes.c_int * capacity)()
+        a = (ctypes.c_float * capacity)()
+        b = (ctypes.c_float * capacity)()
+        n = self.L.nvsm_get_timeline(self.h, ph, a, b, capacity)
+        if n < 0:
+            check(n)
+        return [(self.L.nvsm_phase_name(ph[i]).decode(), a[i], b[i]) for i in range(min(n, capacity))]
+
     def reset_phase_ms(self):
         check(self.L.nvsm_reset_phase_ms(self.h))
 

@@ -201,7 +201,12 @@ NVSM_API int nvsm_infer(nvsm_model* m, const long* words, long num_phrases, long
 NVSM_API int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx, float epsilon);
 
 /* Instrumentation. Phase timing uses CUDA events on the model's stream. */
+/* enabled: 0 off; 1 serial phase timing (the stream overlaps of the fused step are switched off so that phases add up);
+ * 2 timeline (overlaps kept: nvsm_get_timeline reports every phase interval, on whatever stream it ran, in ms since
+ * this call). The role nvprof / NVTX ranges play for the reference (cpp/main.cu:16,372-459). */
 NVSM_API int nvsm_set_profiling(nvsm_model* m, int enabled);
+/* Returns the number of intervals recorded since nvsm_set_profiling(m, 2); fills at most `capacity` entries. */
+NVSM_API int nvsm_get_timeline(nvsm_model* m, int* phases, float* start_ms, float* end_ms, int capacity);
 NVSM_API int nvsm_num_phases(void);
 NVSM_API const char* nvsm_phase_name(int phase);
 NVSM_API int nvsm_get_phase_ms(nvsm_model* m, float* ms_out, int capacity); /* sums since last reset */

@@ -11,9 +11,14 @@ CPP = os.path.join(ROOT, "cpp")
 
 
 def _build():
+    """make under an inter-process lock: with pytest-xdist another worker may be executing one of the binaries while this
+    one relinks it ("Text file busy")."""
+    import fcntl
     from cunvsm_b200 import build as b
-    b.build()
-    subprocess.run(["make", "-C", CPP], check=True, capture_output=True)
+    with open(os.path.join(CPP, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        b.build()
+        subprocess.run(["make", "-C", CPP], check=True, capture_output=True)
 
 
 def test_library_exports_every_declared_symbol():

@@ -29,22 +29,33 @@ def test_sharded_step_matches_single_gpu(gemm_mode):
     assert "MULTI_GPU_OK" in res.stdout
 
 
-def test_allgather_sparse_mode_matches_single_gpu_trajectory():
-    """NVSM_SPARSE_ALLGATHER: 2 ranks x 3 steps == 1 GPU x 3 steps on the whole batch, all five optimisers."""
-    if _ngpus() < 2:
-        pytest.skip("needs at least 2 GPUs")
-    env = dict(os.environ, NVSM_TEST_GEMM_MODE="0", NVSM_TEST_SPARSE_MODE="1")
-    # One unexplained failure in two runs on 2xB200 at the end of round 1 (output not kept, DESIGN.md §5): a failing
-    # first attempt is reported as a warning with its output and the worker is run once more on a fresh port.
-    import warnings
-    res = None
-    for attempt, port in enumerate(("29610", "29611")):
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-               "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "dist_worker.py")]
-        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
-        if res.returncode == 0:
-            break
-        if attempt == 0:
-            warnings.warn("all-gather worker failed on the first attempt:\n" + res.stdout[-3000:] + res.stderr[-3000:])
+def _run_worker(world, port, env):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "MULTI_GPU_OK" in res.stdout and "sparse=allgather" in res.stdout
+    return res.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_allgather_sparse_mode_matches_single_gpu_trajectory(world):
+    """NVSM_SPARSE_ALLGATHER: `world` ranks x 3 steps == 1 GPU x 3 steps on the whole batch, all five optimisers. Strict: no
+    retry. The intermittent failure of round 1 was root-caused with the worker's soak mode (NVSM_TEST_SOAK, 12 passes x 2
+    ranks plus a 1-rank control without any exchange, gpurun_out/soak_r2b.log / soak_control_r2c.log): with hard_tanh in
+    the Adam combinations 3-5 of 12 passes mismatch -- and 4 of 8 with ONE rank, where nothing is exchanged -- while
+    with tanh 0 of 24 do. It is the clip boundary's 0/1 derivative flipping under a different batch-norm summation
+    order, amplified by Adam's normalised step; not an ordering race. The Adam combinations run with tanh."""
+    if _ngpus() < world:
+        pytest.skip("needs at least %d GPUs" % world)
+    env = dict(os.environ, NVSM_TEST_GEMM_MODE="0", NVSM_TEST_SPARSE_MODE="1")
+    out = _run_worker(world, 29610 + world, env)
+    assert "MULTI_GPU_OK world=%d" % world in out and "sparse=allgather" in out
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_sharded_step_matches_single_gpu_wide(world):
+    """The sharded-step check of test_sharded_step_matches_single_gpu on 4 and 8 ranks (fp32 GEMMs)."""
+    if _ngpus() < world:
+        pytest.skip("needs at least %d GPUs" % world)
+    out = _run_worker(world, 29620 + world, dict(os.environ, NVSM_TEST_GEMM_MODE="0"))
+    assert "MULTI_GPU_OK world=%d" % world in out
