@@ -322,7 +322,9 @@ def run_reference(args, w, rank):
         line = dict(base, value=r["value"], ms_per_step=r["ms_per_step"],
                     config={"workload": w["name"], "update_method": w["update_method"], "per_gpu_batch": B,
                             "global_batch": B,
-                            "reference_build": "unmodified /root/reference/cpp/*.cu, nvcc -O3 -use_fast_math float32 NDEBUG, "
+                            "reference_build": "unmodified /root/reference/cpp/*.cu, nvcc -O3 -use_fast_math float32 NDEBUG (the reference's "
+                                               "flags except -default-stream per-thread, CMakeLists.txt:73: one host thread issues "
+                                               "the step here, so the legacy default stream orders the same launches identically), "
                                                "cuBLAS SGEMM + cuDNN batch-norm, over oracle/ref_shim's reconstruction of "
                                                "the un-vendored device_matrix (one Thrust/CUDA kernel per op, size-bucketed caching "
                                                "pool for cnmem)"},
@@ -472,7 +474,7 @@ def run_ours(args, w, rank, world, local_rank):
                         bias_negative_samples=w["bias_neg"])
     tc = nv.TrainConfig(batch_size=B, window_size=w["n"], num_random_entities=w["z"],
                         regularization_lambda=w["lam"], learning_rate=w["lr"], update_method=method, adam_mode=mode)
-    stream = torch.cuda.Stream(device=local_rank)
+    stream = torch.cuda.Stream(device=local_rank, priority=env_int("NVSM_MAIN_PRIO", 0))   # (-1: above the library's side streams)
     sparse_mode = 1 if args.sparse_sync == "allgather" else 0
 
     def make_model(gemm_mode):

@@ -11,6 +11,15 @@ typedef long idx_t;  // reference: `typedef long int32` (include/cuNVSM/base.h:2
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Programmatic dependent launch (sm_90+). A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may become resident while the kernel in front of it in the stream is still draining: pdl_wait() blocks until that
+// grid has completed and its writes are visible (call it before the first dependent global access; everything above
+// it -- barrier init, TMEM allocation, shared-memory zeroing -- overlaps the predecessor's tail). pdl_launch_dependents()
+// in the predecessor lets the dependent grid start being scheduled once every block of the predecessor has issued it
+// (or exited). Both are no-ops for launches without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- vector access: VEC == 4 (16-byte rows) or VEC == 1 (any dim) -----------------
 template <int VEC>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC]) {

@@ -252,6 +252,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // programmatic dependent launch: the set-up above overlaps the tail of the kernel in front; operands are only read
+    // (and C written) behind this point; the kernel behind may start its own set-up as this one's CTAs retire
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // tile -> (m0, n0, first k-block, number of k-blocks)
     auto decode = [&](int t, int& m0, int& n0, int& kb0, int& nkb, int& split) {

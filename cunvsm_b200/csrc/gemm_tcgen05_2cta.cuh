@@ -117,6 +117,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    asm volatile("griddepcontrol.wait;" ::: "memory");                 // (see gemm_tc_kernel)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     auto decode = [&](int t, int& m0, int& n0) {
         n0 = (t % p.n_tiles) * p.bn;

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
                                                           long num_out, int window,
                                                           float* __restrict__ out, int ld_out, int tf32,
                                                           float* __restrict__ out_lo) {
+    pdl_launch_dependents();   // the forward GEMM behind may set up (barriers, TMEM) while the last blocks drain
     const int lane = threadIdx.x & 31;
     const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) gather_mean_lanes_kernel(const float* __r
 #define NVSM_GATHER_U 2   // measured on C2 (us): U=1 83.2, 2 81.5, 3 90.9, 5 87.9, 10 117 -- occupancy beats loads in flight
 #endif
     constexpr int U = NVSM_GATHER_U;   // words in flight per lane: U * K independent 16-byte loads
+    pdl_launch_dependents();   // the forward GEMM behind may set up (barriers, TMEM) while the last blocks drain
     const int lane = threadIdx.x & 31;
     const int sl = lane & (LG - 1);
     const int grp = lane / LG;
@@ -299,8 +301,14 @@ __global__ void __launch_bounds__(1024) col_stats_reduce_finalize_kernel(const f
                                                                          const float* __restrict__ bias,
                                                                          float* __restrict__ scale, float* __restrict__ shift,
                                                                          const PeerXchg* __restrict__ xp, unsigned long long epoch,
-                                                                         int* __restrict__ xchg_error) {
+                                                                         int* __restrict__ xchg_error,
+                                                                         double* __restrict__ zero_buf, int zero_n) {
     constexpr int C = 8, S = 128;   // blockDim = C columns x S slices
+    pdl_wait();                // (launched as a programmatic dependent of the forward GEMM)
+    pdl_launch_dependents();
+    // accumulators of the kernels behind this one (backward column sums + loss): zeroed here instead of by a memset
+    // operation at the head of the step
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_n; i += gridDim.x * blockDim.x) zero_buf[i] = 0.0;
     __shared__ double sm[2][32][C];
     const int cl = threadIdx.x & (C - 1), slice = threadIdx.x / C;
     const int col = blockIdx.x * C + cl;
@@ -431,12 +439,14 @@ struct ScoreParams {
     // normalised dot product e.y / |e| are kept for the backward pass (cpp/cuda_utils.cu:69-127).
     float* enorm;          // [B*R] nullable
     float* escore;         // [B*R] nullable
-    // N > 1 with the NVLink peer exchange: the last block to finish all-reduces col_sums + loss_acc (contiguous,
-    // [2*dd + 1]) across the ranks inside this kernel (peer_sums_tail). Null: single GPU, or the caller reduces.
+    // Last-block tail (score_sums_tail; xchg_counter null = off). N > 1 with the NVLink peer exchange (xchg non-null):
+    // col_sums + loss_acc (contiguous, [2*dd + 1]) are all-reduced across the ranks inside this kernel. loss_host
+    // (mapped pinned, nullable): the final loss sum is written there, no D2H copy in the stream.
     const PeerXchg* xchg;
     unsigned long long xchg_epoch;
     unsigned int* xchg_counter;
     int* xchg_error;
+    double* loss_host;
 };
 
 // Reduce four per-lane partial sums across the warp with 6 shuffles (instead of 20): after the
@@ -610,7 +620,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreParams p) {
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)smem[t]);
     if (threadIdx.x == 0) atomicAdd(p.loss_acc, (double)smem[2 * dd]);
-    if (p.xchg) peer_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error);
+    score_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error, p.loss_host);
 }
 
 // =====================================================================================
@@ -679,6 +689,8 @@ __global__ void __launch_bounds__(256) bn_backward_cols_kernel(float* __restrict
                                                                float* __restrict__ gb, float* __restrict__ mean_dy,
                                                                float* __restrict__ mean_dyx, long rows, int dd,
                                                                int tf32, float* __restrict__ lo_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int nvec = dd >> 2;
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nthreads = (long)gridDim.x * blockDim.x;

@@ -222,6 +222,10 @@ struct nvsm_model {
     cudaStream_t gt_stream = nullptr;            // fused steps: grad_transform GEMM (+ all-reduce) under the word update
     cudaEvent_t dx_ready = nullptr;
     bool gt_side = false, in_fused_step = false, no_fused_reduce = false;
+    int buckets_at = 0;
+    int pdl = 0;               // programmatic dependent launches along the main-stream kernel chain: bit mask over the
+                               // kPdl* launch sites (NVSM_PDL)
+    cudaEvent_t build_gate = nullptr;
     cudaEvent_t gt_ready = nullptr, gt_reduced_ev = nullptr;
     bool gt_allreduce_pending = false;
     // NVSM_SPARSE_ALLGATHER: every rank applies the table updates of ALL rows (exact single-GPU trajectory).
@@ -318,6 +322,30 @@ int grid_for(const nvsm_model* m, long work_items, int items_per_block, int bloc
         if (le_ != cudaSuccess)                                                     \
             return fail("launch %s: %s (%s:%d)", #kernel, cudaGetErrorString(le_),  \
                         __FILE__, __LINE__);                                        \
+    } while (0)
+
+enum { kPdlGemmFwd = 0, kPdlStats = 1, kPdlScore = 2, kPdlBnBwd = 3, kPdlGemmGt = 4, kPdlGemmGp = 5, kPdlNone = 30 };
+// Same, as a programmatic dependent of the kernel in front of it in the stream (m->pdl; see common.cuh:pdl_wait). Only for
+// kernels that execute pdl_wait() before their first dependent global access.
+#define LAUNCH_PDL(m, bit, kernel, grid, block, smem, ...)                                            \
+    do {                                                                                           \
+        if (!((m)->pdl >> (bit) & 1)) {                                                                      \
+            kernel<<<(grid), (block), (smem), (m)->stream>>>(__VA_ARGS__);                         \
+        } else {                                                                                   \
+            cudaLaunchConfig_t cfg_ = {};                                                          \
+            cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block);                                \
+            cfg_.dynamicSmemBytes = (smem); cfg_.stream = (m)->stream;                             \
+            cudaLaunchAttribute at_[1];                                                            \
+            at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                        \
+            at_[0].val.programmaticStreamSerializationAllowed = 1;                                 \
+            cfg_.attrs = at_; cfg_.numAttrs = 1;                                                   \
+            cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                        \
+        }                                                                                          \
+        (m)->launches++;                                                                           \
+        cudaError_t le_ = cudaPeekAtLastError();                                                   \
+        if (le_ != cudaSuccess)                                                                    \
+            return fail("launch %s: %s (%s:%d)", #kernel, cudaGetErrorString(le_),                 \
+                        __FILE__, __LINE__);                                                       \
     } while (0)
 
 ActParams act_params(const nvsm_model* m, bool use_bn) {
@@ -421,7 +449,7 @@ bool tc_shapes_ok(int dw, int dd) {
 int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
                 float* C, int ldc, int splits, long split_stride, float alpha, const float* bias,
                 int* splits_out = nullptr, const float* A_lo = nullptr, const float* B_lo = nullptr,
-                float* stat_part = nullptr, int* stat_rows_out = nullptr) {
+                float* stat_part = nullptr, int* stat_rows_out = nullptr, int pdl_bit = kPdlNone) {
     // stat_part: fused column statistics of C (tc::Params::stat_part); *stat_rows_out = partial rows written, 0 when
     // this launch could not fuse them (the caller then runs col_stats4_kernel)
     const bool split3 = A_lo != nullptr && B_lo != nullptr;
@@ -458,8 +486,8 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
             const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
             const int num_tiles = p.m_tiles * p.n_tiles;
             const int grid = 2 * std::min(num_tiles, m->num_sms / 2);
-            if (split3) LAUNCH(m, (tc::gemm_tc2_kernel<true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
-            else LAUNCH(m, (tc::gemm_tc2_kernel<false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+            if (split3) LAUNCH_PDL(m, pdl_bit, (tc::gemm_tc2_kernel<true>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
+            else LAUNCH_PDL(m, pdl_bit, (tc::gemm_tc2_kernel<false>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p);
             if (splits_out) *splits_out = 1;
             if (stat_rows_out && fuse_stats) *stat_rows_out = grid * 4;
             return 0;
@@ -505,7 +533,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
     const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = std::min(num_tiles, m->num_sms);
-#define NVSM_TC_LAUNCH(A_, B_, S_, K_) LAUNCH(m, (tc::gemm_tc_kernel<A_, B_, S_, K_>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p)
+#define NVSM_TC_LAUNCH(A_, B_, S_, K_) LAUNCH_PDL(m, pdl_bit, (tc::gemm_tc_kernel<A_, B_, S_, K_>), grid, tc::kThreads, smem, tmA, tmB, tmAlo, tmBlo, p)
     if (kb == 32) {
         if (!mn_major && !split3) NVSM_TC_LAUNCH(false, false, false, 32);
         else if (!mn_major) NVSM_TC_LAUNCH(false, false, true, 32);
@@ -595,8 +623,8 @@ int launch_score(nvsm_model* m, const ScoreParams& sp) {
 
 template <int NCH>
 int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t smem) {
-    if (q.s.dd == NCH * 128) LAUNCH(m, (score_ring_kernel<NCH, true>), grid, q.warps * 32, smem, q);
-    else LAUNCH(m, (score_ring_kernel<NCH, false>), grid, q.warps * 32, smem, q);
+    if (q.s.dd == NCH * 128) LAUNCH_PDL(m, kPdlScore, (score_ring_kernel<NCH, true>), grid, q.warps * 32, smem, q);
+    else LAUNCH_PDL(m, kPdlScore, (score_ring_kernel<NCH, false>), grid, q.warps * 32, smem, q);
     return 0;
 }
 
@@ -685,11 +713,24 @@ int forward(nvsm_model* m, BatchSlot* s) {
     m->have_forward = false;
     m->have_gradients = false;
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));
-    if (m->pull && !exact_sparse(m)) TRY(start_bucket_build(m, s));  // (gathered ids only exist at update time)
+    // Reference buckets of the pull update: built on the auxiliary stream under the forward pass. buckets_at (experiment
+    // knob NVSM_BUCKETS_AT) = main-stream point behind which the build may start: 0 step start, 1 gather, 2 forward GEMM.
+    auto build_at = [&](int stage) -> int {
+        if (!(m->pull && !exact_sparse(m)) || m->buckets_at != stage) return 0;   // (gathered ids only exist at update time)
+        if (stage > 0) {
+            CU(cudaEventRecord(m->build_gate, m->stream));
+            CU(cudaStreamWaitEvent(m->aux_stream, m->build_gate, 0));
+        }
+        return start_bucket_build(m, s);
+    };
+    TRY(build_at(0));
     const bool bn = m->cfg.batch_normalization != 0;
     const int dw = m->dw, dd = m->dd;
 
-    CU(cudaMemsetAsync(m->dsums, 0, (5 * (size_t)dd + 1) * sizeof(double), m->stream));
+    // Batch-wide accumulators. On the tensor-core batch-norm path nothing needs a memset operation in the stream: the
+    // forward sums are overwritten by col_stats_reduce_finalize_kernel, which also zeroes the backward sums + loss.
+    const bool zero_in_finalize = m->cfg.batch_normalization != 0 && m->use_tc;
+    if (!zero_in_finalize) CU(cudaMemsetAsync(m->dsums, 0, (5 * (size_t)dd + 1) * sizeof(double), m->stream));
 
     // (1) phrase representations: weighted mean of the word rows. (A cp.async-ring variant like
     // score_ring_kernel and a fully unrolled window were both measured slower: the gather has almost
@@ -722,6 +763,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
     if (m->l2_phrase)   // Normalizer::forward on the phrase representations, in place (cpp/objective.cu:134-140)
         LAUNCH(m, row_l2_normalize_kernel, grid_for(m, B, 8, 8), 256, 0, m->P, m->P_lo, B, dw, m->ldP, m->use_tc ? 1 : 0, m->p_norms);
     phase_end(m);
+    TRY(build_at(1));
 
     // (2) projection Z = P . T (+ b when batch-norm is off).
     int stat_rows = 0;   // > 0: the GEMM epilogue wrote that many partial rows of column statistics into stat_part
@@ -734,11 +776,13 @@ int forward(nvsm_model* m, BatchSlot* s) {
         // batch-norm: the column sums / sums of squares of Z come out of the GEMM's epilogue (no second pass over Z)
         float* const fuse = (bn && !getenv("NVSM_NO_FUSED_STATS")) ? m->stat_part : (float*)nullptr;
         TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b, nullptr,
-                        m->P_lo, m->Tt_lo, fuse, &stat_rows));
+                        m->P_lo, m->Tt_lo, fuse, &stat_rows, kPdlGemmFwd));
     } else {
         TRY((run_sgemm<false, false>(m, (int)B, dd, dw, m->P, m->ldP, m->T, dd, m->Z, dd, 1, 1.0f, bn ? nullptr : m->b)));
     }
     phase_end(m);
+
+    TRY(build_at(2));
 
     // (3) batch statistics over the (global) batch.
     if (bn && m->use_tc) {
@@ -755,16 +799,17 @@ int forward(nvsm_model* m, BatchSlot* s) {
                 LAUNCH(m, col_stats4_kernel, nblk, 256, (size_t)rpp * 2 * dd * sizeof(float), m->Z, B, dd, m->stat_part);
             }
             if (m->nranks <= 1) {
-                LAUNCH(m, col_stats_reduce_finalize_kernel<false>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                LAUNCH_PDL(m, kPdlStats, col_stats_reduce_finalize_kernel<false>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
                        1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift,
-                       (const PeerXchg*)nullptr, 0ull, (int*)nullptr);
+                       (const PeerXchg*)nullptr, 0ull, (int*)nullptr, m->bwd_sums(), 2 * dd + 1);
             } else if (fused_xchg(m)) {
                 // partial rows -> local sums -> NVLink exchange -> global mean / invstd in ONE launch (per-block flags)
                 const unsigned long long epoch = ++m->peer_epoch[0];
-                LAUNCH(m, col_stats_reduce_finalize_kernel<true>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
+                LAUNCH_PDL(m, kPdlStats, col_stats_reduce_finalize_kernel<true>, (dd + 7) / 8, 1024, 0, m->stat_part, nblk, dd, (double)m->Bglobal,
                        1e-4 /* cpp/objective.cu:114 */, m->fwd_sums(), m->mean, m->invstd, m->b, m->bn_scale, m->bn_shift,
-                       (const PeerXchg*)m->peer_dev, epoch, m->peer_error);
+                       (const PeerXchg*)m->peer_dev, epoch, m->peer_error, m->bwd_sums(), 2 * dd + 1);
             } else {
+                CU(cudaMemsetAsync(m->bwd_sums(), 0, (2 * (size_t)dd + 1) * sizeof(double), m->stream));
                 LAUNCH(m, col_stats_reduce_kernel, (2 * dd + 31) / 32, 256, 0, m->stat_part, nblk, 2 * dd, m->fwd_sums());
             }
         }
@@ -821,10 +866,15 @@ int forward(nvsm_model* m, BatchSlot* s) {
         sp.enorm = m->l2_entity ? m->enorm : nullptr;
         sp.escore = m->l2_entity ? m->escore : nullptr;
         // N > 1: the backward column sums + loss are all-reduced by the score kernel's last block (peer_sums_tail)
-        sp.xchg = nullptr; sp.xchg_epoch = 0; sp.xchg_counter = nullptr; sp.xchg_error = nullptr;
+        // and, whenever the reduction is not left to ncclAllReduce, writes the loss into the pinned read-back ring
+        sp.xchg = nullptr; sp.xchg_epoch = 0; sp.xchg_counter = nullptr; sp.xchg_error = nullptr; sp.loss_host = nullptr;
         if (fused_xchg(m)) {
             sp.xchg = m->peer_dev; sp.xchg_epoch = ++m->peer_epoch[3];
-            sp.xchg_counter = m->xchg_counter; sp.xchg_error = m->peer_error;
+            sp.xchg_error = m->peer_error;
+        }
+        if (m->nranks <= 1 || fused_xchg(m)) {
+            sp.xchg_counter = m->xchg_counter;
+            sp.loss_host = m->loss_host + (m->forward_count % nvsm_model::kCostRing);
         }
         m->entity_prep_done = false;
         TRY(dispatch_score(m, sp));
@@ -833,7 +883,8 @@ int forward(nvsm_model* m, BatchSlot* s) {
     if (!fused_xchg(m)) TRY(allreduce(m, m->bwd_sums(), 2 * (size_t)dd + 1, true, 3));
     {
         const int slot = (int)(m->forward_count % nvsm_model::kCostRing);
-        CU(cudaMemcpyAsync(m->loss_host + slot, m->loss_acc(), sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        if (!(m->nranks <= 1 || fused_xchg(m)))   // (otherwise the score kernel's last block wrote it: score_sums_tail)
+            CU(cudaMemcpyAsync(m->loss_host + slot, m->loss_acc(), sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CU(cudaEventRecord(m->loss_ev[slot], m->stream));
         m->loss_B[slot] = m->Bglobal;
         m->forward_count++;
@@ -877,7 +928,9 @@ int backward(nvsm_model* m) {
     if (bn) {
         if (cols_kernel) {
             const int grid = grid_for(m, B * dd / 4, 256 * 4, 8);
-            LAUNCH(m, bn_backward_cols_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, (const double*)m->bwd_sums(),
+            // (not while the entity update waits on the auxiliary stream for the score kernel's event: an early-resident
+            // bn_backward grid gets in front of it and the two no longer overlap, C2 +39 us)
+            LAUNCH_PDL(m, (m->entity_async ? kPdlNone : kPdlBnBwd), bn_backward_cols_kernel, grid, 256, 0, m->Gp, m->Z, m->mean, m->invstd, (const double*)m->bwd_sums(),
                    (double)m->Bglobal, m->score_shifted ? (const float*)m->b : (const float*)nullptr, m->gb, m->mean_dy,
                    m->mean_dyx, B, dd, m->use_tc ? 1 : 0, m->Gp_lo);
         } else if (vec4_ok(dd)) {
@@ -907,7 +960,7 @@ int backward(nvsm_model* m) {
             // batch otherwise becomes 128 one-k-block CTAs whose partials the projection update then has to sum (C5: 22 us)
             const int want = std::max(1, std::min(std::min(m->gt_splits, m->num_sms / mtiles), (int)(B / 256)));
             TRY(run_gemm_tc(m, true, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, want, nT, 1.0f, nullptr, &nparts,
-                            m->P_lo, m->Gp_lo));
+                            m->P_lo, m->Gp_lo, nullptr, nullptr, kPdlGemmGt));
         } else {
             TRY((run_sgemm<true, false>(m, dw, dd, (int)B, m->P, m->ldP, m->Gp, dd, m->gT_part, dd, nz, 1.0f, nullptr)));
         }
@@ -922,7 +975,8 @@ int backward(nvsm_model* m) {
         phase_begin(m, PH_GEMM_GP);
         const float inv_n = (float)std::exp(-std::log((double)m->n));
         if (m->use_tc)
-            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->Tr, dd, m->gP, dw, 1, 0, inv_n, nullptr, nullptr, m->Gp_lo, m->Tr_lo));
+            TRY(run_gemm_tc(m, false, (int)B, dw, dd, m->Gp, dd, m->Tr, dd, m->gP, dw, 1, 0, inv_n, nullptr, nullptr, m->Gp_lo, m->Tr_lo,
+                            nullptr, nullptr, kPdlGemmGp));
         else
             TRY((run_sgemm<false, true>(m, (int)B, dw, dd, m->Gp, dd, m->T, dd, m->gP, dw, 1, inv_n, nullptr)));
         if (m->l2_phrase)   // Normalizer::backward on grad_phrase (cpp/objective.cu:461-468); linear, so 1/n commutes
@@ -1852,6 +1906,7 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
     if (m->gt_stream) cudaStreamDestroy(m->gt_stream);
     if (m->dx_ready) cudaEventDestroy(m->dx_ready);
+    if (m->build_gate) cudaEventDestroy(m->build_gate);
     if (m->gt_ready) cudaEventDestroy(m->gt_ready);
     if (m->gt_reduced_ev) cudaEventDestroy(m->gt_reduced_ev);
     float* fl[] = {m->W, m->E, m->T, m->b, m->Tt, m->Tr, m->P_lo, m->Gp_lo, m->Tt_lo, m->Tr_lo, m->optW.m, m->optW.v, m->optW.acc, m->optW.agg, m->optE.m, m->optE.v,
@@ -1955,6 +2010,9 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
         { const char* e = getenv("NVSM_GT_SIDE"); m->gt_side = e ? atoi(e) != 0 : false; }
         m->no_fused_reduce = getenv("NVSM_NO_FUSED_REDUCE") != nullptr;
+        { const char* e = getenv("NVSM_PDL"); m->pdl = e ? atoi(e) : 0; }
+        { const char* e = getenv("NVSM_BUCKETS_AT"); m->buckets_at = e ? std::max(0, std::min(2, atoi(e))) : 0; }
+        CU(cudaEventCreateWithFlags(&m->build_gate, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->score_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->entity_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->word_rows_done, cudaEventDisableTiming));
@@ -2053,7 +2111,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             CU(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
         }
-        CU(cudaHostAlloc((void**)&m->loss_host, sizeof(double) * nvsm_model::kCostRing, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&m->loss_host, sizeof(double) * nvsm_model::kCostRing, cudaHostAllocMapped | cudaHostAllocPortable));
+        TRY(dev_alloc(&m->xchg_counter, 1));
         CU(cudaHostAlloc((void**)&m->id_flags, 2 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         m->id_flags[0] = m->id_flags[1] = 0;
         for (auto& e : m->loss_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2777,7 +2836,6 @@ int nvsm_comm_peer_export(nvsm_model* m, char* handles_out_128) {
         TRY(dev_alloc(&m->peer_flags, nslots * kPeerFlagStride));
         TRY(dev_alloc(&m->peer_error, 1));
         TRY(dev_alloc(&m->peer_dev, 1));
-        TRY(dev_alloc(&m->xchg_counter, 1));
         m->no_fused_xchg = getenv("NVSM_NO_FUSED_XCHG") != nullptr;
         CU(cudaDeviceSynchronize());
     }

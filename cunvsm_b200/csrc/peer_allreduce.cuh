@@ -36,7 +36,7 @@ __device__ __forceinline__ size_t peer_flag_index(const PeerXchg& x, int kind, i
 // Building blocks of the exchanges that are FUSED into compute kernels (the producer's last stage pushes its partial
 // result over NVLink, the same kernel -- or block -- waits for the peers' and goes on with the reduced values):
 //   col_stats_reduce_finalize_kernel<true>  batch-norm forward sums: partial-row reduction -> exchange -> mean / invstd
-//   peer_sums_tail (score kernels)          backward column sums + loss: the last block to finish exchanges them
+//   score_sums_tail (score kernels)         backward column sums + loss: the last block to finish exchanges them
 // Call with threads `t` = 0 .. nranks-1 of one warp / block, after every pushing thread's __threadfence_system() and a
 // barrier among them.
 __device__ __forceinline__ void peer_publish(const PeerXchg& x, int kind, int parity, int blk, unsigned long long epoch, int t) {
@@ -63,34 +63,45 @@ __device__ __forceinline__ double peer_inbox_value(const PeerXchg& x, int kind, 
     return __ldcg(x.inbox[x.rank] + peer_slot_index(x, kind, parity, p) + i);
 }
 
-// Tail of the score kernels at N > 1: every block has added its column sums / loss to `buf` [n] with double atomics; the
-// last block to arrive (done_counter) pushes the GPU's totals to every peer, waits for theirs and leaves the global sums
-// in `buf` -- in rank order, so bit-identical on every rank. Replaces a separate one-block all-reduce launch between the
-// score kernel and batch-norm backward. All threads of the block must call it.
-__device__ __forceinline__ void peer_sums_tail(const PeerXchg* __restrict__ xp, double* __restrict__ buf, int n,
-                                               unsigned long long epoch, int kind, unsigned int* __restrict__ done_counter,
-                                               int* __restrict__ error_flag) {
+// Tail of the score kernels: every block has added its column sums / loss to `buf` [n] with double atomics (loss = last
+// element). The last block to arrive (done_counter)
+//   * at N > 1 with the peer exchange (xp != null): pushes the GPU's totals to every peer, waits for theirs and leaves
+//     the global sums in `buf` -- in rank order, so bit-identical on every rank. Replaces a separate one-block all-reduce
+//     launch between the score kernel and batch-norm backward;
+//   * writes the loss to `loss_host` (mapped pinned memory, nullable): no device-to-host copy operation sits in the
+//     stream between the score kernel and the backward pass.
+// All threads of the block must call it. No static shared memory (score_ring_kernel opts into all 227 KB as dynamic).
+__device__ __forceinline__ void score_sums_tail(const PeerXchg* __restrict__ xp, double* __restrict__ buf, int n,
+                                                unsigned long long epoch, int kind, unsigned int* __restrict__ done_counter,
+                                                int* __restrict__ error_flag, double* __restrict__ loss_host) {
+    if (!done_counter) return;
     __threadfence();      // this thread's atomics on buf are performed before the counter moves
     __syncthreads();
     int mine = 0;
     if (threadIdx.x == 0) mine = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1 : 0;
-    if (!__syncthreads_or(mine)) return;   // (no static shared memory: score_ring_kernel opts into all 227 KB as dynamic)
+    if (!__syncthreads_or(mine)) return;
     __threadfence();
-    const PeerXchg& x = *xp;
-    const int parity = (int)(epoch & 1ull);
-    for (int p = 0; p < x.nranks; ++p) {
-        double* dst = x.inbox[p] + peer_slot_index(x, kind, parity, x.rank);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(buf + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    peer_publish(x, kind, parity, 0, epoch, threadIdx.x);
-    peer_wait(x, kind, parity, 0, epoch, threadIdx.x, error_flag);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double s = 0.0;
-        for (int p = 0; p < x.nranks; ++p) s += peer_inbox_value(x, kind, parity, p, i);
-        buf[i] = s;
+    if (xp) {
+        const PeerXchg& x = *xp;
+        const int parity = (int)(epoch & 1ull);
+        for (int p = 0; p < x.nranks; ++p) {
+            double* dst = x.inbox[p] + peer_slot_index(x, kind, parity, x.rank);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(buf + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        peer_publish(x, kind, parity, 0, epoch, threadIdx.x);
+        peer_wait(x, kind, parity, 0, epoch, threadIdx.x, error_flag);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double s = 0.0;
+            for (int p = 0; p < x.nranks; ++p) s += peer_inbox_value(x, kind, parity, p, i);
+            buf[i] = s;
+            if (i == n - 1 && loss_host) { *loss_host = s; __threadfence_system(); }
+        }
+    } else if (threadIdx.x == 0 && loss_host) {
+        *loss_host = __ldcg(buf + n - 1);
+        __threadfence_system();
     }
     if (threadIdx.x == 0) *done_counter = 0u;   // next launch
 }

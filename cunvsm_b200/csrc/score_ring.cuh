@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     uint64_t* bars = reinterpret_cast<uint64_t*>(sums + 2 * dd + 2);
 
     for (int t = threadIdx.x; t < 2 * dd + 1; t += blockDim.x) sums[t] = 0.f;
+    pdl_wait();                // (programmatic dependent of the statistics kernel: nothing global is touched above)
+    pdl_launch_dependents();
     if (p.act.use_bn)
         for (int t = threadIdx.x; t < dd; t += blockDim.x) { bnp[t] = q.bn_scale[t]; bnp[dd + t] = q.bn_shift[t]; }
     __syncthreads();
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * dd; t += blockDim.x) atomicAdd(p.col_sums + t, (double)sums[t]);
     if (threadIdx.x == 0) atomicAdd(p.loss_acc, (double)sums[2 * dd]);
-    if (p.xchg) peer_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error);
+    score_sums_tail(p.xchg, p.col_sums, 2 * dd + 1, p.xchg_epoch, 3, p.xchg_counter, p.xchg_error, p.loss_host);
     (void)nvec;
 }
 
