@@ -408,6 +408,18 @@ def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
     got = one_step(pm, nv.Batch(Bg // world, w["n"]).fill(sf, sl, sfw, sw), sids)
     peer_err = pm.comm_peer_status()[1]
     pm.close()
+
+    def fused_step(model, batch, entity_ids):
+        """the one-call step bench.py times (N > 1: every reduction inside compute kernels over NVLink inboxes)"""
+        model.train_step(batch, entity_ids, w["lr"])
+        return {"fused_loss": model.last_cost(), "fused_T": model.get_tensor(nv.TRANSFORM), "fused_b": model.get_tensor(nv.BIAS)}
+
+    pm = nv.Model(w["V"], w["D"], desc, mk(Bg // world), device=local_rank, gemm_mode=args.gemm_mode)
+    pm.initialize(nv.RNG(1))
+    sharding.init_model_comm(pm, dist, rank, world, peer_exchange=not args.no_peer)
+    got.update(fused_step(pm, nv.Batch(Bg // world, w["n"]).fill(sf, sl, sfw, sw), sids))
+    peer_err = max(peer_err, pm.comm_peer_status()[1])
+    pm.close()
     report = None
     if rank == 0:
         tol = 2e-4 if args.gemm_mode != 1 else 2e-2
@@ -415,10 +427,15 @@ def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
         um.initialize(nv.RNG(1))
         want = one_step(um, nv.Batch(Bg, w["n"]).fill(f, labels, fw, iw), ids)
         um.close()
-        vs_un = {k: (abs(got[k] - want[k]) / abs(want[k]) if k == "loss" else rel_err(got[k], want[k])) for k in got}
+        um = nv.Model(w["V"], w["D"], desc, mk(Bg), device=local_rank, gemm_mode=args.gemm_mode)
+        um.initialize(nv.RNG(1))
+        want.update(fused_step(um, nv.Batch(Bg, w["n"]).fill(f, labels, fw, iw), ids))
+        um.close()
+        vs_un = {k: (abs(got[k] - want[k]) / abs(want[k]) if k.endswith("loss") else rel_err(got[k], want[k])) for k in got}
         report = {"global_batch": Bg, "ranks": world, "tolerance": tol, "vs_unsharded": vs_un,
                   "what": "one sharded step vs one GPU on the concatenated batch and vs oracle/_ref (reference, float32): "
-                          "loss relative; tensors max|a-b| / max|b|; T and b after the update"}
+                          "loss relative; tensors max|a-b| / max|b|; T and b after the update; fused_* = the same step through the "
+                          "one-call API the bench times (grad_transform exchanged through the NVLink inboxes, no NCCL)"}
         worst = max(vs_un.values())
         try:
             from oracle import ref_binding as R
@@ -437,7 +454,8 @@ def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
                 ref["grad_transform"], ref["grad_bias"] = rm.get("grad_transform"), rm.get("grad_bias")
                 rm.update(w["lr"], rm.scaled_lambda())
                 ref["T"], ref["b"] = rm.get("transform"), rm.get("bias")
-                vs_ref = {k: (abs(got[k] - ref[k]) / abs(ref[k]) if k == "loss" else rel_err(got[k], ref[k])) for k in ref}
+                ref["fused_loss"], ref["fused_T"], ref["fused_b"] = ref["loss"], ref["T"], ref["b"]   # same step, one call
+                vs_ref = {k: (abs(got[k] - ref[k]) / abs(ref[k]) if k.endswith("loss") else rel_err(got[k], ref[k])) for k in ref}
                 vs_ref["sampled_ids_bit_exact"] = ids_equal
                 report["vs_reference"] = vs_ref
                 worst = max(worst, max(v for k, v in vs_ref.items() if k != "sampled_ids_bit_exact"))

@@ -1179,10 +1179,34 @@ struct TransformUpdateParams {
     // ... and the tensor-core operand copies of the NEW T for the next step's GEMMs: Tr = rn_tf32(T) [dw, dd],
     // Tt = its transpose [dd, ldT] (K-major B operand of the forward GEMM) and the 3xTF32 remainders
     float* Tr; float* Tt; float* Tr_lo; float* Tt_lo; int dd; int ldT;
+    // N > 1, fused grad_transform exchange (gt_reduce_push_kernel): gT_part = this rank's gT inbox of the running parity
+    // ([nranks][nT], written by the peers over NVLink), nparts = nranks; before reading element k wait until the flag
+    // of chunk k / xchg_chunk from every rank has reached xchg_epoch. Null: off.
+    const PeerXchg* xchg; unsigned long long xchg_epoch; int xchg_chunk; int* xchg_error;
 };
 
 __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUpdateParams p) {
     const long total = p.nT + p.nb;
+    if (p.xchg) {
+        // Fused grad_transform exchange: the elements of this block (one grid-stride pass: the grid covers `total`) live in
+        // at most `span` consecutive chunks; thread (c, r) polls the flag of chunk c from rank r, one system-scope fence
+        // per polling thread, then the block goes on (per-thread acquire loads measured +11 us on the step).
+        const PeerXchg& x = *p.xchg;
+        const int parity = (int)(p.xchg_epoch & 1ull);
+        const long e0 = (long)blockIdx.x * blockDim.x, e1 = min(p.nT, e0 + (long)blockDim.x) - 1;
+        if (e0 < p.nT) {
+            const int c0 = (int)(e0 / p.xchg_chunk), span = (int)(e1 / p.xchg_chunk) - c0 + 1;
+            for (int t = threadIdx.x; t < span * x.nranks; t += blockDim.x) {
+                const int c = c0 + t / x.nranks, r = t % x.nranks;
+                const volatile unsigned long long* f = x.flags[x.rank] + peer_flag_index(x, kPeerKindGt, parity, r, c);
+                long spins = 0;
+                while (*f < p.xchg_epoch)
+                    if (++spins > (1L << 26)) { atomicExch(p.xchg_error, 1); break; }
+                __threadfence_system();
+            }
+        }
+        __syncthreads();
+    }
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
         const bool is_bias = t >= p.nT;
         const long k = is_bias ? t - p.nT : t;
@@ -1190,6 +1214,10 @@ __global__ void __launch_bounds__(256) transform_update_kernel(const TransformUp
         float g;
         if (is_bias) {
             g = p.gb[k];
+        } else if (p.gT_part && p.xchg) {
+            g = 0.f;
+            for (int r = 0; r < p.nparts; ++r) g += __ldcg(p.gT_part + (long)r * p.nT + k);   // rank order, past L1
+            p.gT_out[k] = g;
         } else if (p.gT_part) {
             // same summation order as reduce_partials_kernel; eight independent loads in flight
             g = 0.f;

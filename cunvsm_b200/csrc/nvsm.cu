@@ -216,12 +216,15 @@ struct nvsm_model {
     double* peer_inbox = nullptr;                // this rank's inbox (exported with CUDA IPC)
     unsigned long long* peer_flags = nullptr;
     void* peer_mapped[2 * kPeerMaxRanks] = {nullptr};   // IPC mappings to close
-    unsigned long long peer_epoch[kPeerKinds] = {0, 0, 0, 0};
+    unsigned long long peer_epoch[kPeerKinds] = {0, 0, 0, 0, 0};
+    bool gt_push_side = false;                   // NVSM_GT_PUSH_SIDE=1: the push kernel on the communication stream (measured slower)
+    bool gt_xchg_pending = false;                // grad_transform went through gt_reduce_push_kernel: update_transform sums the inbox
+    int gt_xchg_chunk = 0;
     int* peer_error = nullptr;
     cudaStream_t comm_stream = nullptr;          // grad_transform all-reduce, under grad_phrase and the word update
     cudaStream_t gt_stream = nullptr;            // fused steps: grad_transform GEMM (+ all-reduce) under the word update
     cudaEvent_t dx_ready = nullptr;
-    bool gt_side = false, in_fused_step = false, no_fused_reduce = false;
+    bool gt_side = false, in_fused_step = false, no_fused_reduce = false, no_fused_gt = false, skip_gt_reduce = false;
     int buckets_at = 0;
     int pdl = 0;               // programmatic dependent launches along the main-stream kernel chain: bit mask over the
                                // kPdl* launch sites (NVSM_PDL)
@@ -966,7 +969,7 @@ int backward(nvsm_model* m) {
         }
         m->gt_nparts = nparts;
         m->gt_reduced = false;
-        if (m->nranks > 1 || m->no_fused_reduce) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
+        if ((m->nranks > 1 && !m->skip_gt_reduce) || m->no_fused_reduce) TRY(reduce_gt_partials(m));   // the all-reduce needs gT itself
         phase_end(m);
         return 0;
     };
@@ -1008,8 +1011,40 @@ int backward(nvsm_model* m) {
         CU(cudaEventRecord(m->gt_reduced_ev, m->gt_stream));
         m->gt_allreduce_pending = true;
     } else {
-        TRY(run_gt());
-        if (m->nranks > 1) {
+        const bool gt_push = fused_xchg(m) && m->in_fused_step && !m->no_fused_gt && m->comm_stream != nullptr;
+        m->skip_gt_reduce = gt_push;
+        const int grc = run_gt();
+        m->skip_gt_reduce = false;
+        if (grc) return grc;
+        if (gt_push) {
+            // Fused steps, NVLink peer exchange: no NCCL in the step. The split-K partial reduction pushes this rank's
+            // grad_transform into every rank's inbox (gt_reduce_push_kernel, on the communication stream under the
+            // grad_phrase GEMM and the word update); transform_update_kernel waits for the peers' flags and sums the
+            // inbox in rank order.
+            const long nT = (long)dw * dd;
+            const int nblk = (int)std::min<long>(kPeerFlagStride, (nT + 255) / 256);
+            const int chunk = (int)((nT + nblk - 1) / nblk);
+            const unsigned long long epoch = ++m->peer_epoch[kPeerKindGt];
+            cudaStream_t main_stream = m->stream;
+            if (!m->profiling && m->gt_push_side) {
+                CU(cudaEventRecord(m->gt_ready, m->stream));
+                CU(cudaStreamWaitEvent(m->comm_stream, m->gt_ready, 0));
+                m->stream = m->comm_stream;
+            }
+            phase_begin(m, PH_ALLREDUCE);
+            gt_reduce_push_kernel<<<(int)((nT + chunk - 1) / chunk), 256, 0, m->stream>>>(m->peer_dev, m->gT_part, m->gt_nparts, nT, chunk, epoch);
+            m->launches++;
+            phase_end(m);
+            const cudaError_t le = cudaPeekAtLastError();
+            if (m->stream != main_stream) {
+                CU(cudaEventRecord(m->gt_reduced_ev, m->comm_stream));
+                m->gt_allreduce_pending = true;
+                m->stream = main_stream;
+            }
+            if (le != cudaSuccess) return fail("launch gt_reduce_push_kernel: %s", cudaGetErrorString(le));
+            m->gt_xchg_pending = true;
+            m->gt_xchg_chunk = chunk;
+        } else if (m->nranks > 1) {
             // grad_transform is only consumed by the projection update at the very end of the step: its all-reduce runs on
             // the communication stream under the grad_phrase GEMM and the word update (joined in update_transform).
             if (m->comm_stream && !m->profiling) {
@@ -1487,7 +1522,16 @@ int update_transform(nvsm_model* m, float lr, float lambda) {
         m->t_transform += 1;
     }
     p.gT_part = nullptr; p.nparts = 0; p.gT_out = m->gT;
-    if (!m->gt_reduced) { p.gT_part = m->gT_part; p.nparts = m->gt_nparts; m->gt_reduced = true; }
+    p.xchg = nullptr; p.xchg_epoch = 0; p.xchg_chunk = 1; p.xchg_error = nullptr;
+    if (m->gt_xchg_pending) {
+        // every rank's grad_transform sits (or is about to land) in this rank's inbox: sum the slots in rank order
+        const unsigned long long epoch = m->peer_epoch[kPeerKindGt];
+        p.gT_part = m->peer.gt_inbox[m->rank] + (size_t)(epoch & 1ull) * m->nranks * m->peer.gt_elems;
+        p.nparts = m->nranks;
+        p.xchg = m->peer_dev; p.xchg_epoch = epoch; p.xchg_chunk = m->gt_xchg_chunk; p.xchg_error = m->peer_error;
+        m->gt_xchg_pending = false;
+        m->gt_reduced = true;
+    } else if (!m->gt_reduced) { p.gT_part = m->gT_part; p.nparts = m->gt_nparts; m->gt_reduced = true; }
     p.Tr = nullptr; p.Tt = nullptr; p.Tr_lo = nullptr; p.Tt_lo = nullptr; p.dd = m->dd; p.ldT = m->ldP;
     if (m->use_tc) { p.Tr = m->Tr; p.Tt = m->Tt; p.Tr_lo = m->Tr_lo; p.Tt_lo = m->Tt_lo; m->t_copies_stale = false; }
     LAUNCH(m, transform_update_kernel, (int)((p.nT + p.nb + 127) / 128), 128, 0, p);
@@ -2010,6 +2054,11 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
         { const char* e = getenv("NVSM_GT_SIDE"); m->gt_side = e ? atoi(e) != 0 : false; }
         m->no_fused_reduce = getenv("NVSM_NO_FUSED_REDUCE") != nullptr;
+        // grad_transform through the NVLink inboxes instead of ncclAllReduce: correct (multi-GPU tests, parity_check) but
+        // measured slower at N = 2 (0.656 / 0.662 ms with the push kernel on the side / main stream vs 0.645 ms with
+        // ncclAllReduce on the side stream, profiles/bench/r2rst_gt_exchange.md), so it is opt-in: NVSM_FUSED_GT=1.
+        { const char* e = getenv("NVSM_FUSED_GT"); m->no_fused_gt = !(e && atoi(e) != 0); }
+        { const char* e = getenv("NVSM_GT_PUSH_SIDE"); m->gt_push_side = e && atoi(e) != 0; }
         { const char* e = getenv("NVSM_PDL"); m->pdl = e ? atoi(e) : 0; }
         { const char* e = getenv("NVSM_BUCKETS_AT"); m->buckets_at = e ? std::max(0, std::min(2, atoi(e))) : 0; }
         CU(cudaEventCreateWithFlags(&m->build_gate, cudaEventDisableTiming));
@@ -2832,7 +2881,10 @@ int nvsm_comm_peer_export(nvsm_model* m, char* handles_out_128) {
         m->peer.nranks = m->nranks; m->peer.rank = m->rank;
         m->peer.slot_doubles = 2 * m->dd + 8;
         const size_t nslots = (size_t)kPeerKinds * 2 * m->nranks;
-        TRY(dev_alloc(&m->peer_inbox, nslots * m->peer.slot_doubles));
+        m->peer.gt_elems = (long)m->dw * m->dd;
+        // one allocation (one IPC handle): the double slots, then the grad_transform inbox [2][nranks][dw * dd] floats
+        const size_t gt_doubles = ((size_t)2 * m->nranks * m->peer.gt_elems + 1) / 2;
+        TRY(dev_alloc(&m->peer_inbox, nslots * m->peer.slot_doubles + gt_doubles));
         TRY(dev_alloc(&m->peer_flags, nslots * kPeerFlagStride));
         TRY(dev_alloc(&m->peer_error, 1));
         TRY(dev_alloc(&m->peer_dev, 1));
@@ -2855,6 +2907,7 @@ int nvsm_comm_peer_import(nvsm_model* m, const char* all_handles) {
         if (p == m->rank) {
             m->peer.inbox[p] = m->peer_inbox;
             m->peer.flags[p] = m->peer_flags;
+            m->peer.gt_inbox[p] = (float*)(m->peer_inbox + (size_t)kPeerKinds * 2 * m->nranks * m->peer.slot_doubles);
             continue;
         }
         cudaIpcMemHandle_t h[2];
@@ -2865,6 +2918,7 @@ int nvsm_comm_peer_import(nvsm_model* m, const char* all_handles) {
         m->peer_mapped[2 * p] = inbox; m->peer_mapped[2 * p + 1] = flags;
         m->peer.inbox[p] = (double*)inbox;
         m->peer.flags[p] = (unsigned long long*)flags;
+        m->peer.gt_inbox[p] = (float*)((double*)inbox + (size_t)kPeerKinds * 2 * m->nranks * m->peer.slot_doubles);
     }
     CU(cudaMemcpy(m->peer_dev, &m->peer, sizeof(PeerXchg), cudaMemcpyHostToDevice));
     m->peer_ready = true;

@@ -14,7 +14,8 @@
 namespace nvsm {
 
 constexpr int kPeerMaxRanks = 16;
-constexpr int kPeerKinds = 4;   // independent reduction sites per step, each with its own epoch counter
+constexpr int kPeerKinds = 5;   // independent reduction sites per step, each with its own epoch counter
+constexpr int kPeerKindGt = 4;  // grad_transform (floats, its own inbox region: PeerXchg::gt_inbox)
 constexpr int kPeerFlagStride = 128;   // flags per (kind, parity, source rank): one per block of a fused exchange (block 0 =
                                        // the stand-alone one-block kernel and the score kernels' last-block tail)
 
@@ -23,6 +24,9 @@ struct PeerXchg {
     int slot_doubles;                       // capacity of one slot
     double* inbox[kPeerMaxRanks];           // inbox[p] = base of rank p's inbox as mapped in THIS process
     unsigned long long* flags[kPeerMaxRanks];
+    // grad_transform exchange: [parity][src_rank][gt_elems] floats behind the double slots of the same allocation
+    float* gt_inbox[kPeerMaxRanks];
+    long gt_elems;
 };
 
 // inbox layout: [kind][parity][src_rank][slot_doubles]; flags: [kind][parity][src_rank][kPeerFlagStride]
@@ -104,6 +108,35 @@ __device__ __forceinline__ void score_sums_tail(const PeerXchg* __restrict__ xp,
         __threadfence_system();
     }
     if (threadIdx.x == 0) *done_counter = 0u;   // next launch
+}
+
+// grad_transform at N > 1 in fused steps, without NCCL: the split-K partial reduction of the GEMM is the producer --
+// block b sums the partials of its chunk of gT (fixed order), stores the result into ITS slot of every rank's gT inbox
+// (own included) with plain NVLink stores and publishes flag b -- and the projection update is the consumer:
+// transform_update_kernel waits for the flags of the chunk an element lives in and sums the nranks slots in rank order
+// (bit-identical T, b on every rank). chunk = elements per block (gridDim.x <= kPeerFlagStride).
+__global__ void __launch_bounds__(256) gt_reduce_push_kernel(const PeerXchg* __restrict__ xp, const float* __restrict__ part,
+                                                             int nparts, long n, int chunk, unsigned long long epoch) {
+    const PeerXchg& x = *xp;
+    const int parity = (int)(epoch & 1ull);
+    const long e0 = (long)blockIdx.x * chunk, e1 = min(n, e0 + chunk);
+    const size_t slot = ((size_t)parity * x.nranks + x.rank) * (size_t)x.gt_elems;
+    for (long i = e0 + threadIdx.x; i < e1; i += blockDim.x) {
+        float s = 0.f;
+        int z = 0;
+        for (; z + 8 <= nparts; z += 8) {   // same summation order as reduce_partials_kernel / transform_update_kernel
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (long)(z + u) * n + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; z < nparts; ++z) s += __ldg(part + (long)z * n + i);
+        for (int p = 0; p < x.nranks; ++p) x.gt_inbox[p][slot + i] = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    peer_publish(x, kPeerKindGt, parity, blockIdx.x, epoch, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(const PeerXchg x, double* __restrict__ buf, int n, int kind,

@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round 2, call 18 (2 GPUs): grad_transform exchanged through NVLink inboxes (gt_reduce_push_kernel -> transform_update_kernel,
+# no NCCL in the fused step) vs ncclAllReduce on the side stream (NVSM_NO_FUSED_GT=1): multi-GPU tests, bench N=2 + parity_check.
+T=${1:-r2r}
+N=${2:-2}
+mkdir -p gpurun_out
+S=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - S )) s] $*"; }
+timeout 500 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/pytest_multi_$T.log 2>&1; stamp "multi-gpu tests rc=$?"
+tail -5 gpurun_out/pytest_multi_$T.log
+b() { local name=$1; shift; timeout 300 python bench.py --gpus $N --steps 200 --warmup 20 --no_cpu_baseline --no_alt --no_probes "$@" > gpurun_out/bench_${T}_$name.json 2> gpurun_out/bench_${T}_$name.err; stamp "bench $name rc=$?"; }
+b gtfused
+NVSM_NO_FUSED_GT=1 b gtnccl --no_parity_check
+b gtfused2 --no_parity_check
+NVSM_NO_FUSED_GT=1 b gtnccl2 --no_parity_check
+NVSM_NO_FUSED_XCHG=1 b allunfused --no_parity_check
+b gtfused_C5 --workload C5
+python - <<PY
+import json, glob
+for f in sorted(glob.glob("gpurun_out/bench_${T}_*.json")):
+    try:
+        d = json.loads([l for l in open(f) if l.startswith("{")][-1])
+        print("%-12s %.4f e2e %.4f" % (f.split("bench_${T}_")[1][:-5], d["ms_per_step"], d["e2e"]["ms_per_step"]), "strong", d.get("strong") and (round(d["strong"]["ms_per_step"], 4), round(d["strong"]["e2e"]["ms_per_step"], 4)), d["clocks"].get("sm_mhz"))
+        if d.get("parity_check"): print("      parity", d["parity_check"]["ok"], d["parity_check"]["max_rel_err"], d["parity_check"]["peer_exchange_error"], d["parity_check"]["vs_unsharded"], d["parity_check"].get("vs_reference"))
+    except Exception as e:
+        print(f, "ERR", e, open(f.replace(".json", ".err")).read()[-1500:])
+PY

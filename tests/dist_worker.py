@@ -69,12 +69,19 @@ def exact_mode(rank, world, local, gemm_mode, collect=None, smooth_adam=False, s
             f, fw, labels, w = make_batch(nrng, B, n, V, D, z)
             ids = ref.generate_labels(labels, srng)
             sf, sfw, sl, sw, sids = sharding.shard_batch(f, fw, labels, w, ids, rank, world)
-            res_full = ref.compute_cost(nv.Batch(B, n).fill(f, labels, fw, w), entity_ids=ids)
-            ref.backprop(res_full, lr)
-            res = dm.compute_cost(nv.Batch(B // world, n).fill(sf, sl, sfw, sw), entity_ids=sids)
-            dm.backprop(res, lr)
             tol = 2e-4 if gemm_mode == 0 else 2e-2
-            c, cf = res.get_cost(), res_full.get_cost()
+            if step == 1:
+                # the fused one-call step: at N > 1 grad_transform travels through gt_reduce_push_kernel /
+                # transform_update_kernel (NVLink inboxes) instead of ncclAllReduce
+                ref.train_step(nv.Batch(B, n).fill(f, labels, fw, w), ids, lr)
+                dm.train_step(nv.Batch(B // world, n).fill(sf, sl, sfw, sw), sids, lr)
+                c, cf = dm.last_cost(), ref.last_cost()
+            else:
+                res_full = ref.compute_cost(nv.Batch(B, n).fill(f, labels, fw, w), entity_ids=ids)
+                ref.backprop(res_full, lr)
+                res = dm.compute_cost(nv.Batch(B // world, n).fill(sf, sl, sfw, sw), entity_ids=sids)
+                dm.backprop(res, lr)
+                c, cf = res.get_cost(), res_full.get_cost()
             if collect is None:
                 assert abs(c - cf) <= tol * abs(cf), (method, mode, step)
             elif not abs(c - cf) <= tol * abs(cf):

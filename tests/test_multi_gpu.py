@@ -52,6 +52,16 @@ def test_allgather_sparse_mode_matches_single_gpu_trajectory(world):
     assert "MULTI_GPU_OK world=%d" % world in out and "sparse=allgather" in out
 
 
+def test_allgather_trajectory_with_grad_transform_over_nvlink_inboxes():
+    """Same trajectory check with the opt-in NCCL-free exchange of grad_transform in the fused step (NVSM_FUSED_GT=1:
+    gt_reduce_push_kernel -> transform_update_kernel's flag wait + rank-ordered inbox sum)."""
+    if _ngpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    env = dict(os.environ, NVSM_TEST_GEMM_MODE="0", NVSM_TEST_SPARSE_MODE="1", NVSM_FUSED_GT="1")
+    out = _run_worker(2, 29630, env)
+    assert "MULTI_GPU_OK world=2" in out and "sparse=allgather" in out
+
+
 @pytest.mark.parametrize("world", [4, 8])
 def test_sharded_step_matches_single_gpu_wide(world):
     """The sharded-step check of test_sharded_step_matches_single_gpu on 4 and 8 ranks (fp32 GEMMs)."""
