@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     const ScoreParams& p = q.s;
     extern __shared__ __align__(128) uint8_t ring_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int dd = p.dd, R = p.R, S = q.stages, W = q.warps;
+    const int dd = FULL ? NCH * 128 : p.dd;   // compile-time row length on the FULL path: immediate offsets, shifts
+    const int R = p.R, S = q.stages, W = q.warps;
     const int nvec = dd / VEC;
     const uint32_t row_bytes = (uint32_t)dd * 4u;
     const uint32_t stage_bytes = (uint32_t)(R + 1) * row_bytes;   // row 0 = Z[i], rows 1..R = E rows
@@ -90,28 +91,32 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     const long my_count = warp0 < p.B ? (p.B - warp0 + nwarps - 1) / nwarps : 0;   // n-grams of this warp
 
     // id of row `lane` and instance weight of an upcoming n-gram
-    auto fetch_meta = [&](long j, idx_t& id0, float& iw) {
+    // (ids are validated against the table size behind every upload: 32 bits hold a row index, one shuffle moves it)
+    auto fetch_meta = [&](long j, uint32_t& id0, float& iw) {
         id0 = 0; iw = 0.f;
         if (j < my_count) {
             const long i = warp0 + j * nwarps;
-            if (lane < R) id0 = __ldg(p.ids + i * R + lane);
+            if (lane < R) id0 = (uint32_t)__ldg(p.ids + i * R + lane);
             iw = __ldg(p.inst_w + i);
         }
     };
-    // One commit group per n-gram (an empty group past the end keeps the group arithmetic uniform).
-    auto issue = [&](long j, idx_t id0) {
+    // One commit group per n-gram (an empty group past the end keeps the group arithmetic uniform). s = stage.
+    // (ncu r2v: the issue sequence was 15 % of the kernel's instructions -- 64-bit id shuffles, a 64-bit j % S -- on a
+    // kernel whose issue slots are 61 % busy.)
+    const float* const e_lane = p.E + lane4;
+    auto issue = [&](long j, uint32_t id0, int s) {
         if (j < my_count) {
             const long i = warp0 + j * nwarps;
-            const int s = (int)(j % S);
             const uint32_t dst = ring_smem_u32(my_stages) + (uint32_t)s * stage_bytes + (uint32_t)lane4 * 4u;
             const float* zsrc = p.Z + i * dd + lane4;
 #pragma unroll
             for (int k = 0; k < NCH; ++k)
                 if (FULL || lane4 + k * 128 < dd) ring_cp16(dst + k * 512u, zsrc + k * 128);
-            for (int r = 0; r < R; ++r) {
-                const idx_t id = __shfl_sync(kFull, id0, r);
-                const float* src = p.E + id * dd + lane4;
-                const uint32_t d = dst + (uint32_t)(1 + r) * row_bytes;
+            uint32_t d = dst + row_bytes;
+#pragma unroll 4
+            for (int r = 0; r < R; ++r, d += row_bytes) {
+                const uint32_t id = __shfl_sync(kFull, id0, r);
+                const float* src = e_lane + (size_t)id * dd;
 #pragma unroll
                 for (int k = 0; k < NCH; ++k)
                     if (FULL || lane4 + k * 128 < dd) ring_cp16(d + k * 512u, src + k * 128);
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    idx_t nid0;
+    uint32_t nid0;
     float niw;
     float iw_q[4] = {0.f, 0.f, 0.f, 0.f};   // instance weights of n-grams j .. j+S-1 (S <= 4), rotated
 #pragma unroll
@@ -128,10 +133,11 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
         if (jj < S - 1) {
             fetch_meta(jj, nid0, niw);
             iw_q[jj] = niw;
-            issue(jj, nid0);
+            issue(jj, nid0, jj);
         }
     }
     fetch_meta(S - 1, nid0, niw);
+    int s = 0;   // stage of n-gram j (j % S, kept incrementally)
 
     float cs[NCH][VEC], cx[NCH][VEC];
 #pragma unroll
@@ -148,10 +154,9 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
         const long i = warp0 + j * nwarps;
         // keep the ring full: n-gram j+S-1 goes into the stage consumed at iteration j-1
         if (S == 1) iw_q[0] = niw; else if (S == 2) iw_q[1] = niw; else if (S == 3) iw_q[2] = niw; else iw_q[3] = niw;
-        issue(j + S - 1, nid0);
+        issue(j + S - 1, nid0, s == 0 ? S - 1 : s - 1);
         fetch_meta(j + S, nid0, niw);
 
-        const int s = (int)(j % S);
         // groups j .. j+S-1 are outstanding: wait until at most S-1 remain, then make every lane's
         // copies visible to the whole warp
         if (S == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -182,11 +187,22 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
             if (p.Y && ok) store_vec<VEC>(p.Y + i * dd + c4, y[k]);
         }
 
-        // ---- pass 1: dot products, row r parked in lane r ----
-        float my_dot = 0.f;
+        // ---- one pass over the staged rows, four at a time: dot products (transposing butterfly, 6 shuffles), the
+        // sigmoid / clamp / log / multiplier chain of THESE four rows (lane l evaluates row 4 bch + (l & 3); the chain of
+        // a row only depends on its own dot product), and Gp += coef_r * E_r while the rows are still in registers.
+        // The former layout (all dot products, ONE chain with lane r = row r, then a second sweep over the rows for Gp)
+        // read every staged row twice: 35 KB of shared-memory traffic per n-gram against 24 KB now, on a kernel whose
+        // shared-memory time (1.8 GB per launch / 36 TB/s) was half of its duration. Same arithmetic per row and same
+        // accumulation order of Gp; the loss is still accumulated by lane r = row r.
+        float gp[NCH][VEC];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) gp[k][v] = 0.f;
         const float* erow = st + dd;     // first entity row
-        // Branch-free: rows past R are clamped to row R-1; their dot products land in lanes >= R
-        // whose coefficient is forced to zero below.
+        const float wneg = iw_q[0] * p.w_scale;
+        float my_prob = 1.f, my_mult = 0.f, my_wgt = 0.f;
+        // Branch-free: rows past R are clamped to row R-1 and get coefficient zero.
         for (int bch = 0; bch < nbatch; ++bch) {
             float4 x[4][NCH];
 #pragma unroll
@@ -202,62 +218,45 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
             for (int rr = 0; rr < 4; ++rr) {
                 dot[rr] = 0.f;
 #pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                    dot[rr] += (y[k][0] * x[rr][k].x + y[k][1] * x[rr][k].y) + (y[k][2] * x[rr][k].z + y[k][3] * x[rr][k].w);
+                for (int k = 0; k < NCH; ++k) {   // (one FMA per element; the four rows are independent chains)
+                    dot[rr] = fmaf(y[k][0], x[rr][k].x, dot[rr]); dot[rr] = fmaf(y[k][1], x[rr][k].y, dot[rr]);
+                    dot[rr] = fmaf(y[k][2], x[rr][k].z, dot[rr]); dot[rr] = fmaf(y[k][3], x[rr][k].w, dot[rr]);
+                }
             }
             const float d = warp_sum4_transposed(dot[0], dot[1], dot[2], dot[3], lane);   // slot (lane>>3)&3
-            const float t = __shfl_sync(kFull, d, (lane & 3) * 8);
-            if ((lane >> 2) == bch) my_dot = t;
-        }
-        // ---- one scalar chain for all rows ----
-        float coef = 0.f;
-        {
-            const int r = lane;
-            const float sign = r == 0 ? 1.0f : -1.0f;
-            const float sv = sign * my_dot;
-            // numerically stable sigmoid (include/cuNVSM/cuda_utils.h:192-214), fast-math intrinsics
-            const float ex = __expf(-fabsf(sv));
-            const float inv = __fdividef(1.0f, 1.0f + ex);
-            float prob = sv >= 0.f ? inv : ex * inv;
-            prob = prob < p.sig_lo_cmp ? p.sig_lo_val : (prob > p.sig_hi_cmp ? p.sig_hi_val : prob);
-            const float wneg = iw_q[0] * p.w_scale;
-            const float wgt = r == 0 ? wneg * p.pos_scale : wneg;
-            const float der = (prob >= p.der_hi_cmp || prob <= p.der_lo_cmp) ? 0.0f : 1.0f - prob;
-            const float m = wgt * (der * p.bsn);
-            if (r < R) {
-                loss += wgt * __logf(prob);
-                p.probs[i * R + r] = prob;
-                p.mult[i * R + r] = m;
-                coef = sign * m;
+            const float my_dot = __shfl_sync(kFull, d, (lane & 3) * 8);                  // row 4 bch + (lane & 3)
+            float coef = 0.f;
+            {
+                const int r = bch * 4 + (lane & 3);
+                const float sign = r == 0 ? 1.0f : -1.0f;
+                const float sv = sign * my_dot;
+                // numerically stable sigmoid (include/cuNVSM/cuda_utils.h:192-214), fast-math intrinsics
+                const float ex = __expf(-fabsf(sv));
+                const float inv = __fdividef(1.0f, 1.0f + ex);
+                float prob = sv >= 0.f ? inv : ex * inv;
+                prob = prob < p.sig_lo_cmp ? p.sig_lo_val : (prob > p.sig_hi_cmp ? p.sig_hi_val : prob);
+                const float wgt = r == 0 ? wneg * p.pos_scale : wneg;
+                const float der = (prob >= p.der_hi_cmp || prob <= p.der_lo_cmp) ? 0.0f : 1.0f - prob;
+                const float m = wgt * (der * p.bsn);
+                if (r < R) coef = sign * m;
+                // every group of four lanes evaluated the same four rows: group bch keeps them, so that after the
+                // sweep lane r holds row r (one coalesced store of probs / mult, one log per row)
+                if ((lane >> 2) == bch) { my_prob = prob; my_mult = m; my_wgt = wgt; }
             }
-        }
-        // ---- pass 2: Gp = sum_r coef_r * E_r ----
-        float gp[NCH][VEC];
-#pragma unroll
-        for (int k = 0; k < NCH; ++k)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) gp[k][v] = 0.f;
-        for (int r0 = 0; r0 < R; r0 += 4) {
-            float4 x[4][NCH];
-            float cf[4];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-                const int rc = min(r0 + rr, R - 1);
-                const float* rp = erow + (size_t)rc * dd + lane4;
-#pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                    x[rr][k] = (FULL || lane4 + k * 128 < dd) ? *reinterpret_cast<const float4*>(rp + k * 128)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float c = __shfl_sync(kFull, coef, rc);
-                cf[rr] = (r0 + rr < R) ? c : 0.f;
-            }
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr)
+                const float cf = __shfl_sync(kFull, coef, rr);
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) {
-                    gp[k][0] += cf[rr] * x[rr][k].x; gp[k][1] += cf[rr] * x[rr][k].y;
-                    gp[k][2] += cf[rr] * x[rr][k].z; gp[k][3] += cf[rr] * x[rr][k].w;
+                    gp[k][0] += cf * x[rr][k].x; gp[k][1] += cf * x[rr][k].y;
+                    gp[k][2] += cf * x[rr][k].z; gp[k][3] += cf * x[rr][k].w;
                 }
+            }
+        }
+        if (lane < R) {   // lane r = row r
+            loss += my_wgt * __logf(my_prob);
+            p.probs[i * R + lane] = my_prob;
+            p.mult[i * R + lane] = my_mult;
         }
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
@@ -282,6 +281,7 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
         // rotate the instance-weight queue; all lanes are done with stage s before it is refilled
 #pragma unroll
         for (int t = 0; t < 3; ++t) iw_q[t] = iw_q[t + 1];
+        s = (s + 1 == S) ? 0 : s + 1;
         __syncwarp();
     }
 #pragma unroll
