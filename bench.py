@@ -410,7 +410,7 @@ def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
     pm.close()
 
     def fused_step(model, batch, entity_ids):
-        """the one-call step bench.py times (N > 1: every reduction inside compute kernels over NVLink inboxes)"""
+        """the one-call step bench.py times (N > 1: the critical-path reductions inside compute kernels over NVLink inboxes)"""
         model.train_step(batch, entity_ids, w["lr"])
         return {"fused_loss": model.last_cost(), "fused_T": model.get_tensor(nv.TRANSFORM), "fused_b": model.get_tensor(nv.BIAS)}
 
@@ -435,7 +435,7 @@ def parity_check(args, w, nv, sharding, dist, rank, world, local_rank):
         report = {"global_batch": Bg, "ranks": world, "tolerance": tol, "vs_unsharded": vs_un,
                   "what": "one sharded step vs one GPU on the concatenated batch and vs oracle/_ref (reference, float32): "
                           "loss relative; tensors max|a-b| / max|b|; T and b after the update; fused_* = the same step through the "
-                          "one-call API the bench times (grad_transform exchanged through the NVLink inboxes, no NCCL)"}
+                          "one-call API the bench times"}
         worst = max(vs_un.values())
         try:
             from oracle import ref_binding as R
@@ -774,12 +774,20 @@ def run_ours(args, w, rank, world, local_rank):
                                   "C ABI, ones filled on the device, not part of the H2D bytes",
                        "host_cores_per_rank": cores_per_rank},
             "e2e": {"value": ngrams / (ms_e2e * 1e-3), "unit": "n-grams/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+                    "d2h": "the 8-byte loss sum of every step, written by the score kernel's last block into pinned host memory "
+                           "(N > 1 without peer memory: cudaMemcpyAsync) and read by the host one step lagged"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "final_cost": final_cost, "alt_single_pass_tf32": alt,
             "collectives": (None if world == 1 else
-                            {"small_reductions": "nvlink peer exchange (peer_allreduce.cuh)" if peer_ok else "ncclAllReduce",
-                             "grad_transform": "ncclAllReduce on a side stream under grad_phrase + word update"}),
+                            {"small_reductions": ("NVLink peer exchange fused into the compute kernels (batch-norm sums: "
+                                                   "col_stats_reduce_finalize_kernel<true>; backward sums + loss: the score kernel's last "
+                                                   "block; peer_allreduce.cuh)" + ("" if not os.environ.get("NVSM_NO_FUSED_XCHG") else
+                                                                                    " -- stand-alone one-block launches (NVSM_NO_FUSED_XCHG)"))
+                              if peer_ok else "ncclAllReduce",
+                             "grad_transform": ("NVLink inboxes (gt_reduce_push_kernel -> transform_update_kernel)"
+                                                if peer_ok and os.environ.get("NVSM_FUSED_GT") == "1" else
+                                                "ncclAllReduce on a side stream under grad_phrase + word update")}),
         }
         if world > 1:
             line["strong"] = strong
