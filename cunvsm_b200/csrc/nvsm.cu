@@ -225,6 +225,11 @@ struct nvsm_model {
     cudaStream_t gt_stream = nullptr;            // fused steps: grad_transform GEMM (+ all-reduce) under the word update
     cudaEvent_t dx_ready = nullptr;
     bool gt_side = false, in_fused_step = false, no_fused_reduce = false, no_fused_gt = false, skip_gt_reduce = false;
+    // experiment knobs of the per-step path (environment, read ONCE in nvsm_create; -1 / 0 = not set)
+    struct Knobs {
+        int tc_2cta = -1, tc_stages = 0, tc_kb = 0, score_w = 0, score_s = 0, stats_bps = 0, sgd_sparse = -1;
+        bool no_ring = false, no_fused_stats = false, no_overlap = false;
+    } knobs;
     int buckets_at = 0;
     int pdl = 0;               // programmatic dependent launches along the main-stream kernel chain: bit mask over the
                                // kPdl* launch sites (NVSM_PDL)
@@ -462,8 +467,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
         // Default: on when one 256-wide tile covers N (the forward projection: B traffic per SM halves, measured
         // 70.2 -> 62.3 us on C2); grad_phrase (N = 300 -> two 160-wide tiles) measured equal (56.2 vs 56.6 us) and
         // stays on the single-SM kernel. NVSM_TC_2CTA=0 / 1 forces it off / on for every eligible GEMM.
-        const char* e = getenv("NVSM_TC_2CTA");
-        const bool want = e ? atoi(e) != 0 : (N > 160 && N <= 256);
+        const bool want = m->knobs.tc_2cta >= 0 ? m->knobs.tc_2cta != 0 : (N > 160 && N <= 256);
         if (want && !mn_major && splits <= 1 && m->num_sms >= 2) {
             tc::Params p;
             p.M = M; p.N = N; p.K = K;
@@ -475,7 +479,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
             p.kb_per_split = (K + tc::kBlockK - 1) / tc::kBlockK;
             p.stage_bytes = (tc::kATileBytes + (uint32_t)(p.bn / 2) * 128u) * (split3 ? 2u : 1u);
             p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
-            { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
+            if (m->knobs.tc_stages) p.stages = std::max(2, std::min(p.stages, m->knobs.tc_stages));
             if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
             p.tmem_cols = 512;   // whole TMEM: both CTAs of the pair must get base 0
             p.C = C; p.ldc = ldc; p.split_stride = 0; p.alpha = alpha; p.bias = bias;
@@ -506,7 +510,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.m_tiles = (M + tc::kBlockM - 1) / tc::kBlockM;
     // k-block per stage: 16 halves the stage (deeper ring, twice the TMA requests and barrier round trips); NVSM_TC_KB overrides
     int kb = 32;   // measured on C2 (3xTF32): k-block 16 = 4-deep ring 72 / 88 / 68 us (fwd, gT, gP) vs k-block 32 = 2-deep 70 / 71 / 57 us
-    { const char* e = getenv("NVSM_TC_KB"); if (e && (atoi(e) == 16 || atoi(e) == 32)) kb = atoi(e); }
+    if (m->knobs.tc_kb == 16 || m->knobs.tc_kb == 32) kb = m->knobs.tc_kb;
     p.kb = kb;
     const int num_kb = (K + kb - 1) / kb;
     splits = std::max(1, std::min(splits, num_kb));
@@ -514,7 +518,7 @@ int run_gemm_tc(nvsm_model* m, bool mn_major, int M, int N, int K, const float* 
     p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
     p.stage_bytes = ((uint32_t)tc::kBlockM * kb * 4u + (uint32_t)p.bn * kb * 4u) * (split3 ? 2u : 1u);
     p.stages = (int)std::min<uint32_t>(8u, (kTcMaxDynSmem - 1024u) / p.stage_bytes);
-    { const char* st = getenv("NVSM_TC_STAGES"); if (st) p.stages = std::max(2, std::min(p.stages, atoi(st))); }
+    if (m->knobs.tc_stages) p.stages = std::max(2, std::min(p.stages, m->knobs.tc_stages));
     if (p.stages < 2) return fail("tensor-core GEMM: tile does not fit in shared memory");
     p.tmem_cols = 32;
     while ((int)p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
@@ -638,14 +642,14 @@ int launch_score_ring(nvsm_model* m, const ScoreRingParams& q, int grid, size_t 
 // The >= 2-stage ring is kept for stages so large that fewer than 8 single-stage warps fit.
 int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
     const int dd = sp.dd, R = sp.R;
-    if (!vec4_ok(dd) || R > 32 || dd > 1024 || getenv("NVSM_NO_RING")) return -1;
+    if (!vec4_ok(dd) || R > 32 || dd > 1024 || m->knobs.no_ring) return -1;
     if (sp.enorm) return -1;   // entity normalisation lives in the register variant (score_kernel)
     const size_t stage_bytes = (size_t)(R + 1) * dd * 4;
     const size_t fixed = (size_t)(4 * dd + 2) * 4 + 8 * 4 * 8;
     const size_t budget = 227 * 1024 - 1024;
     int W = 8, S = 0;
-    const char* ew = getenv("NVSM_SCORE_W"); const char* es = getenv("NVSM_SCORE_S");
-    if (ew) W = std::max(1, std::min(8, atoi(ew)));
+    const bool ew = m->knobs.score_w > 0, es = m->knobs.score_s > 0;
+    if (ew) W = std::max(1, std::min(8, m->knobs.score_w));
     if (!ew && !es) {
         // single stage: blocks of W warps, as many blocks per SM as fit; the block size that keeps the most warps
         // resident wins (C3, R = 17: 18 KB per stage -> one 8-warp block per SM = 12.5 % occupancy in ncu r2a, three
@@ -663,7 +667,7 @@ int try_score_ring(nvsm_model* m, const ScoreParams& sp) {
             S = (int)std::min<size_t>(4, (budget - fixed) / (W * stage_bytes));
             if (S >= 2 || ew) break;
         }
-        if (es) S = std::min(S, std::max(1, atoi(es)));
+        if (es) S = std::min(S, std::max(1, m->knobs.score_s));
     }
     if (S < 1) return -1;
     ScoreRingParams q;
@@ -777,7 +781,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
             m->t_copies_stale = false;
         }
         // batch-norm: the column sums / sums of squares of Z come out of the GEMM's epilogue (no second pass over Z)
-        float* const fuse = (bn && !getenv("NVSM_NO_FUSED_STATS")) ? m->stat_part : (float*)nullptr;
+        float* const fuse = (bn && !m->knobs.no_fused_stats) ? m->stat_part : (float*)nullptr;
         TRY(run_gemm_tc(m, false, (int)B, dd, dw, m->P, m->ldP, m->Tt, m->ldP, m->Z, dd, 1, 0, 1.0f, bn ? nullptr : m->b, nullptr,
                         m->P_lo, m->Tt_lo, fuse, &stat_rows, kPdlGemmFwd));
     } else {
@@ -795,7 +799,7 @@ int forward(nvsm_model* m, BatchSlot* s) {
         {
             const int nvec = dd / 4, tpr = std::min(nvec, 256), rpp = 256 / tpr;
             int bps = 4;   // blocks per SM (NVSM_STATS_BPS: experiment knob)
-            { const char* e = getenv("NVSM_STATS_BPS"); if (e) bps = std::max(1, std::min(8, atoi(e))); }
+            if (m->knobs.stats_bps) bps = std::max(1, std::min(8, m->knobs.stats_bps));
             int nblk = stat_rows;
             if (nblk == 0) {
                 nblk = grid_for(m, B, 16, bps);
@@ -1272,7 +1276,7 @@ int launch_sgd_pull(nvsm_model* m, bool entities, float decay, float lr, bool to
     // sgd_pull_sparse_kernel: no dense decay and at most ~2 references per row on average (C3 entities 1.7, C5 0.13): the
     // scan and the per-row load chain are the cost. Denser tables keep the plain row loop (more warps, fewer registers).
     bool sparse = !touch_all && (double)(entities ? m->B * m->R : m->B * m->n) <= 2.0 * (double)(entities ? m->D : m->V);
-    { const char* e = getenv("NVSM_SGD_SPARSE"); if (e) sparse = !touch_all && atoi(e) != 0; }
+    if (m->knobs.sgd_sparse >= 0) sparse = !touch_all && m->knobs.sgd_sparse != 0;
     if (entities) {
         if (!sparse)
             LAUNCH(m, (sgd_pull_kernel<VEC, NCH, true>), grid, 256, 0, m->E, m->D, m->dd, m->e_offsets, m->e_refs,
@@ -1651,7 +1655,7 @@ int update(nvsm_model* m, float lr, float lambda) {
 // the main stream. The bandwidth-bound update and the pipeline-bound GEMMs share the SMs; nothing they touch overlaps
 // (E, its moments, mult, Y | Gp, P, T, gT, gP). Same arithmetic, same order per table.
 int start_entity_update(nvsm_model* m, float lr, float lambda) {
-    if (m->profiling || exact_sparse(m) || m->l2_entity || m->has_pair || !m->has_text || getenv("NVSM_NO_OVERLAP")) return 0;
+    if (m->profiling || exact_sparse(m) || m->l2_entity || m->has_pair || !m->has_text || m->knobs.no_overlap) return 0;
     if (lr < 0.f || lambda < 0.f) return 0;   // update() reports it
     CU(cudaEventRecord(m->score_done, m->stream));
     CU(cudaStreamWaitEvent(m->aux_stream, m->score_done, 0));
@@ -2052,6 +2056,15 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
         CU(cudaEventCreateWithFlags(&m->dx_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->gt_ready, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&m->gt_reduced_ev, cudaEventDisableTiming));
+        {
+            auto env_int = [](const char* name, int unset) { const char* e = getenv(name); return e ? atoi(e) : unset; };
+            m->knobs.tc_2cta = env_int("NVSM_TC_2CTA", -1); m->knobs.tc_stages = env_int("NVSM_TC_STAGES", 0);
+            m->knobs.tc_kb = env_int("NVSM_TC_KB", 0); m->knobs.score_w = env_int("NVSM_SCORE_W", 0);
+            m->knobs.score_s = env_int("NVSM_SCORE_S", 0); m->knobs.stats_bps = env_int("NVSM_STATS_BPS", 0);
+            m->knobs.sgd_sparse = env_int("NVSM_SGD_SPARSE", -1); m->knobs.no_ring = getenv("NVSM_NO_RING") != nullptr;
+            m->knobs.no_fused_stats = getenv("NVSM_NO_FUSED_STATS") != nullptr;
+            m->knobs.no_overlap = getenv("NVSM_NO_OVERLAP") != nullptr;
+        }
         { const char* e = getenv("NVSM_GT_SIDE"); m->gt_side = e ? atoi(e) != 0 : false; }
         m->no_fused_reduce = getenv("NVSM_NO_FUSED_REDUCE") != nullptr;
         // grad_transform through the NVLink inboxes instead of ncclAllReduce: correct (multi-GPU tests, parity_check) but

@@ -479,3 +479,49 @@ def test_device_sampled_step_equals_host_sampled_step():
         assert abs(a.last_cost() - b.last_cost()) <= 1e-6 * abs(a.last_cost())
     assert b.sampler_state() == rng_a.state
     assert_close(b.get_tensor(nv.ENTITY_REPRS), a.get_tensor(nv.ENTITY_REPRS), 1e-5, 1e-6)
+
+
+def test_timeline_mode_reports_overlapped_phases_and_does_not_change_results():
+    """nvsm_set_profiling(m, 2): the stream overlaps of the fused step stay on, every phase reports (start, end) against one
+    origin; the step's results are the ones of an unprofiled model (same kernels, same order per table)."""
+    V, D, dw, dd, n, z, B = 9000, 9000, 300, 256, 10, 10, 4096
+    kw = dict(n=n, z=z, B=B, nonlinearity=nv.TANH, bn=True, method=nv.ADAM, adam_mode=nv.DENSE_UPDATE_DENSE_VARIANCE,
+              gemm_mode=nv.GEMM_3XTF32)   # (tanh: no clip boundary for round-off to flip, see DESIGN.md section 5)
+    a, _, rng_a = twin_models(V, D, dw, dd, **kw)
+    b, _, rng_b = twin_models(V, D, dw, dd, **kw)
+    f, fw, labels, w = make_batch(np.random.default_rng(5), B, n, V, D, z)
+    ids = a.generate_labels(labels, rng_a)
+    batch = nv.Batch(B, n).fill(f, labels, fw, w)
+    b.set_profiling(2)
+    for m in (a, b):
+        m.train_step(batch, ids, 0.01)
+        m.train_step(batch, ids, 0.01)
+    tl = b.timeline()
+    b.set_profiling(0)
+    names = [t[0] for t in tl]
+    for ph in ("gather_mean", "gemm_fwd", "score_loss_bwd", "bn_backward", "gemm_grad_transform", "gemm_grad_phrase",
+               "update_entities", "update_words", "update_transform", "bucket_build"):
+        assert names.count(ph) == 2, (ph, names)
+    assert all(0.0 <= s <= e for _, s, e in tl)
+    ent = [t for t in tl if t[0] == "update_entities"][0]
+    gp = [t for t in tl if t[0] == "gemm_grad_phrase"][0]
+    assert ent[1] < gp[2], "the entity update runs on the auxiliary stream under the backward GEMMs"
+    # (not bit-for-bit: the order of a row's references inside its bucket follows the arrival order of integer atomics)
+    assert abs(a.last_cost() - b.last_cost()) <= 1e-6 * abs(a.last_cost())
+    for name in (nv.WORD_REPRS, nv.ENTITY_REPRS, nv.TRANSFORM, nv.BIAS):
+        assert_close(b.get_tensor(name), a.get_tensor(name), 1e-5, 1e-6, name)
+    a.close(); b.close()
+
+
+def test_programmatic_dependent_launch_mode_keeps_parity():
+    """NVSM_PDL=63 (every launch site as a programmatic dependent of the kernel in front of it) in a fresh process: the
+    tensor-core forward / backward and three-step training cases still match the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NVSM_PDL="63")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                          "-k", "tf32_tensor_core_gemms or three_training_steps or full_size_c2_full_adam"],
+                         env=env, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
