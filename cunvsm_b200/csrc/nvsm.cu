@@ -123,6 +123,10 @@ struct nvsm_model {
     // batches
     std::vector<BatchSlot> slots;  // cfg.num_batch_slots staged + 2 live (host-fed) slots
     int next_live = 0;
+    int live_slots = 3;   // host-fed batches in flight. With 2 the upload of batch k+2 (H2D, id validation, device sampling) had to
+                          // wait for step k to release its slot and then ran under step k+1's gather / forward GEMM (e2e timeline
+                          // r2B: gather 75 -> 83 us, GEMM 76 -> 81 us); with 3 it starts as soon as the host enqueues it, under
+                          // step k's backward / update: C2 e2e 0.619 -> 0.611 ms, C3 1.043 -> 1.031 ms (NVSM_LIVE_SLOTS=2|3|4)
     BatchSlot* cur = nullptr;      // batch of the running forward result
     long B = 0;                    // local instances of the running step
     long Bglobal = 0;
@@ -185,6 +189,9 @@ struct nvsm_model {
     int rng_cur = 0;
     bool rng_seeded = false;
     int *smp_counts = nullptr, *smp_offsets = nullptr, *smp_scan = nullptr, *smp_error = nullptr;
+    int2* smp_rej_items = nullptr;     // rare-rejection path of the sampler (sampler.cuh: RejList)
+    int* smp_rej_count = nullptr;      // [2], by call parity
+    unsigned long smp_calls = 0;
     double* smp_cdf = nullptr;         // [D] cumulative distribution of the negatives (null: uniform, the reference's)
     long smp_capacity = 0;             // candidate chunks allocated
 
@@ -228,7 +235,7 @@ struct nvsm_model {
     // experiment knobs of the per-step path (environment, read ONCE in nvsm_create; -1 / 0 = not set)
     struct Knobs {
         int tc_2cta = -1, tc_stages = 0, tc_kb = 0, score_w = 0, score_s = 0, stats_bps = 0, sgd_sparse = -1;
-        bool no_ring = false, no_fused_stats = false, no_overlap = false;
+        bool no_ring = false, no_fused_stats = false, no_overlap = false, sampler_scan = false;
     } knobs;
     int buckets_at = 0;
     int pdl = 0;               // programmatic dependent launches along the main-stream kernel chain: bit mask over the
@@ -298,6 +305,7 @@ int collect_phases(nvsm_model* m) {
     CU(cudaStreamSynchronize(m->stream));
     if (m->aux_stream) CU(cudaStreamSynchronize(m->aux_stream));
     if (m->gt_stream) CU(cudaStreamSynchronize(m->gt_stream));
+    if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));
     for (auto& ev : m->pending) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev.a, ev.b);
@@ -1702,6 +1710,8 @@ int ensure_sampler(nvsm_model* m) {
         TRY(dev_alloc(&m->rng_dev, 2));
         TRY(dev_alloc(&m->smp_error, 1));
         TRY(dev_alloc(&m->smp_scan, 2 * 1024 + 2));
+        TRY(dev_alloc(&m->smp_rej_items, kRejListCap));
+        TRY(dev_alloc(&m->smp_rej_count, 2));
     }
     const long chunks = sampler_candidates(m->maxB * std::max(1, m->z), m->D) / kSamplerChunk;
     if (chunks > m->smp_capacity) {
@@ -1753,6 +1763,22 @@ int sample_labels_device(nvsm_model* m, const idx_t* labels, idx_t* ids, long B,
         p.counts = m->smp_counts; p.offsets = m->smp_offsets;
     }
     const int grid = (int)((nchunks + 255) / 256);
+    {
+        // expected rejected candidates of this call; the list path holds kRejListCap chunks (overflow -> error flag)
+        const unsigned long urngrange = 2147483645ul;
+        const double p_rej = (double)(urngrange + 1 - (unsigned long)p.past) / (double)(urngrange + 1);
+        if (!m->knobs.sampler_scan && p_rej * (double)p.num_candidates <= 512.0) {
+            RejList rl;
+            rl.items = m->smp_rej_items;
+            rl.count = m->smp_rej_count + (m->smp_calls & 1);
+            rl.count_next = m->smp_rej_count + ((m->smp_calls + 1) & 1);
+            m->smp_calls++;
+            LAUNCH(m, sampler_count_list_kernel, grid, 256, 0, p, rl);
+            LAUNCH(m, sampler_fill_list_kernel, std::max(grid, (int)((B + 255) / 256)), 256, 0, p, rl);
+            m->rng_cur ^= 1;
+            return 0;
+        }
+    }
     LAUNCH(m, sampler_count_kernel, grid, 256, 0, p);
     const int nb = (int)((nchunks + 1023) / 1024);
     LAUNCH(m, scan_blocks_kernel, nb, 1024, 0, m->smp_counts, nchunks, m->smp_offsets, m->smp_scan, (int*)nullptr);
@@ -1852,7 +1878,7 @@ int upload_batch(nvsm_model* m, BatchSlot* s, const long* features, const float*
 
 BatchSlot* next_live_slot(nvsm_model* m) {
     BatchSlot* s = &m->slots[m->cfg.num_batch_slots + m->next_live];
-    m->next_live ^= 1;
+    m->next_live = (m->next_live + 1) % m->live_slots;
     return s;
 }
 
@@ -1982,7 +2008,8 @@ void nvsm_destroy(nvsm_model* m) {
     if (m->heavy_e_dev) cudaFree(m->heavy_e_dev);
     if (m->heavy_w_dev) cudaFree(m->heavy_w_dev);
     if (m->smp_cdf) cudaFree(m->smp_cdf);
-    int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error};
+    if (m->smp_rej_items) cudaFree(m->smp_rej_items);
+    int* sl[] = {m->smp_counts, m->smp_offsets, m->smp_scan, m->smp_error, m->smp_rej_count};
     for (int* p : sl)
         if (p) cudaFree(p);
     for (auto& s : m->slots) {
@@ -2064,6 +2091,7 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             m->knobs.sgd_sparse = env_int("NVSM_SGD_SPARSE", -1); m->knobs.no_ring = getenv("NVSM_NO_RING") != nullptr;
             m->knobs.no_fused_stats = getenv("NVSM_NO_FUSED_STATS") != nullptr;
             m->knobs.no_overlap = getenv("NVSM_NO_OVERLAP") != nullptr;
+            m->knobs.sampler_scan = getenv("NVSM_SAMPLER_SCAN") != nullptr;   // always the count / scan / fill path
         }
         { const char* e = getenv("NVSM_GT_SIDE"); m->gt_side = e ? atoi(e) != 0 : false; }
         m->no_fused_reduce = getenv("NVSM_NO_FUSED_REDUCE") != nullptr;
@@ -2166,7 +2194,8 @@ int nvsm_create(const nvsm_config* cfg, nvsm_model** out) {
             if (method == NVSM_ADAGRAD) TRY(dev_alloc(&m->wcoef, maxB * m->n));
             if (std::max(V, D) > 1024L * 1024L) m->pull = false;  // two-level scan limit
         }
-        m->slots.resize(m->cfg.num_batch_slots + 2);
+        { const char* e = getenv("NVSM_LIVE_SLOTS"); if (e) m->live_slots = std::max(2, std::min(4, atoi(e))); }
+        m->slots.resize(m->cfg.num_batch_slots + m->live_slots);
         for (auto& s : m->slots) {
             TRY(dev_alloc(&s.features, maxB * m->n)); TRY(dev_alloc(&s.fweights, maxB * m->n));
             TRY(dev_alloc(&s.ids, maxB * m->R)); TRY(dev_alloc(&s.weights, maxB)); TRY(dev_alloc(&s.labels, maxB));
@@ -2531,6 +2560,8 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
     if (s->in_use) { TRY(join_unconsumed_buckets(m)); CU(cudaEventRecord(s->consumed, m->stream)); s->ever_consumed = true; }
     if (s->ever_consumed) CU(cudaStreamWaitEvent(cs, s->consumed, 0));
     s->in_use = false;
+    cudaEvent_t tl_begin = nullptr;   // timeline mode: the copy-stream work of this batch as an "h2d" interval
+    if (m->timeline) { tl_begin = get_event(m); cudaEventRecord(tl_begin, cs); }
     CU(cudaMemcpyAsync(s->features, features, sizeof(long) * B * m->n, cudaMemcpyHostToDevice, cs));
     TRY(upload_weights(m, cs, s->fweights, fw, B * m->n, &s->fw_ones));
     CU(cudaMemcpyAsync(s->labels, labels, sizeof(long) * B, cudaMemcpyHostToDevice, cs));
@@ -2546,6 +2577,11 @@ int nvsm_step_sampled(nvsm_model* m, const long* features, const float* fw, cons
         const int src = sample_labels_device(m, s->labels, s->ids, s->B, m->z, m->D);
         m->stream = main_stream; m->profiling = prof;
         if (src) return src;
+    }
+    if (tl_begin) {
+        cudaEvent_t tl_end = get_event(m);
+        cudaEventRecord(tl_end, cs);
+        m->pending.push_back({PH_H2D, tl_begin, tl_end});
     }
     CU(cudaEventRecord(s->ready, cs));   // "ready" covers the copies and the sampled ids (bucket build waits on it)
     CU(cudaStreamWaitEvent(m->stream, s->ready, 0));

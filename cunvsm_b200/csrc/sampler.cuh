@@ -88,6 +88,76 @@ __global__ void __launch_bounds__(256) sampler_fill_kernel(const SamplerParams p
     }
 }
 
+// Rare-rejection path (what every table below ~2^27 rows takes: the rejection probability of libstdc++'s down-scaling loop is
+// (2^31 - 2) mod D / (2^31 - 2), 1.6e-5 for D = 50k, i.e. ~8 rejected candidates in a 512 000-draw batch): instead of
+// a per-chunk count array + three scan launches + a total launch, the count kernel appends the few chunks that saw a
+// rejection to a short list and the fill kernel derives its chunk's offset from that list:
+//   offset(t) = chunk * t - sum_{listed chunks c < t} rejected(c).
+// Two launches instead of six on the copy stream, which runs under the main stream's gather / forward GEMM.
+constexpr int kRejListCap = 2048;
+
+struct RejList {
+    int2* items;        // (chunk, rejected candidates in it), unordered
+    int* count;         // entries appended by THIS call
+    int* count_next;    // the other parity's counter: reset by the fill kernel for the next call
+};
+
+__global__ void __launch_bounds__(256) sampler_count_list_kernel(const SamplerParams p, const RejList rl) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nchunks = p.num_candidates / kSamplerChunk;
+    if (t >= nchunks) return;
+    unsigned int x = lehmer_mulmod(lehmer_pow((unsigned long long)t * kSamplerChunk), *p.state_in);
+    int rej = 0;
+#pragma unroll
+    for (int k = 0; k < kSamplerChunk; ++k) {
+        x = lehmer_mulmod(x, kLehmerA);
+        rej += (x - 1u) >= p.past;
+    }
+    if (rej > 0) {
+        const int slot = atomicAdd(rl.count, 1);
+        if (slot < kRejListCap) rl.items[slot] = make_int2((int)t, rej);
+    }
+}
+
+__global__ void __launch_bounds__(256) sampler_fill_list_kernel(const SamplerParams p, const RejList rl) {
+    __shared__ int2 s_items[256];
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nchunks = p.num_candidates / kSamplerChunk;
+    // positives
+    const long B = p.num_draws / max(p.z, 1);
+    for (long i = t; i < (p.z > 0 ? B : 0); i += (long)gridDim.x * blockDim.x) p.ids[i * p.R] = p.labels[i];
+    const int listed = *rl.count;
+    const int n = min(listed, kRejListCap);
+    long before = 0, total_rej = 0;   // rejected candidates in chunks before mine / overall
+    for (int base = 0; base < n; base += 256) {
+        __syncthreads();
+        if (base + (int)threadIdx.x < n) s_items[threadIdx.x] = rl.items[base + threadIdx.x];
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int k = 0; k < m; ++k) {
+            total_rej += s_items[k].y;
+            if (s_items[k].x < t) before += s_items[k].y;
+        }
+    }
+    if (t == 0) {
+        if (listed > kRejListCap || p.num_candidates - total_rej < p.num_draws) *p.error_flag = 1;
+        *rl.count_next = 0;
+    }
+    if (t >= nchunks) return;
+    long g = t * kSamplerChunk - before;
+    if (g >= p.num_draws) return;
+    unsigned int x = lehmer_mulmod(lehmer_pow((unsigned long long)t * kSamplerChunk), *p.state_in);
+    for (int k = 0; k < kSamplerChunk && g < p.num_draws; ++k) {
+        x = lehmer_mulmod(x, kLehmerA);
+        const unsigned int ret = x - 1u;
+        if (ret < p.past) {
+            p.ids[(g / p.z) * p.R + 1 + (g % p.z)] = (idx_t)(ret / p.scaling);
+            if (g == p.num_draws - 1) *p.state_out = x;
+            ++g;
+        }
+    }
+}
+
 // offsets[nchunks] = total accepted (scan_add_kernel wrote its own `total` argument there)
 __global__ void sampler_total_kernel(const int* __restrict__ counts, int* __restrict__ offsets, long nchunks) {
     offsets[nchunks] = offsets[nchunks - 1] + counts[nchunks - 1];
