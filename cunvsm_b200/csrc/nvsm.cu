@@ -2709,9 +2709,10 @@ int nvsm_set_profiling(nvsm_model* m, int enabled) {
 }
 
 int nvsm_get_timeline(nvsm_model* m, int* phases, float* start_ms, float* end_ms, int capacity) {
-    if (!m) return fail("null model");
-    CU(cudaSetDevice(m->device));
-    TRY(collect_phases(m));
+    // (a count, not a status: errors are -1 with the message in nvsm_last_error)
+    if (!m) { fail("null model"); return -1; }
+    if (cudaSetDevice(m->device) != cudaSuccess) { fail("cudaSetDevice(%d) failed", m->device); return -1; }
+    if (collect_phases(m) != 0) return -1;
     const int n = (int)m->intervals.size();
     for (int i = 0; i < n && i < capacity; ++i) {
         if (phases) phases[i] = m->intervals[i].phase;

@@ -493,7 +493,7 @@ class Model:
         b = (ctypes.c_float * capacity)()
         n = self.L.nvsm_get_timeline(self.h, ph, a, b, capacity)
         if n < 0:
-            check(n)
+            check(1)
         return [(self.L.nvsm_phase_name(ph[i]).decode(), a[i], b[i]) for i in range(min(n, capacity))]
 
     def reset_phase_ms(self):

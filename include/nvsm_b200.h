@@ -205,7 +205,8 @@ NVSM_API int nvsm_increment_parameter(nvsm_model* m, const char* name, long idx,
  * 2 timeline (overlaps kept: nvsm_get_timeline reports every phase interval, on whatever stream it ran, in ms since
  * this call). The role nvprof / NVTX ranges play for the reference (cpp/main.cu:16,372-459). */
 NVSM_API int nvsm_set_profiling(nvsm_model* m, int enabled);
-/* Returns the number of intervals recorded since nvsm_set_profiling(m, 2); fills at most `capacity` entries. */
+/* Returns the number of intervals recorded since nvsm_set_profiling(m, 2) (-1 on error, message in nvsm_last_error);
+ * fills at most `capacity` entries. */
 NVSM_API int nvsm_get_timeline(nvsm_model* m, int* phases, float* start_ms, float* end_ms, int capacity);
 NVSM_API int nvsm_num_phases(void);
 NVSM_API const char* nvsm_phase_name(int phase);
