@@ -113,13 +113,17 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
             for (int k = 0; k < NCH; ++k)
                 if (FULL || lane4 + k * 128 < dd) ring_cp16(dst + k * 512u, zsrc + k * 128);
             uint32_t d = dst + row_bytes;
-#pragma unroll 4
-            for (int r = 0; r < R; ++r, d += row_bytes) {
-                const uint32_t id = __shfl_sync(kFull, id0, r);
-                const float* src = e_lane + (size_t)id * dd;
+            for (int r0 = 0; r0 < R; r0 += 4, d += 4 * row_bytes) {   // groups of four, predicated: no remainder loop
 #pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                    if (FULL || lane4 + k * 128 < dd) ring_cp16(d + k * 512u, src + k * 128);
+                for (int rr = 0; rr < 4; ++rr) {
+                    const uint32_t id = __shfl_sync(kFull, id0, (r0 + rr) & 31);
+                    if (r0 + rr < R) {
+                        const float* src = e_lane + (size_t)id * dd;
+#pragma unroll
+                        for (int k = 0; k < NCH; ++k)
+                            if (FULL || lane4 + k * 128 < dd) ring_cp16(d + (uint32_t)rr * row_bytes + k * 512u, src + k * 128);
+                    }
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -150,8 +154,9 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
     const float clip_min = p.act.clip_min, clip_max = p.act.clip_max;
     const int nbatch = (R + 3) >> 2;
 
+    long i = warp0 - nwarps;
     for (long j = 0; j < my_count; ++j) {
-        const long i = warp0 + j * nwarps;
+        i += nwarps;   // n-gram of iteration j: warp0 + j * nwarps
         // keep the ring full: n-gram j+S-1 goes into the stage consumed at iteration j-1
         if (S == 1) iw_q[0] = niw; else if (S == 2) iw_q[1] = niw; else if (S == 3) iw_q[2] = niw; else iw_q[3] = niw;
         issue(j + S - 1, nid0, s == 0 ? S - 1 : s - 1);
@@ -205,13 +210,23 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
         // Branch-free: rows past R are clamped to row R-1 and get coefficient zero.
         for (int bch = 0; bch < nbatch; ++bch) {
             float4 x[4][NCH];
+            const float* rp0 = erow + (size_t)(bch * 4) * dd + lane4;
+            if (bch * 4 + 3 < R) {   // a full group: offsets are immediates on the FULL path
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const float* rp = erow + (size_t)min(bch * 4 + rr, R - 1) * dd + lane4;
+                for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                    x[rr][k] = (FULL || lane4 + k * 128 < dd) ? *reinterpret_cast<const float4*>(rp + k * 128)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < NCH; ++k)
+                        x[rr][k] = (FULL || lane4 + k * 128 < dd) ? *reinterpret_cast<const float4*>(rp0 + rr * dd + k * 128)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const float* rp = erow + (size_t)min(bch * 4 + rr, R - 1) * dd + lane4;
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k)
+                        x[rr][k] = (FULL || lane4 + k * 128 < dd) ? *reinterpret_cast<const float4*>(rp + k * 128)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             float dot[4];
 #pragma unroll
@@ -265,7 +280,8 @@ __global__ void __launch_bounds__(256) score_ring_kernel(const ScoreRingParams q
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const float yy = y[k][v];
-                const float dv = is_tanh ? (1.0f - yy * yy) : ((yy > clip_min && yy < clip_max) ? 1.0f : 0.0f);
+                // (clip_min == -clip_max, host: act_params)
+                const float dv = is_tanh ? (1.0f - yy * yy) : (fabsf(yy) < clip_max ? 1.0f : 0.0f);
                 dy[v] = dv * gp[k][v];
                 cs[k][v] += dy[v];
                 cx[k][v] += dy[v] * tt[k][v];   // sum dy * (xhat + bias); the bias term is removed by the caller

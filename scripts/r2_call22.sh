@@ -1,11 +1,11 @@
 #!/bin/bash
-# Round 2, call 23 (1 GPU): score_ring_kernel one-sweep + instruction diet (32-bit id shuffles, incremental stage index, FMA chains,
-# lane r = row r stores) vs the two-pass kernel (libnvsm_b200_twopass.so) on one box; parity suites; ncu of the new kernel.
+# Round 2, calls 23 and 32 (1 GPU): score_ring_kernel variants, new (libnvsm_b200.so) vs the previous build (libnvsm_b200_prev.so) on one box;
+# lane r = row r stores) vs the two-pass kernel (libnvsm_b200_prev.so) on one box; parity suites; ncu of the new kernel.
 T=${1:-r2w}
 mkdir -p gpurun_out
 S=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - S )) s] $*"; }
-OLD=$PWD/cunvsm_b200/libnvsm_b200_twopass.so
+OLD=$PWD/cunvsm_b200/libnvsm_b200_prev.so
 timeout 500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py tests/test_gpu_reference.py -m gpu -q -n 4 --maxfail=10 > gpurun_out/pytest_$T.log 2>&1; stamp "parity suites rc=$?"
 tail -3 gpurun_out/pytest_$T.log
 b() { local name=$1; shift; timeout 200 python bench.py --steps 200 --warmup 20 --no_cpu_baseline --no_alt --no_probes "$@" > gpurun_out/bench_${T}_$name.json 2> gpurun_out/bench_${T}_$name.err; stamp "bench $name rc=$?"; }

@@ -277,7 +277,9 @@ def test_null_weights_mean_uniform_weights_bit_exact():
             assert implicit.uniform_feature_weights_ and implicit.uniform_weights_ and not explicit.uniform_weights_
         ra, rb = a.compute_cost(explicit, entity_ids=ids), b.compute_cost(implicit, entity_ids=ids)
         ca, cb = ra.get_cost(), rb.get_cost()
-        assert (ca == cb) if step == 0 else abs(ca - cb) <= 2e-6 * abs(ca), (step, ca, cb)
+        # (round-off, not bitwise, from the first step on: the per-block loss is combined with float atomics in shared
+        # memory, whose order follows the warps' finishing order)
+        assert abs(ca - cb) <= 2e-6 * abs(ca), (step, ca, cb)
         a.backprop(ra, 0.01); b.backprop(rb, 0.01)
         a.train_step(explicit, ids, 0.01); b.train_step(implicit, ids, 0.01)        # copy-stream upload path
         a.stage_batch(1, explicit, ids); b.stage_batch(1, implicit, ids)            # staged path
